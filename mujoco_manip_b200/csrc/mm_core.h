@@ -1,0 +1,1194 @@
+// Physics substep of the pick-and-place scene for ONE environment handled by a G-lane group.
+//
+// Replaces, for this scene only, what the reference reaches through libmujoco on its step hot path:
+//   mj_step    (mujoco_manip/env.py:119-121, gym_env.py:558)
+//   mj_forward (mujoco_manip/env.py:117,161, gym_env.py:560)
+//   mj_jac     (mujoco_manip/controller.py:101-108)
+// Algorithms (SURVEY.md Appendix A for the semantics that are reproduced):
+//   * kinematics of the 7R+gripper chain, world-origin spatial axes S_i for all 27 dofs
+//   * CRBA with compact rigid-body inertias (m, h, Ibar) about the world origin -> 9x9 robot block;
+//     the cube blocks are constant diag(m, I)
+//   * RNEA in the same coordinates for the bias forces
+//   * box-box / plane-box narrow phase, contacts grouped by BODY PAIR
+//   * pyramidal soft constraints solved by Newton with exact line search, MATRIX-FREE:
+//     J is never stored; every J*x, J^T*f and J^T D J goes through per-body-pair 6-vectors / 6x6 blocks
+//   * implicitfast integration (block diagonal: 9x9 robot factor, scalar cube updates)
+#pragma once
+#include "mm_model.h"
+
+namespace mm {
+
+constexpr int MAXCON = 128;   // contacts per env (oracle max: 44 in scripted episodes, 76 in random-action stress)
+constexpr int MAXROW = MAXCON * 6;
+constexpr int MAXPAIR = 16;   // simultaneously touching body pairs
+constexpr int MAXSPEC = 10;   // equality + at most one limit row per robot joint
+constexpr int MAXSURV = 128;  // geom pairs surviving the broad phase
+constexpr double MINVAL_D = 1e-15;
+
+// meta word of a contact
+//  bits 0-3 pair slot | 4-7 class A | 8-11 class B | 12 condim-4 (cube) | 13-18 active-row bits | 19 robot-obstacle | 20-28 candidate index
+MM_HD int meta_slot(int m) { return m & 15; }
+MM_HD int meta_dim4(int m) { return (m >> 12) & 1; }
+
+template <class T>
+struct Scratch {
+  T qpos[NQ], qvel[NV], ctrl[NU], warm[NV];
+  T bpos[NDB][3], bR[NDB][9];
+  T S[NV][6];
+  T Mr[NROB * NROB];
+  T fs[NV], as[NV], qacc[NV], Ma[NV], grad[NV], search[NV], Mv[NV], fc[NV];
+  T H[NV * NV];
+  T tmp6[NV][6];
+  T inert[2][NROB][10];
+  T pairK[MAXPAIR][21], pairW[MAXPAIR][6], pairF[MAXPAIR][6];
+  T specD[MAXSPEC], specJaref[MAXSPEC], specJv[MAXSPEC], specAref[MAXSPEC];
+  T boxc[13][3];
+  T actf[NU];
+  T target[3];
+  int pairkey[MAXPAIR];
+  int specdof[MAXSPEC];  // -1: equality row (e7 - e8); else dof | (negative sign ? 256 : 0)
+  int surv[MAXSURV];
+  int actsat[NU];
+  int ncon, npair, nspec, nsurv, overflow, niter, hvalid;
+};
+
+// per-env slice of the global workspace (streamed, coalesced across lanes: index = contact / row)
+template <class T>
+struct Work {
+  T* cpos;  // [3][MAXCON]
+  T* cn;    // [3][MAXCON]
+  T* ct1;   // [3][MAXCON]
+  T* cdist; // [MAXCON]
+  T* cD;    // [MAXCON]
+  T* aref;  // [MAXROW]
+  T* Jaref; // [MAXROW]
+  T* Jv;    // [MAXROW]
+  int* cmeta;  // [MAXCON]
+};
+constexpr int WORK_REALS = MAXCON * 11 + MAXROW * 3;
+constexpr int WORK_INTS = MAXCON;
+template <class T>
+MM_HD Work<T> make_work(T* reals, int* ints) {
+  Work<T> w;
+  w.cpos = reals; w.cn = reals + 3 * MAXCON; w.ct1 = reals + 6 * MAXCON; w.cdist = reals + 9 * MAXCON;
+  w.cD = reals + 10 * MAXCON; w.aref = reals + 11 * MAXCON; w.Jaref = w.aref + MAXROW; w.Jv = w.Jaref + MAXROW;
+  w.cmeta = ints;
+  return w;
+}
+
+MM_HD int dofmask(int cls) {
+  if (cls == 0) return 0;
+  if (cls <= 7) return (1 << cls) - 1;
+  if (cls == 8) return 0x7F | (1 << 7);
+  if (cls == 9) return 0x7F | (1 << 8);
+  return 0x3F << (9 + 6 * (cls - CLS_CUBE0));
+}
+
+// ------------------------------------------------------------------------------------------------
+// group Cholesky (lower, in place, row-major ld = n) and solve
+// ------------------------------------------------------------------------------------------------
+template <class T, int G>
+MM_HDN void chol_factor(const Grp<G>& g, T* A, int n) {
+  for (int j = 0; j < n; j++) {
+    T d = A[j * n + j];
+    if (d < (T)MINVAL_D) d = (T)MINVAL_D;
+    T l = tsqrt(d), inv = (T)1 / l;
+    g.sync();
+    for (int i = j + 1 + g.lane; i < n; i += G) A[i * n + j] *= inv;
+    if (g.lane == 0) A[j * n + j] = l;
+    g.sync();
+    for (int i = j + 1 + g.lane; i < n; i += G) {
+      T lij = A[i * n + j];
+      for (int k = j + 1; k <= i; k++) A[i * n + k] -= lij * A[k * n + j];
+    }
+    g.sync();
+  }
+}
+
+template <class T, int G>
+MM_HDN void chol_solve(const Grp<G>& g, const T* L, int n, T* x) {
+  for (int k = 0; k < n; k++) {
+    T xk = x[k] / L[k * n + k];
+    g.sync();
+    if (g.lane == 0) x[k] = xk;
+    for (int i = k + 1 + g.lane; i < n; i += G) x[i] -= L[i * n + k] * xk;
+    g.sync();
+  }
+  for (int k = n - 1; k >= 0; k--) {
+    T xk = x[k] / L[k * n + k];
+    g.sync();
+    if (g.lane == 0) x[k] = xk;
+    for (int i = g.lane; i < k; i += G) x[i] -= L[k * n + i] * xk;
+    g.sync();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// kinematics + world-origin spatial axes (replaces mj_kinematics / mj_comPos / mj_jac data)
+// ------------------------------------------------------------------------------------------------
+template <class T>
+MM_HD void quat2mat(T* m, const T* q) {
+  T w = q[0], x = q[1], y = q[2], z = q[3];
+  m[0] = w * w + x * x - y * y - z * z; m[1] = 2 * (x * y - w * z); m[2] = 2 * (x * z + w * y);
+  m[3] = 2 * (x * y + w * z); m[4] = w * w - x * x + y * y - z * z; m[5] = 2 * (y * z - w * x);
+  m[6] = 2 * (x * z - w * y); m[7] = 2 * (y * z + w * x); m[8] = w * w - x * x - y * y + z * z;
+}
+
+template <class T, int G>
+MM_HDN void fk(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md) {
+  for (int i = g.lane; i < NARM; i += G) tsincos(s.qpos[i], &s.tmp6[i][0], &s.tmp6[i][1]);
+  g.sync();
+  for (int t = g.lane; t < 4; t += G) {
+    if (t == 0) {
+      T Rp[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, pp[3] = {0, 0, 0};
+      for (int k = 0; k < NARM; k++) {
+        T v[3], Rf[9];
+        rot(v, Rp, md.link_pos[k]);
+        for (int a = 0; a < 3; a++) { pp[a] += v[a]; s.bpos[k][a] = pp[a]; }
+        matmul3(Rf, Rp, md.link_R[k]);
+        T sn = s.tmp6[k][0], cs = s.tmp6[k][1];
+        for (int r = 0; r < 3; r++) {
+          Rp[3 * r] = Rf[3 * r] * cs + Rf[3 * r + 1] * sn;
+          Rp[3 * r + 1] = Rf[3 * r + 1] * cs - Rf[3 * r] * sn;
+          Rp[3 * r + 2] = Rf[3 * r + 2];
+        }
+        for (int a = 0; a < 9; a++) s.bR[k][a] = Rp[a];
+      }
+      T v[3], Rh[9], ph[3];
+      rot(v, Rp, md.link_pos[7]);
+      for (int a = 0; a < 3; a++) { ph[a] = pp[a] + v[a]; s.bpos[DB_HAND][a] = ph[a]; }
+      matmul3(Rh, Rp, md.link_R[7]);
+      for (int a = 0; a < 9; a++) s.bR[DB_HAND][a] = Rh[a];
+      for (int f = 0; f < 2; f++) {
+        T Rf[9];
+        matmul3(Rf, Rh, md.link_R[8 + f]);
+        rot(v, Rh, md.link_pos[8 + f]);
+        T q = s.qpos[7 + f];
+        for (int a = 0; a < 3; a++) s.bpos[DB_LF + f][a] = ph[a] + v[a] + Rf[3 * a + 1] * q;
+        for (int a = 0; a < 9; a++) s.bR[DB_LF + f][a] = Rf[a];
+      }
+    } else {
+      int j = t - 1;
+      T* q = s.qpos + 9 + 7 * j + 3;
+      T nn = tsqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+      if (nn < (T)MINVAL_D) { q[0] = 1; q[1] = q[2] = q[3] = 0; }
+      else { T inv = (T)1 / nn; for (int a = 0; a < 4; a++) q[a] *= inv; }
+      for (int a = 0; a < 3; a++) s.bpos[DB_CUBE0 + j][a] = s.qpos[9 + 7 * j + a];
+      quat2mat(s.bR[DB_CUBE0 + j], q);
+    }
+  }
+  g.sync();
+  for (int i = g.lane; i < NV; i += G) {
+    T* S = s.S[i];
+    if (i < NARM) {
+      T a[3] = {s.bR[i][2], s.bR[i][5], s.bR[i][8]};
+      S[0] = a[0]; S[1] = a[1]; S[2] = a[2];
+      cross3(S + 3, s.bpos[i], a);
+    } else if (i < NROB) {
+      const T* R = s.bR[DB_LF + (i - 7)];
+      S[0] = S[1] = S[2] = 0; S[3] = R[1]; S[4] = R[4]; S[5] = R[7];
+    } else {
+      int d = i - 9, j = d / 6, k = d % 6;
+      if (k < 3) { for (int a = 0; a < 6; a++) S[a] = 0; S[3 + k] = 1; }
+      else {
+        const T* R = s.bR[DB_CUBE0 + j];
+        T a[3] = {R[k - 3], R[3 + k - 3], R[6 + k - 3]};
+        S[0] = a[0]; S[1] = a[1]; S[2] = a[2];
+        cross3(S + 3, s.bpos[DB_CUBE0 + j], a);
+      }
+    }
+  }
+  for (int b = g.lane; b < 13; b += G) {
+    if (b < 10) {
+      int body = md.box_body[b];
+      T v[3];
+      rot(v, s.bR[body], md.box_pos[b]);
+      for (int a = 0; a < 3; a++) s.boxc[b][a] = s.bpos[body][a] + v[a];
+    } else {
+      for (int a = 0; a < 3; a++) s.boxc[b][a] = s.bpos[b][a];  // db 10..12
+    }
+  }
+  g.sync();
+}
+
+// ------------------------------------------------------------------------------------------------
+// smooth dynamics: robot mass matrix (CRBA), bias (RNEA), passive + actuation, qacc_smooth (A5)
+// ------------------------------------------------------------------------------------------------
+// compact inertia about the world origin: {m, h[3], Ixx, Iyy, Izz, Ixy, Ixz, Iyz};  (n;f) = I (w;v)
+template <class T>
+MM_HD void inertia_apply(const T* I, const T* V, T* F) {
+  const T* w = V; const T* v = V + 3; const T* h = I + 1;
+  T hv[3], hw[3];
+  cross3(hv, h, v);
+  cross3(hw, h, w);
+  F[0] = I[4] * w[0] + I[7] * w[1] + I[8] * w[2] + hv[0];
+  F[1] = I[7] * w[0] + I[5] * w[1] + I[9] * w[2] + hv[1];
+  F[2] = I[8] * w[0] + I[9] * w[1] + I[6] * w[2] + hv[2];
+  F[3] = I[0] * v[0] - hw[0]; F[4] = I[0] * v[1] - hw[1]; F[5] = I[0] * v[2] - hw[2];
+}
+
+MM_HD int ib_parent(int k) { return k <= 6 ? k - 1 : 6; }
+
+template <class T, int G>
+MM_HDN void dyn_smooth(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md) {
+  // individual compact inertias
+  for (int ib = g.lane; ib < NROB; ib += G) {
+    int d = ib < 7 ? ib : ib + 1;
+    const T* R = s.bR[d];
+    T c[3], v[3];
+    rot(v, R, md.ib_com[ib]);
+    for (int a = 0; a < 3; a++) c[a] = s.bpos[d][a] + v[a];
+    const T* J = md.ib_inertia[ib];
+    T Ib[9] = {J[0], J[3], J[4], J[3], J[1], J[5], J[4], J[5], J[2]}, t[9], Iw[9], Rt[9];
+    for (int i = 0; i < 3; i++) for (int k = 0; k < 3; k++) Rt[3 * i + k] = R[3 * k + i];
+    matmul3(t, R, Ib);
+    matmul3(Iw, t, Rt);
+    T m = md.ib_mass[ib], cc = dot3(c, c);
+    T* o = s.inert[0][ib];
+    o[0] = m; o[1] = m * c[0]; o[2] = m * c[1]; o[3] = m * c[2];
+    o[4] = Iw[0] + m * (cc - c[0] * c[0]); o[5] = Iw[4] + m * (cc - c[1] * c[1]); o[6] = Iw[8] + m * (cc - c[2] * c[2]);
+    o[7] = Iw[1] - m * c[0] * c[1]; o[8] = Iw[2] - m * c[0] * c[2]; o[9] = Iw[5] - m * c[1] * c[2];
+  }
+  // spatial velocities / bias accelerations along the chain (lane 0), world origin coordinates
+  T* Vb = s.H;            // [9][6]
+  T* Ab = s.H + 54;       // [9][6]
+  T* fb = s.H + 108;      // [9][6]
+  if (g.lane == 0) {
+    for (int k = 0; k < NROB; k++) {
+      int p = ib_parent(k);
+      T Vp[6], Ap[6];
+      if (p < 0) { for (int a = 0; a < 6; a++) { Vp[a] = 0; Ap[a] = 0; } Ap[5] = -md.gravity_z; }
+      else for (int a = 0; a < 6; a++) { Vp[a] = Vb[6 * p + a]; Ap[a] = Ab[6 * p + a]; }
+      const T* S = s.S[k];
+      T qd = s.qvel[k];
+      // A_k = A_p + (V_p x S_k) qd ; V_k = V_p + S_k qd
+      T c1[3], c2[3], c3[3];
+      cross3(c1, Vp, S);          // w x Sw
+      cross3(c2, Vp, S + 3);      // w x Sv
+      cross3(c3, Vp + 3, S);      // v x Sw
+      for (int a = 0; a < 3; a++) {
+        Ab[6 * k + a] = Ap[a] + c1[a] * qd;
+        Ab[6 * k + 3 + a] = Ap[3 + a] + (c2[a] + c3[a]) * qd;
+      }
+      for (int a = 0; a < 6; a++) Vb[6 * k + a] = Vp[a] + S[a] * qd;
+    }
+  }
+  g.sync();
+  // composite inertias (component-parallel suffix sums)
+  for (int c = g.lane; c < 10; c += G) {
+    s.inert[1][8][c] = s.inert[0][8][c];
+    s.inert[1][7][c] = s.inert[0][7][c];
+    T acc = s.inert[0][6][c] + s.inert[0][7][c] + s.inert[0][8][c];
+    s.inert[1][6][c] = acc;
+    for (int k = 5; k >= 0; k--) { acc += s.inert[0][k][c]; s.inert[1][k][c] = acc; }
+  }
+  // body forces f_k = I_k A_k + V_k x* (I_k V_k)
+  for (int k = g.lane; k < NROB; k += G) {
+    T IA[6], IV[6];
+    inertia_apply(s.inert[0][k], Ab + 6 * k, IA);
+    inertia_apply(s.inert[0][k], Vb + 6 * k, IV);
+    const T* w = Vb + 6 * k; const T* v = w + 3;
+    T c1[3], c2[3], c3[3];
+    cross3(c1, w, IV);       // w x n
+    cross3(c2, v, IV + 3);   // v x f
+    cross3(c3, w, IV + 3);   // w x f
+    for (int a = 0; a < 3; a++) { fb[6 * k + a] = IA[a] + c1[a] + c2[a]; fb[6 * k + 3 + a] = IA[3 + a] + c3[a]; }
+  }
+  // actuators (A5): position servos on the arm, tendon servo on the gripper
+  for (int a = g.lane; a < NU; a += G) {
+    T c = tclamp(s.ctrl[a], md.ctrl_lo[a], md.ctrl_hi[a]);
+    T len = a < NARM ? s.qpos[a] : (T)0.5 * (s.qpos[7] + s.qpos[8]);
+    T vel = a < NARM ? s.qvel[a] : (T)0.5 * (s.qvel[7] + s.qvel[8]);
+    T f = md.act_gain[a] * c + md.act_b1[a] * len + md.act_b2[a] * vel;
+    int sat = 0;
+    if (f <= md.frc_lo[a]) { f = md.frc_lo[a]; sat = 1; }
+    else if (f >= md.frc_hi[a]) { f = md.frc_hi[a]; sat = 1; }
+    s.actf[a] = f;
+    s.actsat[a] = sat;
+  }
+  g.sync();
+  // F_j = Ic_j S_j
+  for (int j = g.lane; j < NROB; j += G) inertia_apply(s.inert[1][j], s.S[j], s.tmp6[j]);
+  // subtree force sums (component-parallel)
+  for (int c = g.lane; c < 6; c += G) {
+    T acc = fb[6 * 6 + c] + fb[6 * 7 + c] + fb[6 * 8 + c];
+    fb[6 * 6 + c] = acc;
+    for (int k = 5; k >= 0; k--) { acc += fb[6 * k + c]; fb[6 * k + c] = acc; }
+  }
+  g.sync();
+  for (int e = g.lane; e < NROB * NROB; e += G) {
+    int i = e / NROB, j = e % NROB;
+    int lo = i < j ? i : j, hi = i < j ? j : i;
+    T v = 0;
+    if (hi <= 6 || lo <= 6 || lo == hi) v = dot6(s.S[lo], s.tmp6[hi]);
+    if (lo >= 7 && hi >= 7 && lo != hi) v = 0;
+    if (i == j) v += md.armature[i];
+    s.Mr[e] = v;
+  }
+  for (int i = g.lane; i < NV; i += G) {
+    if (i < NROB) {
+      T bias = dot6(s.S[i], fb + 6 * i);
+      T act = i < NARM ? s.actf[i] : (T)0.5 * s.actf[7];
+      s.fs[i] = -md.damping[i] * s.qvel[i] - bias + act;
+    } else {
+      int k = (i - 9) % 6;
+      s.fs[i] = k == 2 ? md.cube_mass * md.gravity_z : (T)0;
+    }
+  }
+  g.sync();
+  // qacc_smooth: robot block via Cholesky (factor kept in H[200..280]), cubes are diagonal
+  T* L = s.H + 200;
+  for (int e = g.lane; e < NROB * NROB; e += G) L[e] = s.Mr[e];
+  for (int i = g.lane; i < NV; i += G) {
+    if (i < NROB) s.as[i] = s.fs[i];
+    else s.as[i] = s.fs[i] / (((i - 9) % 6) < 3 ? md.cube_mass : md.cube_inertia);
+  }
+  g.sync();
+  chol_factor<T, G>(g, L, NROB);
+  chol_solve<T, G>(g, L, NROB, s.as);
+}
+
+// y = M x  (robot block + diagonal cubes)
+template <class T, int G>
+MM_HDN void mulM(const Grp<G>& g, const Scratch<T>& s, const ModelDev<T>& md, const T* x, T* y) {
+  for (int i = g.lane; i < NV; i += G) {
+    if (i < NROB) {
+      T a = 0;
+      for (int k = 0; k < NROB; k++) a += s.Mr[i * NROB + k] * x[k];
+      y[i] = a;
+    } else y[i] = x[i] * (((i - 9) % 6) < 3 ? md.cube_mass : md.cube_inertia);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// collision: plane-box and box-box only in this round (robot hulls: see DESIGN.md)
+// ------------------------------------------------------------------------------------------------
+template <class T>
+struct BoxRef { const T* c; const T* R; const T* s; };
+
+template <class T>
+MM_HD BoxRef<T> get_box(const Scratch<T>& s, const ModelDev<T>& md, int b, const T* ident) {
+  BoxRef<T> r;
+  r.s = md.box_size[b];
+  int body = md.box_body[b];
+  if (body < 0) { r.c = md.box_pos[b]; r.R = ident; }
+  else { r.c = s.boxc[b < 10 ? b : b - 16]; r.R = s.bR[body]; }
+  return r;
+}
+
+// returns number of contact points; normal nrm (A -> B), pts[k] position, dist[k] (negative)
+template <class T>
+MM_HDN int box_box(const BoxRef<T>& A_, const BoxRef<T>& B_, T* nrm, T pts[8][3], T* dist) {
+  const T *pa = A_.c, *Ra = A_.R, *sa = A_.s, *pb = B_.c, *Rb = B_.R, *sb = B_.s;
+  T A[3][3], B[3][3];
+  for (int i = 0; i < 3; i++) for (int k = 0; k < 3; k++) { A[i][k] = Ra[3 * k + i]; B[i][k] = Rb[3 * k + i]; }
+  T dp[3] = {pb[0] - pa[0], pb[1] - pa[1], pb[2] - pa[2]};
+  T C[3][3], Q[3][3];
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { C[i][j] = dot3(A[i], B[j]); Q[i][j] = tabs(C[i][j]); }
+  T best = (T)1e30, bn[3] = {0, 0, 0};
+  int code = -1;
+  for (int i = 0; i < 3; i++) {
+    T t = dot3(dp, A[i]);
+    T pen = sa[i] + sb[0] * Q[i][0] + sb[1] * Q[i][1] + sb[2] * Q[i][2] - tabs(t);
+    if (pen < 0) return 0;
+    if (pen < best) { best = pen; code = i; T sg = t < 0 ? (T)-1 : (T)1; for (int k = 0; k < 3; k++) bn[k] = sg * A[i][k]; }
+  }
+  for (int j = 0; j < 3; j++) {
+    T t = dot3(dp, B[j]);
+    T pen = sb[j] + sa[0] * Q[0][j] + sa[1] * Q[1][j] + sa[2] * Q[2][j] - tabs(t);
+    if (pen < 0) return 0;
+    // a face of B must be clearly better than A's (parallel faces tie to rounding error)
+    if (pen < best * (T)(1 - 1e-6) - (T)1e-12) { best = pen; code = 3 + j; T sg = t < 0 ? (T)-1 : (T)1; for (int k = 0; k < 3; k++) bn[k] = sg * B[j][k]; }
+  }
+  T ebest = (T)1e30, en[3] = {0, 0, 0};
+  int ecode = -1;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      T L[3];
+      cross3(L, A[i], B[j]);
+      T ln = tsqrt(dot3(L, L));
+      if (ln < (T)1e-6) continue;
+      T inv = (T)1 / ln;
+      for (int k = 0; k < 3; k++) L[k] *= inv;
+      T t = dot3(dp, L), ra = 0, rb = 0;
+      for (int k = 0; k < 3; k++) { ra += sa[k] * tabs(dot3(A[k], L)); rb += sb[k] * tabs(dot3(B[k], L)); }
+      T pen = ra + rb - tabs(t);
+      if (pen < 0) return 0;
+      if (pen < ebest) { ebest = pen; ecode = 3 * i + j; T sg = t < 0 ? (T)-1 : (T)1; for (int k = 0; k < 3; k++) en[k] = sg * L[k]; }
+    }
+  if (ecode >= 0 && ebest * (T)1.05 < best) {
+    int i = ecode / 3, j = ecode % 3;
+    T ea[3] = {pa[0], pa[1], pa[2]}, eb[3] = {pb[0], pb[1], pb[2]};
+    for (int a = 0; a < 3; a++) {
+      if (a != i) { T sg = dot3(en, A[a]) > 0 ? (T)1 : (T)-1; for (int k = 0; k < 3; k++) ea[k] += sg * sa[a] * A[a][k]; }
+      if (a != j) { T sg = dot3(en, B[a]) > 0 ? (T)-1 : (T)1; for (int k = 0; k < 3; k++) eb[k] += sg * sb[a] * B[a][k]; }
+    }
+    T w[3] = {ea[0] - eb[0], ea[1] - eb[1], ea[2] - eb[2]};
+    T uv = C[i][j], uw = dot3(A[i], w), vw = dot3(B[j], w);
+    T den = (T)1 - uv * uv;
+    T sp = (uv * vw - uw) / den, tp = (vw - uv * uw) / den;
+    sp = tclamp(sp, -sa[i], sa[i]);
+    tp = tclamp(tp, -sb[j], sb[j]);
+    for (int k = 0; k < 3; k++) { pts[0][k] = (T)0.5 * ((ea[k] + sp * A[i][k]) + (eb[k] + tp * B[j][k])); nrm[k] = en[k]; }
+    dist[0] = -ebest;
+    return 1;
+  }
+  bool refA = code < 3;
+  int ax = refA ? code : code - 3;
+  const T* pr = refA ? pa : pb; const T* sr = refA ? sa : sb;
+  const T* pi = refA ? pb : pa; const T* si = refA ? sb : sa;
+  T (*Rr)[3] = refA ? A : B;
+  T (*Ri)[3] = refA ? B : A;
+  T nref[3];
+  for (int k = 0; k < 3; k++) { nref[k] = refA ? bn[k] : -bn[k]; nrm[k] = bn[k]; }
+  int iax = 0;
+  T mx = -1;
+  for (int a = 0; a < 3; a++) { T v = tabs(dot3(nref, Ri[a])); if (v > mx) { mx = v; iax = a; } }
+  T isg = dot3(nref, Ri[iax]) > 0 ? (T)-1 : (T)1;
+  int u = (iax + 1) % 3, v = (iax + 2) % 3;
+  T poly[16][3], outp[16][3];
+  int np = 4;
+  const int su[4] = {1, -1, -1, 1}, sv[4] = {1, 1, -1, -1};
+  for (int q = 0; q < 4; q++)
+    for (int k = 0; k < 3; k++)
+      poly[q][k] = pi[k] + isg * si[iax] * Ri[iax][k] + (T)su[q] * si[u] * Ri[u][k] + (T)sv[q] * si[v] * Ri[v][k];
+  int t1 = (ax + 1) % 3, t2 = (ax + 2) % 3;
+  for (int side = 0; side < 4 && np > 0; side++) {
+    int ta = side < 2 ? t1 : t2;
+    T sg = (side & 1) ? (T)-1 : (T)1, lim = sr[ta];
+    int no = 0;
+    for (int q = 0; q < np; q++) {
+      const T* P = poly[q];
+      const T* Qn = poly[(q + 1) % np];
+      T rp[3] = {P[0] - pr[0], P[1] - pr[1], P[2] - pr[2]}, rq[3] = {Qn[0] - pr[0], Qn[1] - pr[1], Qn[2] - pr[2]};
+      T dP = sg * dot3(rp, Rr[ta]) - lim, dQ = sg * dot3(rq, Rr[ta]) - lim;
+      // 1 nm band: vertices on a side plane (exactly aligned pads) are inside, no sliver crossings
+      const T ce = (T)1e-9;
+      if (dP <= ce) { for (int k = 0; k < 3; k++) outp[no][k] = P[k]; no++; }
+      if ((dP < -ce && dQ > ce) || (dP > ce && dQ < -ce)) {
+        T tt = dP / (dP - dQ);
+        for (int k = 0; k < 3; k++) outp[no][k] = P[k] + tt * (Qn[k] - P[k]);
+        no++;
+      }
+    }
+    np = no;
+    for (int q = 0; q < np; q++) for (int k = 0; k < 3; k++) poly[q][k] = outp[q][k];
+  }
+  T sgn = dot3(nref, Rr[ax]) > 0 ? (T)1 : (T)-1;
+  int cnt = 0;
+  for (int q = 0; q < np && cnt < 8; q++) {
+    T r[3] = {poly[q][0] - pr[0], poly[q][1] - pr[1], poly[q][2] - pr[2]};
+    T depth = sr[ax] - sgn * dot3(r, Rr[ax]);
+    if (depth <= 0) continue;
+    for (int k = 0; k < 3; k++) pts[cnt][k] = poly[q][k] + nref[k] * depth * (T)0.5;
+    dist[cnt] = -depth;
+    cnt++;
+  }
+  return cnt;
+}
+
+// floor plane z = 0 (normal +z) vs box: penetrating corners, at most 4
+template <class T>
+MM_HDN int plane_box(const BoxRef<T>& B_, T* nrm, T pts[8][3], T* dist) {
+  nrm[0] = 0; nrm[1] = 0; nrm[2] = 1;
+  int cnt = 0;
+  for (int i = 0; i < 8 && cnt < 4; i++) {
+    T loc[3] = {(i & 1) ? B_.s[0] : -B_.s[0], (i & 2) ? B_.s[1] : -B_.s[1], (i & 4) ? B_.s[2] : -B_.s[2]}, c[3];
+    rot(c, B_.R, loc);
+    for (int k = 0; k < 3; k++) c[k] += B_.c[k];
+    T d = c[2];
+    if (d < 0) {
+      pts[cnt][0] = c[0]; pts[cnt][1] = c[1]; pts[cnt][2] = c[2] - d * (T)0.5;
+      dist[cnt] = d;
+      cnt++;
+    }
+  }
+  return cnt;
+}
+
+template <class T>
+MM_HD void make_tangent(const T* n, T* t1) {  // mju_makeFrame rule (A3)
+  T t[3] = {0, 0, 0};
+  if (n[1] < (T)0.5 && n[1] > (T)-0.5) t[1] = 1; else t[2] = 1;
+  T pr = dot3(n, t);
+  for (int k = 0; k < 3; k++) t[k] -= pr * n[k];
+  T inv = (T)1 / tsqrt(dot3(t, t));
+  for (int k = 0; k < 3; k++) t1[k] = t[k] * inv;
+}
+
+template <class T, int G>
+MM_HDN void collide(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>& w) {
+  const T ident[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  // broad phase: ordered compaction of the surviving candidates
+  int nsurv = 0;
+  for (int base = 0; base < NCAND; base += G) {
+    int ci = base + g.lane;
+    int keep = 0;
+    if (ci < NCAND) {
+      int a = md.cand[ci][0], b = md.cand[ci][1];
+      BoxRef<T> Bb = get_box(s, md, b, ident);
+      T rb = md.box_rbound[b];
+      if (a == PLANE_ID) keep = Bb.c[2] < rb;
+      else {
+        BoxRef<T> Ba = get_box(s, md, a, ident);
+        if (md.box_body[a] < 0) {  // axis-aligned static box vs bounding sphere of the dynamic box
+          T d2 = 0;
+          for (int k = 0; k < 3; k++) {
+            T d = tabs(Bb.c[k] - Ba.c[k]) - Ba.s[k];
+            if (d > 0) d2 += d * d;
+          }
+          keep = d2 < rb * rb;
+        } else {
+          T r[3] = {Bb.c[0] - Ba.c[0], Bb.c[1] - Ba.c[1], Bb.c[2] - Ba.c[2]};
+          T rs = rb + md.box_rbound[a];
+          keep = dot3(r, r) < rs * rs;
+        }
+      }
+    }
+    int tot;
+    int off = g.scan_excl(keep, &tot);
+    if (keep && nsurv + off < MAXSURV) s.surv[nsurv + off] = ci;
+    nsurv += tot;
+  }
+  if (nsurv > MAXSURV) { nsurv = MAXSURV; if (g.lane == 0) s.overflow |= 1; }
+  g.sync();
+  // narrow phase, ordered compaction of the contacts
+  int ncon = 0;
+  for (int base = 0; base < nsurv; base += G) {
+    int si = base + g.lane;
+    int cnt = 0, a = 0, b = 0, ci_ = 0;
+    T nrm[3], pts[8][3], dist[8];
+    if (si < nsurv) {
+      int ci = s.surv[si];
+      ci_ = ci;
+      a = md.cand[ci][0]; b = md.cand[ci][1];
+      BoxRef<T> Bb = get_box(s, md, b, ident);
+      if (a == PLANE_ID) cnt = plane_box(Bb, nrm, pts, dist);
+      else { BoxRef<T> Ba = get_box(s, md, a, ident); cnt = box_box(Ba, Bb, nrm, pts, dist); }
+    }
+    int tot;
+    int off = g.scan_excl(cnt, &tot);
+    if (cnt > 0) {
+      int ca = a == PLANE_ID ? 0 : md.box_class[a], cb = md.box_class[b];
+      int cube = (a != PLANE_ID && md.box_cube[a]) || md.box_cube[b];
+      T tran = (a == PLANE_ID ? (T)0 : md.box_invw[a]) + md.box_invw[b];
+      T mu = cube ? (T)2 : (T)1;
+      T t1[3];
+      make_tangent(nrm, t1);
+      for (int k = 0; k < cnt; k++) {
+        int c = ncon + off + k;
+        if (c >= MAXCON) break;
+        for (int d = 0; d < 3; d++) { w.cpos[d * MAXCON + c] = pts[k][d]; w.cn[d * MAXCON + c] = nrm[d]; w.ct1[d * MAXCON + c] = t1[d]; }
+        w.cdist[c] = dist[k];
+        // impedance / regulariser (A4): default solref (0.02, 1), solimp (0.9, 0.95, 0.001, 0.5, 2)
+        T x = tabs(dist[k]) / (T)0.001, imp;
+        if (x >= 1) imp = (T)0.95;
+        else { T y = x <= (T)0.5 ? 2 * x * x : 1 - 2 * (1 - x) * (1 - x); imp = (T)0.9 + y * (T)0.05; }
+        T R0 = (1 - imp) / imp * tran * (1 + mu * mu);
+        if (R0 < (T)MINVAL_D) R0 = (T)MINVAL_D;
+        w.cD[c] = (T)1 / (2 * mu * mu * R0);
+        // bit 19: robot geom against a static obstacle box (table / bins; the floor does not count,
+        // gym_env.py:137-152,341-350)
+        int robobs = a != PLANE_ID && ((ca >= 1 && ca <= 9 && md.box_body[b] < 0) || (cb >= 1 && cb <= 9 && md.box_body[a] < 0));
+        w.cmeta[c] = (ca << 4) | (cb << 8) | (cube << 12) | (robobs << 19) | (ci_ << 20);
+      }
+    }
+    ncon += tot;
+  }
+  if (ncon > MAXCON) { ncon = MAXCON; if (g.lane == 0) s.overflow |= 2; }
+  g.sync();
+  // pair slots: contacts are ordered by (classA, classB); a new slot starts where the key changes
+  int npair = 0;
+  for (int base = 0; base < ncon; base += G) {
+    int c = base + g.lane;
+    int head = 0, key = 0, m = 0;
+    if (c < ncon) {
+      m = w.cmeta[c];
+      key = (m >> 4) & 0xFF;
+      head = (c == 0) || (((w.cmeta[c - 1] >> 4) & 0xFF) != key);
+    }
+    int tot;
+    int off = g.scan_excl(head, &tot);
+    g.sync();  // every lane has read its neighbour's meta word before any is rewritten
+    if (c < ncon) {
+      int slot = npair + off + head - 1;
+      if (slot >= MAXPAIR) slot = MAXPAIR - 1;
+      w.cmeta[c] = (m & ~15) | slot;
+      if (head && npair + off < MAXPAIR) s.pairkey[npair + off] = key;
+    }
+    npair += tot;
+  }
+  if (npair > MAXPAIR) { npair = MAXPAIR; if (g.lane == 0) s.overflow |= 4; }
+  if (g.lane == 0) { s.ncon = ncon; s.npair = npair; s.nsurv = nsurv; }
+  g.sync();
+}
+
+// ------------------------------------------------------------------------------------------------
+// matrix-free Jacobian products through body-pair twists / wrenches
+// ------------------------------------------------------------------------------------------------
+template <class T, int G>
+MM_HDN void pair_twists(const Grp<G>& g, Scratch<T>& s, const T* x) {
+  int np = s.npair;
+  for (int idx = g.lane; idx < np * 6; idx += G) {
+    int p = idx / 6, c = idx % 6;
+    int key = s.pairkey[p];
+    int mA = dofmask(key & 15), mB = dofmask((key >> 4) & 15);
+    T acc = 0;
+    for (int i = 0; i < NV; i++) {
+      int sg = ((mB >> i) & 1) - ((mA >> i) & 1);
+      if (sg) acc += (T)sg * x[i] * s.S[i][c];
+    }
+    s.pairW[p][c] = acc;
+  }
+  g.sync();
+}
+
+template <class T>
+struct ConGeom { T pos[3], n[3], t1[3], t2[3]; };
+template <class T>
+MM_HD void load_con(const Work<T>& w, int c, ConGeom<T>& q) {
+  for (int d = 0; d < 3; d++) { q.pos[d] = w.cpos[d * MAXCON + c]; q.n[d] = w.cn[d * MAXCON + c]; q.t1[d] = w.ct1[d * MAXCON + c]; }
+  cross3(q.t2, q.n, q.t1);
+}
+
+// rows of J*x for every contact (out[c*6 + r]) and special row (outspec[k])
+template <class T, int G>
+MM_HDN void mulJ(const Grp<G>& g, Scratch<T>& s, const Work<T>& w, const T* x, T* out, T* outspec) {
+  pair_twists<T, G>(g, s, x);
+  int ncon = s.ncon;
+  for (int c = g.lane; c < ncon; c += G) {
+    ConGeom<T> q;
+    load_con(w, c, q);
+    int m = w.cmeta[c];
+    const T* W = s.pairW[meta_slot(m)];
+    T u[3];
+    cross3(u, W, q.pos);
+    for (int d = 0; d < 3; d++) u[d] += W[3 + d];
+    T un = dot3(q.n, u), u1 = dot3(q.t1, u), u2 = dot3(q.t2, u);
+    T mu = meta_dim4(m) ? (T)2 : (T)1;
+    out[c * 6 + 0] = un + mu * u1; out[c * 6 + 1] = un - mu * u1;
+    out[c * 6 + 2] = un + mu * u2; out[c * 6 + 3] = un - mu * u2;
+    if (meta_dim4(m)) {
+      T u3 = dot3(q.n, W);  // torsional friction coefficient of cube contacts = 1.0
+      out[c * 6 + 4] = un + u3; out[c * 6 + 5] = un - u3;
+    }
+  }
+  for (int k = g.lane; k < s.nspec; k += G) {
+    int d = s.specdof[k];
+    outspec[k] = d < 0 ? x[7] - x[8] : ((d & 256) ? -x[d & 255] : x[d & 255]);
+  }
+  g.sync();
+}
+
+// ------------------------------------------------------------------------------------------------
+// constraint rows (A4): per-contact D is set in collide(); here the reference accelerations
+// ------------------------------------------------------------------------------------------------
+template <class T>
+MM_HD T impedance_generic(const T* solimp, T pos) {
+  T dmin = solimp[0], dmax = solimp[1], width = solimp[2], mid = solimp[3], power = solimp[4];
+  T x = tabs(pos) / width;
+  if (x >= 1) return dmax;
+  if (x <= 0) return dmin;
+  T y;
+  if (power == (T)2) y = x <= mid ? x * x / mid : 1 - (1 - x) * (1 - x) / (1 - mid);
+  else y = x <= mid ? (T)pow((double)x, (double)power) / (T)pow((double)mid, (double)power - 1)
+                    : 1 - (T)pow((double)(1 - x), (double)power) / (T)pow((double)(1 - mid), (double)power - 1);
+  return dmin + y * (dmax - dmin);
+}
+
+template <class T, int G>
+MM_HDN void make_constraints(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>& w) {
+  const T h = md.timestep;
+  if (g.lane == 0) {
+    int n = 0;
+    // joint equality f1 = f2 : solref (0.005, 1) -> refsafe, solimp (0.95, 0.99, 0.001, 0.5, 2)
+    {
+      T pos = s.qpos[7] - s.qpos[8], vel = s.qvel[7] - s.qvel[8];
+      T tc = tmax(md.eq_solref[0], 2 * h), dr = md.eq_solref[1], dmax = md.eq_solimp[1];
+      T K = (T)1 / (dmax * dmax * tc * tc * dr * dr), B = (T)2 / (dmax * tc);
+      T imp = impedance_generic(md.eq_solimp, pos);
+      T R = tmax((T)MINVAL_D, (1 - imp) / imp * md.eq_invw);
+      s.specdof[n] = -1; s.specD[n] = (T)1 / R; s.specAref[n] = -B * vel - K * imp * pos;
+      n++;
+    }
+    const T dsolimp[5] = {(T)0.9, (T)0.95, (T)0.001, (T)0.5, (T)2};
+    const T tc = tmax((T)0.02, 2 * h), dmax = (T)0.95;
+    const T K = (T)1 / (dmax * dmax * tc * tc), B = (T)2 / (dmax * tc);
+    for (int i = 0; i < NROB; i++) {
+      T q = s.qpos[i];
+      T dlo = q - md.jnt_lo[i], dhi = md.jnt_hi[i] - q;
+      for (int side = 0; side < 2; side++) {
+        T dist = side == 0 ? dlo : dhi;
+        if (dist < 0 && n < MAXSPEC) {
+          T imp = impedance_generic(dsolimp, dist);
+          T R = tmax((T)MINVAL_D, (1 - imp) / imp * md.dof_invw[i]);
+          T vel = side == 0 ? s.qvel[i] : -s.qvel[i];
+          s.specdof[n] = i | (side ? 256 : 0); s.specD[n] = (T)1 / R; s.specAref[n] = -B * vel - K * imp * dist;
+          n++;
+        }
+      }
+    }
+    s.nspec = n;
+  }
+  g.sync();
+  // contact aref_r = -B (J qvel)_r - K imp dist
+  mulJ<T, G>(g, s, w, s.qvel, w.aref, s.specJv /*scratch, ignored*/);
+  {
+    const T tc = tmax((T)0.02, 2 * h), dmax = (T)0.95;
+    const T K = (T)1 / (dmax * dmax * tc * tc), B = (T)2 / (dmax * tc);
+    int ncon = s.ncon;
+    for (int c = g.lane; c < ncon; c += G) {
+      T dist = w.cdist[c];
+      T x = tabs(dist) / (T)0.001, imp;
+      if (x >= 1) imp = (T)0.95;
+      else { T y = x <= (T)0.5 ? 2 * x * x : 1 - 2 * (1 - x) * (1 - x); imp = (T)0.9 + y * (T)0.05; }
+      int nr = meta_dim4(w.cmeta[c]) ? 6 : 4;
+      for (int r = 0; r < nr; r++) w.aref[c * 6 + r] = -B * w.aref[c * 6 + r] - K * imp * dist;
+    }
+  }
+  g.sync();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Newton solver (A6)
+// ------------------------------------------------------------------------------------------------
+// Constraint update at the current Jaref: active set, cost, qfrc_constraint (s.fc); when `buildK`
+// also the per-pair 6x6 blocks K_p = sum_active D y y^T.  Returns constraint cost; *changed is set
+// when any active bit differs from the stored one.
+template <class T, int G>
+MM_HDN T update_constraint(const Grp<G>& g, Scratch<T>& s, Work<T>& w, bool buildK, int* changed) {
+  int np = s.npair;
+  for (int idx = g.lane; idx < np * 6; idx += G) s.pairF[idx / 6][idx % 6] = 0;
+  if (buildK) for (int idx = g.lane; idx < np * 21; idx += G) s.pairK[idx / 21][idx % 21] = 0;
+  g.sync();
+  T cost = 0;
+  int chg = 0;
+  int ncon = s.ncon;
+  for (int base = 0; base < ncon; base += G) {
+    int c = base + g.lane;
+    bool valid = c < ncon;
+    T F[6] = {0, 0, 0, 0, 0, 0};
+    T Kc[21];
+    if (buildK) for (int k = 0; k < 21; k++) Kc[k] = 0;
+    int slot = -1 - g.lane;  // invalid lanes never merge
+    if (valid) {
+      ConGeom<T> q;
+      load_con(w, c, q);
+      int m = w.cmeta[c];
+      slot = meta_slot(m);
+      T D = w.cD[c];
+      int dim4 = meta_dim4(m), nr = dim4 ? 6 : 4;
+      T mu = dim4 ? (T)2 : (T)1;
+      int bits = 0;
+      T pxn[3], px1[3], px2[3];
+      cross3(pxn, q.pos, q.n);
+      cross3(px1, q.pos, q.t1);
+      cross3(px2, q.pos, q.t2);
+      for (int r = 0; r < nr; r++) {
+        T ja = w.Jaref[c * 6 + r];
+        if (ja < 0) {
+          bits |= 1 << r;
+          T f = -D * ja;
+          cost += (T)0.5 * D * ja * ja;
+          // y_r = [pos x d + tau ; d]
+          T y[6];
+          T sg = (r & 1) ? (T)-1 : (T)1;
+          if (r < 2) for (int d = 0; d < 3; d++) { y[d] = pxn[d] + sg * mu * px1[d]; y[3 + d] = q.n[d] + sg * mu * q.t1[d]; }
+          else if (r < 4) for (int d = 0; d < 3; d++) { y[d] = pxn[d] + sg * mu * px2[d]; y[3 + d] = q.n[d] + sg * mu * q.t2[d]; }
+          else for (int d = 0; d < 3; d++) { y[d] = pxn[d] + sg * q.n[d]; y[3 + d] = q.n[d]; }
+          for (int d = 0; d < 6; d++) F[d] += f * y[d];
+          if (buildK) {
+            int k = 0;
+            for (int a = 0; a < 6; a++) { T da = D * y[a]; for (int b = 0; b <= a; b++) Kc[k++] += da * y[b]; }
+          }
+        }
+      }
+      int old = (m >> 13) & 63;
+      if (old != bits) { chg = 1; w.cmeta[c] = (m & ~(63 << 13)) | (bits << 13); }
+    }
+    // segmented inclusive scan over lanes (keys are non-decreasing); segment tails commit
+    if (G > 1) {
+      for (int o = 1; o < G; o <<= 1) {
+        int ks = g.shfl_up(slot, o);
+        bool take = g.lane >= o && ks == slot;
+        for (int d = 0; d < 6; d++) { T t = g.shfl_up(F[d], o); if (take) F[d] += t; }
+        if (buildK) for (int k = 0; k < 21; k++) { T t = g.shfl_up(Kc[k], o); if (take) Kc[k] += t; }
+      }
+    }
+    int nxt = g.shfl_down(slot, 1);
+    bool tail = valid && (G == 1 || g.lane == G - 1 || nxt != slot);
+    if (tail) {
+      for (int d = 0; d < 6; d++) s.pairF[slot][d] += F[d];
+      if (buildK) for (int k = 0; k < 21; k++) s.pairK[slot][k] += Kc[k];
+    }
+    g.sync();
+  }
+  // special rows
+  for (int k = g.lane; k < s.nspec; k += G) {
+    T ja = s.specJaref[k];
+    if (s.specdof[k] < 0 || ja < 0) cost += (T)0.5 * s.specD[k] * ja * ja;
+  }
+  cost = g.sum(cost);
+  *changed = g.any(chg);
+  // qfrc_constraint
+  for (int i = g.lane; i < NV; i += G) {
+    T acc = 0;
+    for (int p = 0; p < np; p++) {
+      int key = s.pairkey[p];
+      int sg = ((dofmask((key >> 4) & 15) >> i) & 1) - ((dofmask(key & 15) >> i) & 1);
+      if (sg) acc += (T)sg * dot6(s.S[i], s.pairF[p]);
+    }
+    for (int k = 0; k < s.nspec; k++) {
+      int d = s.specdof[k];
+      T ja = s.specJaref[k];
+      if (d < 0) { if (i == 7) acc += -s.specD[k] * ja; else if (i == 8) acc -= -s.specD[k] * ja; }
+      else if ((d & 255) == i && ja < 0) acc += ((d & 256) ? (T)-1 : (T)1) * (-s.specD[k] * ja);
+    }
+    s.fc[i] = acc;
+  }
+  g.sync();
+  return cost;
+}
+
+// H = M + J^T D J over the active rows, assembled from the per-pair blocks; then factor in place
+template <class T, int G>
+MM_HDN void build_factor_H(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md) {
+  for (int e = g.lane; e < NV * NV; e += G) {
+    int i = e / NV, j = e % NV;
+    T v = 0;
+    if (i < NROB && j < NROB) v = s.Mr[i * NROB + j];
+    else if (i == j) v = ((i - 9) % 6) < 3 ? md.cube_mass : md.cube_inertia;
+    s.H[e] = v;
+  }
+  g.sync();
+  if (g.lane == 0) {
+    for (int k = 0; k < s.nspec; k++) {
+      int d = s.specdof[k];
+      T D = s.specD[k];
+      if (d < 0) { s.H[7 * NV + 7] += D; s.H[8 * NV + 8] += D; s.H[8 * NV + 7] -= D; s.H[7 * NV + 8] -= D; }
+      else if (s.specJaref[k] < 0) s.H[(d & 255) * (NV + 1)] += D;
+    }
+  }
+  for (int p = 0; p < s.npair; p++) {
+    int key = s.pairkey[p];
+    int mA = dofmask(key & 15), mB = dofmask((key >> 4) & 15);
+    int mm_ = mA ^ mB;  // dofs shared by both bodies cancel (sigma = 0)
+    const T* K = s.pairK[p];
+    g.sync();
+    for (int j = g.lane; j < NV; j += G) {
+      if (!((mm_ >> j) & 1)) continue;
+      const T* S = s.S[j];
+      T sg = ((mB >> j) & 1) ? (T)1 : (T)-1;
+      // symmetric packed K (lower, row-major): K[a][b] = K[a*(a+1)/2 + b], b <= a
+      for (int a = 0; a < 6; a++) {
+        T acc = 0;
+        for (int b = 0; b < 6; b++) acc += (a >= b ? K[a * (a + 1) / 2 + b] : K[b * (b + 1) / 2 + a]) * S[b];
+        s.tmp6[j][a] = sg * acc;
+      }
+    }
+    g.sync();
+    for (int e = g.lane; e < NV * NV; e += G) {
+      int i = e / NV, j = e % NV;
+      if (j > i) continue;
+      if (!((mm_ >> i) & 1) || !((mm_ >> j) & 1)) continue;
+      T sg = ((mB >> i) & 1) ? (T)1 : (T)-1;
+      s.H[e] += sg * dot6(s.S[i], s.tmp6[j]);
+    }
+  }
+  g.sync();
+  chol_factor<T, G>(g, s.H, NV);
+}
+
+// derivative / curvature of the cost along `search` at step alpha
+template <class T, int G>
+MM_HDN void ls_eval(const Grp<G>& g, const Scratch<T>& s, const Work<T>& w, T alpha, T qg1, T qg2, T* d1, T* d2) {
+  T a1 = 0, a2 = 0;
+  int ncon = s.ncon;
+  for (int c = g.lane; c < ncon; c += G) {
+    T D = w.cD[c];
+    int nr = meta_dim4(w.cmeta[c]) ? 6 : 4;
+    for (int r = 0; r < nr; r++) {
+      T jv = w.Jv[c * 6 + r];
+      T x = w.Jaref[c * 6 + r] + alpha * jv;
+      if (x < 0) { a1 += D * jv * x; a2 += D * jv * jv; }
+    }
+  }
+  for (int k = g.lane; k < s.nspec; k += G) {
+    T jv = s.specJv[k], x = s.specJaref[k] + alpha * jv;
+    if (s.specdof[k] < 0 || x < 0) { a1 += s.specD[k] * jv * x; a2 += s.specD[k] * jv * jv; }
+  }
+  a1 = g.sum(a1);
+  a2 = g.sum(a2);
+  *d1 = a1 + qg1 + 2 * alpha * qg2;
+  *d2 = a2 + 2 * qg2;
+}
+
+template <class T, int G>
+MM_HDN void solve(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>& w) {
+  const T scale_inv = md.meaninertia * (T)NV;
+  const T scale = (T)1 / scale_inv;
+  const T tol = (T)1e-8;
+  int ncon = s.ncon;
+  int changed;
+  // warmstart selection: cost at qacc_smooth vs cost at qacc_warmstart
+  mulJ<T, G>(g, s, w, s.as, w.Jv, s.specJv);
+  for (int c = g.lane; c < ncon; c += G) for (int r = 0; r < 6; r++) w.Jv[c * 6 + r] -= w.aref[c * 6 + r];
+  for (int k = g.lane; k < s.nspec; k += G) s.specJv[k] -= s.specAref[k];
+  g.sync();
+  T cost_sm;
+  {
+    T cst = 0;
+    for (int c = g.lane; c < ncon; c += G) {
+      T D = w.cD[c];
+      int nr = meta_dim4(w.cmeta[c]) ? 6 : 4;
+      for (int r = 0; r < nr; r++) { T ja = w.Jv[c * 6 + r]; if (ja < 0) cst += (T)0.5 * D * ja * ja; }
+    }
+    for (int k = g.lane; k < s.nspec; k += G) {
+      T ja = s.specJv[k];
+      if (s.specdof[k] < 0 || ja < 0) cst += (T)0.5 * s.specD[k] * ja * ja;
+    }
+    cost_sm = g.sum(cst);
+  }
+  mulJ<T, G>(g, s, w, s.warm, w.Jaref, s.specJaref);
+  for (int c = g.lane; c < ncon; c += G) for (int r = 0; r < 6; r++) w.Jaref[c * 6 + r] -= w.aref[c * 6 + r];
+  for (int k = g.lane; k < s.nspec; k += G) s.specJaref[k] -= s.specAref[k];
+  mulM<T, G>(g, s, md, s.warm, s.Ma);
+  g.sync();
+  T cost_ws;
+  {
+    T cst = 0;
+    for (int c = g.lane; c < ncon; c += G) {
+      T D = w.cD[c];
+      int nr = meta_dim4(w.cmeta[c]) ? 6 : 4;
+      for (int r = 0; r < nr; r++) { T ja = w.Jaref[c * 6 + r]; if (ja < 0) cst += (T)0.5 * D * ja * ja; }
+    }
+    for (int k = g.lane; k < s.nspec; k += G) {
+      T ja = s.specJaref[k];
+      if (s.specdof[k] < 0 || ja < 0) cst += (T)0.5 * s.specD[k] * ja * ja;
+    }
+    for (int i = g.lane; i < NV; i += G) cst += (T)0.5 * (s.Ma[i] - s.fs[i]) * (s.warm[i] - s.as[i]);
+    cost_ws = g.sum(cst);
+  }
+  if (cost_ws < cost_sm) {
+    for (int i = g.lane; i < NV; i += G) s.qacc[i] = s.warm[i];
+  } else {
+    for (int i = g.lane; i < NV; i += G) s.qacc[i] = s.as[i];
+    for (int c = g.lane; c < ncon; c += G) for (int r = 0; r < 6; r++) w.Jaref[c * 6 + r] = w.Jv[c * 6 + r];
+    for (int k = g.lane; k < s.nspec; k += G) s.specJaref[k] = s.specJv[k];
+    g.sync();
+    mulM<T, G>(g, s, md, s.qacc, s.Ma);
+  }
+  g.sync();
+  // clear stored active bits so that the first update reports a change (forces the H build)
+  for (int c = g.lane; c < ncon; c += G) w.cmeta[c] &= ~(63 << 13);
+  g.sync();
+  T cost = update_constraint<T, G>(g, s, w, true, &changed);
+  {
+    T ga = 0;
+    for (int i = g.lane; i < NV; i += G) ga += (T)0.5 * (s.Ma[i] - s.fs[i]) * (s.qacc[i] - s.as[i]);
+    cost += g.sum(ga);
+  }
+  // spec-row active pattern (limits) folded into `changed` tracking via a small bitmask
+  int specbits = 0;
+  for (int k = 0; k < s.nspec; k++) if (s.specdof[k] < 0 || s.specJaref[k] < 0) specbits |= 1 << k;
+  build_factor_H<T, G>(g, s, md);
+  int iter = 0;
+  while (iter < 100) {
+    // gradient and Newton direction
+    for (int i = g.lane; i < NV; i += G) { T gr = s.Ma[i] - s.fs[i] - s.fc[i]; s.grad[i] = gr; s.search[i] = -gr; }
+    g.sync();
+    chol_solve<T, G>(g, s.H, NV, s.search);
+    // line search set-up
+    T sn = 0, qg1 = 0, qg2 = 0;
+    mulM<T, G>(g, s, md, s.search, s.Mv);
+    mulJ<T, G>(g, s, w, s.search, w.Jv, s.specJv);
+    for (int i = g.lane; i < NV; i += G) {
+      sn += s.search[i] * s.search[i];
+      qg1 += s.search[i] * (s.Ma[i] - s.fs[i]);
+      qg2 += (T)0.5 * s.search[i] * s.Mv[i];
+    }
+    sn = tsqrt(g.sum(sn)); qg1 = g.sum(qg1); qg2 = g.sum(qg2);
+    if (sn < (T)MINVAL_D) break;
+    T gtol = tol * (T)0.01 * sn * scale_inv;
+    T lo = 0, hi = -1, a = 0, d1, d2;
+    ls_eval<T, G>(g, s, w, (T)0, qg1, qg2, &d1, &d2);
+    if (d1 >= 0) break;
+    for (int it = 0; it < 50; it++) {
+      T an = a - d1 / d2;
+      if (hi > 0 && !(an > lo && an < hi)) an = (T)0.5 * (lo + hi);
+      a = an;
+      ls_eval<T, G>(g, s, w, a, qg1, qg2, &d1, &d2);
+      if (tabs(d1) < gtol) break;
+      if (d1 < 0) lo = a; else hi = a;
+    }
+    if (a == 0) break;
+    // move
+    for (int i = g.lane; i < NV; i += G) { s.qacc[i] += a * s.search[i]; s.Ma[i] += a * s.Mv[i]; }
+    for (int c = g.lane; c < ncon; c += G) for (int r = 0; r < 6; r++) w.Jaref[c * 6 + r] += a * w.Jv[c * 6 + r];
+    for (int k = g.lane; k < s.nspec; k += G) s.specJaref[k] += a * s.specJv[k];
+    g.sync();
+    T oldcost = cost;
+    // active-set probe first (cheap), K only when it changed
+    cost = update_constraint<T, G>(g, s, w, false, &changed);
+    int sb = 0;
+    for (int k = 0; k < s.nspec; k++) if (s.specdof[k] < 0 || s.specJaref[k] < 0) sb |= 1 << k;
+    if (sb != specbits) { changed = 1; specbits = sb; }
+    {
+      T ga = 0, gn = 0;
+      for (int i = g.lane; i < NV; i += G) {
+        ga += (T)0.5 * (s.Ma[i] - s.fs[i]) * (s.qacc[i] - s.as[i]);
+        T gr = s.Ma[i] - s.fs[i] - s.fc[i];
+        gn += gr * gr;
+      }
+      cost += g.sum(ga);
+      gn = tsqrt(g.sum(gn));
+      iter++;
+      T improvement = scale * (oldcost - cost), gradient = scale * gn;
+#if defined(MM_TRACE) && !defined(__CUDA_ARCH__)
+      printf("  it %d alpha %.6e cost %.12e impr %.3e grad %.3e changed %d\n", iter, (double)a, (double)cost, (double)improvement, (double)gradient, changed);
+#endif
+      if (improvement < tol || gradient < tol) break;
+    }
+    if (changed) {
+      int dummy;
+      update_constraint<T, G>(g, s, w, true, &dummy);
+      build_factor_H<T, G>(g, s, md);
+    }
+  }
+  if (g.lane == 0) s.niter = iter;
+  for (int i = g.lane; i < NV; i += G) s.warm[i] = s.qacc[i];
+  g.sync();
+}
+
+// full forward at the current (qpos, qvel, ctrl): everything mj_forward computes that the path needs
+template <class T, int G>
+MM_HDN void forward(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>& w) {
+  fk<T, G>(g, s, md);
+  dyn_smooth<T, G>(g, s, md);
+  collide<T, G>(g, s, md, w);
+  make_constraints<T, G>(g, s, md, w);
+  solve<T, G>(g, s, md, w);
+}
+
+// ------------------------------------------------------------------------------------------------
+// implicitfast (A7)
+// ------------------------------------------------------------------------------------------------
+template <class T, int G>
+MM_HDN void integrate(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md) {
+  const T h = md.timestep;
+  T* MH = s.H;
+  T* acc = s.grad;
+  for (int e = g.lane; e < NROB * NROB; e += G) {
+    int i = e / NROB, j = e % NROB;
+    T v = s.Mr[e];
+    if (i == j) {
+      v += h * md.damping[i];
+      if (i < NARM && !s.actsat[i]) v -= h * md.act_b2[i];
+    }
+    if (i >= 7 && j >= 7 && !s.actsat[7]) v -= h * md.act_b2[7] * (T)0.25;
+    MH[e] = v;
+  }
+  for (int i = g.lane; i < NV; i += G) {
+    T f = s.fs[i] + s.fc[i];
+    acc[i] = i < NROB ? f : f / (((i - 9) % 6) < 3 ? md.cube_mass : md.cube_inertia);
+  }
+  g.sync();
+  chol_factor<T, G>(g, MH, NROB);
+  chol_solve<T, G>(g, MH, NROB, acc);
+  for (int i = g.lane; i < NV; i += G) s.qvel[i] += h * acc[i];
+  g.sync();
+  for (int i = g.lane; i < NROB + 3; i += G) {
+    if (i < NROB) s.qpos[i] += h * s.qvel[i];
+    else {
+      int j = i - NROB;
+      T* q = s.qpos + 9 + 7 * j;
+      const T* v = s.qvel + 9 + 6 * j;
+      for (int a = 0; a < 3; a++) q[a] += h * v[a];
+      T wn = tsqrt(dot3(v + 3, v + 3));
+      if (wn * h >= (T)MINVAL_D) {
+        T sn, cs;
+        tsincos(wn * h * (T)0.5, &sn, &cs);
+        T inv = sn / wn;
+        T dq[4] = {cs, v[3] * inv, v[4] * inv, v[5] * inv}, *qq = q + 3, r[4];
+        r[0] = qq[0] * dq[0] - qq[1] * dq[1] - qq[2] * dq[2] - qq[3] * dq[3];
+        r[1] = qq[0] * dq[1] + qq[1] * dq[0] + qq[2] * dq[3] - qq[3] * dq[2];
+        r[2] = qq[0] * dq[2] - qq[1] * dq[3] + qq[2] * dq[0] + qq[3] * dq[1];
+        r[3] = qq[0] * dq[3] + qq[1] * dq[2] - qq[2] * dq[1] + qq[3] * dq[0];
+        T nn = (T)1 / tsqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2] + r[3] * r[3]);
+        for (int a = 0; a < 4; a++) qq[a] = r[a] * nn;
+      }
+    }
+  }
+  g.sync();
+}
+
+// ------------------------------------------------------------------------------------------------
+// DLS IK (controller.py:87-137) on the kinematics left by the LAST position stage (staleness quirk,
+// SURVEY 3.3) and the CURRENT joint angles.  Writes ctrl[0..6].
+// ------------------------------------------------------------------------------------------------
+template <class T>
+MM_HDN void orientation_error(const T* Rc, T* out) {
+  // R_err = TARGET_ORI * Rc^T with TARGET_ORI = [[0,1,0],[1,0,0],[0,0,-1]]  (controller.py:12-18, 21-43)
+  T E[9];
+  for (int j = 0; j < 3; j++) { E[j] = Rc[3 * j + 1]; E[3 + j] = Rc[3 * j]; E[6 + j] = -Rc[3 * j + 2]; }
+  T tv = tclamp((E[0] + E[4] + E[8] - 1) / 2, (T)-1, (T)1);
+  T ang = tacos(tv);
+  if (ang < (T)1e-6) { out[0] = out[1] = out[2] = 0; return; }
+  T sc = ang / (2 * tsin(ang));
+  out[0] = (E[7] - E[5]) * sc; out[1] = (E[2] - E[6]) * sc; out[2] = (E[3] - E[1]) * sc;
+}
+
+template <class T, int G>
+MM_HDN void ik(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md) {
+  if (g.lane == 0) {
+    const T* ee = s.bpos[DB_HAND];
+    T J[6][NARM], e[6], z[NARM], b[6];
+    for (int i = 0; i < NARM; i++) {
+      const T* S = s.S[i];
+      T c[3];
+      cross3(c, S, ee);  // a x ee + (p x a)
+      for (int d = 0; d < 3; d++) { J[d][i] = c[d] + S[3 + d]; J[3 + d][i] = S[d]; }
+      z[i] = (T)0.5 * (md.home[i] - s.qpos[i]);
+    }
+    for (int d = 0; d < 3; d++) e[d] = s.target[d] - ee[d];
+    orientation_error(s.bR[DB_HAND], e + 3);
+    T A[36];
+    for (int i = 0; i < 6; i++) {
+      T jz = 0;
+      for (int c = 0; c < NARM; c++) jz += J[i][c] * z[c];
+      b[i] = e[i] - jz;
+      for (int j = 0; j <= i; j++) {
+        T a = 0;
+        for (int c = 0; c < NARM; c++) a += J[i][c] * J[j][c];
+        A[6 * i + j] = a + (i == j ? (T)1e-3 : (T)0);
+      }
+    }
+    // 6x6 Cholesky solve
+    for (int j = 0; j < 6; j++) {
+      T d = A[6 * j + j];
+      for (int k = 0; k < j; k++) d -= A[6 * j + k] * A[6 * j + k];
+      T l = tsqrt(d);
+      A[6 * j + j] = l;
+      for (int i = j + 1; i < 6; i++) {
+        T t = A[6 * i + j];
+        for (int k = 0; k < j; k++) t -= A[6 * i + k] * A[6 * j + k];
+        A[6 * i + j] = t / l;
+      }
+    }
+    for (int i = 0; i < 6; i++) { T t = b[i]; for (int k = 0; k < i; k++) t -= A[6 * i + k] * b[k]; b[i] = t / A[6 * i + i]; }
+    for (int i = 5; i >= 0; i--) { T t = b[i]; for (int k = i + 1; k < 6; k++) t -= A[6 * k + i] * b[k]; b[i] = t / A[6 * i + i]; }
+    T dq[NARM], nn = 0;
+    for (int c = 0; c < NARM; c++) {
+      T a = z[c];
+      for (int i = 0; i < 6; i++) a += J[i][c] * b[i];
+      dq[c] = a;
+      nn += a * a;
+    }
+    nn = tsqrt(nn);
+    T sc = nn > (T)5 ? (T)5 / nn : (T)1;
+    for (int c = 0; c < NARM; c++) s.ctrl[c] = tclamp(s.qpos[c] + dq[c] * sc, md.jnt_lo[c], md.jnt_hi[c]);
+  }
+  g.sync();
+}
+
+}  // namespace mm

@@ -1,0 +1,115 @@
+// TEST-ONLY host build of the kernel source with a 1-lane group (G = 1).
+// Built by tests/ (g++) into tests/_build/libmm_emul.so so that the kernel LOGIC can be checked
+// against the oracle on machines without a GPU (`-m "not gpu"` tests).  It is never loaded by the
+// mujoco_manip_b200 package: the product path is the CUDA library and fails loudly without it.
+#define MM_MODEL_HOST_FILL
+#include <cstring>
+#include <vector>
+
+#include "mm_env.h"
+
+using namespace mm;
+
+namespace {
+template <class T>
+struct Ctx {
+  ModelDev<T> md;
+  Scratch<T> s;
+  std::vector<T> wr;
+  std::vector<int> wi;
+  Work<T> w;
+  Ctx() : wr(WORK_REALS), wi(WORK_INTS) {
+    fill_model(md);
+    w = make_work(wr.data(), wi.data());
+    std::memset(&s, 0, sizeof s);
+  }
+};
+template <class T>
+Ctx<T>& ctx() {
+  static thread_local Ctx<T> c;
+  return c;
+}
+
+StatePtrs state_from(void** p) {
+  StatePtrs st;
+  st.qpos = (double*)p[0]; st.qvel = (double*)p[1]; st.ctrl = (double*)p[2]; st.warm = (double*)p[3];
+  st.tinit = (double*)p[4]; st.eepose = (double*)p[5]; st.fsm_f = (double*)p[6]; st.hwm = (double*)p[7];
+  st.step_count = (int*)p[8]; st.task = (int*)p[9]; st.fsm_i = (int*)p[10]; st.flags = (int*)p[11]; st.diag = (int*)p[12];
+  return st;
+}
+StepOut out_from(void** p) {
+  StepOut o;
+  o.obs = (float*)p[0]; o.reward = (float*)p[1]; o.terminated = (unsigned char*)p[2]; o.truncated = (unsigned char*)p[3];
+  o.success = (unsigned char*)p[4]; o.reward_components = (float*)p[5];
+  return o;
+}
+
+template <class T>
+void do_reset(int n, void** sp, const unsigned char* mask, const double* obj_xy, const int* task, float* obs, float* tgt) {
+  Ctx<T>& c = ctx<T>();
+  StatePtrs st = state_from(sp);
+  Grp<1> g{0, 1u};
+  for (long e = 0; e < n; e++) {
+    if (mask && !mask[e]) continue;
+    env_reset<T, 1>(g, c.s, c.md, c.w, st, e, obj_xy ? obj_xy + 6 * e : nullptr, task[2 * e], task[2 * e + 1], obs, tgt);
+  }
+}
+template <class T>
+void do_step(int n, void** sp, const float* actions, int mode, int reward_type, int max_steps, void** op, const float* tgt) {
+  Ctx<T>& c = ctx<T>();
+  StatePtrs st = state_from(sp);
+  StepOut out = out_from(op);
+  Grp<1> g{0, 1u};
+  for (long e = 0; e < n; e++) env_step<T, 1>(g, c.s, c.md, c.w, st, e, actions, mode, reward_type, max_steps, out, tgt);
+}
+}  // namespace
+
+extern "C" {
+
+void emul_reset(int n, void** state, const unsigned char* mask, const double* obj_xy, const int* task, float* obs,
+                float* tgt_kp, int use_float) {
+  if (use_float) do_reset<float>(n, state, mask, obj_xy, task, obs, tgt_kp);
+  else do_reset<double>(n, state, mask, obj_xy, task, obs, tgt_kp);
+}
+
+void emul_step(int n, void** state, const float* actions, int mode, int reward_type, int max_steps, void** out,
+               const float* tgt_kp, int use_float) {
+  if (use_float) do_step<float>(n, state, actions, mode, reward_type, max_steps, out, tgt_kp);
+  else do_step<double>(n, state, actions, mode, reward_type, max_steps, out, tgt_kp);
+}
+
+void emul_fsm_plan(int n, void** state, int nsteps, float* actions /*[n,10]*/) {
+  StatePtrs st = state_from(state);
+  for (long e = 0; e < n; e++) fsm_plan_one(st, e, nsteps, actions ? actions + e * ACTION_STRIDE : nullptr);
+}
+
+// One forward pass on a raw state with every intermediate exposed (FP64), for stage-wise parity tests.
+void emul_forward_debug(const double* qpos, const double* qvel, const double* ctrl, const double* warm, double* Mr,
+                        double* fs, double* as, double* qacc, double* fc, double* bpos, double* bR, int* ncon,
+                        double* cpos, double* cn, double* cdist, int* cmeta, int* niter) {
+  Ctx<double>& c = ctx<double>();
+  Scratch<double>& s = c.s;
+  Grp<1> g{0, 1u};
+  for (int i = 0; i < NQ; i++) s.qpos[i] = qpos[i];
+  for (int i = 0; i < NV; i++) { s.qvel[i] = qvel[i]; s.warm[i] = warm[i]; }
+  for (int i = 0; i < NU; i++) s.ctrl[i] = ctrl[i];
+  s.overflow = 0;
+  forward<double, 1>(g, s, c.md, c.w);
+  std::memcpy(Mr, s.Mr, sizeof s.Mr);
+  std::memcpy(fs, s.fs, sizeof s.fs);
+  std::memcpy(as, s.as, sizeof s.as);
+  std::memcpy(qacc, s.qacc, sizeof s.qacc);
+  std::memcpy(fc, s.fc, sizeof s.fc);
+  std::memcpy(bpos, s.bpos, sizeof s.bpos);
+  std::memcpy(bR, s.bR, sizeof s.bR);
+  *ncon = s.ncon;
+  *niter = s.niter;
+  for (int k = 0; k < s.ncon; k++) {
+    for (int d = 0; d < 3; d++) { cpos[3 * k + d] = c.w.cpos[d * MAXCON + k]; cn[3 * k + d] = c.w.cn[d * MAXCON + k]; }
+    cdist[k] = c.w.cdist[k];
+    cmeta[k] = c.w.cmeta[k];
+  }
+}
+
+int emul_scratch_bytes(int use_float) { return use_float ? (int)sizeof(Scratch<float>) : (int)sizeof(Scratch<double>); }
+}

@@ -1,0 +1,156 @@
+// Lane-group abstraction: G lanes of a warp cooperate on ONE environment.
+//   G = 32 : warp per env          G = 16 / 8 : two / four envs per warp
+//   G = 1  : host build only (tests/ "1-lane emulation" of the very same kernel source, used to debug
+//            the kernel logic against the oracle on machines without a GPU; never a product path).
+// All loops over per-env items are written `for (i = g.lane; i < n; i += G)`, all reductions go
+// through the group (xor-butterfly shuffles inside the aligned G-lane segment of the warp).
+#pragma once
+#include <cmath>
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define MM_HD __host__ __device__ __forceinline__
+#define MM_HDN __host__ __device__
+#else
+#define MM_HD inline
+#define MM_HDN
+#endif
+
+namespace mm {
+
+template <int G>
+struct Grp {
+  int lane;       // 0..G-1 inside the group
+  unsigned mask;  // lanes of this group inside the warp
+
+  MM_HD void sync() const {
+#ifdef __CUDA_ARCH__
+    if (G > 1) __syncwarp(mask);
+#endif
+  }
+  template <class T>
+  MM_HD T sum(T v) const {
+#ifdef __CUDA_ARCH__
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+#endif
+    return v;
+  }
+  MM_HD int any(int pred) const {
+#ifdef __CUDA_ARCH__
+    if (G > 1) return (__ballot_sync(mask, pred) & mask) != 0;
+#endif
+    return pred != 0;
+  }
+  MM_HD int isum(int v) const {
+#ifdef __CUDA_ARCH__
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+#endif
+    return v;
+  }
+  MM_HD int imax(int v) const {
+#ifdef __CUDA_ARCH__
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) { int t = __shfl_xor_sync(mask, v, o); v = t > v ? t : v; }
+#endif
+    return v;
+  }
+  // exclusive prefix sum over the lanes of the group; *total receives the group sum
+  MM_HD int scan_excl(int v, int* total) const {
+    int incl = v;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+    for (int o = 1; o < G; o <<= 1) {
+      int t = __shfl_up_sync(mask, incl, o, G);
+      if (lane >= o) incl += t;
+    }
+    *total = __shfl_sync(mask, incl, G - 1, G);
+#else
+    *total = incl;
+#endif
+    return incl - v;
+  }
+  template <class T>
+  MM_HD T shfl_up(T v, int o) const {
+#ifdef __CUDA_ARCH__
+    return __shfl_up_sync(mask, v, o, G);
+#else
+    return v;
+#endif
+  }
+  template <class T>
+  MM_HD T shfl_down(T v, int o) const {
+#ifdef __CUDA_ARCH__
+    return __shfl_down_sync(mask, v, o, G);
+#else
+    return v;
+#endif
+  }
+  template <class T>
+  MM_HD T bcast(T v, int src) const {
+#ifdef __CUDA_ARCH__
+    return __shfl_sync(mask, v, src, G);
+#else
+    return v;
+#endif
+  }
+};
+
+// ---- small vector helpers ----------------------------------------------------------------------
+template <class T> MM_HD T dot3(const T* a, const T* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+template <class T> MM_HD void cross3(T* r, const T* a, const T* b) {
+  T x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+template <class T> MM_HD T dot6(const T* a, const T* b) {
+  return a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3] + a[4] * b[4] + a[5] * b[5];
+}
+// r = R (row-major 3x3) * v
+template <class T> MM_HD void rot(T* r, const T* R, const T* v) {
+  T x = R[0] * v[0] + R[1] * v[1] + R[2] * v[2];
+  T y = R[3] * v[0] + R[4] * v[1] + R[5] * v[2];
+  T z = R[6] * v[0] + R[7] * v[1] + R[8] * v[2];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+template <class T> MM_HD void rotT(T* r, const T* R, const T* v) {
+  T x = R[0] * v[0] + R[3] * v[1] + R[6] * v[2];
+  T y = R[1] * v[0] + R[4] * v[1] + R[7] * v[2];
+  T z = R[2] * v[0] + R[5] * v[1] + R[8] * v[2];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+template <class T> MM_HD void matmul3(T* r, const T* a, const T* b) {
+  T t[9];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) t[3 * i + j] = a[3 * i] * b[j] + a[3 * i + 1] * b[3 + j] + a[3 * i + 2] * b[6 + j];
+#pragma unroll
+  for (int i = 0; i < 9; i++) r[i] = t[i];
+}
+template <class T> MM_HD T tmax(T a, T b) { return a > b ? a : b; }
+template <class T> MM_HD T tmin(T a, T b) { return a < b ? a : b; }
+template <class T> MM_HD T tabs(T a) { return a < 0 ? -a : a; }
+template <class T> MM_HD T tclamp(T x, T lo, T hi) { return x < lo ? lo : (x > hi ? hi : x); }
+MM_HD float tsqrt(float x) { return sqrtf(x); }
+MM_HD double tsqrt(double x) { return sqrt(x); }
+MM_HD void tsincos(float x, float* s, float* c) {
+#ifdef __CUDA_ARCH__
+  sincosf(x, s, c);
+#else
+  *s = sinf(x); *c = cosf(x);
+#endif
+}
+MM_HD void tsincos(double x, double* s, double* c) {
+#ifdef __CUDA_ARCH__
+  sincos(x, s, c);
+#else
+  *s = sin(x); *c = cos(x);
+#endif
+}
+MM_HD float tacos(float x) { return acosf(x); }
+MM_HD double tacos(double x) { return acos(x); }
+MM_HD float tsin(float x) { return sinf(x); }
+MM_HD double tsin(double x) { return sin(x); }
+
+}  // namespace mm

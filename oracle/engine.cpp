@@ -383,7 +383,9 @@ static void box_box(Data& d, int g1, int g2) {
     double t = dot3(dp, B[j]);
     double pen = sb[j] + sa[0] * Q[0][j] + sa[1] * Q[1][j] + sa[2] * Q[2][j] - std::fabs(t);
     if (pen < 0) return;
-    if (pen < best) { best = pen; code = 3 + j; double sg = t < 0 ? -1 : 1; for (int k = 0; k < 3; k++) bn[k] = sg * B[j][k]; }
+    // a face of the second box must be clearly better: exactly parallel faces (left/right pads, cube
+    // on table) tie to rounding error and the choice would otherwise flip with the last bit
+    if (pen < best * (1 - 1e-6) - 1e-12) { best = pen; code = 3 + j; double sg = t < 0 ? -1 : 1; for (int k = 0; k < 3; k++) bn[k] = sg * B[j][k]; }
   }
   // edge x edge axes (face axes preferred: an edge axis must be clearly better)
   double ebest = 1e300, en[3] = {0, 0, 0};
@@ -459,8 +461,11 @@ static void box_box(Data& d, int g1, int g2) {
       const double* Qn = poly[(q + 1) % np];
       double rp[3] = {P[0] - pr[0], P[1] - pr[1], P[2] - pr[2]}, rq[3] = {Qn[0] - pr[0], Qn[1] - pr[1], Qn[2] - pr[2]};
       double dP = sg * dot3(rp, Rr[ta]) - lim, dQ = sg * dot3(rq, Rr[ta]) - lim;
-      if (dP <= 0) { for (int k = 0; k < 3; k++) out[no][k] = P[k]; no++; }
-      if ((dP < 0 && dQ > 0) || (dP > 0 && dQ < 0)) {
+      // 1 nm band: vertices lying on a side plane (exactly aligned pads) count as inside and do not
+      // spawn sliver crossings whose existence would depend on the last bit
+      const double ce = 1e-9;
+      if (dP <= ce) { for (int k = 0; k < 3; k++) out[no][k] = P[k]; no++; }
+      if ((dP < -ce && dQ > ce) || (dP > ce && dQ < -ce)) {
         double tt = dP / (dP - dQ);
         for (int k = 0; k < 3; k++) out[no][k] = P[k] + tt * (Qn[k] - P[k]);
         no++;

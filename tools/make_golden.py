@@ -1,0 +1,214 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference package (imported read-only from
+/root/reference) on top of the CPU oracle engine through oracle/fake_mujoco.py.
+
+What these fixtures pin: everything the reference implements in Python above the engine boundary -
+action decode, DLS IK, the pick-and-place FSM, rewards, observation packing, reset/RNG order - as
+executed by the reference's own code.  The engine underneath is the oracle restatement (MuJoCo is
+not installable here), so engine-level trajectories remain "parity unpinned" against real MuJoCo.
+
+Run here only (the GPU box has no /root/reference):  python tools/make_golden.py
+"""
+import os
+import sys
+
+sys.dont_write_bytecode = True  # never write __pycache__ into the reference tree
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+
+import numpy as np  # noqa: E402
+
+from oracle import fake_mujoco  # noqa: E402
+
+fake_mujoco.install("/root/reference")
+
+from mujoco_manip import pose_utils as P  # noqa: E402
+from mujoco_manip.constants import ACTION_REPEAT, TASK_SETS  # noqa: E402
+from mujoco_manip.controller import TARGET_ORI  # noqa: E402
+from mujoco_manip.gym_env import PickPlaceGymEnv  # noqa: E402
+from mujoco_manip.pick_and_place import PickAndPlaceTask  # noqa: E402
+from mujoco_manip.randomization import _sample_separated_positions  # noqa: E402
+
+OUT = os.path.join(REPO, "tests", "golden")
+OBS_KEYS = ["state", "state.ee.pos_quat_g", "state.ee.pos_rot6d_g", "state.ee.pos_quat_g_rel",
+            "state.ee.pos_rot6d_g_rel", "target_bin_onehot", "target_obj_onehot"]
+KP_KEYS = ["keypoints_overhead", "keypoints_wrist", "target_obj_keypoints_overhead", "target_bin_keypoints_overhead"]
+
+
+def pack_obs(obs):
+    return np.concatenate([np.asarray(obs[k], dtype=np.float32).ravel() for k in OBS_KEYS + KP_KEYS])
+
+
+def get_actions(target_pos, g, init_inv):  # same arithmetic as scripts/generate_dataset.py:56-80
+    T = P.pos_rotmat_to_se3(target_pos, TARGET_ORI)
+    Tr = init_inv @ T
+    return {"abs_pos": np.array([*target_pos, g], dtype=np.float32),
+            "ee_pos_quat_g": P.se3_to_pos_quat_g(T, g), "ee_pos_rot6d_g": P.se3_to_pos_rot6d_g(T, g),
+            "ee_pos_quat_g_rel": P.se3_to_pos_quat_g(Tr, g), "ee_pos_rot6d_g_rel": P.se3_to_pos_rot6d_g(Tr, g)}
+
+
+def snapshot(env):
+    d = env.pick_place_env.data
+    return dict(qpos=d.qpos.copy(), qvel=d.qvel.copy(), ctrl=d.ctrl.copy(), warm=d.qacc_warmstart.copy(),
+                ee_pos=env.robot.ee_pos, ee_R=env.robot.ee_xmat.ravel())
+
+
+def fsm_episode(mode, task, randomize, seed, reward_type="dense", max_steps=400):
+    env = PickPlaceGymEnv(task=None, tasks="all", action_mode=mode, reward_type=reward_type,
+                          randomize_objects=randomize)
+    obs, _ = env.reset(seed=seed, options={"task": task})
+    fsm = PickAndPlaceTask(env.pick_place_env, env.robot, env.controller, tasks=[task])
+    init_inv = np.linalg.inv(env.initial_ee_se3)
+    rec = {k: [] for k in ("action", "obs", "reward", "terminated", "truncated", "success", "fsm_state", "target",
+                           "gripper", "qpos", "qvel", "ctrl", "warm", "ee_pos", "ee_R", "rc", "counter")}
+    init = snapshot(env)
+    obs0 = pack_obs(obs)
+    n = 0
+    while not fsm.is_done and n < max_steps:
+        fsm.plan(n_steps=ACTION_REPEAT)
+        tp = fsm.target_pos if fsm.target_pos is not None else env.robot.ee_pos
+        a = get_actions(tp, fsm.gripper_val, init_inv)[mode]
+        rec["fsm_state"].append(fsm.state.value)
+        rec["counter"].append(fsm.settle_counter)
+        rec["target"].append(np.array(tp, dtype=np.float64))
+        rec["gripper"].append(fsm.gripper_val)
+        pad = np.zeros(10, dtype=np.float32)
+        pad[: a.size] = a
+        rec["action"].append(pad)
+        obs, r, te, tr, info = env.step(a)
+        s = snapshot(env)
+        for k in ("qpos", "qvel", "ctrl", "warm", "ee_pos", "ee_R"):
+            rec[k].append(s[k])
+        rec["obs"].append(pack_obs(obs))
+        rec["reward"].append(r)
+        rec["terminated"].append(te)
+        rec["truncated"].append(tr)
+        rec["success"].append(info["success"])
+        rec["rc"].append(info.get("reward_components", np.zeros(6, dtype=np.float32)))
+        n += 1
+    out = {k: np.array(v) for k, v in rec.items()}
+    out.update(init_qpos=init["qpos"], init_ee_pos=init["ee_pos"], init_ee_R=init["ee_R"], obs0=obs0,
+               T_init=env.initial_ee_se3, final_fsm_state=fsm.state.value,
+               obj_idx=["obj_red", "obj_green", "obj_blue"].index(task[0]),
+               bin_idx=["bin_red", "bin_green", "bin_blue"].index(task[1]))
+    env.close()
+    return out
+
+
+def random_rollout(mode, seed, n_steps=50, reward_type="dense", stress=False):
+    env = PickPlaceGymEnv(task=("obj_red", "bin_red"), action_mode=mode, reward_type=reward_type)
+    obs, _ = env.reset(seed=seed)
+    rng = np.random.default_rng(seed)
+    T_init = env.initial_ee_se3
+    init_inv = np.linalg.inv(T_init)
+    rec = {k: [] for k in ("action", "obs", "reward", "terminated", "truncated", "success", "qpos", "qvel", "ctrl",
+                           "warm", "ee_pos", "ee_R", "ncon")}
+    obs0 = pack_obs(obs)
+    for t in range(n_steps):
+        if stress:  # drive the hand low: finger/hand hulls against table, bins and cubes
+            w = np.array([rng.uniform(-0.3, 0.3), rng.uniform(0.30, 0.65), rng.uniform(0.20, 0.40)])
+        else:
+            w = np.array([rng.uniform(-0.3, 0.3), rng.uniform(0.30, 0.65), rng.uniform(0.30, 0.60)])
+        g = float(rng.uniform() > 0.5)
+        # random (unused) rotation to exercise the decoders
+        q = rng.normal(size=4)
+        q /= np.linalg.norm(q)
+        Rr = P.quat_xyzw_to_rotmat(q)
+        T = P.pos_rotmat_to_se3(w, Rr)
+        Tr = init_inv @ T
+        a = {"abs_pos": np.array([*w, g], dtype=np.float32), "ee_pos_quat_g": P.se3_to_pos_quat_g(T, g),
+             "ee_pos_rot6d_g": P.se3_to_pos_rot6d_g(T, g), "ee_pos_quat_g_rel": P.se3_to_pos_quat_g(Tr, g),
+             "ee_pos_rot6d_g_rel": P.se3_to_pos_rot6d_g(Tr, g)}[mode]
+        pad = np.zeros(10, dtype=np.float32)
+        pad[: a.size] = a
+        rec["action"].append(pad)
+        obs, r, te, tr, info = env.step(a)
+        s = snapshot(env)
+        for k in ("qpos", "qvel", "ctrl", "warm", "ee_pos", "ee_R"):
+            rec[k].append(s[k])
+        rec["obs"].append(pack_obs(obs))
+        rec["reward"].append(r)
+        rec["terminated"].append(te)
+        rec["truncated"].append(tr)
+        rec["success"].append(info["success"])
+        rec["ncon"].append(env.pick_place_env.data.ncon)
+    out = {k: np.array(v) for k, v in rec.items()}
+    out.update(obs0=obs0, T_init=T_init)
+    env.close()
+    return out
+
+
+def pose_vectors(seed=0):
+    rng = np.random.default_rng(seed)
+    Rs, quats, r6, T8, T10, d8, d10 = [], [], [], [], [], [], []
+    for i in range(64):
+        q = rng.normal(size=4)
+        q /= np.linalg.norm(q)
+        R = P.quat_xyzw_to_rotmat(q)
+        if i < 4:  # exercise each branch of the R->quat conversion
+            R = [np.eye(3), np.diag([1.0, -1, -1]), np.diag([-1.0, 1, -1]), np.diag([-1.0, -1, 1])][i]
+        p = rng.uniform(-1, 1, size=3)
+        g = float(rng.uniform())
+        T = P.pos_rotmat_to_se3(p, R)
+        Rs.append(R)
+        quats.append(P.rotmat_to_quat_xyzw(R))
+        r6.append(P.rotmat_to_6d(R))
+        v8, v10 = P.se3_to_pos_quat_g(T, g), P.se3_to_pos_rot6d_g(T, g)
+        d8.append(v8)
+        d10.append(v10)
+        T8.append(P.se3_from_pos_quat_g(v8))
+        a10 = v10.copy()
+        a10[3:9] *= rng.uniform(0.5, 2.0)  # un-normalised 6D input
+        a10[6:9] += 0.3 * a10[3:6]
+        T10.append(np.concatenate([a10.astype(np.float64), P.se3_from_pos_rot6d_g(a10).ravel()]))
+    return dict(R=np.array(Rs), quat=np.array(quats), rot6d=np.array(r6), dof8=np.array(d8), dof10=np.array(d10),
+                T_from8=np.array(T8), in10_T_from10=np.array(T10))
+
+
+def reset_vectors():
+    seeds = [0, 1, 7, 42, 123, 2684470948, 4091952314, 233227757, 3276785861]
+    xy, task, obs0, qpos = [], [], [], []
+    env = PickPlaceGymEnv(tasks="all", randomize_objects=True, action_mode="ee_pos_rot6d_g_rel")
+    for s in seeds:
+        obs, _ = env.reset(seed=s)
+        d = env.pick_place_env.data
+        xy.append(np.array([d.qpos[9:11], d.qpos[16:18], d.qpos[23:25]]))
+        task.append([["obj_red", "obj_green", "obj_blue"].index(env.obj_name),
+                     ["bin_red", "bin_green", "bin_blue"].index(env.bin_name)])
+        obs0.append(pack_obs(obs))
+        qpos.append(d.qpos.copy())
+    # raw sampler draws too
+    rng = np.random.default_rng(42)
+    first = np.array(_sample_separated_positions(rng, 3, (-0.20, 0.20), (0.30, 0.45), 0.08))
+    ss = np.random.SeedSequence(42).spawn(8)
+    ep_seeds = np.array([int(c.generate_state(1)[0]) for c in ss], dtype=np.uint64)
+    env.close()
+    return dict(seeds=np.array(seeds, dtype=np.uint64), obj_xy=np.array(xy), task=np.array(task), obs0=np.array(obs0),
+                qpos=np.array(qpos), sampler42=first, episode_seeds42=ep_seeds,
+                task_sets_all=np.array([[["obj_red", "obj_green", "obj_blue"].index(o), ["bin_red", "bin_green", "bin_blue"].index(b)]
+                                        for o, b in TASK_SETS["all"]]),
+                task_sets_cross=np.array([[["obj_red", "obj_green", "obj_blue"].index(o), ["bin_red", "bin_green", "bin_blue"].index(b)]
+                                          for o, b in TASK_SETS["cross"]]))
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, "pose_utils.npz"), **pose_vectors())
+    np.savez_compressed(os.path.join(OUT, "reset_seeds.npz"), **reset_vectors())
+    # config 1: the reference's own CPU-runnable case
+    np.savez_compressed(os.path.join(OUT, "fsm_quat_rel_red_red.npz"),
+                        **fsm_episode("ee_pos_quat_g_rel", ("obj_red", "bin_red"), False, None))
+    np.savez_compressed(os.path.join(OUT, "fsm_abs_green_blue_seed42_staged.npz"),
+                        **fsm_episode("abs_pos", ("obj_green", "bin_blue"), True, 42, reward_type="staged"))
+    np.savez_compressed(os.path.join(OUT, "fsm_rot6d_rel_blue_red_seed7.npz"),
+                        **fsm_episode("ee_pos_rot6d_g_rel", ("obj_blue", "bin_red"), True, 7))
+    for mode in ("abs_pos", "ee_pos_quat_g", "ee_pos_rot6d_g", "ee_pos_quat_g_rel", "ee_pos_rot6d_g_rel"):
+        np.savez_compressed(os.path.join(OUT, f"random50_{mode}.npz"), **random_rollout(mode, 1234, 50))
+    np.savez_compressed(os.path.join(OUT, "stress30_abs_pos_staged.npz"),
+                        **random_rollout("abs_pos", 99, 30, reward_type="staged", stress=True))
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()

@@ -553,10 +553,117 @@ def emit_header(model, path):
         f.write("".join(out))
 
 
+
+# ---------------------------------------------------------------------------------------------
+# specialised tables for the CUDA kernels (structure-exploiting layout)
+# ---------------------------------------------------------------------------------------------
+def emit_dev_header(model, path):
+    """Tables in the kernels' own numbering.
+
+    dynamic bodies db: 0..6 link1..link7, 7 hand, 8 left finger, 9 right finger, 10..12 cubes.
+    inertial bodies ib = joints 0..8: link1..6, link7+hand (merged rigidly), left, right finger.
+    chain classes: 0 static, 1..7 link1..7 (hand == 7), 8 left finger, 9 right finger, 10..12 cubes.
+    boxes (oracle geom order so that geom1/geom2 roles agree): 0..9 pads, 10 tabletop, 11..25 bins,
+    26..28 cubes; id 29 = floor plane.
+    """
+    B, J, G = model["bodies"], model["joints"], model["geoms"]
+    name2b = {b["name"]: i for i, b in enumerate(B)}
+    chain = ["link1", "link2", "link3", "link4", "link5", "link6", "link7", "hand", "left_finger", "right_finger"]
+    link_pos = [B[name2b[n]]["pos"] for n in chain]
+    link_R = [q2R(B[name2b[n]]["quat"]).reshape(9) for n in chain]
+    # merged link7 + hand
+    b7, bh = B[name2b["link7"]], B[name2b["hand"]]
+    Rh = q2R(bh["quat"])
+    ch = np.array(bh["pos"]) + Rh @ np.array(bh["ipos"])
+    c7 = np.array(b7["ipos"])
+    m = b7["mass"] + bh["mass"]
+    c = (b7["mass"] * c7 + bh["mass"] * ch) / m
+
+    def pax(mass, d):
+        return mass * (np.dot(d, d) * np.eye(3) - np.outer(d, d))
+
+    I = np.asarray(b7["inertia"]) + pax(b7["mass"], c7 - c) + Rh @ np.asarray(bh["inertia"]) @ Rh.T + pax(bh["mass"], ch - c)
+    ib_names = ["link1", "link2", "link3", "link4", "link5", "link6", "link7", "left_finger", "right_finger"]
+    ib_mass, ib_com, ib_I = [], [], []
+    for n in ib_names:
+        b = B[name2b[n]]
+        if n == "link7":
+            mm_, cc, II = m, c, I
+        else:
+            mm_, cc, II = b["mass"], np.array(b["ipos"]), np.asarray(b["inertia"])
+        ib_mass.append(mm_)
+        ib_com.append(cc)
+        ib_I.append([II[0, 0], II[1, 1], II[2, 2], II[0, 1], II[0, 2], II[1, 2]])
+    # boxes
+    db_of_body = {name2b[n]: i for i, n in enumerate(chain)}
+    for k, n in enumerate(["obj_red", "obj_green", "obj_blue"]):
+        db_of_body[name2b[n]] = 10 + k
+    cls_of_body = {name2b[n]: min(i + 1, 7) for i, n in enumerate(chain[:8])}
+    cls_of_body[name2b["left_finger"]] = 8
+    cls_of_body[name2b["right_finger"]] = 9
+    for k, n in enumerate(["obj_red", "obj_green", "obj_blue"]):
+        cls_of_body[name2b[n]] = 10 + k
+    X = fk_qpos0(model)
+    box_ids = [i for i, g in enumerate(G) if g["type"] == GT_BOX]
+    assert len(box_ids) == 29
+    gid2box = {g: k for k, g in enumerate(box_ids)}
+    plane_gid = [i for i, g in enumerate(G) if g["type"] == GT_PLANE][0]
+    gid2box[plane_gid] = 29
+    box_size, box_pos, box_body, box_class, box_invw, box_cube = [], [], [], [], [], []
+    for gi in box_ids:
+        g = G[gi]
+        b = g["body"]
+        assert np.allclose(g["quat"], [1, 0, 0, 0])
+        box_size.append(g["size"])
+        if B[b]["weld"] == 0:  # static: world position (bodies are axis aligned)
+            p, R = X[b]
+            assert np.allclose(R, np.eye(3))
+            box_pos.append((p + np.array(g["pos"])).tolist())
+            box_body.append(-1)
+            box_class.append(0)
+        else:
+            box_pos.append(g["pos"])
+            box_body.append(db_of_body[b])
+            box_class.append(cls_of_body[b])
+        box_invw.append(model["body_invweight0"][b][0])
+        box_cube.append(int(g["condim"] == 4))
+    # candidate list restricted to plane-box / box-box, sorted by (classA, classB) so that contacts
+    # of one body pair are contiguous (the kernels reduce per body pair)
+    cand = []
+    for g1, g2 in model["pairs"]:
+        t1, t2 = G[g1]["type"], G[g2]["type"]
+        if (t1, t2) not in ((GT_PLANE, GT_BOX), (GT_BOX, GT_BOX)):
+            continue
+        a, b_ = gid2box[g1], gid2box[g2]
+        ca = 0 if a == 29 else box_class[a]
+        cb = box_class[b_]
+        cand.append((ca, cb, a, b_))
+    cand.sort()
+    out = []
+    out.append("// GENERATED by tools/modelc.py - specialised tables for the CUDA kernels. Do not edit.\n#pragma once\n")
+    out.append(f"#define MMD_NBOX 29\n#define MMD_PLANE 29\n#define MMD_NCAND {len(cand)}\n")
+    out.append(carr("mmd_link_pos", "double", link_pos))
+    out.append(carr("mmd_link_R", "double", link_R))
+    out.append(carr("mmd_ib_mass", "double", ib_mass))
+    out.append(carr("mmd_ib_com", "double", ib_com))
+    out.append(carr("mmd_ib_inertia", "double", ib_I))
+    out.append(carr("mmd_box_size", "double", box_size))
+    out.append(carr("mmd_box_pos", "double", box_pos))
+    out.append(carr("mmd_box_body", "int", box_body))
+    out.append(carr("mmd_box_class", "int", box_class))
+    out.append(carr("mmd_box_invw", "double", box_invw))
+    out.append(carr("mmd_box_cube", "int", box_cube))
+    out.append(carr("mmd_cand", "int", [[c[2], c[3]] for c in cand]))
+    with open(path, "w") as f:
+        f.write("".join(out))
+    return cand
+
 def main():
     data_dir = sys.argv[1] if len(sys.argv) > 1 else "/root/reference/mujoco_manip/data"
     model = compile_model(data_dir)
     emit_header(model, os.path.join(REPO, "mujoco_manip_b200", "csrc", "model_gen.h"))
+    cand = emit_dev_header(model, os.path.join(REPO, "mujoco_manip_b200", "csrc", "model_dev_gen.h"))
+    print("device candidate pairs:", len(cand))
 
     def clean(o):
         if isinstance(o, np.ndarray):
