@@ -1,0 +1,352 @@
+// CUDA kernels (sm_100a) + the C ABI of include/mm_manip.h.
+// One G-lane group per environment (G = 32 warp-per-env, 16 / 8 = two / four envs per warp);
+// per-env matrices live in shared memory, streamed per-contact data in a global workspace that the
+// lanes touch with consecutive indices.  No CPU fallback: every entry point needs a CUDA device.
+#define MM_MODEL_HOST_FILL
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/mm_manip.h"
+#include "mm_env.h"
+#include "mm_rng.h"
+
+using namespace mm;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(const std::string& m) { g_err = m; return -1; }
+#define CK(x)                                                                        \
+  do {                                                                               \
+    cudaError_t e_ = (x);                                                            \
+    if (e_ != cudaSuccess) return fail(std::string(#x) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+constexpr int BLOCK = 128;
+
+struct StepParams {
+  StatePtrs st;
+  StepOut out;
+  const float* actions;
+  const void* model;
+  void* work_reals;
+  int* work_ints;
+  float* tgt_kp;
+  const unsigned char* mask;
+  const double* obj_xy;
+  const int* task;
+  float* obs;
+  long n;
+  int mode, reward_type, max_steps;
+};
+
+template <class T>
+__device__ __forceinline__ size_t model_bytes() { return (sizeof(ModelDev<T>) + 15) & ~size_t(15); }
+
+template <class T, int G>
+__device__ __forceinline__ bool setup(const StepParams& p, unsigned char* smem, ModelDev<T>*& md, Scratch<T>*& sc,
+                                      Grp<G>& g, long& e) {
+  md = reinterpret_cast<ModelDev<T>*>(smem);
+  // one model copy per CTA (word-wise cooperative copy from global)
+  const int* src = reinterpret_cast<const int*>(p.model);
+  int* dst = reinterpret_cast<int*>(smem);
+  for (int i = threadIdx.x; i < (int)(sizeof(ModelDev<T>) / 4); i += BLOCK) dst[i] = src[i];
+  __syncthreads();
+  constexpr int GPB = BLOCK / G;
+  int gi = threadIdx.x / G;
+  e = (long)blockIdx.x * GPB + gi;
+  sc = reinterpret_cast<Scratch<T>*>(smem + model_bytes<T>()) + gi;
+  g.lane = threadIdx.x % G;
+  int inwarp = (threadIdx.x % 32) / G;
+  g.mask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (inwarp * G));
+  return e < p.n;
+}
+
+template <class T, int G>
+__global__ void __launch_bounds__(BLOCK) k_step(StepParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  ModelDev<T>* md;
+  Scratch<T>* sc;
+  Grp<G> g;
+  long e;
+  if (!setup<T, G>(p, smem, md, sc, g, e)) return;
+  Work<T> w = make_work(reinterpret_cast<T*>(p.work_reals) + e * WORK_REALS, p.work_ints + e * WORK_INTS);
+  env_step<T, G>(g, *sc, *md, w, p.st, e, p.actions, p.mode, p.reward_type, p.max_steps, p.out, p.tgt_kp);
+}
+
+template <class T, int G>
+__global__ void __launch_bounds__(BLOCK) k_reset(StepParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  ModelDev<T>* md;
+  Scratch<T>* sc;
+  Grp<G> g;
+  long e;
+  if (!setup<T, G>(p, smem, md, sc, g, e)) return;
+  if (p.mask && !p.mask[e]) return;
+  Work<T> w = make_work(reinterpret_cast<T*>(p.work_reals) + e * WORK_REALS, p.work_ints + e * WORK_INTS);
+  env_reset<T, G>(g, *sc, *md, w, p.st, e, p.obj_xy ? p.obj_xy + 6 * e : nullptr, p.task[2 * e], p.task[2 * e + 1], p.obs,
+                  p.tgt_kp);
+}
+
+__global__ void k_fsm(StatePtrs st, long n, int nsteps, float* actions) {
+  long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n) fsm_plan_one(st, e, nsteps, actions ? actions + e * ACTION_STRIDE : nullptr);
+}
+
+// Philox placement + task draw for every env (mm_rng.h); thread per env
+__global__ void k_sample(unsigned long long seed, long long gid0, const long long* episode, long n, double xlo, double xhi,
+                         double ylo, double yhi, double min_sep, int npool, double* xy, int* task_draw, int* attempts) {
+  long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  unsigned long long gid = (unsigned long long)(gid0 + e);
+  unsigned ep = (unsigned)episode[e];
+  double p[6];
+  int na = philox_place(seed, gid, ep, xlo, xhi, ylo, yhi, min_sep, 1000, p);
+  for (int k = 0; k < 6; k++) xy[6 * e + k] = p[k];
+  if (task_draw) task_draw[e] = philox_task(seed, gid, ep, npool);
+  if (attempts) attempts[e] = na;
+}
+
+// FMA-throughput microbenchmark: the measured denominator of the CUDA-core roofline (bench.py)
+template <class T>
+__global__ void __launch_bounds__(256) k_peak(T* out, int iters, T a, T b) {
+  T x[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) x[k] = (T)(threadIdx.x + k);
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int k = 0; k < 16; k++) x[k] = x[k] * a + b;
+  }
+  T acc = 0;
+#pragma unroll
+  for (int k = 0; k < 16; k++) acc += x[k];
+  if (acc == (T)-12345) out[0] = acc;  // never true; keeps the chain alive
+}
+
+}  // namespace
+
+struct mm_handle {
+  mm_config cfg;
+  void* d_model = nullptr;
+  void* d_work_reals = nullptr;
+  int* d_work_ints = nullptr;
+  float* d_tgt = nullptr;
+  // staging for the host-buffer path
+  float* d_actions = nullptr;
+  float* d_obs = nullptr;
+  float* d_reward = nullptr;
+  unsigned char* d_flags = nullptr;  // terminated | truncated | success, N each
+  long long launches = 0;
+  size_t smem = 0;
+};
+
+namespace {
+
+size_t real_bytes(const mm_config* c) { return c->precision ? 4 : 8; }
+
+template <class T, int G>
+size_t smem_bytes() { return ((sizeof(ModelDev<T>) + 15) & ~size_t(15)) + (BLOCK / G) * sizeof(Scratch<T>); }
+
+template <class T, int G>
+int prepare() {
+  size_t sm = smem_bytes<T, G>();
+  CK(cudaFuncSetAttribute(k_step<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  CK(cudaFuncSetAttribute(k_reset<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  return 0;
+}
+
+template <class T, int G>
+int launch(bool reset, const StepParams& p, cudaStream_t s) {
+  constexpr int GPB = BLOCK / G;
+  unsigned grid = (unsigned)((p.n + GPB - 1) / GPB);
+  size_t sm = smem_bytes<T, G>();
+  if (reset) k_reset<T, G><<<grid, BLOCK, sm, s>>>(p);
+  else k_step<T, G><<<grid, BLOCK, sm, s>>>(p);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+#define DISPATCH(h, fn, ...)                                                   \
+  ((h)->cfg.precision == 0                                                     \
+       ? ((h)->cfg.group == 32 ? fn<double, 32>(__VA_ARGS__)                   \
+          : (h)->cfg.group == 16 ? fn<double, 16>(__VA_ARGS__)                 \
+                                 : fn<double, 8>(__VA_ARGS__))                 \
+       : ((h)->cfg.group == 32 ? fn<float, 32>(__VA_ARGS__)                    \
+          : (h)->cfg.group == 16 ? fn<float, 16>(__VA_ARGS__)                  \
+                                 : fn<float, 8>(__VA_ARGS__)))
+
+StatePtrs to_ptrs(const mm_state* s) {
+  StatePtrs st;
+  st.qpos = s->qpos; st.qvel = s->qvel; st.ctrl = s->ctrl; st.warm = s->warm; st.tinit = s->tinit; st.eepose = s->eepose;
+  st.fsm_f = s->fsm_f; st.hwm = s->hwm; st.step_count = s->step_count; st.task = s->task; st.fsm_i = s->fsm_i;
+  st.flags = s->flags; st.diag = s->diag;
+  return st;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* mm_last_error(void) { return g_err.c_str(); }
+
+size_t mm_workspace_bytes(const mm_config* cfg) {
+  size_t n = (size_t)cfg->num_envs;
+  return n * ((size_t)WORK_REALS * real_bytes(cfg) + (size_t)WORK_INTS * 4 + 4 * 4 + (ACTION_STRIDE + OBS_DIM + 1) * 4 + 3);
+}
+
+int mm_create(const mm_config* cfg, mm_handle** out) {
+  if (!cfg || !out) return fail("mm_create: null argument");
+  if (cfg->num_envs <= 0) return fail("mm_create: num_envs must be positive");
+  if (cfg->group != 8 && cfg->group != 16 && cfg->group != 32) return fail("mm_create: group must be 8, 16 or 32");
+  if (cfg->precision != 0 && cfg->precision != 1) return fail("mm_create: precision must be 0 (f64) or 1 (f32)");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail("mm_create: no CUDA device (this library has no CPU path)");
+  CK(cudaSetDevice(cfg->device));
+  mm_handle* h = new mm_handle();
+  h->cfg = *cfg;
+  size_t n = (size_t)cfg->num_envs;
+  if (cfg->precision == 0) {
+    ModelDev<double> m;
+    std::memset(&m, 0, sizeof m);
+    fill_model(m);
+    CK(cudaMalloc(&h->d_model, sizeof m));
+    CK(cudaMemcpy(h->d_model, &m, sizeof m, cudaMemcpyHostToDevice));
+  } else {
+    ModelDev<float> m;
+    std::memset(&m, 0, sizeof m);
+    fill_model(m);
+    CK(cudaMalloc(&h->d_model, sizeof m));
+    CK(cudaMemcpy(h->d_model, &m, sizeof m, cudaMemcpyHostToDevice));
+  }
+  CK(cudaMalloc(&h->d_work_reals, n * WORK_REALS * real_bytes(cfg)));
+  CK(cudaMalloc(&h->d_work_ints, n * WORK_INTS * sizeof(int)));
+  CK(cudaMalloc(&h->d_tgt, n * 4 * sizeof(float)));
+  CK(cudaMemset(h->d_tgt, 0, n * 4 * sizeof(float)));
+  CK(cudaMalloc(&h->d_actions, n * ACTION_STRIDE * sizeof(float)));
+  CK(cudaMalloc(&h->d_obs, n * OBS_DIM * sizeof(float)));
+  CK(cudaMalloc(&h->d_reward, n * sizeof(float)));
+  CK(cudaMalloc(&h->d_flags, n * 3));
+  if (DISPATCH(h, prepare) != 0) return -1;
+  *out = h;
+  return 0;
+}
+
+void mm_destroy(mm_handle* h) {
+  if (!h) return;
+  cudaFree(h->d_model); cudaFree(h->d_work_reals); cudaFree(h->d_work_ints); cudaFree(h->d_tgt);
+  cudaFree(h->d_actions); cudaFree(h->d_obs); cudaFree(h->d_reward); cudaFree(h->d_flags);
+  delete h;
+}
+
+int mm_reset(mm_handle* h, const mm_state* st, const uint8_t* mask, const double* obj_xy, const int32_t* task,
+             float* obs, void* stream) {
+  if (!h || !st || !task) return fail("mm_reset: null argument");
+  StepParams p{};
+  p.st = to_ptrs(st);
+  p.model = h->d_model; p.work_reals = h->d_work_reals; p.work_ints = h->d_work_ints; p.tgt_kp = h->d_tgt;
+  p.mask = mask; p.obj_xy = obj_xy; p.task = task; p.obs = obs; p.n = h->cfg.num_envs;
+  p.reward_type = h->cfg.reward_type; p.max_steps = h->cfg.max_episode_steps;
+  h->launches++;
+  return DISPATCH(h, launch, true, p, (cudaStream_t)stream);
+}
+
+int mm_step(mm_handle* h, const mm_state* st, const float* actions, int action_mode, const mm_step_out* out,
+            void* stream) {
+  if (!h || !st || !actions || !out) return fail("mm_step: null argument");
+  if (action_mode < 0 || action_mode > 4) return fail("mm_step: bad action_mode");
+  StepParams p{};
+  p.st = to_ptrs(st);
+  p.out.obs = out->obs; p.out.reward = out->reward; p.out.terminated = out->terminated; p.out.truncated = out->truncated;
+  p.out.success = out->success; p.out.reward_components = out->reward_components;
+  p.actions = actions; p.model = h->d_model; p.work_reals = h->d_work_reals; p.work_ints = h->d_work_ints;
+  p.tgt_kp = h->d_tgt; p.n = h->cfg.num_envs; p.mode = action_mode; p.reward_type = h->cfg.reward_type;
+  p.max_steps = h->cfg.max_episode_steps;
+  h->launches++;
+  return DISPATCH(h, launch, false, p, (cudaStream_t)stream);
+}
+
+int mm_step_host(mm_handle* h, const mm_state* st, const float* h_actions, int action_mode, float* h_obs,
+                 float* h_reward, uint8_t* h_terminated, uint8_t* h_truncated, uint8_t* h_success, void* stream) {
+  if (!h || !st || !h_actions) return fail("mm_step_host: null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  size_t n = (size_t)h->cfg.num_envs;
+  CK(cudaMemcpyAsync(h->d_actions, h_actions, n * ACTION_STRIDE * sizeof(float), cudaMemcpyHostToDevice, s));
+  mm_step_out o;
+  o.obs = h->d_obs; o.reward = h->d_reward; o.terminated = h->d_flags; o.truncated = h->d_flags + n;
+  o.success = h->d_flags + 2 * n; o.reward_components = nullptr;
+  int rc = mm_step(h, st, h->d_actions, action_mode, &o, stream);
+  if (rc) return rc;
+  if (h_obs) CK(cudaMemcpyAsync(h_obs, h->d_obs, n * OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (h_reward) CK(cudaMemcpyAsync(h_reward, h->d_reward, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (h_terminated) CK(cudaMemcpyAsync(h_terminated, h->d_flags, n, cudaMemcpyDeviceToHost, s));
+  if (h_truncated) CK(cudaMemcpyAsync(h_truncated, h->d_flags + n, n, cudaMemcpyDeviceToHost, s));
+  if (h_success) CK(cudaMemcpyAsync(h_success, h->d_flags + 2 * n, n, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int mm_fsm_plan(mm_handle* h, const mm_state* st, int n_steps, float* actions_out, void* stream) {
+  if (!h || !st) return fail("mm_fsm_plan: null argument");
+  long n = h->cfg.num_envs;
+  k_fsm<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(to_ptrs(st), n, n_steps, actions_out);
+  CK(cudaGetLastError());
+  h->launches++;
+  return 0;
+}
+
+int mm_sample_placements(mm_handle* h, uint64_t seed, int64_t env_id_offset, const int64_t* episode_index, double x_lo,
+                         double x_hi, double y_lo, double y_hi, double min_separation, int32_t npool, double* obj_xy,
+                         int32_t* task_draw, int32_t* attempts, void* stream) {
+  if (!h || !episode_index || !obj_xy) return fail("mm_sample_placements: null argument");
+  if (npool <= 0) return fail("mm_sample_placements: npool must be positive");
+  long n = h->cfg.num_envs;
+  k_sample<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      (unsigned long long)seed, (long long)env_id_offset, (const long long*)episode_index, n, x_lo, x_hi, y_lo, y_hi,
+      min_separation, npool, obj_xy, task_draw, attempts);
+  CK(cudaGetLastError());
+  h->launches++;
+  return 0;
+}
+
+int mm_measure_fma_peak(int device, int fp64, double* tflops) {
+  if (!tflops) return fail("mm_measure_fma_peak: null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail("mm_measure_fma_peak: no CUDA device");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  void* buf;
+  CK(cudaMalloc(&buf, 64));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  const int iters = 4096, blocks = prop.multiProcessorCount * 8, threads = 256;
+  double best = 0;
+  for (int rep = 0; rep < 6; rep++) {
+    CK(cudaEventRecord(e0));
+    if (fp64) k_peak<double><<<blocks, threads>>>((double*)buf, iters, 1.0000001, 1e-9);
+    else k_peak<float><<<blocks, threads>>>((float*)buf, iters, 1.0000001f, 1e-9f);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    double fl = 2.0 * 16 * (double)iters * blocks * threads;
+    double tf = fl / (ms * 1e-3) * 1e-12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(buf);
+  *tflops = best;
+  return 0;
+}
+
+int mm_launch_count(mm_handle* h, long long* out) {
+  if (!h || !out) return fail("mm_launch_count: null argument");
+  *out = h->launches;
+  return 0;
+}
+
+}  // extern "C"

@@ -93,6 +93,7 @@ void orc_stats(void* h, long long* out) {
   const Stats& s = ((Env*)h)->d.stats;
   out[0] = s.substeps; out[1] = s.ncon; out[2] = s.nefc; out[3] = s.newton_iters; out[4] = s.ls_evals;
   out[5] = s.narrow_tests; out[6] = s.ccd_tests; out[7] = s.max_ncon; out[8] = s.max_nefc; out[9] = s.max_newton;
+  out[10] = s.forwards; out[11] = s.nnzJ; out[12] = s.nnzJ2;
 }
 void orc_stats_clear(void* h) { std::memset(&((Env*)h)->d.stats, 0, sizeof(Stats)); }
 
@@ -139,7 +140,7 @@ int orc_run_fsm_episode(void* h, const double* obj_xy, int obj_idx, int bin_idx,
 // CPU baseline: `n_envs` independent envs, `n_steps` env-steps each, random world-frame targets
 // (SURVEY 8d config 2 distribution) in the given action mode, spread over `nthreads` host threads.
 // Returns env-steps per second.
-double orc_bench_random(int n_envs, int n_steps, int mode, unsigned seed, int nthreads, int flags) {
+double orc_bench_random2(int n_envs, int n_steps, int mode, unsigned seed, int nthreads, int flags, long long* stats_out /*13 or null*/) {
   std::vector<Env*> envs(n_envs);
   for (int i = 0; i < n_envs; i++) {
     envs[i] = (Env*)orc_new();
@@ -175,8 +176,23 @@ double orc_bench_random(int n_envs, int n_steps, int mode, unsigned seed, int nt
   for (int t = 0; t < nthreads; t++) th.emplace_back(work, t);
   for (auto& x : th) x.join();
   double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  if (stats_out) {
+    for (int k = 0; k < 13; k++) stats_out[k] = 0;
+    for (auto e : envs) {
+      long long o[13];
+      orc_stats(e, o);
+      for (int k = 0; k < 13; k++) {
+        if (k >= 7 && k <= 9) stats_out[k] = std::max(stats_out[k], o[k]);
+        else stats_out[k] += o[k];
+      }
+    }
+  }
   for (auto e : envs) delete e;
   return (double)n_envs * n_steps / dt;
+}
+
+double orc_bench_random(int n_envs, int n_steps, int mode, unsigned seed, int nthreads, int flags) {
+  return orc_bench_random2(n_envs, n_steps, mode, seed, nthreads, flags, nullptr);
 }
 
 }  // extern "C"

@@ -854,6 +854,12 @@ void forward(Data& d) {
   chol_solve(L, NV, d.qacc_smooth);
   fwd_constraint(d);
   d.stats.ncon += d.ncon; d.stats.nefc += d.nefc; d.stats.newton_iters += d.solver_niter;
+  d.stats.forwards++;
+  for (int r = 0; r < d.nefc; r++) {
+    int nz = 0;
+    for (int i = 0; i < NV; i++) nz += d.efc_J[(size_t)r * NV + i] != 0.0;
+    d.stats.nnzJ += nz; d.stats.nnzJ2 += (long long)nz * nz;
+  }
   d.stats.max_ncon = std::max(d.stats.max_ncon, d.ncon);
   d.stats.max_nefc = std::max(d.stats.max_nefc, d.nefc);
   d.stats.max_newton = std::max(d.stats.max_newton, d.solver_niter);

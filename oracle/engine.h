@@ -39,6 +39,7 @@ struct Contact {
 struct Stats {  // work counters exported for the roofline FLOP model
   long long substeps, ncon, nefc, newton_iters, ls_evals, narrow_tests, ccd_tests;
   int max_ncon, max_nefc, max_newton;
+  long long forwards, nnzJ, nnzJ2;  // forward passes; nonzeros of the constraint Jacobian and sum of squared row nonzeros
 };
 
 struct Data {

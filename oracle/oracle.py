@@ -75,6 +75,8 @@ def lib():
         L.orc_run_fsm_episode.restype = C.c_int
         L.orc_bench_random.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint, C.c_int, C.c_int]
         L.orc_bench_random.restype = C.c_double
+        L.orc_bench_random2.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint, C.c_int, C.c_int, C.c_void_p]
+        L.orc_bench_random2.restype = C.c_double
         _lib = L
     return _lib
 
@@ -203,11 +205,9 @@ class OracleEnv:
                     has_target=int(st[4]), target=t, transit_end=te)
 
     def stats(self):
-        s = np.zeros(10, dtype=np.int64)
+        s = np.zeros(13, dtype=np.int64)
         self.L.orc_stats(self.h, s.ctypes.data)
-        keys = ("substeps", "ncon", "nefc", "newton_iters", "ls_evals", "narrow_tests", "ccd_tests", "max_ncon",
-                "max_nefc", "max_newton")
-        return dict(zip(keys, s.tolist()))
+        return dict(zip(STAT_KEYS, s.tolist()))
 
     def stats_clear(self):
         self.L.orc_stats_clear(self.h)
@@ -221,6 +221,17 @@ class OracleEnv:
         hist = np.zeros(12, dtype=np.int32)
         s = self.L.orc_run_fsm_episode(self.h, p, int(obj_idx), int(bin_idx), int(max_steps), C.addressof(n), hist.ctypes.data)
         return bool(s), n.value, hist
+
+
+STAT_KEYS = ("substeps", "ncon", "nefc", "newton_iters", "ls_evals", "narrow_tests", "ccd_tests", "max_ncon", "max_nefc",
+             "max_newton", "forwards", "nnzJ", "nnzJ2")
+
+
+def bench_random_stats(n_envs, n_steps, mode="ee_pos_quat_g_rel", seed=1234, nthreads=1, flags=0):
+    """-> (env-steps/s, work counters summed over the sample) - feeds bench.py's FLOP model."""
+    s = np.zeros(13, dtype=np.int64)
+    v = lib().orc_bench_random2(n_envs, n_steps, ACTION_MODES.index(mode), seed, nthreads, flags, s.ctypes.data)
+    return v, dict(zip(STAT_KEYS, s.tolist()))
 
 
 def bench_random(n_envs, n_steps, mode="ee_pos_quat_g_rel", seed=1234, nthreads=1, flags=0):

@@ -1,0 +1,220 @@
+"""Parity tests proper: the CUDA path (through the C ABI, via PickPlaceVecEnv) against the CPU oracle
+and the committed golden vectors.  Run on the B200 box with `-m gpu`."""
+import os
+
+import numpy as np
+import pytest
+
+from hostlib import GOLDEN, MODES, reltol
+
+pytestmark = pytest.mark.gpu
+
+# north_star: per-step qpos, qvel and EE pose within 1e-5 relative over the first 50 steps,
+# |a-b| <= TOL * max(|b|, 1)
+TOL = 1e-5
+
+
+def _load(name):
+    return np.load(os.path.join(GOLDEN, name))
+
+
+def _make(n, dev, **kw):
+    from mujoco_manip_b200 import PickPlaceVecEnv
+
+    kw.setdefault("auto_reset", False)
+    kw.setdefault("rng", "numpy")
+    return PickPlaceVecEnv(n, device=dev, **kw)
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.mark.parametrize("group", [32, 16, 8])
+@pytest.mark.parametrize("mode", MODES)
+def test_f64_random_rollout_vs_oracle(cuda_device, oracle_lib, mode, group):
+    """50 seeded random-action steps, 4 envs: 2 copies of the golden action stream + 2 fresh streams."""
+    import torch
+
+    g = _load(f"random50_{mode}.npz")
+    rng = np.random.default_rng(5)
+    n = 4
+    env = _make(n, cuda_device, task=("obj_red", "bin_red"), action_mode=mode, group=group)
+    env.reset()
+    orcs = [oracle_lib.OracleEnv(action_mode=mode, flags=1) for _ in range(n)]
+    for o in orcs:
+        o.reset(None, 0, 0)
+    for t in range(50):
+        acts = np.repeat(g["action"][t][None], n, axis=0)
+        for k in (2, 3):
+            acts[k, :3] += rng.uniform(-0.05, 0.05, size=3).astype(np.float32)
+        obs, r, te, tr, info = env.step(torch.from_numpy(acts[:, : env.action_dim]).to(cuda_device))
+        qpos, qvel, ee = _np(env.state["qpos"]), _np(env.state["qvel"]), _np(env.state["eepose"])
+        for k in range(n):
+            o_obs, o_r, o_te, o_tr, o_info = orcs[k].step(acts[k])
+            assert reltol(qpos[k], orcs[k].qpos, TOL) < TOL, f"qpos env {k} step {t}"
+            assert reltol(qvel[k], orcs[k].qvel, TOL) < TOL, f"qvel env {k} step {t}"
+            assert reltol(ee[k][:3], orcs[k].xpos[9], TOL) < TOL
+            assert reltol(ee[k][3:], orcs[k].xmat[9], TOL) < TOL
+            np.testing.assert_allclose(_np(env.obs_packed)[k], o_obs, rtol=0, atol=2e-5)
+            assert abs(float(r[k]) - o_r) < 1e-4
+            assert bool(te[k]) == o_te and bool(tr[k]) == o_tr and bool(info["success"][k]) == o_info["success"]
+    assert np.array_equal(qpos[0], qpos[1])  # identical inputs -> bit-identical envs
+
+
+@pytest.mark.parametrize("fname,reward", [
+    ("fsm_quat_rel_red_red.npz", "dense"),
+    ("fsm_abs_green_blue_seed42_staged.npz", "staged"),
+    ("fsm_rot6d_rel_blue_red_seed7.npz", "dense"),
+])
+def test_f64_fsm_episode_vs_oracle(cuda_device, oracle_lib, fname, reward):
+    """Scripted expert episode (config 1): FSM state indices bit-exact vs the reference's own FSM
+    (golden), trajectory within tolerance vs the oracle."""
+    g = _load(fname)
+    q = g["init_qpos"]
+    xy = np.array([q[9:11], q[16:18], q[23:25]])
+    oi, bi = int(g["obj_idx"]), int(g["bin_idx"])
+    env = _make(2, cuda_device, action_mode="abs_pos", reward_type=reward)
+    from mujoco_manip_b200.constants import BINS, OBJECTS
+
+    env.reset(options={"task": (OBJECTS[oi], BINS[bi]), "obj_xy": np.stack([xy, xy])})
+    orc = oracle_lib.OracleEnv(action_mode="abs_pos", reward_type=reward, flags=1)
+    orc.reset(xy, oi, bi)
+    orc.fsm_reset()
+    n = g["fsm_state"].shape[0]
+    done_at = None
+    for t in range(n + 40):
+        a = env.fsm_plan(16)
+        orc.fsm_plan(16)
+        f = orc.fsm_get()
+        fs = _np(env.state["fsm_i"])
+        assert int(fs[0, 0]) == f["state"] and int(fs[0, 2]) == f["counter"], f"FSM differs from oracle at {t}"
+        if f["state"] == 11:
+            done_at = t
+            break
+        np.testing.assert_allclose(_np(a)[0], orc.fsm_action(), rtol=0, atol=1e-6)
+        obs, r, te, tr, info = env.step(a)
+        o_obs, o_r, o_te, o_tr, o_info = orc.step(orc.fsm_action())
+        assert reltol(_np(env.state["qpos"])[0], orc.qpos, TOL) < 1e-4, f"step {t}"
+        assert abs(float(r[0]) - o_r) < 1e-3
+    assert done_at is not None
+    # the hull-free oracle run has the same phase sequence as the reference run in the golden file
+    assert abs(done_at - n) <= 2
+
+
+def test_f32_tracks_oracle(cuda_device, oracle_lib):
+    """FP32 arithmetic (throughput path) on the arm/gripper dofs; bound stated, not the 1e-5 bar."""
+    import torch
+
+    g = _load("random50_ee_pos_quat_g_rel.npz")
+    env = _make(2, cuda_device, task=("obj_red", "bin_red"), precision="f32")
+    env.reset()
+    orc = oracle_lib.OracleEnv(flags=1)
+    orc.reset(None, 0, 0)
+    worst = 0.0
+    for t in range(50):
+        a = np.repeat(g["action"][t][None], 2, axis=0)
+        env.step(torch.from_numpy(a[:, :8]).to(cuda_device))
+        orc.step(g["action"][t])
+        worst = max(worst, reltol(_np(env.state["qpos"])[0][:9], orc.qpos[:9], 1.0))
+    assert worst < 5e-3, worst
+
+
+def test_philox_bit_exact(cuda_device):
+    from oracle import philox
+
+    env = _make(64, cuda_device, randomize_objects=True, rng="philox", seed=42, env_id_offset=1000, tasks="all")
+    env.reset()
+    xy = _np(env._obj_xy).reshape(64, 3, 2)
+    tk = _np(env._task)
+    pool = _np(env._pool_idx)
+    for i in range(64):
+        exp, att = philox.place(42, 1000 + i, 0)
+        assert np.array_equal(xy[i], exp), i
+        assert int(_np(env.last_attempts)[i]) == att
+        assert tuple(tk[i]) == tuple(pool[philox.task_draw(42, 1000 + i, 0, 9)])
+    env.reset()  # second episode uses episode index 1
+    xy2 = _np(env._obj_xy).reshape(64, 3, 2)
+    assert np.array_equal(xy2[5], philox.place(42, 1005, 1)[0])
+
+
+def test_sharding_invariance(cuda_device):
+    """Two 'ranks' of 32 envs (env_id_offset 0 / 32) == one launch of 64 envs, bit for bit."""
+    import torch
+
+    kw = dict(randomize_objects=True, rng="philox", seed=7, tasks="cross", action_mode="abs_pos", precision="f32")
+    full = _make(64, cuda_device, **kw)
+    a_, b_ = _make(32, cuda_device, env_id_offset=0, **kw), _make(32, cuda_device, env_id_offset=32, **kw)
+    for e in (full, a_, b_):
+        e.reset()
+    for t in range(3):
+        acts = [e.fsm_plan(16).clone() for e in (full, a_, b_)]
+        for e, a in zip((full, a_, b_), acts):
+            e.step(a)
+    q = _np(full.state["qpos"])
+    assert np.array_equal(q[:32], _np(a_.state["qpos"])) and np.array_equal(q[32:], _np(b_.state["qpos"]))
+
+
+def test_large_batch_properties(cuda_device):
+    """Full-size properties (config 2 size): identical copies stay identical, unit quaternions,
+    cubes stay on the table, finite state, step counts advance."""
+    import torch
+
+    n = 4096
+    env = _make(n, cuda_device, task=("obj_red", "bin_red"), precision="f32")
+    env.reset()
+    gen = torch.Generator(device=cuda_device).manual_seed(1234)
+    for t in range(6):
+        a = torch.zeros((n, 8), device=cuda_device)
+        a[:, :3] = (torch.rand((n // 2, 3), device=cuda_device, generator=gen) * 0.2 - 0.1).repeat(2, 1)
+        a[:, 6] = 1.0
+        a[:, 7] = (torch.rand(n // 2, device=cuda_device, generator=gen) > 0.5).float().repeat(2)
+        env.step(a)
+    q = env.state["qpos"]
+    assert torch.isfinite(q).all() and torch.isfinite(env.state["qvel"]).all()
+    assert torch.equal(q[: n // 2], q[n // 2:])
+    for o in range(3):
+        quat = q[:, 9 + 7 * o + 3: 9 + 7 * o + 7]
+        assert torch.allclose(quat.norm(dim=1), torch.ones(n, dtype=quat.dtype, device=cuda_device), atol=1e-6)
+        assert (q[:, 9 + 7 * o + 2] > 0.2).all()
+    assert (env.state["step_count"] == 6).all()
+    assert int(env.state["diag"][:, 2].max()) == 0  # no workspace overflow
+
+
+def test_host_buffer_step_matches_device_step(cuda_device):
+    """mm_step_host (the e2e path) == mm_step."""
+    import ctypes as C
+
+    import torch
+
+    from mujoco_manip_b200 import _lib
+
+    n = 8
+    e1, e2 = _make(n, cuda_device, action_mode="abs_pos"), _make(n, cuda_device, action_mode="abs_pos")
+    e1.reset()
+    e2.reset()
+    a = torch.tensor([[0.1, 0.45, 0.4, 1.0]] * n, dtype=torch.float32)
+    e1.step(a.to(cuda_device))
+    ha = torch.zeros((n, 10), dtype=torch.float32).pin_memory()
+    ha[:, :4] = a
+    hobs = torch.zeros((n, 85), dtype=torch.float32).pin_memory()
+    hr = torch.zeros(n, dtype=torch.float32).pin_memory()
+    _lib.check(e2._L.mm_step_host(e2._h, C.byref(e2._st), ha.data_ptr(), 0, hobs.data_ptr(), hr.data_ptr(), None, None, None,
+                                  e2._stream()), "mm_step_host")
+    assert torch.equal(hobs, e1.obs_packed.cpu())
+    assert torch.equal(e1.state["qpos"], e2.state["qpos"])
+
+
+def test_autoreset_and_stats(cuda_device):
+    import torch
+
+    env = _make(16, cuda_device, action_mode="abs_pos", max_episode_steps=3, auto_reset=True, rng="philox",
+                randomize_objects=True)
+    env.reset()
+    a = torch.tensor([[0.0, 0.45, 0.5, 1.0]] * 16, device=cuda_device)
+    for t in range(3):
+        obs, r, te, tr, info = env.step(a)
+    assert bool(tr.all())
+    assert (env.state["step_count"] == 0).all()  # already reset
+    assert float(env.stats[0]) == 16.0 and float(env.stats[2]) == 48.0
+    assert (env.episode_index == 2).all()
