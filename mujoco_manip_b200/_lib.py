@@ -46,22 +46,34 @@ class MMStepOut(C.Structure):
                 ("success", C.c_void_p), ("reward_components", C.c_void_p)]
 
 
-NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "--shared",
-              "-Xcompiler", "-fPIC"]
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC"]
+BUILD_DIR = os.path.join(_HERE, "_C", "obj")
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/mm_kernels.cu for sm_100a into _C/libmm_manip.so (nvcc cross-compiles without a GPU)."""
-    srcs = [os.path.join(SRC_DIR, f) for f in os.listdir(SRC_DIR) if f.endswith((".h", ".cu"))]
-    srcs.append(os.path.join(REPO, "include", "mm_manip.h"))
-    if not force and os.path.exists(LIB_PATH):
-        t = os.path.getmtime(LIB_PATH)
-        if all(os.path.getmtime(s) <= t for s in srcs):
-            return LIB_PATH
-    os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
-    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH,
-                                                                           os.path.join(SRC_DIR, "mm_kernels.cu")]
-    subprocess.check_call(cmd)
+    """Compile csrc/*.cu for sm_100a into _C/libmm_manip.so (nvcc cross-compiles without a GPU).
+    One translation unit per (precision, group) kernel instantiation, compiled in parallel."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    hdrs = [os.path.join(SRC_DIR, f) for f in os.listdir(SRC_DIR) if f.endswith((".h", ".cuh"))]
+    hdrs.append(os.path.join(REPO, "include", "mm_manip.h"))
+    units = sorted(f for f in os.listdir(SRC_DIR) if f.endswith(".cu"))
+    os.makedirs(BUILD_DIR, exist_ok=True)
+    newest_hdr = max(os.path.getmtime(h) for h in hdrs)
+
+    def compile_one(u):
+        src, obj = os.path.join(SRC_DIR, u), os.path.join(BUILD_DIR, u[:-3] + ".o")
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) >= max(newest_hdr, os.path.getmtime(src)):
+            return obj, False
+        cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+        subprocess.check_call(cmd)
+        return obj, True
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        res = list(ex.map(compile_one, units))
+    objs = [o for o, _ in res]
+    if force or any(c for _, c in res) or not os.path.exists(LIB_PATH):
+        subprocess.check_call(["nvcc", "--shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + objs)
     return LIB_PATH
 
 

@@ -14,7 +14,7 @@
 //     J is never stored; every J*x, J^T*f and J^T D J goes through per-body-pair 6-vectors / 6x6 blocks
 //   * implicitfast integration (block diagonal: 9x9 robot factor, scalar cube updates)
 #pragma once
-#include "mm_model.h"
+#include "mm_ccd.h"
 
 namespace mm {
 
@@ -42,7 +42,6 @@ struct Scratch {
   T inert[2][NROB][10];
   T pairK[MAXPAIR][21], pairW[MAXPAIR][6], pairF[MAXPAIR][6];
   T specD[MAXSPEC], specJaref[MAXSPEC], specJv[MAXSPEC], specAref[MAXSPEC];
-  T boxc[13][3];
   T actf[NU];
   T target[3];
   int pairkey[MAXPAIR];
@@ -64,15 +63,18 @@ struct Work {
   T* Jaref; // [MAXROW]
   T* Jv;    // [MAXROW]
   int* cmeta;  // [MAXCON]
+  EpaMem<T> epa;
 };
-constexpr int WORK_REALS = MAXCON * 11 + MAXROW * 3;
-constexpr int WORK_INTS = MAXCON;
+constexpr int WORK_REALS = MAXCON * 11 + MAXROW * 3 + EPA_REALS;
+constexpr int WORK_INTS = MAXCON + EPA_INTS;
 template <class T>
 MM_HD Work<T> make_work(T* reals, int* ints) {
   Work<T> w;
   w.cpos = reals; w.cn = reals + 3 * MAXCON; w.ct1 = reals + 6 * MAXCON; w.cdist = reals + 9 * MAXCON;
   w.cD = reals + 10 * MAXCON; w.aref = reals + 11 * MAXCON; w.Jaref = w.aref + MAXROW; w.Jv = w.Jaref + MAXROW;
   w.cmeta = ints;
+  w.epa.vert = w.Jv + MAXROW; w.epa.face = w.epa.vert + EPA_MAXV * 6;
+  w.epa.fidx = ints + MAXCON; w.epa.edge = w.epa.fidx + EPA_MAXF;
   return w;
 }
 
@@ -196,16 +198,6 @@ MM_HDN void fk(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md) {
         S[0] = a[0]; S[1] = a[1]; S[2] = a[2];
         cross3(S + 3, s.bpos[DB_CUBE0 + j], a);
       }
-    }
-  }
-  for (int b = g.lane; b < 13; b += G) {
-    if (b < 10) {
-      int body = md.box_body[b];
-      T v[3];
-      rot(v, s.bR[body], md.box_pos[b]);
-      for (int a = 0; a < 3; a++) s.boxc[b][a] = s.bpos[body][a] + v[a];
-    } else {
-      for (int a = 0; a < 3; a++) s.boxc[b][a] = s.bpos[b][a];  // db 10..12
     }
   }
   g.sync();
@@ -366,14 +358,25 @@ MM_HDN void mulM(const Grp<G>& g, const Scratch<T>& s, const ModelDev<T>& md, co
 template <class T>
 struct BoxRef { const T* c; const T* R; const T* s; };
 
+// world pose of geom `gi`: position into pos[3]; returns the orientation (body frame or identity)
 template <class T>
-MM_HD BoxRef<T> get_box(const Scratch<T>& s, const ModelDev<T>& md, int b, const T* ident) {
-  BoxRef<T> r;
-  r.s = md.box_size[b];
-  int body = md.box_body[b];
-  if (body < 0) { r.c = md.box_pos[b]; r.R = ident; }
-  else { r.c = s.boxc[b < 10 ? b : b - 16]; r.R = s.bR[body]; }
-  return r;
+MM_HD const T* geom_pose(const Scratch<T>& s, const GeomDev<T>& gm, int gi, const T* ident, T* pos) {
+  int body = gm.body[gi];
+  if (body < 0) { pos[0] = gm.pos[gi][0]; pos[1] = gm.pos[gi][1]; pos[2] = gm.pos[gi][2]; return ident; }
+  const T* R = s.bR[body];
+  T v[3];
+  rot(v, R, gm.pos[gi]);
+  for (int k = 0; k < 3; k++) pos[k] = s.bpos[body][k] + v[k];
+  return R;
+}
+// centre of the bounding sphere of geom `gi`
+template <class T>
+MM_HD void geom_bcenter(const Scratch<T>& s, const GeomDev<T>& gm, int gi, T* c) {
+  int body = gm.body[gi];
+  if (body < 0) { c[0] = gm.bc[gi][0]; c[1] = gm.bc[gi][1]; c[2] = gm.bc[gi][2]; return; }
+  T v[3];
+  rot(v, s.bR[body], gm.bc[gi]);
+  for (int k = 0; k < 3; k++) c[k] = s.bpos[body][k] + v[k];
 }
 
 // returns number of contact points; normal nrm (A -> B), pts[k] position, dist[k] (negative)
@@ -516,33 +519,81 @@ MM_HD void make_tangent(const T* n, T* t1) {  // mju_makeFrame rule (A3)
   for (int k = 0; k < 3; k++) t1[k] = t[k] * inv;
 }
 
+// plane z = 0 vs convex hull: deepest vertex, one contact
+template <class T>
+MM_HDN int plane_hull(const T* gpos, const T* R, const T* V, int nvert, T* nrm, T pts[8][3], T* dist) {
+  nrm[0] = 0; nrm[1] = 0; nrm[2] = 1;
+  T nl[3] = {R[6], R[7], R[8]};  // R^T n
+  int best = 0;
+  T bv = (T)1e30;
+  for (int i = 0; i < nvert; i++) {
+    T v = V[3 * i] * nl[0] + V[3 * i + 1] * nl[1] + V[3 * i + 2] * nl[2];
+    if (v < bv) { bv = v; best = i; }
+  }
+  T c[3];
+  rot(c, R, V + 3 * best);
+  for (int k = 0; k < 3; k++) c[k] += gpos[k];
+  T d = c[2];
+  if (d < 0) {
+    pts[0][0] = c[0]; pts[0][1] = c[1]; pts[0][2] = c[2] - d * (T)0.5;
+    dist[0] = d;
+    return 1;
+  }
+  return 0;
+}
+
+template <class T>
+MM_HD void fill_shape(const Scratch<T>& s, const GeomDev<T>& gm, int gi, const T* ident, Shape<T>& sh) {
+  sh.type = gm.type[gi];
+  sh.R = geom_pose(s, gm, gi, ident, sh.pos);
+  sh.size[0] = gm.size[gi][0]; sh.size[1] = gm.size[gi][1]; sh.size[2] = gm.size[gi][2];
+  sh.verts = &gm.hull[gm.vadr[gi]][0];
+  sh.nvert = gm.vnum[gi];
+}
+
+// impedance / regulariser of a contact (A4): default solref (0.02, 1), solimp (0.9, 0.95, 0.001, 0.5, 2)
+template <class T>
+MM_HD void store_contact(Work<T>& w, int c, const T* pos, const T* nrm, const T* t1, T dist, T tran, T mu, int meta) {
+  for (int d = 0; d < 3; d++) { w.cpos[d * MAXCON + c] = pos[d]; w.cn[d * MAXCON + c] = nrm[d]; w.ct1[d * MAXCON + c] = t1[d]; }
+  w.cdist[c] = dist;
+  T x = tabs(dist) / (T)0.001, imp;
+  if (x >= 1) imp = (T)0.95;
+  else { T y = x <= (T)0.5 ? 2 * x * x : 1 - 2 * (1 - x) * (1 - x); imp = (T)0.9 + y * (T)0.05; }
+  T R0 = (1 - imp) / imp * tran * (1 + mu * mu);
+  if (R0 < (T)MINVAL_D) R0 = (T)MINVAL_D;
+  w.cD[c] = (T)1 / (2 * mu * mu * R0);
+  w.cmeta[c] = meta;
+}
+
 template <class T, int G>
 MM_HDN void collide(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>& w) {
   const T ident[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  const GeomDev<T>& gm = *md.geom;
   // broad phase: ordered compaction of the surviving candidates
   int nsurv = 0;
-  for (int base = 0; base < NCAND; base += G) {
+  for (int base = 0; base < NPAIRC; base += G) {
     int ci = base + g.lane;
     int keep = 0;
-    if (ci < NCAND) {
-      int a = md.cand[ci][0], b = md.cand[ci][1];
-      BoxRef<T> Bb = get_box(s, md, b, ident);
-      T rb = md.box_rbound[b];
-      if (a == PLANE_ID) keep = Bb.c[2] < rb;
-      else {
-        BoxRef<T> Ba = get_box(s, md, a, ident);
-        if (md.box_body[a] < 0) {  // axis-aligned static box vs bounding sphere of the dynamic box
-          T d2 = 0;
-          for (int k = 0; k < 3; k++) {
-            T d = tabs(Bb.c[k] - Ba.c[k]) - Ba.s[k];
-            if (d > 0) d2 += d * d;
-          }
-          keep = d2 < rb * rb;
-        } else {
-          T r[3] = {Bb.c[0] - Ba.c[0], Bb.c[1] - Ba.c[1], Bb.c[2] - Ba.c[2]};
-          T rs = rb + md.box_rbound[a];
-          keep = dot3(r, r) < rs * rs;
+    if (ci < NPAIRC) {
+      int a = gm.pair[ci][0], b = gm.pair[ci][1];
+      int ta = gm.type[a];
+      T cb[3];
+      geom_bcenter(s, gm, b, cb);
+      T rb = gm.rbound[b];
+      if (ta == GT_PLANE) keep = gm.type[b] != GT_CYL && !(cb[2] > rb);
+      else if (ta == GT_BOX && gm.body[a] < 0) {  // axis-aligned static box vs bounding sphere
+        T d2 = 0;
+        for (int k = 0; k < 3; k++) {
+          T d = tabs(cb[k] - gm.pos[a][k]) - gm.size[a][k];
+          if (d > 0) d2 += d * d;
         }
+        keep = !(d2 > rb * rb);
+      } else {
+        T ca[3];
+        geom_bcenter(s, gm, a, ca);
+        T r[3] = {cb[0] - ca[0], cb[1] - ca[1], cb[2] - ca[2]};
+        T rs = rb + gm.rbound[a];
+        keep = !(dot3(r, r) > rs * rs);
       }
     }
     int tot;
@@ -556,42 +607,77 @@ MM_HDN void collide(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<
   int ncon = 0;
   for (int base = 0; base < nsurv; base += G) {
     int si = base + g.lane;
-    int cnt = 0, a = 0, b = 0, ci_ = 0;
+    int cnt = 0, a = 0, b = 0, ci_ = 0, pend = 0;
     T nrm[3], pts[8][3], dist[8];
+    SP<T> sx[4];
     if (si < nsurv) {
       int ci = s.surv[si];
       ci_ = ci;
-      a = md.cand[ci][0]; b = md.cand[ci][1];
-      BoxRef<T> Bb = get_box(s, md, b, ident);
-      if (a == PLANE_ID) cnt = plane_box(Bb, nrm, pts, dist);
-      else { BoxRef<T> Ba = get_box(s, md, a, ident); cnt = box_box(Ba, Bb, nrm, pts, dist); }
+      a = gm.pair[ci][0]; b = gm.pair[ci][1];
+      int ta = gm.type[a], tb = gm.type[b];
+      if (tb == GT_BOX && (ta == GT_PLANE || ta == GT_BOX)) {
+        T pb[3], pa[3];
+        BoxRef<T> Bb;
+        Bb.R = geom_pose(s, gm, b, ident, pb); Bb.c = pb; Bb.s = gm.size[b];
+        if (ta == GT_PLANE) cnt = plane_box(Bb, nrm, pts, dist);
+        else {
+          BoxRef<T> Ba;
+          Ba.R = geom_pose(s, gm, a, ident, pa); Ba.c = pa; Ba.s = gm.size[a];
+          cnt = box_box(Ba, Bb, nrm, pts, dist);
+        }
+      } else if (ta == GT_PLANE) {
+        T pb[3];
+        const T* Rb = geom_pose(s, gm, b, ident, pb);
+        cnt = plane_hull(pb, Rb, &gm.hull[gm.vadr[b]][0], gm.vnum[b], nrm, pts, dist);
+      } else {
+        Shape<T> s1, s2;
+        fill_shape(s, gm, a, ident, s1);
+        fill_shape(s, gm, b, ident, s2);
+        if (gjk(s1, s2, sx)) { cnt = 1; pend = 1; }
+      }
     }
     int tot;
     int off = g.scan_excl(cnt, &tot);
-    if (cnt > 0) {
-      int ca = a == PLANE_ID ? 0 : md.box_class[a], cb = md.box_class[b];
-      int cube = (a != PLANE_ID && md.box_cube[a]) || md.box_cube[b];
-      T tran = (a == PLANE_ID ? (T)0 : md.box_invw[a]) + md.box_invw[b];
-      T mu = cube ? (T)2 : (T)1;
+    int ca = gm.cls[a], cb_ = gm.cls[b];
+    int cube = gm.cube[a] || gm.cube[b];
+    T tran = gm.invw[a] + gm.invw[b];
+    T mu = cube ? (T)2 : (T)1;
+    // robot geom against an obstacle geom (table / bins; the floor does not count, gym_env.py:137-152,341-350)
+    int robobs = (ca >= 1 && ca <= 9 && gm.obst[b]) || (cb_ >= 1 && cb_ <= 9 && gm.obst[a]);
+    int meta = (ca << 4) | (cb_ << 8) | (cube << 12) | (robobs << 19) | (ci_ << 20);
+    if (cnt > 0 && !pend) {
       T t1[3];
       make_tangent(nrm, t1);
       for (int k = 0; k < cnt; k++) {
         int c = ncon + off + k;
         if (c >= MAXCON) break;
-        for (int d = 0; d < 3; d++) { w.cpos[d * MAXCON + c] = pts[k][d]; w.cn[d * MAXCON + c] = nrm[d]; w.ct1[d * MAXCON + c] = t1[d]; }
-        w.cdist[c] = dist[k];
-        // impedance / regulariser (A4): default solref (0.02, 1), solimp (0.9, 0.95, 0.001, 0.5, 2)
-        T x = tabs(dist[k]) / (T)0.001, imp;
-        if (x >= 1) imp = (T)0.95;
-        else { T y = x <= (T)0.5 ? 2 * x * x : 1 - 2 * (1 - x) * (1 - x); imp = (T)0.9 + y * (T)0.05; }
-        T R0 = (1 - imp) / imp * tran * (1 + mu * mu);
-        if (R0 < (T)MINVAL_D) R0 = (T)MINVAL_D;
-        w.cD[c] = (T)1 / (2 * mu * mu * R0);
-        // bit 19: robot geom against a static obstacle box (table / bins; the floor does not count,
-        // gym_env.py:137-152,341-350)
-        int robobs = a != PLANE_ID && ((ca >= 1 && ca <= 9 && md.box_body[b] < 0) || (cb >= 1 && cb <= 9 && md.box_body[a] < 0));
-        w.cmeta[c] = (ca << 4) | (cb << 8) | (cube << 12) | (robobs << 19) | (ci_ << 20);
+        store_contact(w, c, pts[k], nrm, t1, dist[k], tran, mu, meta);
       }
+    }
+    // penetrating convex pairs: EPA one pair at a time (the polytope lives in the env's workspace)
+    unsigned pm = g.ballot(pend);
+    while (pm) {
+      int src = 0;
+      while (!((pm >> src) & 1u)) src++;
+      pm &= pm - 1;
+      if (g.lane == src) {
+        Shape<T> s1, s2;
+        fill_shape(s, gm, a, ident, s1);
+        fill_shape(s, gm, b, ident, s2);
+        T pos[3], depth, t1[3] = {0, 1, 0};
+        int c = ncon + off;
+        bool ok = epa(s1, s2, sx, w.epa, pos, nrm, &depth);
+        if (c < MAXCON) {
+          if (ok) { make_tangent(nrm, t1); store_contact(w, c, pos, nrm, t1, -depth, tran, mu, meta); }
+          else {  // degenerate polytope: keep the slot, make it inert
+            const T up[3] = {0, 0, 1};
+            pos[0] = pos[1] = pos[2] = 0;
+            store_contact(w, c, pos, up, t1, (T)0, tran, mu, meta);
+            w.cD[c] = 0;
+          }
+        }
+      }
+      g.sync();
     }
     ncon += tot;
   }

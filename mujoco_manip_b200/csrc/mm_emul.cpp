@@ -14,12 +14,15 @@ namespace {
 template <class T>
 struct Ctx {
   ModelDev<T> md;
+  GeomDev<T> gm;
   Scratch<T> s;
   std::vector<T> wr;
   std::vector<int> wi;
   Work<T> w;
   Ctx() : wr(WORK_REALS), wi(WORK_INTS) {
     fill_model(md);
+    fill_geom(gm);
+    md.geom = &gm;
     w = make_work(wr.data(), wi.data());
     std::memset(&s, 0, sizeof s);
   }

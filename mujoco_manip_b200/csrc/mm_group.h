@@ -42,6 +42,16 @@ struct Grp {
 #endif
     return pred != 0;
   }
+  // bit i set when lane i of the group has pred != 0
+  MM_HD unsigned ballot(int pred) const {
+#ifdef __CUDA_ARCH__
+    if (G > 1) {
+      unsigned b = __ballot_sync(mask, pred) & mask;
+      return G == 32 ? b : (b >> (__ffs(mask) - 1));
+    }
+#endif
+    return pred ? 1u : 0u;
+  }
   MM_HD int isum(int v) const {
 #ifdef __CUDA_ARCH__
 #pragma unroll

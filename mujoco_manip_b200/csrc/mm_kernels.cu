@@ -10,7 +10,7 @@
 #include <string>
 
 #include "../../include/mm_manip.h"
-#include "mm_env.h"
+#include "mm_launch.cuh"
 #include "mm_rng.h"
 
 using namespace mm;
@@ -24,72 +24,6 @@ int fail(const std::string& m) { g_err = m; return -1; }
     cudaError_t e_ = (x);                                                            \
     if (e_ != cudaSuccess) return fail(std::string(#x) + ": " + cudaGetErrorString(e_)); \
   } while (0)
-
-constexpr int BLOCK = 128;
-
-struct StepParams {
-  StatePtrs st;
-  StepOut out;
-  const float* actions;
-  const void* model;
-  void* work_reals;
-  int* work_ints;
-  float* tgt_kp;
-  const unsigned char* mask;
-  const double* obj_xy;
-  const int* task;
-  float* obs;
-  long n;
-  int mode, reward_type, max_steps;
-};
-
-template <class T>
-__device__ __forceinline__ size_t model_bytes() { return (sizeof(ModelDev<T>) + 15) & ~size_t(15); }
-
-template <class T, int G>
-__device__ __forceinline__ bool setup(const StepParams& p, unsigned char* smem, ModelDev<T>*& md, Scratch<T>*& sc,
-                                      Grp<G>& g, long& e) {
-  md = reinterpret_cast<ModelDev<T>*>(smem);
-  // one model copy per CTA (word-wise cooperative copy from global)
-  const int* src = reinterpret_cast<const int*>(p.model);
-  int* dst = reinterpret_cast<int*>(smem);
-  for (int i = threadIdx.x; i < (int)(sizeof(ModelDev<T>) / 4); i += BLOCK) dst[i] = src[i];
-  __syncthreads();
-  constexpr int GPB = BLOCK / G;
-  int gi = threadIdx.x / G;
-  e = (long)blockIdx.x * GPB + gi;
-  sc = reinterpret_cast<Scratch<T>*>(smem + model_bytes<T>()) + gi;
-  g.lane = threadIdx.x % G;
-  int inwarp = (threadIdx.x % 32) / G;
-  g.mask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (inwarp * G));
-  return e < p.n;
-}
-
-template <class T, int G>
-__global__ void __launch_bounds__(BLOCK) k_step(StepParams p) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  ModelDev<T>* md;
-  Scratch<T>* sc;
-  Grp<G> g;
-  long e;
-  if (!setup<T, G>(p, smem, md, sc, g, e)) return;
-  Work<T> w = make_work(reinterpret_cast<T*>(p.work_reals) + e * WORK_REALS, p.work_ints + e * WORK_INTS);
-  env_step<T, G>(g, *sc, *md, w, p.st, e, p.actions, p.mode, p.reward_type, p.max_steps, p.out, p.tgt_kp);
-}
-
-template <class T, int G>
-__global__ void __launch_bounds__(BLOCK) k_reset(StepParams p) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  ModelDev<T>* md;
-  Scratch<T>* sc;
-  Grp<G> g;
-  long e;
-  if (!setup<T, G>(p, smem, md, sc, g, e)) return;
-  if (p.mask && !p.mask[e]) return;
-  Work<T> w = make_work(reinterpret_cast<T*>(p.work_reals) + e * WORK_REALS, p.work_ints + e * WORK_INTS);
-  env_reset<T, G>(g, *sc, *md, w, p.st, e, p.obj_xy ? p.obj_xy + 6 * e : nullptr, p.task[2 * e], p.task[2 * e + 1], p.obs,
-                  p.tgt_kp);
-}
 
 __global__ void k_fsm(StatePtrs st, long n, int nsteps, float* actions) {
   long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -131,6 +65,7 @@ __global__ void __launch_bounds__(256) k_peak(T* out, int iters, T a, T b) {
 struct mm_handle {
   mm_config cfg;
   void* d_model = nullptr;
+  void* d_geom = nullptr;
   void* d_work_reals = nullptr;
   int* d_work_ints = nullptr;
   float* d_tgt = nullptr;
@@ -147,36 +82,26 @@ namespace {
 
 size_t real_bytes(const mm_config* c) { return c->precision ? 4 : 8; }
 
-template <class T, int G>
-size_t smem_bytes() { return ((sizeof(ModelDev<T>) + 15) & ~size_t(15)) + (BLOCK / G) * sizeof(Scratch<T>); }
+typedef cudaError_t (*prepare_fn)();
+typedef cudaError_t (*launch_fn)(bool, const StepParams&, cudaStream_t);
+int inst_index(const mm_config& c) { return (c.precision ? 3 : 0) + (c.group == 32 ? 0 : (c.group == 16 ? 1 : 2)); }
+const prepare_fn PREPARE[6] = {prepare_f64_32, prepare_f64_16, prepare_f64_8, prepare_f32_32, prepare_f32_16, prepare_f32_8};
+const launch_fn LAUNCH[6] = {launch_f64_32, launch_f64_16, launch_f64_8, launch_f32_32, launch_f32_16, launch_f32_8};
 
-template <class T, int G>
-int prepare() {
-  size_t sm = smem_bytes<T, G>();
-  CK(cudaFuncSetAttribute(k_step<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  CK(cudaFuncSetAttribute(k_reset<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+template <class T>
+int upload_model(mm_handle* h) {
+  static GeomDev<T> gm;  // ~40 KB: filled once per process
+  fill_geom(gm);
+  CK(cudaMalloc(&h->d_geom, sizeof gm));
+  CK(cudaMemcpy(h->d_geom, &gm, sizeof gm, cudaMemcpyHostToDevice));
+  ModelDev<T> m;
+  std::memset(&m, 0, sizeof m);
+  fill_model(m);
+  m.geom = reinterpret_cast<const GeomDev<T>*>(h->d_geom);
+  CK(cudaMalloc(&h->d_model, sizeof m));
+  CK(cudaMemcpy(h->d_model, &m, sizeof m, cudaMemcpyHostToDevice));
   return 0;
 }
-
-template <class T, int G>
-int launch(bool reset, const StepParams& p, cudaStream_t s) {
-  constexpr int GPB = BLOCK / G;
-  unsigned grid = (unsigned)((p.n + GPB - 1) / GPB);
-  size_t sm = smem_bytes<T, G>();
-  if (reset) k_reset<T, G><<<grid, BLOCK, sm, s>>>(p);
-  else k_step<T, G><<<grid, BLOCK, sm, s>>>(p);
-  CK(cudaGetLastError());
-  return 0;
-}
-
-#define DISPATCH(h, fn, ...)                                                   \
-  ((h)->cfg.precision == 0                                                     \
-       ? ((h)->cfg.group == 32 ? fn<double, 32>(__VA_ARGS__)                   \
-          : (h)->cfg.group == 16 ? fn<double, 16>(__VA_ARGS__)                 \
-                                 : fn<double, 8>(__VA_ARGS__))                 \
-       : ((h)->cfg.group == 32 ? fn<float, 32>(__VA_ARGS__)                    \
-          : (h)->cfg.group == 16 ? fn<float, 16>(__VA_ARGS__)                  \
-                                 : fn<float, 8>(__VA_ARGS__)))
 
 StatePtrs to_ptrs(const mm_state* s) {
   StatePtrs st;
@@ -210,17 +135,9 @@ int mm_create(const mm_config* cfg, mm_handle** out) {
   h->cfg = *cfg;
   size_t n = (size_t)cfg->num_envs;
   if (cfg->precision == 0) {
-    ModelDev<double> m;
-    std::memset(&m, 0, sizeof m);
-    fill_model(m);
-    CK(cudaMalloc(&h->d_model, sizeof m));
-    CK(cudaMemcpy(h->d_model, &m, sizeof m, cudaMemcpyHostToDevice));
+    if (upload_model<double>(h) != 0) return -1;
   } else {
-    ModelDev<float> m;
-    std::memset(&m, 0, sizeof m);
-    fill_model(m);
-    CK(cudaMalloc(&h->d_model, sizeof m));
-    CK(cudaMemcpy(h->d_model, &m, sizeof m, cudaMemcpyHostToDevice));
+    if (upload_model<float>(h) != 0) return -1;
   }
   CK(cudaMalloc(&h->d_work_reals, n * WORK_REALS * real_bytes(cfg)));
   CK(cudaMalloc(&h->d_work_ints, n * WORK_INTS * sizeof(int)));
@@ -230,14 +147,14 @@ int mm_create(const mm_config* cfg, mm_handle** out) {
   CK(cudaMalloc(&h->d_obs, n * OBS_DIM * sizeof(float)));
   CK(cudaMalloc(&h->d_reward, n * sizeof(float)));
   CK(cudaMalloc(&h->d_flags, n * 3));
-  if (DISPATCH(h, prepare) != 0) return -1;
+  CK(PREPARE[inst_index(h->cfg)]());
   *out = h;
   return 0;
 }
 
 void mm_destroy(mm_handle* h) {
   if (!h) return;
-  cudaFree(h->d_model); cudaFree(h->d_work_reals); cudaFree(h->d_work_ints); cudaFree(h->d_tgt);
+  cudaFree(h->d_model); cudaFree(h->d_geom); cudaFree(h->d_work_reals); cudaFree(h->d_work_ints); cudaFree(h->d_tgt);
   cudaFree(h->d_actions); cudaFree(h->d_obs); cudaFree(h->d_reward); cudaFree(h->d_flags);
   delete h;
 }
@@ -251,7 +168,8 @@ int mm_reset(mm_handle* h, const mm_state* st, const uint8_t* mask, const double
   p.mask = mask; p.obj_xy = obj_xy; p.task = task; p.obs = obs; p.n = h->cfg.num_envs;
   p.reward_type = h->cfg.reward_type; p.max_steps = h->cfg.max_episode_steps;
   h->launches++;
-  return DISPATCH(h, launch, true, p, (cudaStream_t)stream);
+  CK(LAUNCH[inst_index(h->cfg)](true, p, (cudaStream_t)stream));
+  return 0;
 }
 
 int mm_step(mm_handle* h, const mm_state* st, const float* actions, int action_mode, const mm_step_out* out,
@@ -266,7 +184,8 @@ int mm_step(mm_handle* h, const mm_state* st, const float* actions, int action_m
   p.tgt_kp = h->d_tgt; p.n = h->cfg.num_envs; p.mode = action_mode; p.reward_type = h->cfg.reward_type;
   p.max_steps = h->cfg.max_episode_steps;
   h->launches++;
-  return DISPATCH(h, launch, false, p, (cudaStream_t)stream);
+  CK(LAUNCH[inst_index(h->cfg)](false, p, (cudaStream_t)stream));
+  return 0;
 }
 
 int mm_step_host(mm_handle* h, const mm_state* st, const float* h_actions, int action_mode, float* h_obs,

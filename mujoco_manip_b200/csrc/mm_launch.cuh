@@ -1,0 +1,116 @@
+// Kernel templates of the step / reset launches and their per-(precision, group) entry points.
+// Each (T, G) pair is instantiated in its own translation unit (mm_inst_*.cu) so the library builds
+// in parallel; mm_kernels.cu holds the C ABI and dispatches through the mm_inst_* functions.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "mm_env.h"
+
+namespace mm {
+
+// threads per CTA: as many envs as fit the 227 KB of shared memory (FP64 scratch is ~20 KB per env)
+template <class T, int G>
+struct BlockCfg { static constexpr int THREADS = (sizeof(T) == 8 && G == 8) ? 64 : 128; };
+
+struct StepParams {
+  StatePtrs st;
+  StepOut out;
+  const float* actions;
+  const void* model;
+  void* work_reals;
+  int* work_ints;
+  float* tgt_kp;
+  const unsigned char* mask;
+  const double* obj_xy;
+  const int* task;
+  float* obs;
+  long n;
+  int mode, reward_type, max_steps;
+};
+
+template <class T>
+__host__ __device__ __forceinline__ size_t model_bytes() { return (sizeof(ModelDev<T>) + 15) & ~size_t(15); }
+
+template <class T, int G>
+__device__ __forceinline__ bool setup(const StepParams& p, unsigned char* smem, ModelDev<T>*& md, Scratch<T>*& sc,
+                                      Grp<G>& g, long& e) {
+  md = reinterpret_cast<ModelDev<T>*>(smem);
+  // one model copy per CTA (word-wise cooperative copy from global)
+  const int* src = reinterpret_cast<const int*>(p.model);
+  int* dst = reinterpret_cast<int*>(smem);
+  constexpr int BLOCK = BlockCfg<T, G>::THREADS;
+  for (int i = threadIdx.x; i < (int)(sizeof(ModelDev<T>) / 4); i += BLOCK) dst[i] = src[i];
+  __syncthreads();
+  constexpr int GPB = BLOCK / G;
+  int gi = threadIdx.x / G;
+  e = (long)blockIdx.x * GPB + gi;
+  sc = reinterpret_cast<Scratch<T>*>(smem + model_bytes<T>()) + gi;
+  g.lane = threadIdx.x % G;
+  int inwarp = (threadIdx.x % 32) / G;
+  g.mask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (inwarp * G));
+  return e < p.n;
+}
+
+template <class T, int G>
+__global__ void __launch_bounds__(BlockCfg<T, G>::THREADS) k_step(StepParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  ModelDev<T>* md;
+  Scratch<T>* sc;
+  Grp<G> g;
+  long e;
+  if (!setup<T, G>(p, smem, md, sc, g, e)) return;
+  Work<T> w = make_work(reinterpret_cast<T*>(p.work_reals) + e * WORK_REALS, p.work_ints + e * WORK_INTS);
+  env_step<T, G>(g, *sc, *md, w, p.st, e, p.actions, p.mode, p.reward_type, p.max_steps, p.out, p.tgt_kp);
+}
+
+template <class T, int G>
+__global__ void __launch_bounds__(BlockCfg<T, G>::THREADS) k_reset(StepParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  ModelDev<T>* md;
+  Scratch<T>* sc;
+  Grp<G> g;
+  long e;
+  if (!setup<T, G>(p, smem, md, sc, g, e)) return;
+  if (p.mask && !p.mask[e]) return;
+  Work<T> w = make_work(reinterpret_cast<T*>(p.work_reals) + e * WORK_REALS, p.work_ints + e * WORK_INTS);
+  env_reset<T, G>(g, *sc, *md, w, p.st, e, p.obj_xy ? p.obj_xy + 6 * e : nullptr, p.task[2 * e], p.task[2 * e + 1], p.obs,
+                  p.tgt_kp);
+}
+
+
+template <class T, int G>
+size_t smem_bytes() { return ((sizeof(ModelDev<T>) + 15) & ~size_t(15)) + (BlockCfg<T, G>::THREADS / G) * sizeof(Scratch<T>); }
+
+template <class T, int G>
+cudaError_t inst_prepare() {
+  size_t sm = smem_bytes<T, G>();
+  cudaError_t e = cudaFuncSetAttribute(k_step<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(k_reset<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+}
+
+template <class T, int G>
+cudaError_t inst_launch(bool reset, const StepParams& p, cudaStream_t s) {
+  constexpr int BLOCK = BlockCfg<T, G>::THREADS;
+  constexpr int GPB = BLOCK / G;
+  unsigned grid = (unsigned)((p.n + GPB - 1) / GPB);
+  size_t sm = smem_bytes<T, G>();
+  if (reset) k_reset<T, G><<<grid, BLOCK, sm, s>>>(p);
+  else k_step<T, G><<<grid, BLOCK, sm, s>>>(p);
+  return cudaGetLastError();
+}
+
+// entry points defined by the mm_inst_*.cu units
+#define MM_DECL_INST(NAME)                 \
+  cudaError_t prepare_##NAME();            \
+  cudaError_t launch_##NAME(bool reset, const StepParams& p, cudaStream_t s);
+MM_DECL_INST(f64_32) MM_DECL_INST(f64_16) MM_DECL_INST(f64_8)
+MM_DECL_INST(f32_32) MM_DECL_INST(f32_16) MM_DECL_INST(f32_8)
+
+#define MM_DEFINE_INST(NAME, T, G)                                                              \
+  namespace mm {                                                                                \
+  cudaError_t prepare_##NAME() { return inst_prepare<T, G>(); }                                 \
+  cudaError_t launch_##NAME(bool reset, const StepParams& p, cudaStream_t s) { return inst_launch<T, G>(reset, p, s); } \
+  }
+
+}  // namespace mm

@@ -7,26 +7,36 @@ namespace mm {
 
 constexpr int NQ = 30, NV = 27, NU = 8, NARM = 7, NROB = 9;
 constexpr int NDB = 13;      // dynamic bodies: link1..7, hand, left/right finger, 3 cubes
-constexpr int NBOX = 29;     // 10 pads, tabletop, 15 bin boxes, 3 cubes (oracle geom order)
-constexpr int PLANE_ID = 29;
-constexpr int NCAND = 279;
+constexpr int NGEOM = 47;    // collision geoms in the oracle's numbering (tools/modelc.py)
+constexpr int NPAIRC = 780;  // candidate geom pairs after the static filters
+constexpr int NHULLV = 1234; // convex-hull vertices of the collision meshes
+enum { GT_PLANE = 0, GT_CYL = 5, GT_BOX = 6, GT_HULL = 7 };
 constexpr int DB_HAND = 7, DB_LF = 8, DB_RF = 9, DB_CUBE0 = 10;
 constexpr int CLS_CUBE0 = 10;
 
+// Collision geometry (read-only, global memory; the same for every env so it stays in L1/L2).
+// Geom frames are aligned with their body frame: world pose = (bpos + bR * pos, bR); static geoms
+// (body < 0) carry world positions.
+template <class T>
+struct GeomDev {
+  T size[NGEOM][3], pos[NGEOM][3], bc[NGEOM][3], rbound[NGEOM], invw[NGEOM];
+  int type[NGEOM], body[NGEOM], cls[NGEOM], cube[NGEOM], obst[NGEOM], vadr[NGEOM], vnum[NGEOM];
+  short pair[NPAIRC][2];  // sorted by (class of geom1, class of geom2): contacts of a body pair are contiguous
+  T hull[NHULLV][3];
+};
+
 template <class T>
 struct ModelDev {
+  const GeomDev<T>* geom;
   T link_pos[10][3];
   T link_R[10][9];
   T jnt_lo[NROB], jnt_hi[NROB], armature[NROB], damping[NROB], dof_invw[NROB];
   T ib_mass[NROB], ib_com[NROB][3], ib_inertia[NROB][6];
   T act_gain[NU], act_b1[NU], act_b2[NU], ctrl_lo[NU], ctrl_hi[NU], frc_lo[NU], frc_hi[NU];
-  T box_size[NBOX][3], box_pos[NBOX][3], box_invw[NBOX], box_rbound[NBOX];
   T cube_mass, cube_inertia;
   T eq_solref[2], eq_solimp[5], eq_invw;
   T key_qpos[NQ], key_ctrl[NU], home[NARM];
   T timestep, gravity_z, meaninertia;
-  int box_body[NBOX], box_class[NBOX], box_cube[NBOX];
-  short cand[NCAND][2];
 };
 
 }  // namespace mm
@@ -40,6 +50,7 @@ struct ModelDev {
 namespace mm {
 template <class T>
 static void fill_model(ModelDev<T>& m) {
+  m.geom = nullptr;
   for (int i = 0; i < 10; i++) {
     for (int k = 0; k < 3; k++) m.link_pos[i][k] = (T)mmd_link_pos[i][k];
     for (int k = 0; k < 9; k++) m.link_R[i][k] = (T)mmd_link_R[i][k];
@@ -63,19 +74,6 @@ static void fill_model(ModelDev<T>& m) {
     m.frc_lo[a] = (T)mm_act_forcerange[a][0];
     m.frc_hi[a] = (T)mm_act_forcerange[a][1];
   }
-  for (int b = 0; b < NBOX; b++) {
-    double r2 = 0;
-    for (int k = 0; k < 3; k++) {
-      m.box_size[b][k] = (T)mmd_box_size[b][k];
-      m.box_pos[b][k] = (T)mmd_box_pos[b][k];
-      r2 += mmd_box_size[b][k] * mmd_box_size[b][k];
-    }
-    m.box_rbound[b] = (T)std::sqrt(r2);
-    m.box_invw[b] = (T)mmd_box_invw[b];
-    m.box_body[b] = mmd_box_body[b];
-    m.box_class[b] = mmd_box_class[b];
-    m.box_cube[b] = mmd_box_cube[b];
-  }
   m.cube_mass = (T)mm_body_mass[16];
   m.cube_inertia = (T)mm_body_inertia[16][0];
   for (int k = 0; k < 2; k++) m.eq_solref[k] = (T)mm_eq_solref[k];
@@ -88,7 +86,18 @@ static void fill_model(ModelDev<T>& m) {
   m.timestep = (T)MM_TIMESTEP;
   m.gravity_z = (T)mm_gravity[2];
   m.meaninertia = (T)MM_MEANINERTIA;
-  for (int c = 0; c < NCAND; c++) { m.cand[c][0] = (short)mmd_cand[c][0]; m.cand[c][1] = (short)mmd_cand[c][1]; }
+}
+
+template <class T>
+static void fill_geom(GeomDev<T>& g) {
+  for (int i = 0; i < NGEOM; i++) {
+    for (int k = 0; k < 3; k++) { g.size[i][k] = (T)mmd_g_size[i][k]; g.pos[i][k] = (T)mmd_g_pos[i][k]; g.bc[i][k] = (T)mmd_g_bc[i][k]; }
+    g.rbound[i] = (T)mmd_g_rbound[i]; g.invw[i] = (T)mmd_g_invw[i];
+    g.type[i] = mmd_g_type[i]; g.body[i] = mmd_g_body[i]; g.cls[i] = mmd_g_class[i]; g.cube[i] = mmd_g_cube[i];
+    g.obst[i] = mmd_g_obst[i]; g.vadr[i] = mmd_g_vadr[i]; g.vnum[i] = mmd_g_vnum[i];
+  }
+  for (int c = 0; c < NPAIRC; c++) { g.pair[c][0] = (short)mmd_pair[c][0]; g.pair[c][1] = (short)mmd_pair[c][1]; }
+  for (int v = 0; v < NHULLV; v++) for (int k = 0; k < 3; k++) g.hull[v][k] = (T)mm_hull[v][k];
 }
 }  // namespace mm
 #endif

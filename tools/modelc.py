@@ -639,24 +639,60 @@ def emit_dev_header(model, path):
         cb = box_class[b_]
         cand.append((ca, cb, a, b_))
     cand.sort()
+    # ---- unified geom table (all 47 collision geoms, oracle numbering) and the full candidate list ----
+    g_type, g_body, g_class, g_cube, g_obst, g_size, g_pos, g_bc, g_rb, g_invw, g_vadr, g_vnum = ([] for _ in range(12))
+    robot_names = set(chain) | {"link0"}
+    for gi, g in enumerate(G):
+        b = g["body"]
+        assert np.allclose(g["quat"], [1, 0, 0, 0]), "kernels assume geom frames aligned with their body"
+        static = B[b]["weld"] == 0
+        if static:
+            p, R = X[b]
+            assert np.allclose(R, np.eye(3))
+            g_pos.append((p + np.array(g["pos"])).tolist())
+            g_bc.append((p + np.array(g["pos"]) + np.array(g["bcenter"])).tolist())
+            g_body.append(-1)
+            g_class.append(0)
+        else:
+            g_pos.append(list(g["pos"]))
+            g_bc.append((np.array(g["pos"]) + np.array(g["bcenter"])).tolist())
+            g_body.append(db_of_body[b])
+            g_class.append(cls_of_body[b])
+        g_type.append(g["type"])
+        g_cube.append(int(g["condim"] == 4))
+        nm = B[b]["name"]
+        g_obst.append(int(static and nm not in ("world", "link0")))  # gym_env.py:137-152
+        g_size.append(list(g["size"]))
+        g_rb.append(g["rbound"])
+        g_invw.append(model["body_invweight0"][b][0])
+        g_vadr.append(g["vadr"])
+        g_vnum.append(g["vnum"])
+    pairs = sorted((g_class[a], g_class[b_], a, b_) for a, b_ in model["pairs"])
     out = []
     out.append("// GENERATED by tools/modelc.py - specialised tables for the CUDA kernels. Do not edit.\n#pragma once\n")
     out.append(f"#define MMD_NBOX 29\n#define MMD_PLANE 29\n#define MMD_NCAND {len(cand)}\n")
+    out.append(f"#define MMD_NGEOM {len(G)}\n#define MMD_NPAIR {len(pairs)}\n#define MMD_NHULLV {len(model['hull'])}\n")
     out.append(carr("mmd_link_pos", "double", link_pos))
     out.append(carr("mmd_link_R", "double", link_R))
     out.append(carr("mmd_ib_mass", "double", ib_mass))
     out.append(carr("mmd_ib_com", "double", ib_com))
     out.append(carr("mmd_ib_inertia", "double", ib_I))
-    out.append(carr("mmd_box_size", "double", box_size))
-    out.append(carr("mmd_box_pos", "double", box_pos))
-    out.append(carr("mmd_box_body", "int", box_body))
-    out.append(carr("mmd_box_class", "int", box_class))
-    out.append(carr("mmd_box_invw", "double", box_invw))
-    out.append(carr("mmd_box_cube", "int", box_cube))
-    out.append(carr("mmd_cand", "int", [[c[2], c[3]] for c in cand]))
+    out.append(carr("mmd_g_type", "int", g_type))
+    out.append(carr("mmd_g_body", "int", g_body))
+    out.append(carr("mmd_g_class", "int", g_class))
+    out.append(carr("mmd_g_cube", "int", g_cube))
+    out.append(carr("mmd_g_obst", "int", g_obst))
+    out.append(carr("mmd_g_vadr", "int", g_vadr))
+    out.append(carr("mmd_g_vnum", "int", g_vnum))
+    out.append(carr("mmd_g_size", "double", g_size))
+    out.append(carr("mmd_g_pos", "double", g_pos))
+    out.append(carr("mmd_g_bc", "double", g_bc))
+    out.append(carr("mmd_g_rbound", "double", g_rb))
+    out.append(carr("mmd_g_invw", "double", g_invw))
+    out.append(carr("mmd_pair", "int", [[c[2], c[3]] for c in pairs]))
     with open(path, "w") as f:
         f.write("".join(out))
-    return cand
+    return pairs
 
 def main():
     data_dir = sys.argv[1] if len(sys.argv) > 1 else "/root/reference/mujoco_manip/data"
