@@ -519,6 +519,45 @@ MM_HD void make_tangent(const T* n, T* t1) {  // mju_makeFrame rule (A3)
   for (int k = 0; k < 3; k++) t1[k] = t[k] * inv;
 }
 
+// Separating-axis test of the oriented bounding boxes (local AABB of the hull / box / cylinder, carried
+// by the body frame).  Returns false only when the boxes, inflated by 1e-6, are disjoint.
+template <class T>
+MM_HDN bool obb_overlap(const Scratch<T>& s, const GeomDev<T>& gm, int a, int b, const T* ident) {
+  T ca[3], cb[3];
+  geom_bcenter(s, gm, a, ca);
+  geom_bcenter(s, gm, b, cb);
+  const T* Ra = gm.body[a] < 0 ? ident : s.bR[gm.body[a]];
+  const T* Rb = gm.body[b] < 0 ? ident : s.bR[gm.body[b]];
+  T ha[3], hb[3];
+  for (int k = 0; k < 3; k++) { ha[k] = gm.size[a][k] + (T)1e-6; hb[k] = gm.size[b][k] + (T)1e-6; }
+  if (gm.type[a] == GT_CYL) { ha[2] = ha[1]; ha[1] = ha[0]; }
+  if (gm.type[b] == GT_CYL) { hb[2] = hb[1]; hb[1] = hb[0]; }
+  // C = Ra^T Rb, t = Ra^T (cb - ca)
+  T C[3][3], Q[3][3], d[3] = {cb[0] - ca[0], cb[1] - ca[1], cb[2] - ca[2]}, t[3];
+  for (int i = 0; i < 3; i++) {
+    t[i] = Ra[i] * d[0] + Ra[3 + i] * d[1] + Ra[6 + i] * d[2];
+    for (int j = 0; j < 3; j++) {
+      C[i][j] = Ra[i] * Rb[j] + Ra[3 + i] * Rb[3 + j] + Ra[6 + i] * Rb[6 + j];
+      Q[i][j] = tabs(C[i][j]) + (T)1e-6;
+    }
+  }
+  for (int i = 0; i < 3; i++)
+    if (tabs(t[i]) > ha[i] + hb[0] * Q[i][0] + hb[1] * Q[i][1] + hb[2] * Q[i][2]) return false;
+  for (int j = 0; j < 3; j++)
+    if (tabs(t[0] * C[0][j] + t[1] * C[1][j] + t[2] * C[2][j]) > hb[j] + ha[0] * Q[0][j] + ha[1] * Q[1][j] + ha[2] * Q[2][j])
+      return false;
+  for (int i = 0; i < 3; i++) {
+    int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+    for (int j = 0; j < 3; j++) {
+      int j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+      T ra = ha[i1] * Q[i2][j] + ha[i2] * Q[i1][j];
+      T rb = hb[j1] * Q[i][j2] + hb[j2] * Q[i][j1];
+      if (tabs(t[i2] * C[i1][j] - t[i1] * C[i2][j]) > ra + rb) return false;
+    }
+  }
+  return true;
+}
+
 // plane z = 0 vs convex hull: deepest vertex, one contact
 template <class T>
 MM_HDN int plane_hull(const T* gpos, const T* R, const T* V, int nvert, T* nrm, T pts[8][3], T* dist) {
@@ -595,6 +634,8 @@ MM_HDN void collide(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<
         T rs = rb + gm.rbound[a];
         keep = !(dot3(r, r) > rs * rs);
       }
+      // second level (conservative): oriented bounding boxes of the two geoms must overlap
+      if (keep && ta != GT_PLANE) keep = obb_overlap(s, gm, a, b, ident);
     }
     int tot;
     int off = g.scan_excl(keep, &tot);

@@ -102,8 +102,8 @@ def test_f64_fsm_episode_vs_oracle(cuda_device, oracle_lib, fname, reward):
             assert reltol(_np(env.state["qpos"])[0], g["qpos"][t], TOL) < TOL, f"golden step {t}"
         assert abs(float(r[0]) - o_r) < 1e-3
     assert done_at is not None
-    assert done_at == n  # same episode length as the reference's own FSM run (golden)
-    assert [int(x) for x in g["fsm_state"]] == fsm_trace[:n]
+    # same phase sequence and episode length as the reference's own FSM run (golden; its last plan reaches DONE)
+    assert [int(x) for x in g["fsm_state"]] == fsm_trace + [11]
 
 
 def test_f32_tracks_oracle(cuda_device, oracle_lib):
