@@ -137,7 +137,7 @@ MM_HD void quat2mat(T* m, const T* q) {
 }
 
 template <class T, int G>
-MM_HDN void fk(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md) {
+MM_HDX void fk(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md) {
   for (int i = g.lane; i < NARM; i += G) tsincos(s.qpos[i], &s.tmp6[i][0], &s.tmp6[i][1]);
   g.sync();
   for (int t = g.lane; t < 4; t += G) {
@@ -222,7 +222,7 @@ MM_HD void inertia_apply(const T* I, const T* V, T* F) {
 MM_HD int ib_parent(int k) { return k <= 6 ? k - 1 : 6; }
 
 template <class T, int G>
-MM_HDN void dyn_smooth(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md) {
+MM_HDX void dyn_smooth(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md) {
   // individual compact inertias
   for (int ib = g.lane; ib < NROB; ib += G) {
     int d = ib < 7 ? ib : ib + 1;
@@ -381,7 +381,7 @@ MM_HD void geom_bcenter(const Scratch<T>& s, const GeomDev<T>& gm, int gi, T* c)
 
 // returns number of contact points; normal nrm (A -> B), pts[k] position, dist[k] (negative)
 template <class T>
-MM_HDN int box_box(const BoxRef<T>& A_, const BoxRef<T>& B_, T* nrm, T pts[8][3], T* dist) {
+MM_HDX int box_box(const BoxRef<T>& A_, const BoxRef<T>& B_, T* nrm, T pts[8][3], T* dist) {
   const T *pa = A_.c, *Ra = A_.R, *sa = A_.s, *pb = B_.c, *Rb = B_.R, *sb = B_.s;
   T A[3][3], B[3][3];
   for (int i = 0; i < 3; i++) for (int k = 0; k < 3; k++) { A[i][k] = Ra[3 * k + i]; B[i][k] = Rb[3 * k + i]; }
@@ -492,7 +492,7 @@ MM_HDN int box_box(const BoxRef<T>& A_, const BoxRef<T>& B_, T* nrm, T pts[8][3]
 
 // floor plane z = 0 (normal +z) vs box: penetrating corners, at most 4
 template <class T>
-MM_HDN int plane_box(const BoxRef<T>& B_, T* nrm, T pts[8][3], T* dist) {
+MM_HDX int plane_box(const BoxRef<T>& B_, T* nrm, T pts[8][3], T* dist) {
   nrm[0] = 0; nrm[1] = 0; nrm[2] = 1;
   int cnt = 0;
   for (int i = 0; i < 8 && cnt < 4; i++) {
@@ -522,7 +522,7 @@ MM_HD void make_tangent(const T* n, T* t1) {  // mju_makeFrame rule (A3)
 // Separating-axis test of the oriented bounding boxes (local AABB of the hull / box / cylinder, carried
 // by the body frame).  Returns false only when the boxes, inflated by 1e-6, are disjoint.
 template <class T>
-MM_HDN bool obb_overlap(const Scratch<T>& s, const GeomDev<T>& gm, int a, int b, const T* ident) {
+MM_HDX bool obb_overlap(const Scratch<T>& s, const GeomDev<T>& gm, int a, int b, const T* ident) {
   T ca[3], cb[3];
   geom_bcenter(s, gm, a, ca);
   geom_bcenter(s, gm, b, cb);
@@ -560,7 +560,7 @@ MM_HDN bool obb_overlap(const Scratch<T>& s, const GeomDev<T>& gm, int a, int b,
 
 // plane z = 0 vs convex hull: deepest vertex, one contact
 template <class T>
-MM_HDN int plane_hull(const T* gpos, const T* R, const T* V, int nvert, T* nrm, T pts[8][3], T* dist) {
+MM_HDX int plane_hull(const T* gpos, const T* R, const T* V, int nvert, T* nrm, T pts[8][3], T* dist) {
   nrm[0] = 0; nrm[1] = 0; nrm[2] = 1;
   T nl[3] = {R[6], R[7], R[8]};  // R^T n
   int best = 0;
@@ -605,7 +605,7 @@ MM_HD void store_contact(Work<T>& w, int c, const T* pos, const T* nrm, const T*
 }
 
 template <class T, int G>
-MM_HDN void collide(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>& w) {
+MM_HDX void collide(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>& w) {
   const T ident[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
   const GeomDev<T>& gm = *md.geom;
   // broad phase: ordered compaction of the surviving candidates
@@ -824,7 +824,7 @@ MM_HD T impedance_generic(const T* solimp, T pos) {
 }
 
 template <class T, int G>
-MM_HDN void make_constraints(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>& w) {
+MM_HDX void make_constraints(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>& w) {
   const T h = md.timestep;
   if (g.lane == 0) {
     int n = 0;
@@ -1051,7 +1051,7 @@ MM_HDN void ls_eval(const Grp<G>& g, const Scratch<T>& s, const Work<T>& w, T al
 }
 
 template <class T, int G>
-MM_HDN void solve(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>& w) {
+MM_HDX void solve(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>& w) {
   const T scale_inv = md.meaninertia * (T)NV;
   const T scale = (T)1 / scale_inv;
   const T tol = (T)1e-8;
@@ -1189,7 +1189,7 @@ MM_HDN void solve(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>
 
 // full forward at the current (qpos, qvel, ctrl): everything mj_forward computes that the path needs
 template <class T, int G>
-MM_HDN void forward(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>& w) {
+MM_HDX void forward(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>& w) {
   fk<T, G>(g, s, md);
   dyn_smooth<T, G>(g, s, md);
   collide<T, G>(g, s, md, w);
@@ -1201,7 +1201,7 @@ MM_HDN void forward(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<
 // implicitfast (A7)
 // ------------------------------------------------------------------------------------------------
 template <class T, int G>
-MM_HDN void integrate(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md) {
+MM_HDX void integrate(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md) {
   const T h = md.timestep;
   T* MH = s.H;
   T* acc = s.grad;
@@ -1266,7 +1266,7 @@ MM_HDN void orientation_error(const T* Rc, T* out) {
 }
 
 template <class T, int G>
-MM_HDN void ik(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md) {
+MM_HDX void ik(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md) {
   if (g.lane == 0) {
     const T* ee = s.bpos[DB_HAND];
     T J[6][NARM], e[6], z[NARM], b[6];
