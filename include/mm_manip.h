@@ -116,6 +116,10 @@ int mm_sample_placements(mm_handle* h, uint64_t seed, int64_t env_id_offset, con
  * best of 5 timed launches - the measured denominator of the roofline bench.py reports. */
 int mm_measure_fma_peak(int device, int fp64, double* tflops);
 
+/* Profiling aid: when `cycles` ([N] int64, device) is non-NULL every mm_step stores the SM clock cycles each env's
+ * step took (per-env latency distribution; the slowest env bounds the launch).  NULL switches it off. */
+int mm_set_cycle_buffer(mm_handle* h, long long* cycles);
+
 /* number of kernels this handle has launched so far */
 int mm_launch_count(mm_handle* h, long long* out);
 

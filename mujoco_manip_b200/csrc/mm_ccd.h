@@ -71,7 +71,7 @@ template <class T> MM_HD void cpy3(T* r, const T* a) { r[0] = a[0]; r[1] = a[1];
 
 // true if the shapes overlap; sx[0..3] then hold a tetrahedron around the origin
 template <class T>
-MM_HDX bool gjk(const Shape<T>& s1, const Shape<T>& s2, SP<T>* sx) {
+MM_HDN bool gjk(const Shape<T>& s1, const Shape<T>& s2, SP<T>* sx) {
   T dir[3] = {s2.pos[0] - s1.pos[0], s2.pos[1] - s1.pos[1], s2.pos[2] - s1.pos[2]};
   if (dot3(dir, dir) < (T)1e-20) { dir[0] = 1; dir[1] = 0; dir[2] = 0; }
   SP<T> a, b, c, d;
@@ -171,7 +171,7 @@ MM_HD void epa_mkface(const EpaMem<T>& m, int f, int ia, int ib, int ic) {
 
 // Outputs contact position (mid witness), normal (shape1 -> shape2) and penetration depth.
 template <class T>
-MM_HDX bool epa(const Shape<T>& s1, const Shape<T>& s2, const SP<T>* sx, const EpaMem<T>& m, T* pos, T* nrm, T* depth) {
+MM_HDN bool epa(const Shape<T>& s1, const Shape<T>& s2, const SP<T>* sx, const EpaMem<T>& m, T* pos, T* nrm, T* depth) {
   int nv = 4, nf = 0;
   for (int i = 0; i < 4; i++) for (int k = 0; k < 3; k++) { m.vert[6 * i + k] = sx[i].v[k]; m.vert[6 * i + 3 + k] = sx[i].a[k]; }
   // initial tetrahedron; the first four faces keep (p0, p2, p1) order when flipped, like the oracle

@@ -39,14 +39,12 @@ struct Scratch {
   T fs[NV], as[NV], qacc[NV], Ma[NV], grad[NV], search[NV], Mv[NV], fc[NV];
   T H[NV * NV];
   T tmp6[NV][6];
-  T inert[2][NROB][10];
   T pairK[MAXPAIR][21], pairW[MAXPAIR][6], pairF[MAXPAIR][6];
   T specD[MAXSPEC], specJaref[MAXSPEC], specJv[MAXSPEC], specAref[MAXSPEC];
   T actf[NU];
   T target[3];
   int pairkey[MAXPAIR];
   int specdof[MAXSPEC];  // -1: equality row (e7 - e8); else dof | (negative sign ? 256 : 0)
-  int surv[MAXSURV];
   int actsat[NU];
   int ncon, npair, nspec, nsurv, overflow, niter, hvalid;
 };
@@ -63,10 +61,11 @@ struct Work {
   T* Jaref; // [MAXROW]
   T* Jv;    // [MAXROW]
   int* cmeta;  // [MAXCON]
+  int* surv;   // [MAXSURV] geom pairs surviving the broad phase
   EpaMem<T> epa;
 };
 constexpr int WORK_REALS = MAXCON * 11 + MAXROW * 3 + EPA_REALS;
-constexpr int WORK_INTS = MAXCON + EPA_INTS;
+constexpr int WORK_INTS = MAXCON + EPA_INTS + MAXSURV;
 template <class T>
 MM_HD Work<T> make_work(T* reals, int* ints) {
   Work<T> w;
@@ -75,6 +74,7 @@ MM_HD Work<T> make_work(T* reals, int* ints) {
   w.cmeta = ints;
   w.epa.vert = w.Jv + MAXROW; w.epa.face = w.epa.vert + EPA_MAXV * 6;
   w.epa.fidx = ints + MAXCON; w.epa.edge = w.epa.fidx + EPA_MAXF;
+  w.surv = w.epa.edge + EPA_MAXE;
   return w;
 }
 
@@ -138,6 +138,8 @@ MM_HD void quat2mat(T* m, const T* q) {
 
 template <class T, int G>
 MM_HDX void fk(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md) {
+  MM_IN_SHARED(&s);
+  MM_IN_GLOBAL(&md);
   for (int i = g.lane; i < NARM; i += G) tsincos(s.qpos[i], &s.tmp6[i][0], &s.tmp6[i][1]);
   g.sync();
   for (int t = g.lane; t < 4; t += G) {
@@ -223,6 +225,10 @@ MM_HD int ib_parent(int k) { return k <= 6 ? k - 1 : 6; }
 
 template <class T, int G>
 MM_HDX void dyn_smooth(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md) {
+  MM_IN_SHARED(&s);
+  MM_IN_GLOBAL(&md);
+  // temporaries live in the (not yet needed) H region: [2][9][10] individual / composite inertias
+  T (*inert)[NROB][10] = reinterpret_cast<T (*)[NROB][10]>(s.H + 300);
   // individual compact inertias
   for (int ib = g.lane; ib < NROB; ib += G) {
     int d = ib < 7 ? ib : ib + 1;
@@ -236,7 +242,7 @@ MM_HDX void dyn_smooth(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md) {
     matmul3(t, R, Ib);
     matmul3(Iw, t, Rt);
     T m = md.ib_mass[ib], cc = dot3(c, c);
-    T* o = s.inert[0][ib];
+    T* o = inert[0][ib];
     o[0] = m; o[1] = m * c[0]; o[2] = m * c[1]; o[3] = m * c[2];
     o[4] = Iw[0] + m * (cc - c[0] * c[0]); o[5] = Iw[4] + m * (cc - c[1] * c[1]); o[6] = Iw[8] + m * (cc - c[2] * c[2]);
     o[7] = Iw[1] - m * c[0] * c[1]; o[8] = Iw[2] - m * c[0] * c[2]; o[9] = Iw[5] - m * c[1] * c[2];
@@ -268,17 +274,17 @@ MM_HDX void dyn_smooth(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md) {
   g.sync();
   // composite inertias (component-parallel suffix sums)
   for (int c = g.lane; c < 10; c += G) {
-    s.inert[1][8][c] = s.inert[0][8][c];
-    s.inert[1][7][c] = s.inert[0][7][c];
-    T acc = s.inert[0][6][c] + s.inert[0][7][c] + s.inert[0][8][c];
-    s.inert[1][6][c] = acc;
-    for (int k = 5; k >= 0; k--) { acc += s.inert[0][k][c]; s.inert[1][k][c] = acc; }
+    inert[1][8][c] = inert[0][8][c];
+    inert[1][7][c] = inert[0][7][c];
+    T acc = inert[0][6][c] + inert[0][7][c] + inert[0][8][c];
+    inert[1][6][c] = acc;
+    for (int k = 5; k >= 0; k--) { acc += inert[0][k][c]; inert[1][k][c] = acc; }
   }
   // body forces f_k = I_k A_k + V_k x* (I_k V_k)
   for (int k = g.lane; k < NROB; k += G) {
     T IA[6], IV[6];
-    inertia_apply(s.inert[0][k], Ab + 6 * k, IA);
-    inertia_apply(s.inert[0][k], Vb + 6 * k, IV);
+    inertia_apply(inert[0][k], Ab + 6 * k, IA);
+    inertia_apply(inert[0][k], Vb + 6 * k, IV);
     const T* w = Vb + 6 * k; const T* v = w + 3;
     T c1[3], c2[3], c3[3];
     cross3(c1, w, IV);       // w x n
@@ -300,7 +306,7 @@ MM_HDX void dyn_smooth(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md) {
   }
   g.sync();
   // F_j = Ic_j S_j
-  for (int j = g.lane; j < NROB; j += G) inertia_apply(s.inert[1][j], s.S[j], s.tmp6[j]);
+  for (int j = g.lane; j < NROB; j += G) inertia_apply(inert[1][j], s.S[j], s.tmp6[j]);
   // subtree force sums (component-parallel)
   for (int c = g.lane; c < 6; c += G) {
     T acc = fb[6 * 6 + c] + fb[6 * 7 + c] + fb[6 * 8 + c];
@@ -381,7 +387,7 @@ MM_HD void geom_bcenter(const Scratch<T>& s, const GeomDev<T>& gm, int gi, T* c)
 
 // returns number of contact points; normal nrm (A -> B), pts[k] position, dist[k] (negative)
 template <class T>
-MM_HDX int box_box(const BoxRef<T>& A_, const BoxRef<T>& B_, T* nrm, T pts[8][3], T* dist) {
+MM_HDN int box_box(const BoxRef<T>& A_, const BoxRef<T>& B_, T* nrm, T pts[8][3], T* dist) {
   const T *pa = A_.c, *Ra = A_.R, *sa = A_.s, *pb = B_.c, *Rb = B_.R, *sb = B_.s;
   T A[3][3], B[3][3];
   for (int i = 0; i < 3; i++) for (int k = 0; k < 3; k++) { A[i][k] = Ra[3 * k + i]; B[i][k] = Rb[3 * k + i]; }
@@ -492,7 +498,7 @@ MM_HDX int box_box(const BoxRef<T>& A_, const BoxRef<T>& B_, T* nrm, T pts[8][3]
 
 // floor plane z = 0 (normal +z) vs box: penetrating corners, at most 4
 template <class T>
-MM_HDX int plane_box(const BoxRef<T>& B_, T* nrm, T pts[8][3], T* dist) {
+MM_HDN int plane_box(const BoxRef<T>& B_, T* nrm, T pts[8][3], T* dist) {
   nrm[0] = 0; nrm[1] = 0; nrm[2] = 1;
   int cnt = 0;
   for (int i = 0; i < 8 && cnt < 4; i++) {
@@ -522,7 +528,7 @@ MM_HD void make_tangent(const T* n, T* t1) {  // mju_makeFrame rule (A3)
 // Separating-axis test of the oriented bounding boxes (local AABB of the hull / box / cylinder, carried
 // by the body frame).  Returns false only when the boxes, inflated by 1e-6, are disjoint.
 template <class T>
-MM_HDX bool obb_overlap(const Scratch<T>& s, const GeomDev<T>& gm, int a, int b, const T* ident) {
+MM_HDN bool obb_overlap(const Scratch<T>& s, const GeomDev<T>& gm, int a, int b, const T* ident) {
   T ca[3], cb[3];
   geom_bcenter(s, gm, a, ca);
   geom_bcenter(s, gm, b, cb);
@@ -560,7 +566,7 @@ MM_HDX bool obb_overlap(const Scratch<T>& s, const GeomDev<T>& gm, int a, int b,
 
 // plane z = 0 vs convex hull: deepest vertex, one contact
 template <class T>
-MM_HDX int plane_hull(const T* gpos, const T* R, const T* V, int nvert, T* nrm, T pts[8][3], T* dist) {
+MM_HDN int plane_hull(const T* gpos, const T* R, const T* V, int nvert, T* nrm, T pts[8][3], T* dist) {
   nrm[0] = 0; nrm[1] = 0; nrm[2] = 1;
   T nl[3] = {R[6], R[7], R[8]};  // R^T n
   int best = 0;
@@ -606,6 +612,10 @@ MM_HD void store_contact(Work<T>& w, int c, const T* pos, const T* nrm, const T*
 
 template <class T, int G>
 MM_HDX void collide(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>& w) {
+  MM_IN_SHARED(&s);
+  MM_IN_GLOBAL(&md);
+  MM_IN_GLOBAL(w.cpos); MM_IN_GLOBAL(w.cn); MM_IN_GLOBAL(w.ct1); MM_IN_GLOBAL(w.cdist); MM_IN_GLOBAL(w.cD); MM_IN_GLOBAL(w.aref);
+  MM_IN_GLOBAL(w.Jaref); MM_IN_GLOBAL(w.Jv); MM_IN_GLOBAL(w.cmeta); MM_IN_GLOBAL(w.surv);
   const T ident[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
   const GeomDev<T>& gm = *md.geom;
   // broad phase: ordered compaction of the surviving candidates
@@ -639,7 +649,7 @@ MM_HDX void collide(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<
     }
     int tot;
     int off = g.scan_excl(keep, &tot);
-    if (keep && nsurv + off < MAXSURV) s.surv[nsurv + off] = ci;
+    if (keep && nsurv + off < MAXSURV) w.surv[nsurv + off] = ci;
     nsurv += tot;
   }
   if (nsurv > MAXSURV) { nsurv = MAXSURV; if (g.lane == 0) s.overflow |= 1; }
@@ -652,7 +662,7 @@ MM_HDX void collide(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<
     T nrm[3], pts[8][3], dist[8];
     SP<T> sx[4];
     if (si < nsurv) {
-      int ci = s.surv[si];
+      int ci = w.surv[si];
       ci_ = ci;
       a = gm.pair[ci][0]; b = gm.pair[ci][1];
       int ta = gm.type[a], tb = gm.type[b];
@@ -825,6 +835,10 @@ MM_HD T impedance_generic(const T* solimp, T pos) {
 
 template <class T, int G>
 MM_HDX void make_constraints(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>& w) {
+  MM_IN_SHARED(&s);
+  MM_IN_GLOBAL(&md);
+  MM_IN_GLOBAL(w.cpos); MM_IN_GLOBAL(w.cn); MM_IN_GLOBAL(w.ct1); MM_IN_GLOBAL(w.cdist); MM_IN_GLOBAL(w.cD); MM_IN_GLOBAL(w.aref);
+  MM_IN_GLOBAL(w.Jaref); MM_IN_GLOBAL(w.Jv); MM_IN_GLOBAL(w.cmeta); MM_IN_GLOBAL(w.surv);
   const T h = md.timestep;
   if (g.lane == 0) {
     int n = 0;
@@ -938,6 +952,7 @@ MM_HDN T update_constraint(const Grp<G>& g, Scratch<T>& s, Work<T>& w, bool buil
       for (int o = 1; o < G; o <<= 1) {
         int ks = g.shfl_up(slot, o);
         bool take = g.lane >= o && ks == slot;
+        if (!g.any(take)) break;  // slots are sorted: no run is longer than o
         for (int d = 0; d < 6; d++) { T t = g.shfl_up(F[d], o); if (take) F[d] += t; }
         if (buildK) for (int k = 0; k < 21; k++) { T t = g.shfl_up(Kc[k], o); if (take) Kc[k] += t; }
       }
@@ -1052,49 +1067,46 @@ MM_HDN void ls_eval(const Grp<G>& g, const Scratch<T>& s, const Work<T>& w, T al
 
 template <class T, int G>
 MM_HDX void solve(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>& w) {
+  MM_IN_SHARED(&s);
+  MM_IN_GLOBAL(&md);
+  MM_IN_GLOBAL(w.cpos); MM_IN_GLOBAL(w.cn); MM_IN_GLOBAL(w.ct1); MM_IN_GLOBAL(w.cdist); MM_IN_GLOBAL(w.cD); MM_IN_GLOBAL(w.aref);
+  MM_IN_GLOBAL(w.Jaref); MM_IN_GLOBAL(w.Jv); MM_IN_GLOBAL(w.cmeta); MM_IN_GLOBAL(w.surv);
   const T scale_inv = md.meaninertia * (T)NV;
   const T scale = (T)1 / scale_inv;
   const T tol = (T)1e-8;
   int ncon = s.ncon;
   int changed;
-  // warmstart selection: cost at qacc_smooth vs cost at qacc_warmstart
-  mulJ<T, G>(g, s, w, s.as, w.Jv, s.specJv);
-  for (int c = g.lane; c < ncon; c += G) for (int r = 0; r < 6; r++) w.Jv[c * 6 + r] -= w.aref[c * 6 + r];
-  for (int k = g.lane; k < s.nspec; k += G) s.specJv[k] -= s.specAref[k];
-  g.sync();
-  T cost_sm;
-  {
+  // warmstart selection: cost at qacc_smooth (which = 0, rows kept in Jv) vs cost at qacc_warmstart
+  // (which = 1, rows kept in Jaref)
+  T cost_sm = 0, cost_ws = 0;
+  for (int which = 0; which < 2; which++) {
+    const T* x = which ? s.warm : s.as;
+    T* rows = which ? w.Jaref : w.Jv;
+    T* srows = which ? s.specJaref : s.specJv;
+    mulJ<T, G>(g, s, w, x, rows, srows);
     T cst = 0;
     for (int c = g.lane; c < ncon; c += G) {
       T D = w.cD[c];
       int nr = meta_dim4(w.cmeta[c]) ? 6 : 4;
-      for (int r = 0; r < nr; r++) { T ja = w.Jv[c * 6 + r]; if (ja < 0) cst += (T)0.5 * D * ja * ja; }
+      for (int r = 0; r < 6; r++) {
+        T ja = rows[c * 6 + r] - w.aref[c * 6 + r];
+        rows[c * 6 + r] = ja;
+        if (r < nr && ja < 0) cst += (T)0.5 * D * ja * ja;
+      }
     }
     for (int k = g.lane; k < s.nspec; k += G) {
-      T ja = s.specJv[k];
+      T ja = srows[k] - s.specAref[k];
+      srows[k] = ja;
       if (s.specdof[k] < 0 || ja < 0) cst += (T)0.5 * s.specD[k] * ja * ja;
     }
-    cost_sm = g.sum(cst);
-  }
-  mulJ<T, G>(g, s, w, s.warm, w.Jaref, s.specJaref);
-  for (int c = g.lane; c < ncon; c += G) for (int r = 0; r < 6; r++) w.Jaref[c * 6 + r] -= w.aref[c * 6 + r];
-  for (int k = g.lane; k < s.nspec; k += G) s.specJaref[k] -= s.specAref[k];
-  mulM<T, G>(g, s, md, s.warm, s.Ma);
-  g.sync();
-  T cost_ws;
-  {
-    T cst = 0;
-    for (int c = g.lane; c < ncon; c += G) {
-      T D = w.cD[c];
-      int nr = meta_dim4(w.cmeta[c]) ? 6 : 4;
-      for (int r = 0; r < nr; r++) { T ja = w.Jaref[c * 6 + r]; if (ja < 0) cst += (T)0.5 * D * ja * ja; }
+    if (which) {
+      mulM<T, G>(g, s, md, s.warm, s.Ma);
+      g.sync();
+      for (int i = g.lane; i < NV; i += G) cst += (T)0.5 * (s.Ma[i] - s.fs[i]) * (s.warm[i] - s.as[i]);
     }
-    for (int k = g.lane; k < s.nspec; k += G) {
-      T ja = s.specJaref[k];
-      if (s.specdof[k] < 0 || ja < 0) cst += (T)0.5 * s.specD[k] * ja * ja;
-    }
-    for (int i = g.lane; i < NV; i += G) cst += (T)0.5 * (s.Ma[i] - s.fs[i]) * (s.warm[i] - s.as[i]);
-    cost_ws = g.sum(cst);
+    cst = g.sum(cst);
+    if (which) cost_ws = cst; else cost_sm = cst;
+    g.sync();
   }
   if (cost_ws < cost_sm) {
     for (int i = g.lane; i < NV; i += G) s.qacc[i] = s.warm[i];
@@ -1106,21 +1118,45 @@ MM_HDX void solve(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>
     mulM<T, G>(g, s, md, s.qacc, s.Ma);
   }
   g.sync();
-  // clear stored active bits so that the first update reports a change (forces the H build)
-  for (int c = g.lane; c < ncon; c += G) w.cmeta[c] &= ~(63 << 13);
-  g.sync();
-  T cost = update_constraint<T, G>(g, s, w, true, &changed);
-  {
-    T ga = 0;
-    for (int i = g.lane; i < NV; i += G) ga += (T)0.5 * (s.Ma[i] - s.fs[i]) * (s.qacc[i] - s.as[i]);
-    cost += g.sum(ga);
-  }
-  // spec-row active pattern (limits) folded into `changed` tracking via a small bitmask
-  int specbits = 0;
-  for (int k = 0; k < s.nspec; k++) if (s.specdof[k] < 0 || s.specJaref[k] < 0) specbits |= 1 << k;
-  build_factor_H<T, G>(g, s, md);
+  // Newton iterations.  One evaluation site per iteration: constraint update (active set, cost, forces),
+  // convergence test of the previous move, then - only when the active set changed - the per-pair
+  // blocks and the factorisation of H.
+  int specbits = -1;
   int iter = 0;
-  while (iter < 100) {
+  T cost = 0, a = 0;
+  bool first = true;
+  while (true) {
+    T oldcost = cost;
+    bool done = false;
+    for (int pass = 0; pass < 2; pass++) {  // pass 1 (per-pair blocks + factorisation) only when the active set changed
+      int chg;
+      T cst = update_constraint<T, G>(g, s, w, pass == 1, &chg);
+      if (pass == 1) { build_factor_H<T, G>(g, s, md); break; }
+      cost = cst;
+      changed = chg;
+      int sb = 0;
+      for (int k = 0; k < s.nspec; k++) if (s.specdof[k] < 0 || s.specJaref[k] < 0) sb |= 1 << k;
+      if (sb != specbits) { changed = 1; specbits = sb; }
+      T ga = 0, gn = 0;
+      for (int i = g.lane; i < NV; i += G) {
+        ga += (T)0.5 * (s.Ma[i] - s.fs[i]) * (s.qacc[i] - s.as[i]);
+        T gr = s.Ma[i] - s.fs[i] - s.fc[i];
+        gn += gr * gr;
+      }
+      cost += g.sum(ga);
+      gn = tsqrt(g.sum(gn));
+      if (!first) {
+        iter++;
+        T improvement = scale * (oldcost - cost), gradient = scale * gn;
+#if defined(MM_TRACE) && !defined(__CUDA_ARCH__)
+        printf("  it %d alpha %.6e cost %.12e impr %.3e grad %.3e changed %d\n", iter, (double)a, (double)cost, (double)improvement, (double)gradient, changed);
+#endif
+        if (improvement < tol || gradient < tol || iter >= 100) { done = true; break; }
+      }
+      if (!(first || changed)) break;
+    }
+    if (done) break;
+    first = false;
     // gradient and Newton direction
     for (int i = g.lane; i < NV; i += G) { T gr = s.Ma[i] - s.fs[i] - s.fc[i]; s.grad[i] = gr; s.search[i] = -gr; }
     g.sync();
@@ -1137,50 +1173,27 @@ MM_HDX void solve(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>
     sn = tsqrt(g.sum(sn)); qg1 = g.sum(qg1); qg2 = g.sum(qg2);
     if (sn < (T)MINVAL_D) break;
     T gtol = tol * (T)0.01 * sn * scale_inv;
-    T lo = 0, hi = -1, a = 0, d1, d2;
-    ls_eval<T, G>(g, s, w, (T)0, qg1, qg2, &d1, &d2);
-    if (d1 >= 0) break;
-    for (int it = 0; it < 50; it++) {
-      T an = a - d1 / d2;
-      if (hi > 0 && !(an > lo && an < hi)) an = (T)0.5 * (lo + hi);
-      a = an;
+    T lo = 0, hi = -1, d1, d2;
+    a = 0;
+    bool flat = false;
+    for (int it = -1; it < 50; it++) {  // it = -1: slope at alpha = 0
+      if (it >= 0) {
+        T an = a - d1 / d2;
+        if (hi > 0 && !(an > lo && an < hi)) an = (T)0.5 * (lo + hi);
+        a = an;
+      }
       ls_eval<T, G>(g, s, w, a, qg1, qg2, &d1, &d2);
+      if (it < 0) { if (d1 >= 0) { flat = true; break; } continue; }
       if (tabs(d1) < gtol) break;
       if (d1 < 0) lo = a; else hi = a;
     }
+    if (flat) break;
     if (a == 0) break;
     // move
     for (int i = g.lane; i < NV; i += G) { s.qacc[i] += a * s.search[i]; s.Ma[i] += a * s.Mv[i]; }
     for (int c = g.lane; c < ncon; c += G) for (int r = 0; r < 6; r++) w.Jaref[c * 6 + r] += a * w.Jv[c * 6 + r];
     for (int k = g.lane; k < s.nspec; k += G) s.specJaref[k] += a * s.specJv[k];
     g.sync();
-    T oldcost = cost;
-    // active-set probe first (cheap), K only when it changed
-    cost = update_constraint<T, G>(g, s, w, false, &changed);
-    int sb = 0;
-    for (int k = 0; k < s.nspec; k++) if (s.specdof[k] < 0 || s.specJaref[k] < 0) sb |= 1 << k;
-    if (sb != specbits) { changed = 1; specbits = sb; }
-    {
-      T ga = 0, gn = 0;
-      for (int i = g.lane; i < NV; i += G) {
-        ga += (T)0.5 * (s.Ma[i] - s.fs[i]) * (s.qacc[i] - s.as[i]);
-        T gr = s.Ma[i] - s.fs[i] - s.fc[i];
-        gn += gr * gr;
-      }
-      cost += g.sum(ga);
-      gn = tsqrt(g.sum(gn));
-      iter++;
-      T improvement = scale * (oldcost - cost), gradient = scale * gn;
-#if defined(MM_TRACE) && !defined(__CUDA_ARCH__)
-      printf("  it %d alpha %.6e cost %.12e impr %.3e grad %.3e changed %d\n", iter, (double)a, (double)cost, (double)improvement, (double)gradient, changed);
-#endif
-      if (improvement < tol || gradient < tol) break;
-    }
-    if (changed) {
-      int dummy;
-      update_constraint<T, G>(g, s, w, true, &dummy);
-      build_factor_H<T, G>(g, s, md);
-    }
   }
   if (g.lane == 0) s.niter = iter;
   for (int i = g.lane; i < NV; i += G) s.warm[i] = s.qacc[i];
@@ -1189,7 +1202,7 @@ MM_HDX void solve(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>
 
 // full forward at the current (qpos, qvel, ctrl): everything mj_forward computes that the path needs
 template <class T, int G>
-MM_HDX void forward(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>& w) {
+MM_HDN void forward(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>& w) {
   fk<T, G>(g, s, md);
   dyn_smooth<T, G>(g, s, md);
   collide<T, G>(g, s, md, w);
@@ -1202,6 +1215,8 @@ MM_HDX void forward(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<
 // ------------------------------------------------------------------------------------------------
 template <class T, int G>
 MM_HDX void integrate(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md) {
+  MM_IN_SHARED(&s);
+  MM_IN_GLOBAL(&md);
   const T h = md.timestep;
   T* MH = s.H;
   T* acc = s.grad;
@@ -1267,6 +1282,8 @@ MM_HDN void orientation_error(const T* Rc, T* out) {
 
 template <class T, int G>
 MM_HDX void ik(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md) {
+  MM_IN_SHARED(&s);
+  MM_IN_GLOBAL(&md);
   if (g.lane == 0) {
     const T* ee = s.bpos[DB_HAND];
     T J[6][NARM], e[6], z[NARM], b[6];

@@ -250,23 +250,25 @@ MM_HDN void env_step(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work
     s.ctrl[7] = gr > 0.5f ? (T)255 : (T)0;
   }
   g.sync();
+  // 16 x (IK, forward, integrate) then the trailing mj_forward (gym_env.py:555-560) - one forward site
   int nonfinite = 0;
-  for (int sub = 0; sub < ACTION_REPEAT; sub++) {
-    ik<T, G>(g, s, md);
-    if (state_bad<T, G>(g, s)) { nonfinite = 1; break; }
+  for (int sub = 0; sub <= ACTION_REPEAT; sub++) {
+    bool last = sub == ACTION_REPEAT;
+    if (!last) ik<T, G>(g, s, md);
+    if (!nonfinite && state_bad<T, G>(g, s)) {
+      // mj_checkPos/Vel/Acc would warn and reset the data; here the env is put back on the keyframe,
+      // flagged (diag[3]) so the host can count it, and only the trailing forward is run
+      nonfinite = 1;
+      for (int i = g.lane; i < NQ; i += G) s.qpos[i] = md.key_qpos[i];
+      for (int i = g.lane; i < NV; i += G) { s.qvel[i] = 0; s.warm[i] = 0; }
+      if (g.lane == 0) st.diag[e * 4 + 3] += 1;
+      g.sync();
+      sub = ACTION_REPEAT;
+      last = true;
+    }
     forward<T, G>(g, s, md, w);
-    integrate<T, G>(g, s, md);
+    if (!last) integrate<T, G>(g, s, md);
   }
-  if (!nonfinite && state_bad<T, G>(g, s)) nonfinite = 1;
-  if (nonfinite) {
-    // mj_checkPos/Vel/Acc would warn and reset the data; here the env is put back on the keyframe
-    // and flagged (diag[3]) so the host can count it.
-    for (int i = g.lane; i < NQ; i += G) s.qpos[i] = md.key_qpos[i];
-    for (int i = g.lane; i < NV; i += G) { s.qvel[i] = 0; s.warm[i] = 0; }
-    if (g.lane == 0) st.diag[e * 4 + 3] += 1;
-    g.sync();
-  }
-  forward<T, G>(g, s, md, w);  // trailing mj_forward (gym_env.py:560): refresh kinematics + warmstart
   bool rc = reward_type == REWARD_STAGED ? any_robot_collision<T, G>(g, s, w) : false;
   store_state<T, G>(g, s, st, e);
   if (g.lane == 0) {
@@ -284,15 +286,16 @@ MM_HDN void env_reset(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Wor
   for (int i = g.lane; i < NU; i += G) s.ctrl[i] = md.key_ctrl[i];
   if (g.lane == 0) { s.overflow = 0; s.ncon = 0; s.npair = 0; s.nspec = 0; s.niter = 0; }
   g.sync();
-  forward<T, G>(g, s, md, w);  // env.py:116-117
-  if (obj_xy) {                 // randomization.py:52-65 + env.py:160-161
-    if (g.lane == 0)
-      for (int o = 0; o < 3; o++) {
-        T* q = s.qpos + 9 + 7 * o;
-        q[0] = (T)obj_xy[2 * o]; q[1] = (T)obj_xy[2 * o + 1]; q[2] = (T)0.26; q[3] = 1; q[4] = q[5] = q[6] = 0;
-      }
-    g.sync();
-    forward<T, G>(g, s, md, w);
+  for (int pass = 0; pass < (obj_xy ? 2 : 1); pass++) {
+    if (pass == 1) {  // randomization.py:52-65 + env.py:160-161
+      if (g.lane == 0)
+        for (int o = 0; o < 3; o++) {
+          T* q = s.qpos + 9 + 7 * o;
+          q[0] = (T)obj_xy[2 * o]; q[1] = (T)obj_xy[2 * o + 1]; q[2] = (T)0.26; q[3] = 1; q[4] = q[5] = q[6] = 0;
+        }
+      g.sync();
+    }
+    forward<T, G>(g, s, md, w);  // env.py:116-117
   }
   store_state<T, G>(g, s, st, e);
   if (g.lane == 0) {

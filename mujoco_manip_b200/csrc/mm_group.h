@@ -11,11 +11,20 @@
 #if defined(__CUDACC__)
 #define MM_HD __host__ __device__ __forceinline__
 #define MM_HDN __host__ __device__
-#define MM_HDX __host__ __device__  // (measured: __noinline__ here is 15% slower - calls lose the shared-memory address space)
+#define MM_HDX __host__ __device__  // (measured twice: __noinline__ stage functions are 10-15% slower, even with address-space hints)
 #else
 #define MM_HD inline
 #define MM_HDN
 #define MM_HDX
+#endif
+
+// address-space hints for the out-of-line functions (a plain reference would compile to generic loads)
+#ifdef __CUDA_ARCH__
+#define MM_IN_SHARED(p) __builtin_assume(__isShared(p))
+#define MM_IN_GLOBAL(p) __builtin_assume(__isGlobal(p))
+#else
+#define MM_IN_SHARED(p)
+#define MM_IN_GLOBAL(p)
 #endif
 
 namespace mm {

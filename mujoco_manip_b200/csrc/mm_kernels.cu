@@ -75,6 +75,7 @@ struct mm_handle {
   float* d_reward = nullptr;
   unsigned char* d_flags = nullptr;  // terminated | truncated | success, N each
   long long launches = 0;
+  long long* d_cycles = nullptr;  // optional per-env cycle counts (mm_set_cycle_buffer)
   size_t smem = 0;
 };
 
@@ -183,6 +184,7 @@ int mm_step(mm_handle* h, const mm_state* st, const float* actions, int action_m
   p.actions = actions; p.model = h->d_model; p.work_reals = h->d_work_reals; p.work_ints = h->d_work_ints;
   p.tgt_kp = h->d_tgt; p.n = h->cfg.num_envs; p.mode = action_mode; p.reward_type = h->cfg.reward_type;
   p.max_steps = h->cfg.max_episode_steps;
+  p.cycles = h->d_cycles;
   h->launches++;
   CK(LAUNCH[inst_index(h->cfg)](false, p, (cudaStream_t)stream));
   return 0;
@@ -259,6 +261,12 @@ int mm_measure_fma_peak(int device, int fp64, double* tflops) {
   }
   cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(buf);
   *tflops = best;
+  return 0;
+}
+
+int mm_set_cycle_buffer(mm_handle* h, long long* cycles) {
+  if (!h) return fail("mm_set_cycle_buffer: null handle");
+  h->d_cycles = cycles;
   return 0;
 }
 

@@ -4,13 +4,22 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "mm_env.h"
 
 namespace mm {
 
-// threads per CTA: as many envs as fit the 227 KB of shared memory (FP64 scratch is ~20 KB per env)
+// One warp per CTA (32 / G envs): the number of resident envs per SM is set by the shared-memory
+// scratch, so small CTAs pack the 227 KB best.  MINB = CTAs per SM the register allocation must allow.
 template <class T, int G>
-struct BlockCfg { static constexpr int THREADS = (sizeof(T) == 8 && G == 8) ? 64 : 128; };
+struct BlockCfg {
+  static constexpr int THREADS = 32;
+  static constexpr int ENVS = 32 / G;
+  static constexpr int MINB = (int)((227 * 1024) / (ENVS * sizeof(Scratch<T>) + 1024)) > 16
+                                  ? 16
+                                  : (int)((227 * 1024) / (ENVS * sizeof(Scratch<T>) + 1024));
+};
 
 struct StepParams {
   StatePtrs st;
@@ -26,25 +35,17 @@ struct StepParams {
   float* obs;
   long n;
   int mode, reward_type, max_steps;
+  long long* cycles;  // [N] or null: SM clock cycles each env's step took (profiling aid)
 };
 
-template <class T>
-__host__ __device__ __forceinline__ size_t model_bytes() { return (sizeof(ModelDev<T>) + 15) & ~size_t(15); }
-
 template <class T, int G>
-__device__ __forceinline__ bool setup(const StepParams& p, unsigned char* smem, ModelDev<T>*& md, Scratch<T>*& sc,
+__device__ __forceinline__ bool setup(const StepParams& p, unsigned char* smem, const ModelDev<T>*& md, Scratch<T>*& sc,
                                       Grp<G>& g, long& e) {
-  md = reinterpret_cast<ModelDev<T>*>(smem);
-  // one model copy per CTA (word-wise cooperative copy from global)
-  const int* src = reinterpret_cast<const int*>(p.model);
-  int* dst = reinterpret_cast<int*>(smem);
-  constexpr int BLOCK = BlockCfg<T, G>::THREADS;
-  for (int i = threadIdx.x; i < (int)(sizeof(ModelDev<T>) / 4); i += BLOCK) dst[i] = src[i];
-  __syncthreads();
-  constexpr int GPB = BLOCK / G;
+  md = reinterpret_cast<const ModelDev<T>*>(p.model);  // read-only, global memory (L1 resident)
+  constexpr int GPB = BlockCfg<T, G>::ENVS;
   int gi = threadIdx.x / G;
   e = (long)blockIdx.x * GPB + gi;
-  sc = reinterpret_cast<Scratch<T>*>(smem + model_bytes<T>()) + gi;
+  sc = reinterpret_cast<Scratch<T>*>(smem) + gi;
   g.lane = threadIdx.x % G;
   int inwarp = (threadIdx.x % 32) / G;
   g.mask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (inwarp * G));
@@ -52,21 +53,23 @@ __device__ __forceinline__ bool setup(const StepParams& p, unsigned char* smem, 
 }
 
 template <class T, int G>
-__global__ void __launch_bounds__(BlockCfg<T, G>::THREADS) k_step(StepParams p) {
+__global__ void __launch_bounds__(BlockCfg<T, G>::THREADS, BlockCfg<T, G>::MINB) k_step(StepParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
-  ModelDev<T>* md;
+  const ModelDev<T>* md;
   Scratch<T>* sc;
   Grp<G> g;
   long e;
   if (!setup<T, G>(p, smem, md, sc, g, e)) return;
   Work<T> w = make_work(reinterpret_cast<T*>(p.work_reals) + e * WORK_REALS, p.work_ints + e * WORK_INTS);
+  long long t0 = p.cycles ? clock64() : 0;
   env_step<T, G>(g, *sc, *md, w, p.st, e, p.actions, p.mode, p.reward_type, p.max_steps, p.out, p.tgt_kp);
+  if (p.cycles && g.lane == 0) p.cycles[e] = clock64() - t0;
 }
 
 template <class T, int G>
-__global__ void __launch_bounds__(BlockCfg<T, G>::THREADS) k_reset(StepParams p) {
+__global__ void __launch_bounds__(BlockCfg<T, G>::THREADS, BlockCfg<T, G>::MINB) k_reset(StepParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
-  ModelDev<T>* md;
+  const ModelDev<T>* md;
   Scratch<T>* sc;
   Grp<G> g;
   long e;
@@ -78,8 +81,14 @@ __global__ void __launch_bounds__(BlockCfg<T, G>::THREADS) k_reset(StepParams p)
 }
 
 
+// MM_EXTRA_SMEM (bytes, environment variable) pads the dynamic shared memory: an occupancy probe for profiling only
+inline size_t extra_smem() {
+  static long v = -1;
+  if (v < 0) { const char* e = getenv("MM_EXTRA_SMEM"); v = e ? atol(e) : 0; }
+  return (size_t)v;
+}
 template <class T, int G>
-size_t smem_bytes() { return ((sizeof(ModelDev<T>) + 15) & ~size_t(15)) + (BlockCfg<T, G>::THREADS / G) * sizeof(Scratch<T>); }
+size_t smem_bytes() { return BlockCfg<T, G>::ENVS * sizeof(Scratch<T>) + extra_smem(); }
 
 template <class T, int G>
 cudaError_t inst_prepare() {

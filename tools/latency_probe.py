@@ -1,0 +1,48 @@
+#!/usr/bin/env python3
+"""Per-env latency distribution of the step kernel (GPU box): which envs are the long poles?
+    python tools/latency_probe.py [--envs 4096] [--steps 40] [--group 16] [--precision f64]"""
+import argparse
+import ctypes as C
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from mujoco_manip_b200 import PickPlaceVecEnv, _lib  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--envs", type=int, default=4096)
+ap.add_argument("--steps", type=int, default=40)
+ap.add_argument("--group", type=int, default=16)
+ap.add_argument("--precision", default="f64")
+a = ap.parse_args()
+dev = torch.device("cuda:0")
+env = PickPlaceVecEnv(a.envs, device=dev, task=("obj_red", "bin_red"), precision=a.precision, group=a.group, seed=1234)
+env.reset()
+cyc = torch.zeros(a.envs, dtype=torch.int64, device=dev)
+_lib.check(env._L.mm_set_cycle_buffer(env._h, cyc.data_ptr()), "cycles")
+gen = torch.Generator(device=dev).manual_seed(1234)
+T0 = env.state["tinit"][0]
+p0, R0 = T0[:3], T0[3:].reshape(3, 3)
+lo = torch.tensor([-0.3, 0.30, 0.30], device=dev, dtype=torch.float64)
+hi = torch.tensor([0.3, 0.65, 0.60], device=dev, dtype=torch.float64)
+for t in range(a.steps):
+    w = lo + (hi - lo) * torch.rand((a.envs, 3), device=dev, dtype=torch.float64, generator=gen)
+    act = torch.zeros((a.envs, 10), device=dev)
+    act[:, :3] = ((w - p0) @ R0).float()
+    act[:, 6] = 1.0
+    act[:, 7] = (torch.rand(a.envs, device=dev, generator=gen) > 0.5).float()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    env.step(act)
+    e1.record()
+    torch.cuda.synchronize()
+    if t % 5 == 4 or t == a.steps - 1:
+        c = cyc.double() / 1.965e6  # ms at 1965 MHz
+        q = torch.quantile(c, torch.tensor([0.5, 0.9, 0.99, 1.0], device=dev, dtype=torch.float64))
+        ncon = env.state["diag"][:, 0].double()
+        worst = int(torch.argmax(c))
+        print(f"step {t}: launch {e0.elapsed_time(e1):.1f} ms | per-env ms p50 {q[0]:.2f} p90 {q[1]:.2f} p99 {q[2]:.2f} max {q[3]:.2f} "
+              f"| sum/SMs {float(c.sum()) / 148:.1f} | ncon mean {float(ncon.mean()):.1f} max {int(ncon.max())} "
+              f"| worst env ncon {int(ncon[worst])} iters {int(env.state['diag'][worst, 1])}")
