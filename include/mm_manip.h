@@ -55,6 +55,8 @@ typedef struct {
   double* eepose;      /* [N,12] EE pose after the last forward (robot.py:50-58) */
   double* fsm_f;       /* [N,6]  FSM target + transit_end (pick_and_place.py:103-104) */
   double* hwm;         /* [N,5]  staged reward high-water marks (gym_env.py:133) */
+  double* kin;         /* [N,18] qpos of the last position stage (arm+fingers 9, cube xyz 9): what data.xpos /
+                                 mj_jac describe between mj_step calls (SURVEY 3.3 staleness quirk) */
   int32_t* step_count; /* [N]    gym_env.py:111                                */
   int32_t* task;       /* [N,2]  object index, bin index (constants.py:3-4)    */
   int32_t* fsm_i;      /* [N,5]  state 1..11, task_index, settle_counter, gripper_open, has_target */
@@ -98,6 +100,15 @@ int mm_step(mm_handle* h, const mm_state* st, const float* actions, int action_m
  * flags D2H and synchronises the stream.  This is the end-to-end path bench.py times as `e2e`. */
 int mm_step_host(mm_handle* h, const mm_state* st, const float* h_actions, int action_mode, float* h_obs,
                  float* h_reward, uint8_t* h_terminated, uint8_t* h_truncated, uint8_t* h_success, void* stream);
+
+/* Engine-level calls for the physics-step-level loops of the reference (main.py:65-91,
+ * pick_and_place.py:279-304, tests/test_controller.py): a combination of
+ *   MM_OP_IK        IKController.compute(target) + set_arm_ctrl (controller.py:87-137, robot.py:65-71) on the
+ *                   kinematics of the last position stage; target [N,3] double, world frame
+ *   MM_OP_FORWARD   mj_forward (env.py:117)
+ *   MM_OP_INTEGRATE with MM_OP_FORWARD: mj_step (env.py:119-121) */
+enum { MM_OP_IK = 1, MM_OP_FORWARD = 2, MM_OP_INTEGRATE = 4 };
+int mm_ops(mm_handle* h, const mm_state* st, int ops, const double* target, void* stream);
 
 /* replaces PickAndPlaceTask.plan(n_steps) (pick_and_place.py:167-277) and the abs_pos action built
  * from it (scripts/generate_dataset.py:145-148).  actions_out: [N,10] float32 or NULL. */

@@ -23,7 +23,7 @@ REWARD_TYPES = ("dense", "sparse", "staged")
 
 # every symbol include/mm_manip.h declares (tests check the built library exports each one)
 EXPORTS = ("mm_create", "mm_destroy", "mm_last_error", "mm_workspace_bytes", "mm_reset", "mm_step", "mm_step_host",
-           "mm_fsm_plan", "mm_launch_count", "mm_sample_placements", "mm_measure_fma_peak", "mm_set_cycle_buffer")
+           "mm_fsm_plan", "mm_launch_count", "mm_sample_placements", "mm_measure_fma_peak", "mm_set_cycle_buffer", "mm_ops")
 
 
 class MMConfig(C.Structure):
@@ -33,7 +33,7 @@ class MMConfig(C.Structure):
 
 # (name, width, is_double) in the order of struct mm_state
 STATE_FIELDS = (("qpos", 30, True), ("qvel", 27, True), ("ctrl", 8, True), ("warm", 27, True), ("tinit", 12, True),
-                ("eepose", 12, True), ("fsm_f", 6, True), ("hwm", 5, True), ("step_count", 1, False),
+                ("eepose", 12, True), ("fsm_f", 6, True), ("hwm", 5, True), ("kin", 18, True), ("step_count", 1, False),
                 ("task", 2, False), ("fsm_i", 5, False), ("flags", 1, False), ("diag", 4, False))
 
 
@@ -102,6 +102,7 @@ def lib():
     L.mm_sample_placements.argtypes = [C.c_void_p, C.c_uint64, C.c_int64, C.c_void_p, C.c_double, C.c_double, C.c_double,
                                        C.c_double, C.c_double, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.mm_measure_fma_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]
+    L.mm_ops.argtypes = [C.c_void_p, C.POINTER(MMState), C.c_int, C.c_void_p, C.c_void_p]
     L.mm_set_cycle_buffer.argtypes = [C.c_void_p, C.c_void_p]
     L.mm_launch_count.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
     _lib = L

@@ -36,8 +36,8 @@ Ctx<T>& ctx() {
 StatePtrs state_from(void** p) {
   StatePtrs st;
   st.qpos = (double*)p[0]; st.qvel = (double*)p[1]; st.ctrl = (double*)p[2]; st.warm = (double*)p[3];
-  st.tinit = (double*)p[4]; st.eepose = (double*)p[5]; st.fsm_f = (double*)p[6]; st.hwm = (double*)p[7];
-  st.step_count = (int*)p[8]; st.task = (int*)p[9]; st.fsm_i = (int*)p[10]; st.flags = (int*)p[11]; st.diag = (int*)p[12];
+  st.tinit = (double*)p[4]; st.eepose = (double*)p[5]; st.fsm_f = (double*)p[6]; st.hwm = (double*)p[7]; st.kin = (double*)p[8];
+  st.step_count = (int*)p[9]; st.task = (int*)p[10]; st.fsm_i = (int*)p[11]; st.flags = (int*)p[12]; st.diag = (int*)p[13];
   return st;
 }
 StepOut out_from(void** p) {
@@ -79,6 +79,15 @@ void emul_step(int n, void** state, const float* actions, int mode, int reward_t
                const float* tgt_kp, int use_float) {
   if (use_float) do_step<float>(n, state, actions, mode, reward_type, max_steps, out, tgt_kp);
   else do_step<double>(n, state, actions, mode, reward_type, max_steps, out, tgt_kp);
+}
+
+void emul_ops(int n, void** state, int ops, const double* target, int use_float) {
+  StatePtrs st = state_from(state);
+  Grp<1> g{0, 1u};
+  for (long e = 0; e < n; e++) {
+    if (use_float) { Ctx<float>& c = ctx<float>(); env_ops<float, 1>(g, c.s, c.md, c.w, st, e, ops, target); }
+    else { Ctx<double>& c = ctx<double>(); env_ops<double, 1>(g, c.s, c.md, c.w, st, e, ops, target); }
+  }
 }
 
 void emul_fsm_plan(int n, void** state, int nsteps, float* actions /*[n,10]*/) {

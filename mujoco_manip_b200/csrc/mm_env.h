@@ -22,6 +22,7 @@ struct StatePtrs {
   double* eepose;    // [N,12]  EE pose after the last forward
   double* fsm_f;     // [N,6]   FSM target(3) + transit_end(3)
   double* hwm;       // [N,5]   staged-reward high-water marks
+  double* kin;       // [N,18]  qpos of the last position stage: arm + fingers (9), cube positions (9)
   int* step_count;   // [N]
   int* task;         // [N,2]   object index, bin index
   int* fsm_i;        // [N,5]   state(1..11), task_index, settle_counter, gripper_open, has_target
@@ -54,6 +55,8 @@ MM_HDN void store_state(const Grp<G>& g, const Scratch<T>& s, const StatePtrs& s
   for (int i = g.lane; i < NU; i += G) st.ctrl[e * NU + i] = (double)s.ctrl[i];
   for (int i = g.lane; i < 12; i += G)
     st.eepose[e * 12 + i] = (double)(i < 3 ? s.bpos[DB_HAND][i] : s.bR[DB_HAND][i - 3]);
+  // kinematics of the last position stage (what data.xpos / mj_jac describe in the reference)
+  for (int i = g.lane; i < 18; i += G) st.kin[e * 18 + i] = (double)(i < 9 ? s.tmp6[18 + i / 6][i % 6] : s.bpos[DB_CUBE0 + (i - 9) / 3][(i - 9) % 3]);
   if (g.lane == 0) {
     st.diag[e * 4 + 0] = s.ncon; st.diag[e * 4 + 1] = s.niter; st.diag[e * 4 + 2] |= s.overflow;
   }
@@ -270,6 +273,8 @@ MM_HDN void env_step(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work
     if (!last) integrate<T, G>(g, s, md);
   }
   bool rc = reward_type == REWARD_STAGED ? any_robot_collision<T, G>(g, s, w) : false;
+  for (int i = g.lane; i < 9; i += G) s.tmp6[18 + i / 6][i % 6] = s.qpos[i];
+  g.sync();
   store_state<T, G>(g, s, st, e);
   if (g.lane == 0) {
     write_reward<T>(s, st, e, reward_type, max_steps, rc, out);
@@ -297,6 +302,8 @@ MM_HDN void env_reset(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Wor
     }
     forward<T, G>(g, s, md, w);  // env.py:116-117
   }
+  for (int i = g.lane; i < 9; i += G) s.tmp6[18 + i / 6][i % 6] = s.qpos[i];
+  g.sync();
   store_state<T, G>(g, s, st, e);
   if (g.lane == 0) {
     for (int i = 0; i < 12; i++) st.tinit[e * 12 + i] = (double)(i < 3 ? s.bpos[DB_HAND][i] : s.bR[DB_HAND][i - 3]);
@@ -320,6 +327,40 @@ MM_HDN void env_reset(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Wor
   if (g.lane == 0 && obs) write_obs<T>(s, st, e, obs + e * OBS_DIM, tgt_kp_all + e * 4);
 }
 
+enum { OP_IK = 1, OP_FORWARD = 2, OP_INTEGRATE = 4 };
+
+// Engine-level calls on env e: IKController.compute + set_arm_ctrl (controller.py:87-137 with the stale
+// kinematics of the last position stage), mj_forward, mj_step = forward + integrate (env.py:117-121).
+template <class T, int G>
+MM_HDN void env_ops(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>& w, const StatePtrs& st, long e,
+                    int ops, const double* target) {
+  load_state<T, G>(g, s, st, e);
+  // kinematics as the last position stage left them
+  for (int i = g.lane; i < 9; i += G) { s.fs[i] = s.qpos[i]; s.qpos[i] = (T)st.kin[e * 18 + i]; }
+  g.sync();
+  fk<T, G>(g, s, md);
+  for (int i = g.lane; i < 9; i += G) s.qpos[i] = s.fs[i];
+  if (g.lane == 0 && target) for (int k = 0; k < 3; k++) s.target[k] = (T)target[3 * e + k];
+  g.sync();
+  if ((ops & OP_IK) && target) ik<T, G>(g, s, md);
+  if (ops & OP_FORWARD) {
+    if (state_bad<T, G>(g, s)) {
+      for (int i = g.lane; i < NQ; i += G) s.qpos[i] = md.key_qpos[i];
+      for (int i = g.lane; i < NV; i += G) { s.qvel[i] = 0; s.warm[i] = 0; }
+      if (g.lane == 0) st.diag[e * 4 + 3] += 1;
+      g.sync();
+    }
+    forward<T, G>(g, s, md, w);
+    for (int i = g.lane; i < 9; i += G) s.tmp6[18 + i / 6][i % 6] = s.qpos[i];  // position-stage qpos for store_state
+    g.sync();
+    if (ops & OP_INTEGRATE) integrate<T, G>(g, s, md);
+  } else {
+    for (int i = g.lane; i < 9; i += G) s.tmp6[18 + i / 6][i % 6] = (T)st.kin[e * 18 + i];
+    g.sync();
+  }
+  store_state<T, G>(g, s, st, e);
+}
+
 // Scripted FSM, one plan(n_steps) call (pick_and_place.py:167-277) + the abs_pos action it implies
 // (scripts/generate_dataset.py:145-148).  Thread per env; reads the cached EE pose and cube positions.
 MM_HDN inline void fsm_plan_one(const StatePtrs& st, long e, int n, float* action_out /*[4] or null*/) {
@@ -328,7 +369,7 @@ MM_HDN inline void fsm_plan_one(const StatePtrs& st, long e, int n, float* actio
   double* te = tg + 3;
   const double* ee = st.eepose + e * 12;
   int obj = st.task[e * 2], bin = st.task[e * 2 + 1];
-  const double* op = st.qpos + e * NQ + 9 + 7 * obj;
+  const double* op = st.kin + e * 18 + 9 + 3 * obj;  // data.xpos of the object at the last position stage
   double bp[3];
   bin_pos(bin, bp);
   double dd = sqrt((ee[0] - tg[0]) * (ee[0] - tg[0]) + (ee[1] - tg[1]) * (ee[1] - tg[1]) + (ee[2] - tg[2]) * (ee[2] - tg[2]));

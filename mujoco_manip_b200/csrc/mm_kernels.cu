@@ -84,7 +84,7 @@ namespace {
 size_t real_bytes(const mm_config* c) { return c->precision ? 4 : 8; }
 
 typedef cudaError_t (*prepare_fn)();
-typedef cudaError_t (*launch_fn)(bool, const StepParams&, cudaStream_t);
+typedef cudaError_t (*launch_fn)(int, const StepParams&, cudaStream_t);
 int inst_index(const mm_config& c) { return (c.precision ? 3 : 0) + (c.group == 32 ? 0 : (c.group == 16 ? 1 : 2)); }
 const prepare_fn PREPARE[6] = {prepare_f64_32, prepare_f64_16, prepare_f64_8, prepare_f32_32, prepare_f32_16, prepare_f32_8};
 const launch_fn LAUNCH[6] = {launch_f64_32, launch_f64_16, launch_f64_8, launch_f32_32, launch_f32_16, launch_f32_8};
@@ -107,7 +107,7 @@ int upload_model(mm_handle* h) {
 StatePtrs to_ptrs(const mm_state* s) {
   StatePtrs st;
   st.qpos = s->qpos; st.qvel = s->qvel; st.ctrl = s->ctrl; st.warm = s->warm; st.tinit = s->tinit; st.eepose = s->eepose;
-  st.fsm_f = s->fsm_f; st.hwm = s->hwm; st.step_count = s->step_count; st.task = s->task; st.fsm_i = s->fsm_i;
+  st.fsm_f = s->fsm_f; st.hwm = s->hwm; st.kin = s->kin; st.step_count = s->step_count; st.task = s->task; st.fsm_i = s->fsm_i;
   st.flags = s->flags; st.diag = s->diag;
   return st;
 }
@@ -169,7 +169,7 @@ int mm_reset(mm_handle* h, const mm_state* st, const uint8_t* mask, const double
   p.mask = mask; p.obj_xy = obj_xy; p.task = task; p.obs = obs; p.n = h->cfg.num_envs;
   p.reward_type = h->cfg.reward_type; p.max_steps = h->cfg.max_episode_steps;
   h->launches++;
-  CK(LAUNCH[inst_index(h->cfg)](true, p, (cudaStream_t)stream));
+  CK(LAUNCH[inst_index(h->cfg)](1, p, (cudaStream_t)stream));
   return 0;
 }
 
@@ -186,7 +186,7 @@ int mm_step(mm_handle* h, const mm_state* st, const float* actions, int action_m
   p.max_steps = h->cfg.max_episode_steps;
   p.cycles = h->d_cycles;
   h->launches++;
-  CK(LAUNCH[inst_index(h->cfg)](false, p, (cudaStream_t)stream));
+  CK(LAUNCH[inst_index(h->cfg)](0, p, (cudaStream_t)stream));
   return 0;
 }
 
@@ -261,6 +261,20 @@ int mm_measure_fma_peak(int device, int fp64, double* tflops) {
   }
   cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(buf);
   *tflops = best;
+  return 0;
+}
+
+int mm_ops(mm_handle* h, const mm_state* st, int ops, const double* target, void* stream) {
+  if (!h || !st) return fail("mm_ops: null argument");
+  if (ops <= 0 || ops > 7) return fail("mm_ops: ops must be a combination of MM_OP_IK, MM_OP_FORWARD, MM_OP_INTEGRATE");
+  if ((ops & MM_OP_INTEGRATE) && !(ops & MM_OP_FORWARD)) return fail("mm_ops: MM_OP_INTEGRATE needs MM_OP_FORWARD");
+  if ((ops & MM_OP_IK) && !target) return fail("mm_ops: MM_OP_IK needs a target array");
+  StepParams p{};
+  p.st = to_ptrs(st);
+  p.model = h->d_model; p.work_reals = h->d_work_reals; p.work_ints = h->d_work_ints; p.tgt_kp = h->d_tgt;
+  p.n = h->cfg.num_envs; p.ops = ops; p.target = target;
+  h->launches++;
+  CK(LAUNCH[inst_index(h->cfg)](2, p, (cudaStream_t)stream));
   return 0;
 }
 

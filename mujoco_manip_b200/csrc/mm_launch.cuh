@@ -35,6 +35,8 @@ struct StepParams {
   float* obs;
   long n;
   int mode, reward_type, max_steps;
+  const double* target;  // [N,3] world EE targets for the IK op, or null
+  int ops;
   long long* cycles;  // [N] or null: SM clock cycles each env's step took (profiling aid)
 };
 
@@ -88,6 +90,18 @@ inline size_t extra_smem() {
   return (size_t)v;
 }
 template <class T, int G>
+__global__ void __launch_bounds__(BlockCfg<T, G>::THREADS, BlockCfg<T, G>::MINB) k_ops(StepParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const ModelDev<T>* md;
+  Scratch<T>* sc;
+  Grp<G> g;
+  long e;
+  if (!setup<T, G>(p, smem, md, sc, g, e)) return;
+  Work<T> w = make_work(reinterpret_cast<T*>(p.work_reals) + e * WORK_REALS, p.work_ints + e * WORK_INTS);
+  env_ops<T, G>(g, *sc, *md, w, p.st, e, p.ops, p.target);
+}
+
+template <class T, int G>
 size_t smem_bytes() { return BlockCfg<T, G>::ENVS * sizeof(Scratch<T>) + extra_smem(); }
 
 template <class T, int G>
@@ -95,16 +109,19 @@ cudaError_t inst_prepare() {
   size_t sm = smem_bytes<T, G>();
   cudaError_t e = cudaFuncSetAttribute(k_step<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_ops<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(k_reset<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
 }
 
 template <class T, int G>
-cudaError_t inst_launch(bool reset, const StepParams& p, cudaStream_t s) {
+cudaError_t inst_launch(int which, const StepParams& p, cudaStream_t s) {  // which: 0 step, 1 reset, 2 ops
   constexpr int BLOCK = BlockCfg<T, G>::THREADS;
   constexpr int GPB = BLOCK / G;
   unsigned grid = (unsigned)((p.n + GPB - 1) / GPB);
   size_t sm = smem_bytes<T, G>();
-  if (reset) k_reset<T, G><<<grid, BLOCK, sm, s>>>(p);
+  if (which == 1) k_reset<T, G><<<grid, BLOCK, sm, s>>>(p);
+  else if (which == 2) k_ops<T, G><<<grid, BLOCK, sm, s>>>(p);
   else k_step<T, G><<<grid, BLOCK, sm, s>>>(p);
   return cudaGetLastError();
 }
@@ -112,14 +129,14 @@ cudaError_t inst_launch(bool reset, const StepParams& p, cudaStream_t s) {
 // entry points defined by the mm_inst_*.cu units
 #define MM_DECL_INST(NAME)                 \
   cudaError_t prepare_##NAME();            \
-  cudaError_t launch_##NAME(bool reset, const StepParams& p, cudaStream_t s);
+  cudaError_t launch_##NAME(int which, const StepParams& p, cudaStream_t s);
 MM_DECL_INST(f64_32) MM_DECL_INST(f64_16) MM_DECL_INST(f64_8)
 MM_DECL_INST(f32_32) MM_DECL_INST(f32_16) MM_DECL_INST(f32_8)
 
 #define MM_DEFINE_INST(NAME, T, G)                                                              \
   namespace mm {                                                                                \
   cudaError_t prepare_##NAME() { return inst_prepare<T, G>(); }                                 \
-  cudaError_t launch_##NAME(bool reset, const StepParams& p, cudaStream_t s) { return inst_launch<T, G>(reset, p, s); } \
+  cudaError_t launch_##NAME(int which, const StepParams& p, cudaStream_t s) { return inst_launch<T, G>(which, p, s); } \
   }
 
 }  // namespace mm

@@ -15,6 +15,7 @@ REWARDS = ("dense", "sparse", "staged")
 
 STATE_FIELDS = [("qpos", 30, np.float64), ("qvel", 27, np.float64), ("ctrl", 8, np.float64), ("warm", 27, np.float64),
                 ("tinit", 12, np.float64), ("eepose", 12, np.float64), ("fsm_f", 6, np.float64), ("hwm", 5, np.float64),
+                ("kin", 18, np.float64),
                 ("step_count", 1, np.int32), ("task", 2, np.int32), ("fsm_i", 5, np.int32), ("flags", 1, np.int32),
                 ("diag", 4, np.int32)]
 
@@ -64,6 +65,10 @@ class EmulEnv:
         self.L.emul_step(self.n, self._sp, a.ctypes.data_as(C.c_void_p), MODES.index(self.mode), REWARDS.index(self.reward),
                          self.max_steps, self._op, self.tgt.ctypes.data_as(C.c_void_p), self.use_float)
         return self.obs.copy(), self.reward_buf.copy(), self.term.astype(bool), self.trunc.astype(bool), self.succ.astype(bool)
+
+    def ops(self, ops, target=None):
+        t = None if target is None else np.ascontiguousarray(target, dtype=np.float64).reshape(self.n, 3)
+        self.L.emul_ops(self.n, self._sp, int(ops), None if t is None else t.ctypes.data_as(C.c_void_p), self.use_float)
 
     def fsm_plan(self, n_steps=16):
         a = np.zeros((self.n, 10), dtype=np.float32)
