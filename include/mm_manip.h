@@ -127,8 +127,15 @@ int mm_sample_placements(mm_handle* h, uint64_t seed, int64_t env_id_offset, con
  * best of 5 timed launches - the measured denominator of the roofline bench.py reports. */
 int mm_measure_fma_peak(int device, int fp64, double* tflops);
 
-/* Profiling aid: when `cycles` ([N] int64, device) is non-NULL every mm_step stores the SM clock cycles each env's
- * step took (per-env latency distribution; the slowest env bounds the launch).  NULL switches it off. */
+/* Load-aware scheduling of mm_step (no reference counterpart; results do not depend on it).  `work` ([N] int32,
+ * device, or NULL) receives each env's busy time of the step (SM cycles / 256); `order` ([N] int32 device permutation,
+ * or NULL = identity) tells which env each execution slot processes.  Passing the envs sorted by the previous step's
+ * `work` (descending) puts envs of similar cost into the same CTA, so the phase barriers of the step kernel wait less. */
+int mm_set_schedule(mm_handle* h, const int32_t* order, int32_t* work);
+
+/* Profiling aid: when `cycles` ([N,9] int64, device) is non-NULL every mm_step stores the SM clock cycles each env's
+ * step took: total, then kinematics+dynamics, broad phase, narrow phase, constraint rows + warm start, (unused),
+ * Newton iterations, IK, integration.  NULL switches it off. */
 int mm_set_cycle_buffer(mm_handle* h, long long* cycles);
 
 /* number of kernels this handle has launched so far */

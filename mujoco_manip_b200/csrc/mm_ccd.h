@@ -1,10 +1,12 @@
 // General convex-convex penetration for geom pairs that involve a collision mesh (convex hull) or a
 // cylinder: GJK overlap test followed by EPA, one contact per pair (MuJoCo `multiccd` off).
-// The iteration rules (start direction, simplex updates, EPA tolerances and caps) are the ones the CPU
-// oracle states in oracle/ccd.h, so that both sides pick the same witness points on flat contacts.
+// The iteration rules (start direction, simplex updates, EPA tolerances, caps and the ORDER in which
+// polytope faces are removed and created) are the ones the CPU oracle states in oracle/ccd.h, so that
+// both sides pick the same witness points on flat contacts.
 //
-// A lane runs GJK for its own pair (registers only).  EPA needs a polytope (<=132 vertices, <=256 faces);
-// it lives in the env's global workspace and pairs that need it are expanded one at a time.
+// The G lanes of an env work on ONE pair at a time: hull support scans, the closest-face search, the
+// visibility test and the creation of new faces are spread over the lanes; the simplex logic is replicated.
+// Reductions break ties like a linear scan (lowest index), so the result does not depend on G.
 #pragma once
 #include "mm_model.h"
 
@@ -12,7 +14,9 @@ namespace mm {
 
 constexpr int EPA_MAXV = 136, EPA_MAXF = 256, EPA_MAXE = 128, EPA_MAXIT = 128;
 constexpr int EPA_REALS = EPA_MAXV * 6 + EPA_MAXF * 4;
-constexpr int EPA_INTS = EPA_MAXF + EPA_MAXE;
+constexpr int EPA_INTS = EPA_MAXF + EPA_MAXE + EPA_MAXV;
+constexpr int EPA_VIS = 1 << 30;
+constexpr int SHAPE_LV = 5;  // ceil(152 / 32): the largest hull has 152 vertices
 
 template <class T>
 struct Shape {
@@ -22,10 +26,13 @@ struct Shape {
   T size[3];      // box half sizes / cylinder (radius, half height)
   const T* verts; // hull vertices in the geom frame (3 * nvert), global memory
   int nvert;
+  // G == 32: this lane's slice of the hull (vertices lane, lane + 32, ...) held in registers for the whole
+  // GJK / EPA run on the pair, so that a support query touches no memory
+  T lv[SHAPE_LV][3];
 };
 
-template <class T>
-MM_HDX void support1(const Shape<T>& s, const T* d, T* out) {
+template <class T, int G>
+MM_HDN void support1(const Grp<G>& g, const Shape<T>& s, const T* d, T* out) {
   const T* R = s.R;
   T l[3] = {R[0] * d[0] + R[3] * d[1] + R[6] * d[2], R[1] * d[0] + R[4] * d[1] + R[7] * d[2],
             R[2] * d[0] + R[5] * d[1] + R[8] * d[2]};
@@ -38,14 +45,33 @@ MM_HDX void support1(const Shape<T>& s, const T* d, T* out) {
     T n = tsqrt(l[0] * l[0] + l[1] * l[1]);
     if (n > (T)1e-14) { p[0] = l[0] / n * s.size[0]; p[1] = l[1] / n * s.size[0]; } else { p[0] = p[1] = 0; }
     p[2] = l[2] >= 0 ? s.size[1] : -s.size[1];
+  } else if (G == 32 && s.nvert <= 32 * SHAPE_LV) {
+    int best = s.nvert;  // lanes without a vertex lose every comparison
+    T bv = (T)-1e30;
+#pragma unroll
+    for (int k = 0; k < SHAPE_LV; k++) {
+      int i = g.lane + 32 * k;
+      T v = s.lv[k][0] * l[0] + s.lv[k][1] * l[1] + s.lv[k][2] * l[2];
+      if (i < s.nvert && v > bv) { bv = v; best = i; }
+    }
+    g.argmax(bv, best);
+    if (best >= s.nvert) best = 0;
+    int kb = best >> 5;
+    T q[3] = {s.lv[0][0], s.lv[0][1], s.lv[0][2]};
+#pragma unroll
+    for (int k = 1; k < SHAPE_LV; k++)
+      if (k == kb) { q[0] = s.lv[k][0]; q[1] = s.lv[k][1]; q[2] = s.lv[k][2]; }
+    p[0] = g.bcast(q[0], best & 31); p[1] = g.bcast(q[1], best & 31); p[2] = g.bcast(q[2], best & 31);
   } else {
-    int best = 0;
+    int best = s.nvert;  // lanes without a vertex lose every comparison
     T bv = (T)-1e30;
     const T* V = s.verts;
-    for (int i = 0; i < s.nvert; i++) {
+    for (int i = g.lane; i < s.nvert; i += G) {
       T v = V[3 * i] * l[0] + V[3 * i + 1] * l[1] + V[3 * i + 2] * l[2];
       if (v > bv) { bv = v; best = i; }
     }
+    g.argmax(bv, best);
+    if (best >= s.nvert) best = 0;
     p[0] = V[3 * best]; p[1] = V[3 * best + 1]; p[2] = V[3 * best + 2];
   }
   out[0] = R[0] * p[0] + R[1] * p[1] + R[2] * p[2] + s.pos[0];
@@ -57,11 +83,11 @@ MM_HDX void support1(const Shape<T>& s, const T* d, T* out) {
 template <class T>
 struct SP { T v[3], a[3]; };
 
-template <class T>
-MM_HDN void support(const Shape<T>& s1, const Shape<T>& s2, const T* d, SP<T>& p) {
+template <class T, int G>
+MM_HDN void support(const Grp<G>& g, const Shape<T>& s1, const Shape<T>& s2, const T* d, SP<T>& p) {
   T nd[3] = {-d[0], -d[1], -d[2]}, b[3];
-  support1(s1, d, p.a);
-  support1(s2, nd, b);
+  support1<T, G>(g, s1, d, p.a);
+  support1<T, G>(g, s2, nd, b);
   for (int k = 0; k < 3; k++) p.v[k] = p.a[k] - b[k];
 }
 
@@ -69,17 +95,17 @@ template <class T> MM_HD void sub3(T* r, const T* a, const T* b) { r[0] = a[0] -
 template <class T> MM_HD void neg3(T* r, const T* a) { r[0] = -a[0]; r[1] = -a[1]; r[2] = -a[2]; }
 template <class T> MM_HD void cpy3(T* r, const T* a) { r[0] = a[0]; r[1] = a[1]; r[2] = a[2]; }
 
-// true if the shapes overlap; sx[0..3] then hold a tetrahedron around the origin
-template <class T>
-MM_HDN bool gjk(const Shape<T>& s1, const Shape<T>& s2, SP<T>* sx) {
+// true if the shapes overlap; sx[0..3] then hold a tetrahedron around the origin (same on every lane)
+template <class T, int G>
+MM_HDN bool gjk(const Grp<G>& g, const Shape<T>& s1, const Shape<T>& s2, SP<T>* sx, unsigned* cnt = nullptr) {
   T dir[3] = {s2.pos[0] - s1.pos[0], s2.pos[1] - s1.pos[1], s2.pos[2] - s1.pos[2]};
   if (dot3(dir, dir) < (T)1e-20) { dir[0] = 1; dir[1] = 0; dir[2] = 0; }
   SP<T> a, b, c, d;
-  support(s1, s2, dir, c);
+  support<T, G>(g, s1, s2, dir, c);
   if (dot3(c.v, dir) < 0) return false;
   neg3(dir, c.v);
   if (dot3(dir, dir) < (T)1e-24) { dir[0] = 1; dir[1] = 0; dir[2] = 0; }
-  support(s1, s2, dir, b);
+  support<T, G>(g, s1, s2, dir, b);
   if (dot3(b.v, dir) < 0) return false;
   T bc[3], nb[3], t[3];
   sub3(bc, c.v, b.v);
@@ -93,8 +119,10 @@ MM_HDN bool gjk(const Shape<T>& s1, const Shape<T>& s2, SP<T>* sx) {
   }
   int n = 2;
   d = c;
+#pragma unroll 1
   for (int it = 0; it < 64; it++) {
-    support(s1, s2, dir, a);
+    if (cnt && g.lane == 0) cnt[1]++;
+    support<T, G>(g, s1, s2, dir, a);
     if (dot3(a.v, dir) < 0) return false;
     T ao[3], ab[3], ac[3];
     neg3(ao, a.v);
@@ -138,17 +166,19 @@ MM_HDN bool gjk(const Shape<T>& s1, const Shape<T>& s2, SP<T>* sx) {
   return false;
 }
 
-// EPA scratch in the env's workspace
+// EPA polytope in the env's workspace (global memory, shared by the lanes of the group)
 template <class T>
 struct EpaMem {
-  T* vert;   // [EPA_MAXV][6]  v(3), a(3)
-  T* face;   // [EPA_MAXF][4]  n(3), d
-  int* fidx; // [EPA_MAXF]     three vertex indices packed 10 bits each
-  int* edge; // [EPA_MAXE]     two vertex indices packed 16 bits each
+  T* vert;    // [EPA_MAXV][6]  v(3), a(3)
+  T* face;    // [EPA_MAXF][4]  n(3), d
+  int* fidx;  // [EPA_MAXF]     three vertex indices packed 10 bits each (+ EPA_VIS while a face is being removed)
+  int* edge;  // [EPA_MAXE]     horizon edges: two vertex indices packed 16 bits each
+  int* canon; // [EPA_MAXV]     lowest vertex index with identical coordinates (edge matching compares coordinates)
 };
 
+// face f from vertices (ia, ib, ic); flip = which two indices swap when the normal points inward
 template <class T>
-MM_HD void epa_mkface(const EpaMem<T>& m, int f, int ia, int ib, int ic) {
+MM_HD void epa_mkface(const EpaMem<T>& m, int f, int ia, int ib, int ic, bool initial) {
   const T *a = m.vert + 6 * ia, *b = m.vert + 6 * ib, *c = m.vert + 6 * ic;
   T e1[3], e2[3], n[3];
   sub3(e1, b, a);
@@ -160,84 +190,116 @@ MM_HD void epa_mkface(const EpaMem<T>& m, int f, int ia, int ib, int ic) {
   T inv = (T)1 / l;
   n[0] *= inv; n[1] *= inv; n[2] *= inv;
   T d = dot3(n, a);
-  if (d < 0) {  // wind outward
+  if (d < 0) {  // wind outward: the oracle swaps p[1], p[2] on the initial tetrahedron and p[0], p[1] on later faces
     F[0] = -n[0]; F[1] = -n[1]; F[2] = -n[2]; F[3] = -d;
-    m.fidx[f] = ib | (ia << 10) | (ic << 20);
+    m.fidx[f] = initial ? (ia | (ic << 10) | (ib << 20)) : (ib | (ia << 10) | (ic << 20));
   } else {
     F[0] = n[0]; F[1] = n[1]; F[2] = n[2]; F[3] = d;
     m.fidx[f] = ia | (ib << 10) | (ic << 20);
   }
 }
 
-// Outputs contact position (mid witness), normal (shape1 -> shape2) and penetration depth.
-template <class T>
-MM_HDN bool epa(const Shape<T>& s1, const Shape<T>& s2, const SP<T>* sx, const EpaMem<T>& m, T* pos, T* nrm, T* depth) {
-  int nv = 4, nf = 0;
-  for (int i = 0; i < 4; i++) for (int k = 0; k < 3; k++) { m.vert[6 * i + k] = sx[i].v[k]; m.vert[6 * i + 3 + k] = sx[i].a[k]; }
-  // initial tetrahedron; the first four faces keep (p0, p2, p1) order when flipped, like the oracle
-  const int tf[4][3] = {{0, 1, 2}, {0, 2, 3}, {0, 3, 1}, {1, 3, 2}};
-  for (int i = 0; i < 4; i++) {
-    const T *a = m.vert + 6 * tf[i][0], *b = m.vert + 6 * tf[i][1], *c = m.vert + 6 * tf[i][2];
-    T e1[3], e2[3], n[3];
-    sub3(e1, b, a);
-    sub3(e2, c, a);
-    cross3(n, e1, e2);
-    T l = tsqrt(dot3(n, n));
-    T* F = m.face + 4 * nf;
-    int i0 = tf[i][0], i1 = tf[i][1], i2 = tf[i][2];
-    if ((double)l < 1e-30) { F[0] = F[1] = F[2] = 0; F[3] = (T)1e30; }
-    else {
-      T inv = (T)1 / l;
-      n[0] *= inv; n[1] *= inv; n[2] *= inv;
-      T d = dot3(n, a);
-      if (d < 0) { F[0] = -n[0]; F[1] = -n[1]; F[2] = -n[2]; F[3] = -d; int t = i1; i1 = i2; i2 = t; }
-      else { F[0] = n[0]; F[1] = n[1]; F[2] = n[2]; F[3] = d; }
-    }
-    m.fidx[nf] = i0 | (i1 << 10) | (i2 << 20);
-    nf++;
+// closest face: minimal d, lowest index among equals
+template <class T, int G>
+MM_HD int epa_best(const Grp<G>& g, const EpaMem<T>& m, int nf) {
+  T bv = (T)3e38;
+  int best = nf;
+  for (int i = g.lane; i < nf; i += G) {
+    T d = m.face[4 * i + 3];
+    if (d < bv) { bv = d; best = i; }
   }
+  g.argmin(bv, best);
+  return best >= nf ? 0 : best;
+}
+
+// Outputs contact position (mid witness), normal (shape1 -> shape2) and penetration depth (same on every lane).
+template <class T, int G>
+MM_HDN bool epa(const Grp<G>& g, const Shape<T>& s1, const Shape<T>& s2, const SP<T>* sx, const EpaMem<T>& m, T* pos,
+                T* nrm, T* depth, unsigned* cnt = nullptr) {
+  int nv = 4, nf = 4;
+  if (g.lane == 0) {
+    for (int i = 0; i < 4; i++) {
+      for (int k = 0; k < 3; k++) { m.vert[6 * i + k] = sx[i].v[k]; m.vert[6 * i + 3 + k] = sx[i].a[k]; }
+      int cn = i;
+      for (int j = i - 1; j >= 0; j--)
+        if (sx[j].v[0] == sx[i].v[0] && sx[j].v[1] == sx[i].v[1] && sx[j].v[2] == sx[i].v[2]) cn = j;
+      m.canon[i] = cn;
+    }
+  }
+  g.sync();
+  if (g.lane == 0) {
+    epa_mkface(m, 0, 0, 1, 2, true);
+    epa_mkface(m, 1, 0, 2, 3, true);
+    epa_mkface(m, 2, 0, 3, 1, true);
+    epa_mkface(m, 3, 1, 3, 2, true);
+  }
+  g.sync();
+#pragma unroll 1
   for (int it = 0; it < EPA_MAXIT; it++) {
-    int best = 0;
-    for (int i = 1; i < nf; i++) if (m.face[4 * i + 3] < m.face[4 * best + 3]) best = i;
+    if (cnt && g.lane == 0) cnt[3]++;
+    int best = epa_best<T, G>(g, m, nf);
     T n[3] = {m.face[4 * best], m.face[4 * best + 1], m.face[4 * best + 2]};
     SP<T> p;
-    support(s1, s2, n, p);
+    support<T, G>(g, s1, s2, n, p);
     T dist = dot3(p.v, n);
     if ((double)(dist - m.face[4 * best + 3]) < 1e-10 || nf >= EPA_MAXF - 8) break;
     int ip = nv++;
-    for (int k = 0; k < 3; k++) { m.vert[6 * ip + k] = p.v[k]; m.vert[6 * ip + 3 + k] = p.a[k]; }
-    int ne = 0;
-    for (int i = 0; i < nf;) {
+    // new vertex, its canonical index, and the visibility flag of every face (spread over the lanes)
+    int cn = ip;
+    for (int j = g.lane; j < ip; j += G) {
+      const T* q = m.vert + 6 * j;
+      if (q[0] == p.v[0] && q[1] == p.v[1] && q[2] == p.v[2] && j < cn) cn = j;
+    }
+    cn = g.imin(cn);
+    if (g.lane == 0) {
+      for (int k = 0; k < 3; k++) { m.vert[6 * ip + k] = p.v[k]; m.vert[6 * ip + 3 + k] = p.a[k]; }
+      m.canon[ip] = cn;
+    }
+    for (int i = g.lane; i < nf; i += G) {
       int fi = m.fidx[i];
-      int id[3] = {fi & 1023, (fi >> 10) & 1023, (fi >> 20) & 1023};
       const T* F = m.face + 4 * i;
       T r[3];
-      sub3(r, p.v, m.vert + 6 * id[0]);
-      if ((double)dot3(F, r) > 1e-14) {
-        for (int e = 0; e < 3; e++) {
-          int ea = id[e], eb = id[(e + 1) % 3];
-          const T *va = m.vert + 6 * ea, *vb = m.vert + 6 * eb;
-          bool found = false;
-          for (int k = 0; k < ne; k++) {
-            const T *ka = m.vert + 6 * (m.edge[k] & 0xFFFF), *kb = m.vert + 6 * (m.edge[k] >> 16);
-            if (ka[0] == vb[0] && ka[1] == vb[1] && ka[2] == vb[2] && kb[0] == va[0] && kb[1] == va[1] && kb[2] == va[2]) {
-              m.edge[k] = m.edge[--ne];
-              found = true;
-              break;
-            }
-          }
-          if (!found && ne < EPA_MAXE) { m.edge[ne] = ea | (eb << 16); ne++; }
-        }
-        --nf;
-        m.fidx[i] = m.fidx[nf];
-        for (int k = 0; k < 4; k++) m.face[4 * i + k] = m.face[4 * nf + k];
-      } else i++;
+      sub3(r, p.v, m.vert + 6 * (fi & 1023));
+      if ((double)dot3(F, r) > 1e-14) m.fidx[i] = fi | EPA_VIS;
     }
+    g.sync();
+    // removal of the visible faces and collection of the horizon, in the oracle's order (integer work, one lane)
+    int ne = 0;
+    if (g.lane == 0) {
+      for (int i = 0; i < nf;) {
+        int fi = m.fidx[i];
+        if (fi & EPA_VIS) {
+          int id[3] = {fi & 1023, (fi >> 10) & 1023, (fi >> 20) & 1023};
+          for (int e = 0; e < 3; e++) {
+            int ea = id[e], eb = id[(e + 1) % 3];
+            int ca = m.canon[ea], cb = m.canon[eb];
+            bool found = false;
+            for (int k = 0; k < ne; k++) {
+              int ed = m.edge[k];
+              if (m.canon[ed & 0xFFFF] == cb && m.canon[ed >> 16] == ca) {  // shared edges appear reversed
+                m.edge[k] = m.edge[--ne];
+                found = true;
+                break;
+              }
+            }
+            if (!found && ne < EPA_MAXE) { m.edge[ne] = ea | (eb << 16); ne++; }
+          }
+          --nf;
+          m.fidx[i] = m.fidx[nf];
+          for (int k = 0; k < 4; k++) m.face[4 * i + k] = m.face[4 * nf + k];
+        } else i++;
+      }
+    }
+    ne = g.bcast(ne, 0);
+    nf = g.bcast(nf, 0);
+    g.sync();
     if (ne == 0) break;
-    for (int k = 0; k < ne && nf < EPA_MAXF; k++) { epa_mkface(m, nf, m.edge[k] & 0xFFFF, m.edge[k] >> 16, ip); nf++; }
+    int add = ne < EPA_MAXF - nf ? ne : EPA_MAXF - nf;
+    for (int k = g.lane; k < add; k += G) { int ed = m.edge[k]; epa_mkface(m, nf + k, ed & 0xFFFF, ed >> 16, ip, false); }
+    nf += add;
+    g.sync();
   }
-  int best = 0;
-  for (int i = 1; i < nf; i++) if (m.face[4 * i + 3] < m.face[4 * best + 3]) best = i;
+  int best = epa_best<T, G>(g, m, nf);
   const T* F = m.face + 4 * best;
   if (!((double)F[3] < 1e29)) return false;
   int fi = m.fidx[best];

@@ -18,6 +18,14 @@
 
 namespace mm {
 
+#ifdef __CUDA_ARCH__
+#define MM_TICK(s, g, slot, t0) do { if ((s).prof) { long long t1_ = clock64(); if ((g).lane == 0) (s).tph[slot] += (unsigned)((t1_ - (t0)) >> 6); (t0) = t1_; } } while (0)
+#define MM_T0(s) ((s).prof ? clock64() : 0)
+#else
+#define MM_TICK(s, g, slot, t0) do { } while (0)
+#define MM_T0(s) 0
+#endif
+
 constexpr int MAXCON = 128;   // contacts per env (oracle max: 44 in scripted episodes, 76 in random-action stress)
 constexpr int MAXROW = MAXCON * 6;
 constexpr int MAXPAIR = 16;   // simultaneously touching body pairs
@@ -36,10 +44,13 @@ struct Scratch {
   T bpos[NDB][3], bR[NDB][9];
   T S[NV][6];
   T Mr[NROB * NROB];
-  T fs[NV], as[NV], qacc[NV], Ma[NV], grad[NV], search[NV], Mv[NV], fc[NV];
+  T fs[NV], as[NV];
+  // ---- contiguous block that is dead during collision (re-used there as clip scratch and EPA polytope) ----
   T H[NV * NV];
   T tmp6[NV][6];
   T pairK[MAXPAIR][21], pairW[MAXPAIR][6], pairF[MAXPAIR][6];
+  T qacc[NV], Ma[NV], grad[NV], search[NV], Mv[NV], fc[NV];
+  // -----------------------------------------------------------------------------------------------------------
   T specD[MAXSPEC], specJaref[MAXSPEC], specJv[MAXSPEC], specAref[MAXSPEC];
   T actf[NU];
   T target[3];
@@ -47,6 +58,11 @@ struct Scratch {
   int specdof[MAXSPEC];  // -1: equality row (e7 - e8); else dof | (negative sign ? 256 : 0)
   int actsat[NU];
   int ncon, npair, nspec, nsurv, overflow, niter, hvalid;
+  unsigned tph[8];  // profiling: cycles/64 spent in fk+dyn | broad | narrow | rows+warmstart | newton | integrate | ik | -
+  int prof;
+  int lone;       // bit c: cube c touches neither the robot nor another cube -> its 6x6 block of H is independent
+  int n_il;       // dofs of the coupled part: robot (9) + the cubes that are not `lone`
+  signed char il[NV], dl[16];
 };
 
 // per-env slice of the global workspace (streamed, coalesced across lanes: index = contact / row)
@@ -73,8 +89,8 @@ MM_HD Work<T> make_work(T* reals, int* ints) {
   w.cD = reals + 10 * MAXCON; w.aref = reals + 11 * MAXCON; w.Jaref = w.aref + MAXROW; w.Jv = w.Jaref + MAXROW;
   w.cmeta = ints;
   w.epa.vert = w.Jv + MAXROW; w.epa.face = w.epa.vert + EPA_MAXV * 6;
-  w.epa.fidx = ints + MAXCON; w.epa.edge = w.epa.fidx + EPA_MAXF;
-  w.surv = w.epa.edge + EPA_MAXE;
+  w.epa.fidx = ints + MAXCON; w.epa.edge = w.epa.fidx + EPA_MAXF; w.epa.canon = w.epa.edge + EPA_MAXE;
+  w.surv = w.epa.canon + EPA_MAXV;
   return w;
 }
 
@@ -121,6 +137,125 @@ MM_HDN void chol_solve(const Grp<G>& g, const T* L, int n, T* x) {
     g.sync();
     if (g.lane == 0) x[k] = xk;
     for (int i = g.lane; i < k; i += G) x[i] -= L[k * n + i] * xk;
+    g.sync();
+  }
+}
+
+// ---- structure-aware factorisation of H = M + J^T D J --------------------------------------------
+// H couples the robot block (9 dofs) with a cube block (6 dofs) only while a robot geom touches that
+// cube, and two cube blocks only while the cubes touch.  A `lone` cube is factored / solved by ONE lane
+// in registers (6x6); the coupled part (robot + non-lone cubes, index list s.il) cooperatively.  Entries
+// outside the coupling pattern stay exactly zero and are skipped.
+template <class T>
+MM_HD void chol6_local(T* A) {  // A -> H[b][b], row stride NV; lower triangle in place
+  T a[21];
+#pragma unroll
+  for (int i = 0; i < 6; i++)
+#pragma unroll
+    for (int j = 0; j <= i; j++) a[i * (i + 1) / 2 + j] = A[i * NV + j];
+#pragma unroll
+  for (int j = 0; j < 6; j++) {
+    T d = a[j * (j + 1) / 2 + j];
+    if (d < (T)MINVAL_D) d = (T)MINVAL_D;
+    T l = tsqrt(d), inv = (T)1 / l;
+    a[j * (j + 1) / 2 + j] = l;
+#pragma unroll
+    for (int i = j + 1; i < 6; i++) a[i * (i + 1) / 2 + j] *= inv;
+#pragma unroll
+    for (int i = j + 1; i < 6; i++)
+#pragma unroll
+      for (int k = j + 1; k <= i; k++) a[i * (i + 1) / 2 + k] -= a[i * (i + 1) / 2 + j] * a[k * (k + 1) / 2 + j];
+  }
+#pragma unroll
+  for (int i = 0; i < 6; i++)
+#pragma unroll
+    for (int j = 0; j <= i; j++) A[i * NV + j] = a[i * (i + 1) / 2 + j];
+}
+
+template <class T>
+MM_HD void solve6_local(const T* L, T* x) {  // L -> H[b][b] (factor), x -> vector + b
+  T v[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) v[i] = x[i];
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+#pragma unroll
+    for (int k = 0; k < i; k++) v[i] -= L[i * NV + k] * v[k];
+    v[i] /= L[i * NV + i];
+  }
+#pragma unroll
+  for (int i = 5; i >= 0; i--) {
+#pragma unroll
+    for (int k = i + 1; k < 6; k++) v[i] -= L[k * NV + i] * v[k];
+    v[i] /= L[i * NV + i];
+  }
+#pragma unroll
+  for (int i = 0; i < 6; i++) x[i] = v[i];
+}
+
+// cooperative Cholesky of the rows / columns listed in il[0..n) of the NV x NV matrix A (zero entries skipped)
+template <class T, int G>
+MM_HDN void chol_factor_list(const Grp<G>& g, T* A, const signed char* il, int n) {
+  for (int jj = 0; jj < n; jj++) {
+    int j = il[jj];
+    T d = A[j * NV + j];
+    if (d < (T)MINVAL_D) d = (T)MINVAL_D;
+    T l = tsqrt(d), inv = (T)1 / l;
+    g.sync();
+    for (int ii = jj + 1 + g.lane; ii < n; ii += G) A[il[ii] * NV + j] *= inv;
+    if (g.lane == 0) A[j * NV + j] = l;
+    g.sync();
+    for (int ii = jj + 1 + g.lane; ii < n; ii += G) {
+      int i = il[ii];
+      T lij = A[i * NV + j];
+      if (lij == 0) continue;
+      for (int kk = jj + 1; kk <= ii; kk++) { int k = il[kk]; A[i * NV + k] -= lij * A[k * NV + j]; }
+    }
+    g.sync();
+  }
+}
+
+// H x = b for the structured factor: lone cubes on lanes 0..2, the coupled part sequentially on lane 3
+// when it is just the robot block, cooperatively otherwise
+template <class T, int G>
+MM_HDN void solve_H(const Grp<G>& g, const Scratch<T>& s, T* x) {
+  const T* L = s.H;
+  int n = s.n_il;
+  if (G >= 4 || G == 1) {
+    for (int c = (G == 1 ? 0 : g.lane); c < 3; c += (G == 1 ? 1 : G))
+      if ((s.lone >> c) & 1) solve6_local(L + (9 + 6 * c) * (NV + 1), x + 9 + 6 * c);
+  }
+  if (n == NROB) {
+    if (g.lane == (G >= 4 ? 3 : 0)) {
+      for (int i = 0; i < NROB; i++) {
+        T v = x[i];
+        for (int k = 0; k < i; k++) v -= L[i * NV + k] * x[k];
+        x[i] = v / L[i * NV + i];
+      }
+      for (int i = NROB - 1; i >= 0; i--) {
+        T v = x[i];
+        for (int k = i + 1; k < NROB; k++) v -= L[k * NV + i] * x[k];
+        x[i] = v / L[i * NV + i];
+      }
+    }
+    g.sync();
+    return;
+  }
+  const signed char* il = s.il;
+  for (int kk = 0; kk < n; kk++) {
+    int k = il[kk];
+    T xk = x[k] / L[k * NV + k];
+    g.sync();
+    if (g.lane == 0) x[k] = xk;
+    for (int ii = kk + 1 + g.lane; ii < n; ii += G) { int i = il[ii]; x[i] -= L[i * NV + k] * xk; }
+    g.sync();
+  }
+  for (int kk = n - 1; kk >= 0; kk--) {
+    int k = il[kk];
+    T xk = x[k] / L[k * NV + k];
+    g.sync();
+    if (g.lane == 0) x[k] = xk;
+    for (int ii = g.lane; ii < kk; ii += G) { int i = il[ii]; x[i] -= L[k * NV + i] * xk; }
     g.sync();
   }
 }
@@ -385,23 +520,36 @@ MM_HD void geom_bcenter(const Scratch<T>& s, const GeomDev<T>& gm, int gi, T* c)
   for (int k = 0; k < 3; k++) c[k] = s.bpos[body][k] + v[k];
 }
 
-// returns number of contact points; normal nrm (A -> B), pts[k] position, dist[k] (negative)
+// Per-lane scratch of the box narrow phase (shared memory, NARROW_SCR reals per lane, NARROW_LANES lanes
+// of a group work at a time): [0,36) axes A, B and their products C, |C|; [36,60) clip polygon;
+// [60,84) clip output, finally the contact points; [27,35) finally the contact distances.
+constexpr int NARROW_SCR = 84, NARROW_LANES = 8, SCR_PTS = 60, SCR_DIST = 27;
+
+// returns number of contact points; normal nrm (A -> B); points / distances (negative) in the scratch
 template <class T>
-MM_HDN int box_box(const BoxRef<T>& A_, const BoxRef<T>& B_, T* nrm, T pts[8][3], T* dist) {
+MM_HDL int box_box(const BoxRef<T>& A_, const BoxRef<T>& B_, T* nrm, T* scr) {
   const T *pa = A_.c, *Ra = A_.R, *sa = A_.s, *pb = B_.c, *Rb = B_.R, *sb = B_.s;
-  T A[3][3], B[3][3];
+  T (*A)[3] = reinterpret_cast<T (*)[3]>(scr);
+  T (*B)[3] = reinterpret_cast<T (*)[3]>(scr + 9);
+  T (*C)[3] = reinterpret_cast<T (*)[3]>(scr + 18);
+  T (*Q)[3] = reinterpret_cast<T (*)[3]>(scr + 27);
+  T (*poly)[3] = reinterpret_cast<T (*)[3]>(scr + 36);
+  T (*outp)[3] = reinterpret_cast<T (*)[3]>(scr + 60);
+  T (*pts)[3] = outp;
+  T* dist = scr + SCR_DIST;
   for (int i = 0; i < 3; i++) for (int k = 0; k < 3; k++) { A[i][k] = Ra[3 * k + i]; B[i][k] = Rb[3 * k + i]; }
   T dp[3] = {pb[0] - pa[0], pb[1] - pa[1], pb[2] - pa[2]};
-  T C[3][3], Q[3][3];
   for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { C[i][j] = dot3(A[i], B[j]); Q[i][j] = tabs(C[i][j]); }
   T best = (T)1e30, bn[3] = {0, 0, 0};
   int code = -1;
+#pragma unroll 1
   for (int i = 0; i < 3; i++) {
     T t = dot3(dp, A[i]);
     T pen = sa[i] + sb[0] * Q[i][0] + sb[1] * Q[i][1] + sb[2] * Q[i][2] - tabs(t);
     if (pen < 0) return 0;
     if (pen < best) { best = pen; code = i; T sg = t < 0 ? (T)-1 : (T)1; for (int k = 0; k < 3; k++) bn[k] = sg * A[i][k]; }
   }
+#pragma unroll 1
   for (int j = 0; j < 3; j++) {
     T t = dot3(dp, B[j]);
     T pen = sb[j] + sa[0] * Q[0][j] + sa[1] * Q[1][j] + sa[2] * Q[2][j] - tabs(t);
@@ -411,7 +559,9 @@ MM_HDN int box_box(const BoxRef<T>& A_, const BoxRef<T>& B_, T* nrm, T pts[8][3]
   }
   T ebest = (T)1e30, en[3] = {0, 0, 0};
   int ecode = -1;
+#pragma unroll 1
   for (int i = 0; i < 3; i++)
+#pragma unroll 1
     for (int j = 0; j < 3; j++) {
       T L[3];
       cross3(L, A[i], B[j]);
@@ -428,6 +578,7 @@ MM_HDN int box_box(const BoxRef<T>& A_, const BoxRef<T>& B_, T* nrm, T pts[8][3]
   if (ecode >= 0 && ebest * (T)1.05 < best) {
     int i = ecode / 3, j = ecode % 3;
     T ea[3] = {pa[0], pa[1], pa[2]}, eb[3] = {pb[0], pb[1], pb[2]};
+#pragma unroll 1
     for (int a = 0; a < 3; a++) {
       if (a != i) { T sg = dot3(en, A[a]) > 0 ? (T)1 : (T)-1; for (int k = 0; k < 3; k++) ea[k] += sg * sa[a] * A[a][k]; }
       if (a != j) { T sg = dot3(en, B[a]) > 0 ? (T)-1 : (T)1; for (int k = 0; k < 3; k++) eb[k] += sg * sb[a] * B[a][k]; }
@@ -455,17 +606,20 @@ MM_HDN int box_box(const BoxRef<T>& A_, const BoxRef<T>& B_, T* nrm, T pts[8][3]
   for (int a = 0; a < 3; a++) { T v = tabs(dot3(nref, Ri[a])); if (v > mx) { mx = v; iax = a; } }
   T isg = dot3(nref, Ri[iax]) > 0 ? (T)-1 : (T)1;
   int u = (iax + 1) % 3, v = (iax + 2) % 3;
-  T poly[16][3], outp[16][3];
   int np = 4;
-  const int su[4] = {1, -1, -1, 1}, sv[4] = {1, 1, -1, -1};
-  for (int q = 0; q < 4; q++)
+#pragma unroll 1
+  for (int q = 0; q < 4; q++) {
+    T su = (q == 0 || q == 3) ? (T)1 : (T)-1, sv = q < 2 ? (T)1 : (T)-1;
     for (int k = 0; k < 3; k++)
-      poly[q][k] = pi[k] + isg * si[iax] * Ri[iax][k] + (T)su[q] * si[u] * Ri[u][k] + (T)sv[q] * si[v] * Ri[v][k];
+      poly[q][k] = pi[k] + isg * si[iax] * Ri[iax][k] + su * si[u] * Ri[u][k] + sv * si[v] * Ri[v][k];
+  }
   int t1 = (ax + 1) % 3, t2 = (ax + 2) % 3;
+#pragma unroll 1
   for (int side = 0; side < 4 && np > 0; side++) {
     int ta = side < 2 ? t1 : t2;
     T sg = (side & 1) ? (T)-1 : (T)1, lim = sr[ta];
     int no = 0;
+#pragma unroll 1
     for (int q = 0; q < np; q++) {
       const T* P = poly[q];
       const T* Qn = poly[(q + 1) % np];
@@ -473,8 +627,8 @@ MM_HDN int box_box(const BoxRef<T>& A_, const BoxRef<T>& B_, T* nrm, T pts[8][3]
       T dP = sg * dot3(rp, Rr[ta]) - lim, dQ = sg * dot3(rq, Rr[ta]) - lim;
       // 1 nm band: vertices on a side plane (exactly aligned pads) are inside, no sliver crossings
       const T ce = (T)1e-9;
-      if (dP <= ce) { for (int k = 0; k < 3; k++) outp[no][k] = P[k]; no++; }
-      if ((dP < -ce && dQ > ce) || (dP > ce && dQ < -ce)) {
+      if (dP <= ce && no < 8) { for (int k = 0; k < 3; k++) outp[no][k] = P[k]; no++; }
+      if (((dP < -ce && dQ > ce) || (dP > ce && dQ < -ce)) && no < 8) {
         T tt = dP / (dP - dQ);
         for (int k = 0; k < 3; k++) outp[no][k] = P[k] + tt * (Qn[k] - P[k]);
         no++;
@@ -485,6 +639,7 @@ MM_HDN int box_box(const BoxRef<T>& A_, const BoxRef<T>& B_, T* nrm, T pts[8][3]
   }
   T sgn = dot3(nref, Rr[ax]) > 0 ? (T)1 : (T)-1;
   int cnt = 0;
+#pragma unroll 1
   for (int q = 0; q < np && cnt < 8; q++) {
     T r[3] = {poly[q][0] - pr[0], poly[q][1] - pr[1], poly[q][2] - pr[2]};
     T depth = sr[ax] - sgn * dot3(r, Rr[ax]);
@@ -498,17 +653,18 @@ MM_HDN int box_box(const BoxRef<T>& A_, const BoxRef<T>& B_, T* nrm, T pts[8][3]
 
 // floor plane z = 0 (normal +z) vs box: penetrating corners, at most 4
 template <class T>
-MM_HDN int plane_box(const BoxRef<T>& B_, T* nrm, T pts[8][3], T* dist) {
+MM_HDL int plane_box(const BoxRef<T>& B_, T* nrm, T* scr) {
   nrm[0] = 0; nrm[1] = 0; nrm[2] = 1;
   int cnt = 0;
+#pragma unroll 1
   for (int i = 0; i < 8 && cnt < 4; i++) {
     T loc[3] = {(i & 1) ? B_.s[0] : -B_.s[0], (i & 2) ? B_.s[1] : -B_.s[1], (i & 4) ? B_.s[2] : -B_.s[2]}, c[3];
     rot(c, B_.R, loc);
     for (int k = 0; k < 3; k++) c[k] += B_.c[k];
     T d = c[2];
     if (d < 0) {
-      pts[cnt][0] = c[0]; pts[cnt][1] = c[1]; pts[cnt][2] = c[2] - d * (T)0.5;
-      dist[cnt] = d;
+      scr[SCR_PTS + 3 * cnt] = c[0]; scr[SCR_PTS + 3 * cnt + 1] = c[1]; scr[SCR_PTS + 3 * cnt + 2] = c[2] - d * (T)0.5;
+      scr[SCR_DIST + cnt] = d;
       cnt++;
     }
   }
@@ -528,7 +684,7 @@ MM_HD void make_tangent(const T* n, T* t1) {  // mju_makeFrame rule (A3)
 // Separating-axis test of the oriented bounding boxes (local AABB of the hull / box / cylinder, carried
 // by the body frame).  Returns false only when the boxes, inflated by 1e-6, are disjoint.
 template <class T>
-MM_HDN bool obb_overlap(const Scratch<T>& s, const GeomDev<T>& gm, int a, int b, const T* ident) {
+MM_HDL bool obb_overlap(const Scratch<T>& s, const GeomDev<T>& gm, int a, int b, const T* ident) {
   T ca[3], cb[3];
   geom_bcenter(s, gm, a, ca);
   geom_bcenter(s, gm, b, cb);
@@ -566,11 +722,12 @@ MM_HDN bool obb_overlap(const Scratch<T>& s, const GeomDev<T>& gm, int a, int b,
 
 // plane z = 0 vs convex hull: deepest vertex, one contact
 template <class T>
-MM_HDN int plane_hull(const T* gpos, const T* R, const T* V, int nvert, T* nrm, T pts[8][3], T* dist) {
+MM_HDL int plane_hull(const T* gpos, const T* R, const T* V, int nvert, T* nrm, T* scr) {
   nrm[0] = 0; nrm[1] = 0; nrm[2] = 1;
   T nl[3] = {R[6], R[7], R[8]};  // R^T n
   int best = 0;
   T bv = (T)1e30;
+#pragma unroll 2
   for (int i = 0; i < nvert; i++) {
     T v = V[3 * i] * nl[0] + V[3 * i + 1] * nl[1] + V[3 * i + 2] * nl[2];
     if (v < bv) { bv = v; best = i; }
@@ -580,20 +737,28 @@ MM_HDN int plane_hull(const T* gpos, const T* R, const T* V, int nvert, T* nrm, 
   for (int k = 0; k < 3; k++) c[k] += gpos[k];
   T d = c[2];
   if (d < 0) {
-    pts[0][0] = c[0]; pts[0][1] = c[1]; pts[0][2] = c[2] - d * (T)0.5;
-    dist[0] = d;
+    scr[SCR_PTS] = c[0]; scr[SCR_PTS + 1] = c[1]; scr[SCR_PTS + 2] = c[2] - d * (T)0.5;
+    scr[SCR_DIST] = d;
     return 1;
   }
   return 0;
 }
 
-template <class T>
-MM_HD void fill_shape(const Scratch<T>& s, const GeomDev<T>& gm, int gi, const T* ident, Shape<T>& sh) {
+template <class T, int G>
+MM_HD void fill_shape(const Grp<G>& g, const Scratch<T>& s, const GeomDev<T>& gm, int gi, const T* ident, Shape<T>& sh) {
   sh.type = gm.type[gi];
   sh.R = geom_pose(s, gm, gi, ident, sh.pos);
   sh.size[0] = gm.size[gi][0]; sh.size[1] = gm.size[gi][1]; sh.size[2] = gm.size[gi][2];
   sh.verts = &gm.hull[gm.vadr[gi]][0];
   sh.nvert = gm.vnum[gi];
+  if (G == 32 && sh.type == GT_HULL) {
+#pragma unroll
+    for (int k = 0; k < SHAPE_LV; k++) {
+      int i = g.lane + 32 * k;
+      if (i >= sh.nvert) i = 0;
+      sh.lv[k][0] = sh.verts[3 * i]; sh.lv[k][1] = sh.verts[3 * i + 1]; sh.lv[k][2] = sh.verts[3 * i + 2];
+    }
+  }
 }
 
 // impedance / regulariser of a contact (A4): default solref (0.02, 1), solimp (0.9, 0.95, 0.001, 0.5, 2)
@@ -610,6 +775,16 @@ MM_HD void store_contact(Work<T>& w, int c, const T* pos, const T* nrm, const T*
   w.cmeta[c] = meta;
 }
 
+// meta word of a contact between geoms a and b (candidate ci)
+template <class T>
+MM_HD int contact_meta(const GeomDev<T>& gm, int a, int b, int ci) {
+  int ca = gm.cls[a], cb = gm.cls[b];
+  int cube = gm.cube[a] || gm.cube[b];
+  // robot geom against an obstacle geom (table / bins; the floor does not count, gym_env.py:137-152,341-350)
+  int robobs = (ca >= 1 && ca <= 9 && gm.obst[b]) || (cb >= 1 && cb <= 9 && gm.obst[a]);
+  return (ca << 4) | (cb << 8) | (cube << 12) | (robobs << 19) | (ci << 20);
+}
+
 template <class T, int G>
 MM_HDX void collide(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>& w) {
   MM_IN_SHARED(&s);
@@ -618,6 +793,7 @@ MM_HDX void collide(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<
   MM_IN_GLOBAL(w.Jaref); MM_IN_GLOBAL(w.Jv); MM_IN_GLOBAL(w.cmeta); MM_IN_GLOBAL(w.surv);
   const T ident[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
   const GeomDev<T>& gm = *md.geom;
+  long long tb0 = MM_T0(s);
   // broad phase: ordered compaction of the surviving candidates
   int nsurv = 0;
   for (int base = 0; base < NPAIRC; base += G) {
@@ -654,14 +830,19 @@ MM_HDX void collide(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<
   }
   if (nsurv > MAXSURV) { nsurv = MAXSURV; if (g.lane == 0) s.overflow |= 1; }
   g.sync();
-  // narrow phase, ordered compaction of the contacts
+  MM_TICK(s, g, 1, tb0);
+  long long tc0 = MM_T0(s);
+  g.phase(3);
+  // narrow phase 1: box / plane pairs, one pair per lane, NARROW_LANES lanes at a time (their clip polygons
+  // live in the shared H region, which is free during collision); ordered compaction of the contacts
+  constexpr int KB = G < NARROW_LANES ? G : NARROW_LANES;
   int ncon = 0;
-  for (int base = 0; base < nsurv; base += G) {
+  for (int base = 0; base < nsurv; base += KB) {
     int si = base + g.lane;
-    int cnt = 0, a = 0, b = 0, ci_ = 0, pend = 0;
-    T nrm[3], pts[8][3], dist[8];
-    SP<T> sx[4];
-    if (si < nsurv) {
+    int cnt = 0, a = 0, b = 0, ci_ = 0;
+    T nrm[3] = {0, 0, 1};
+    T* scr = s.H + (g.lane < KB ? g.lane : 0) * NARROW_SCR;
+    if (g.lane < KB && si < nsurv) {
       int ci = w.surv[si];
       ci_ = ci;
       a = gm.pair[ci][0]; b = gm.pair[ci][1];
@@ -670,70 +851,77 @@ MM_HDX void collide(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<
         T pb[3], pa[3];
         BoxRef<T> Bb;
         Bb.R = geom_pose(s, gm, b, ident, pb); Bb.c = pb; Bb.s = gm.size[b];
-        if (ta == GT_PLANE) cnt = plane_box(Bb, nrm, pts, dist);
+        if (ta == GT_PLANE) cnt = plane_box(Bb, nrm, scr);
         else {
           BoxRef<T> Ba;
           Ba.R = geom_pose(s, gm, a, ident, pa); Ba.c = pa; Ba.s = gm.size[a];
-          cnt = box_box(Ba, Bb, nrm, pts, dist);
+          cnt = box_box(Ba, Bb, nrm, scr);
         }
-      } else if (ta == GT_PLANE) {
+      } else if (ta == GT_PLANE && tb == GT_HULL) {
         T pb[3];
         const T* Rb = geom_pose(s, gm, b, ident, pb);
-        cnt = plane_hull(pb, Rb, &gm.hull[gm.vadr[b]][0], gm.vnum[b], nrm, pts, dist);
-      } else {
-        Shape<T> s1, s2;
-        fill_shape(s, gm, a, ident, s1);
-        fill_shape(s, gm, b, ident, s2);
-        if (gjk(s1, s2, sx)) { cnt = 1; pend = 1; }
+        cnt = plane_hull(pb, Rb, &gm.hull[gm.vadr[b]][0], gm.vnum[b], nrm, scr);
       }
     }
     int tot;
     int off = g.scan_excl(cnt, &tot);
-    int ca = gm.cls[a], cb_ = gm.cls[b];
-    int cube = gm.cube[a] || gm.cube[b];
-    T tran = gm.invw[a] + gm.invw[b];
-    T mu = cube ? (T)2 : (T)1;
-    // robot geom against an obstacle geom (table / bins; the floor does not count, gym_env.py:137-152,341-350)
-    int robobs = (ca >= 1 && ca <= 9 && gm.obst[b]) || (cb_ >= 1 && cb_ <= 9 && gm.obst[a]);
-    int meta = (ca << 4) | (cb_ << 8) | (cube << 12) | (robobs << 19) | (ci_ << 20);
-    if (cnt > 0 && !pend) {
+    if (cnt > 0) {
       T t1[3];
       make_tangent(nrm, t1);
+      int cube = gm.cube[a] || gm.cube[b];
+      T tran = gm.invw[a] + gm.invw[b];
+      int meta = contact_meta(gm, a, b, ci_);
       for (int k = 0; k < cnt; k++) {
         int c = ncon + off + k;
         if (c >= MAXCON) break;
-        store_contact(w, c, pts[k], nrm, t1, dist[k], tran, mu, meta);
+        store_contact(w, c, scr + SCR_PTS + 3 * k, nrm, t1, scr[SCR_DIST + k], tran, cube ? (T)2 : (T)1, meta);
       }
-    }
-    // penetrating convex pairs: EPA one pair at a time (the polytope lives in the env's workspace)
-    unsigned pm = g.ballot(pend);
-    while (pm) {
-      int src = 0;
-      while (!((pm >> src) & 1u)) src++;
-      pm &= pm - 1;
-      if (g.lane == src) {
-        Shape<T> s1, s2;
-        fill_shape(s, gm, a, ident, s1);
-        fill_shape(s, gm, b, ident, s2);
-        T pos[3], depth, t1[3] = {0, 1, 0};
-        int c = ncon + off;
-        bool ok = epa(s1, s2, sx, w.epa, pos, nrm, &depth);
-        if (c < MAXCON) {
-          if (ok) { make_tangent(nrm, t1); store_contact(w, c, pos, nrm, t1, -depth, tran, mu, meta); }
-          else {  // degenerate polytope: keep the slot, make it inert
-            const T up[3] = {0, 0, 1};
-            pos[0] = pos[1] = pos[2] = 0;
-            store_contact(w, c, pos, up, t1, (T)0, tran, mu, meta);
-            w.cD[c] = 0;
-          }
-        }
-      }
-      g.sync();
     }
     ncon += tot;
+    g.sync();
+  }
+  g.phase(3);
+  long long tx0 = MM_T0(s);
+  // EPA polytope: faces, their index words, horizon edges and canonical vertex ids live in SHARED memory (the H /
+  // tmp6 / pair-block region, free during collision: the sequential face-removal loop must not wait on global
+  // memory); vertices stay in the env's global workspace.
+  static_assert(sizeof(s.H) + sizeof(s.tmp6) + sizeof(s.pairK) + sizeof(s.pairW) + sizeof(s.pairF) + 6 * sizeof(s.qacc) >=
+                    EPA_MAXF * 4 * sizeof(T) + EPA_INTS * sizeof(int), "EPA workspace does not fit the shared scratch");
+  EpaMem<T> em;
+  em.vert = w.epa.vert;
+  em.face = s.H;
+  em.fidx = reinterpret_cast<int*>(s.H + EPA_MAXF * 4);
+  em.edge = em.fidx + EPA_MAXF;
+  em.canon = em.edge + EPA_MAXE;
+  // narrow phase 2: general convex pairs (mesh hulls, cylinders): GJK + EPA by the whole group, one pair at a
+  // time (support scans, face searches and face creation are spread over the lanes); contacts are appended
+  for (int si = 0; si < nsurv; si++) {
+    int ci = w.surv[si];
+    int a = gm.pair[ci][0], b = gm.pair[ci][1];
+    int ta = gm.type[a], tb = gm.type[b];
+    if (ta == GT_PLANE || (ta == GT_BOX && tb == GT_BOX)) continue;
+    Shape<T> s1, s2;
+    fill_shape<T, G>(g, s, gm, a, ident, s1);
+    fill_shape<T, G>(g, s, gm, b, ident, s2);
+    SP<T> sx[4];
+    T pos[3] = {0, 0, 0}, pn[3] = {0, 0, 1}, depth = 0;
+    unsigned* pc = s.prof ? s.tph + 4 : nullptr;  // profiling counters: gjk calls / iterations, epa calls / iterations
+    if (pc && g.lane == 0) pc[0]++;
+    if (!gjk<T, G>(g, s1, s2, sx, pc)) continue;
+    if (pc && g.lane == 0) pc[2]++;
+    if (!epa<T, G>(g, s1, s2, sx, em, pos, pn, &depth, pc)) continue;
+    if (g.lane == 0 && ncon < MAXCON) {
+      T t1[3];
+      make_tangent(pn, t1);
+      int cube = gm.cube[a] || gm.cube[b];
+      store_contact(w, ncon, pos, pn, t1, -depth, gm.invw[a] + gm.invw[b], cube ? (T)2 : (T)1, contact_meta(gm, a, b, ci));
+    }
+    ncon++;
+    g.sync();
   }
   if (ncon > MAXCON) { ncon = MAXCON; if (g.lane == 0) s.overflow |= 2; }
   g.sync();
+  MM_TICK(s, g, 3, tx0);
   // pair slots: contacts are ordered by (classA, classB); a new slot starts where the key changes
   int npair = 0;
   for (int base = 0; base < ncon; base += G) {
@@ -758,6 +946,7 @@ MM_HDX void collide(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<
   if (npair > MAXPAIR) { npair = MAXPAIR; if (g.lane == 0) s.overflow |= 4; }
   if (g.lane == 0) { s.ncon = ncon; s.npair = npair; s.nsurv = nsurv; }
   g.sync();
+  MM_TICK(s, g, 2, tc0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -949,6 +1138,7 @@ MM_HDN T update_constraint(const Grp<G>& g, Scratch<T>& s, Work<T>& w, bool buil
     }
     // segmented inclusive scan over lanes (keys are non-decreasing); segment tails commit
     if (G > 1) {
+#pragma unroll 1
       for (int o = 1; o < G; o <<= 1) {
         int ks = g.shfl_up(slot, o);
         bool take = g.lane >= o && ks == slot;
@@ -992,22 +1182,55 @@ MM_HDN T update_constraint(const Grp<G>& g, Scratch<T>& s, Work<T>& w, bool buil
   return cost;
 }
 
+// (row, column) of the e-th entry of a packed lower triangle, row-major, up to 27 rows
+template <class T>
+MM_HD void tri_rc(int e, int* r, int* c) {
+  int i = (int)((sqrtf((float)(8 * e + 1)) - 1.0f) * 0.5f);
+  while ((i + 1) * (i + 2) / 2 <= e) i++;
+  while (i * (i + 1) / 2 > e) i--;
+  *r = i; *c = e - i * (i + 1) / 2;
+}
+
+// which cube blocks are independent this forward pass (from the touching body pairs)
+template <class T, int G>
+MM_HDN void analyse_coupling(const Grp<G>& g, Scratch<T>& s) {
+  int busy = 0;  // cubes that touch the robot or another cube
+  for (int p = 0; p < s.npair; p++) {
+    int key = s.pairkey[p], ca = key & 15, cb = (key >> 4) & 15;
+    bool ra = ca >= 1 && ca <= 9, rb = cb >= 1 && cb <= 9;
+    int qa = ca >= CLS_CUBE0 ? ca - CLS_CUBE0 : -1, qb = cb >= CLS_CUBE0 ? cb - CLS_CUBE0 : -1;
+    if (ra && qb >= 0) busy |= 1 << qb;
+    if (rb && qa >= 0) busy |= 1 << qa;
+    if (qa >= 0 && qb >= 0) busy |= (1 << qa) | (1 << qb);
+  }
+  if (g.lane == 0) {
+    int n = 0;
+    for (int i = 0; i < NROB; i++) s.il[n++] = (signed char)i;
+    for (int c = 0; c < 3; c++)
+      if ((busy >> c) & 1) for (int k = 0; k < 6; k++) s.il[n++] = (signed char)(9 + 6 * c + k);
+    s.n_il = n;
+    s.lone = (~busy) & 7;
+  }
+  g.sync();
+}
+
 // H = M + J^T D J over the active rows, assembled from the per-pair blocks; then factor in place
 template <class T, int G>
 MM_HDN void build_factor_H(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md) {
-  for (int e = g.lane; e < NV * NV; e += G) {
-    int i = e / NV, j = e % NV;
+  for (int e = g.lane; e < NV * (NV + 1) / 2; e += G) {
+    int i, j;
+    tri_rc<T>(e, &i, &j);
     T v = 0;
-    if (i < NROB && j < NROB) v = s.Mr[i * NROB + j];
+    if (i < NROB) v = s.Mr[i * NROB + j];
     else if (i == j) v = ((i - 9) % 6) < 3 ? md.cube_mass : md.cube_inertia;
-    s.H[e] = v;
+    s.H[i * NV + j] = v;
   }
   g.sync();
   if (g.lane == 0) {
     for (int k = 0; k < s.nspec; k++) {
       int d = s.specdof[k];
       T D = s.specD[k];
-      if (d < 0) { s.H[7 * NV + 7] += D; s.H[8 * NV + 8] += D; s.H[8 * NV + 7] -= D; s.H[7 * NV + 8] -= D; }
+      if (d < 0) { s.H[7 * NV + 7] += D; s.H[8 * NV + 8] += D; s.H[8 * NV + 7] -= D; }
       else if (s.specJaref[k] < 0) s.H[(d & 255) * (NV + 1)] += D;
     }
   }
@@ -1017,28 +1240,35 @@ MM_HDN void build_factor_H(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md
     int mm_ = mA ^ mB;  // dofs shared by both bodies cancel (sigma = 0)
     const T* K = s.pairK[p];
     g.sync();
+    // dofs of this pair in ascending order (rank = number of lower set bits), and u_k = sigma K S
     for (int j = g.lane; j < NV; j += G) {
       if (!((mm_ >> j) & 1)) continue;
+      int k = tpopc(mm_ & ((1 << j) - 1));
+      s.dl[k] = (signed char)j;
       const T* S = s.S[j];
       T sg = ((mB >> j) & 1) ? (T)1 : (T)-1;
       // symmetric packed K (lower, row-major): K[a][b] = K[a*(a+1)/2 + b], b <= a
       for (int a = 0; a < 6; a++) {
         T acc = 0;
         for (int b = 0; b < 6; b++) acc += (a >= b ? K[a * (a + 1) / 2 + b] : K[b * (b + 1) / 2 + a]) * S[b];
-        s.tmp6[j][a] = sg * acc;
+        s.tmp6[k][a] = sg * acc;
       }
     }
     g.sync();
-    for (int e = g.lane; e < NV * NV; e += G) {
-      int i = e / NV, j = e % NV;
-      if (j > i) continue;
-      if (!((mm_ >> i) & 1) || !((mm_ >> j) & 1)) continue;
+    int nd = tpopc(mm_);
+    for (int e = g.lane; e < nd * (nd + 1) / 2; e += G) {
+      int a, b;
+      tri_rc<T>(e, &a, &b);
+      int i = s.dl[a], j = s.dl[b];
       T sg = ((mB >> i) & 1) ? (T)1 : (T)-1;
-      s.H[e] += sg * dot6(s.S[i], s.tmp6[j]);
+      s.H[i * NV + j] += sg * dot6(s.S[i], s.tmp6[b]);
     }
   }
   g.sync();
-  chol_factor<T, G>(g, s.H, NV);
+  // factor: independent cube blocks on single lanes, the coupled part cooperatively
+  for (int c = (G == 1 ? 0 : g.lane); c < 3; c += (G == 1 ? 1 : G))
+    if ((s.lone >> c) & 1) chol6_local(s.H + (9 + 6 * c) * (NV + 1));
+  chol_factor_list<T, G>(g, s.H, s.il, s.n_il);
 }
 
 // derivative / curvature of the cost along `search` at step alpha
@@ -1071,6 +1301,7 @@ MM_HDX void solve(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>
   MM_IN_GLOBAL(&md);
   MM_IN_GLOBAL(w.cpos); MM_IN_GLOBAL(w.cn); MM_IN_GLOBAL(w.ct1); MM_IN_GLOBAL(w.cdist); MM_IN_GLOBAL(w.cD); MM_IN_GLOBAL(w.aref);
   MM_IN_GLOBAL(w.Jaref); MM_IN_GLOBAL(w.Jv); MM_IN_GLOBAL(w.cmeta); MM_IN_GLOBAL(w.surv);
+  analyse_coupling<T, G>(g, s);
   const T scale_inv = md.meaninertia * (T)NV;
   const T scale = (T)1 / scale_inv;
   const T tol = (T)1e-8;
@@ -1124,8 +1355,11 @@ MM_HDX void solve(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>
   int specbits = -1;
   int iter = 0;
   T cost = 0, a = 0;
-  bool first = true;
+  bool first = true, finished = false;
+  g.phase(3);
+  long long tn0 = MM_T0(s);
   while (true) {
+   if (!finished) {
     T oldcost = cost;
     bool done = false;
     for (int pass = 0; pass < 2; pass++) {  // pass 1 (per-pair blocks + factorisation) only when the active set changed
@@ -1155,12 +1389,16 @@ MM_HDX void solve(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>
       }
       if (!(first || changed)) break;
     }
-    if (done) break;
+    if (done) finished = true;
+   }
+   if (g.all_done(finished)) break;
+   if (finished) continue;
+   {
     first = false;
     // gradient and Newton direction
     for (int i = g.lane; i < NV; i += G) { T gr = s.Ma[i] - s.fs[i] - s.fc[i]; s.grad[i] = gr; s.search[i] = -gr; }
     g.sync();
-    chol_solve<T, G>(g, s.H, NV, s.search);
+    solve_H<T, G>(g, s, s.search);
     // line search set-up
     T sn = 0, qg1 = 0, qg2 = 0;
     mulM<T, G>(g, s, md, s.search, s.Mv);
@@ -1171,7 +1409,7 @@ MM_HDX void solve(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>
       qg2 += (T)0.5 * s.search[i] * s.Mv[i];
     }
     sn = tsqrt(g.sum(sn)); qg1 = g.sum(qg1); qg2 = g.sum(qg2);
-    if (sn < (T)MINVAL_D) break;
+    if (sn < (T)MINVAL_D) { finished = true; continue; }
     T gtol = tol * (T)0.01 * sn * scale_inv;
     T lo = 0, hi = -1, d1, d2;
     a = 0;
@@ -1187,14 +1425,16 @@ MM_HDX void solve(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>
       if (tabs(d1) < gtol) break;
       if (d1 < 0) lo = a; else hi = a;
     }
-    if (flat) break;
-    if (a == 0) break;
+    if (flat) { finished = true; continue; }
+    if (a == 0) { finished = true; continue; }
     // move
     for (int i = g.lane; i < NV; i += G) { s.qacc[i] += a * s.search[i]; s.Ma[i] += a * s.Mv[i]; }
     for (int c = g.lane; c < ncon; c += G) for (int r = 0; r < 6; r++) w.Jaref[c * 6 + r] += a * w.Jv[c * 6 + r];
     for (int k = g.lane; k < s.nspec; k += G) s.specJaref[k] += a * s.specJv[k];
     g.sync();
+   }
   }
+
   if (g.lane == 0) s.niter = iter;
   for (int i = g.lane; i < NV; i += G) s.warm[i] = s.qacc[i];
   g.sync();
@@ -1203,11 +1443,19 @@ MM_HDX void solve(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>
 // full forward at the current (qpos, qvel, ctrl): everything mj_forward computes that the path needs
 template <class T, int G>
 MM_HDN void forward(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>& w) {
+  g.phase(3);
+  long long t0 = MM_T0(s);
   fk<T, G>(g, s, md);
   dyn_smooth<T, G>(g, s, md);
+  MM_TICK(s, g, 0, t0);
+  g.phase(2);
+  t0 = MM_T0(s);
   collide<T, G>(g, s, md, w);
+  g.phase(2);
+  t0 = MM_T0(s);
   make_constraints<T, G>(g, s, md, w);
   solve<T, G>(g, s, md, w);
+
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -51,7 +51,7 @@ template <class T>
 void do_reset(int n, void** sp, const unsigned char* mask, const double* obj_xy, const int* task, float* obs, float* tgt) {
   Ctx<T>& c = ctx<T>();
   StatePtrs st = state_from(sp);
-  Grp<1> g{0, 1u};
+  Grp<1> g{0, 1u, 0, 0, 0};
   for (long e = 0; e < n; e++) {
     if (mask && !mask[e]) continue;
     env_reset<T, 1>(g, c.s, c.md, c.w, st, e, obj_xy ? obj_xy + 6 * e : nullptr, task[2 * e], task[2 * e + 1], obs, tgt);
@@ -62,7 +62,7 @@ void do_step(int n, void** sp, const float* actions, int mode, int reward_type, 
   Ctx<T>& c = ctx<T>();
   StatePtrs st = state_from(sp);
   StepOut out = out_from(op);
-  Grp<1> g{0, 1u};
+  Grp<1> g{0, 1u, 0, 0, 0};
   for (long e = 0; e < n; e++) env_step<T, 1>(g, c.s, c.md, c.w, st, e, actions, mode, reward_type, max_steps, out, tgt);
 }
 }  // namespace
@@ -83,7 +83,7 @@ void emul_step(int n, void** state, const float* actions, int mode, int reward_t
 
 void emul_ops(int n, void** state, int ops, const double* target, int use_float) {
   StatePtrs st = state_from(state);
-  Grp<1> g{0, 1u};
+  Grp<1> g{0, 1u, 0, 0, 0};
   for (long e = 0; e < n; e++) {
     if (use_float) { Ctx<float>& c = ctx<float>(); env_ops<float, 1>(g, c.s, c.md, c.w, st, e, ops, target); }
     else { Ctx<double>& c = ctx<double>(); env_ops<double, 1>(g, c.s, c.md, c.w, st, e, ops, target); }
@@ -101,7 +101,7 @@ void emul_forward_debug(const double* qpos, const double* qvel, const double* ct
                         double* cpos, double* cn, double* cdist, int* cmeta, int* niter) {
   Ctx<double>& c = ctx<double>();
   Scratch<double>& s = c.s;
-  Grp<1> g{0, 1u};
+  Grp<1> g{0, 1u, 0, 0, 0};
   for (int i = 0; i < NQ; i++) s.qpos[i] = qpos[i];
   for (int i = 0; i < NV; i++) { s.qvel[i] = qvel[i]; s.warm[i] = warm[i]; }
   for (int i = 0; i < NU; i++) s.ctrl[i] = ctrl[i];

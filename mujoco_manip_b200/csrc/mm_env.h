@@ -44,7 +44,7 @@ MM_HDN void load_state(const Grp<G>& g, Scratch<T>& s, const StatePtrs& st, long
   for (int i = g.lane; i < NQ; i += G) s.qpos[i] = (T)st.qpos[e * NQ + i];
   for (int i = g.lane; i < NV; i += G) { s.qvel[i] = (T)st.qvel[e * NV + i]; s.warm[i] = (T)st.warm[e * NV + i]; }
   for (int i = g.lane; i < NU; i += G) s.ctrl[i] = (T)st.ctrl[e * NU + i];
-  if (g.lane == 0) { s.overflow = 0; s.ncon = 0; s.npair = 0; s.nspec = 0; s.niter = 0; }
+  if (g.lane == 0) { s.overflow = 0; s.ncon = 0; s.npair = 0; s.nspec = 0; s.niter = 0; s.prof = 0; for (int k = 0; k < 8; k++) s.tph[k] = 0; }
   g.sync();
 }
 
@@ -237,8 +237,10 @@ MM_HDN bool state_bad(const Grp<G>& g, const Scratch<T>& s) {
 template <class T, int G>
 MM_HDN void env_step(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>& w, const StatePtrs& st, long e,
                      const float* action, int mode, int reward_type, int max_steps, const StepOut& out,
-                     const float* tgt_kp_all) {
+                     const float* tgt_kp_all, bool dummy = false, long long* prof = nullptr) {
   load_state<T, G>(g, s, st, e);
+  if (prof && g.lane == 0) s.prof = 1;
+  g.sync();
   fk<T, G>(g, s, md);  // state after reset / the previous step's trailing mj_forward
   if (g.lane == 0) {
     // decode_action (gym_env.py:252-281): only the translation reaches the controller; rotation is
@@ -253,25 +255,29 @@ MM_HDN void env_step(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work
     s.ctrl[7] = gr > 0.5f ? (T)255 : (T)0;
   }
   g.sync();
-  // 16 x (IK, forward, integrate) then the trailing mj_forward (gym_env.py:555-560) - one forward site
-  int nonfinite = 0;
+  // 16 x (IK, forward, integrate) then the trailing mj_forward (gym_env.py:555-560) - one forward site.
+  // Non-finite state: mj_checkPos / mj_checkVel would warn and reset the data; here the env is put back on
+  // the keyframe, flagged (diag[3]) so the host can count it, and stepping continues (as mj_step does).
   for (int sub = 0; sub <= ACTION_REPEAT; sub++) {
     bool last = sub == ACTION_REPEAT;
+    g.phase(1);
+    long long ti0 = MM_T0(s);
     if (!last) ik<T, G>(g, s, md);
-    if (!nonfinite && state_bad<T, G>(g, s)) {
-      // mj_checkPos/Vel/Acc would warn and reset the data; here the env is put back on the keyframe,
-      // flagged (diag[3]) so the host can count it, and only the trailing forward is run
-      nonfinite = 1;
+
+    if (state_bad<T, G>(g, s)) {
       for (int i = g.lane; i < NQ; i += G) s.qpos[i] = md.key_qpos[i];
       for (int i = g.lane; i < NV; i += G) { s.qvel[i] = 0; s.warm[i] = 0; }
-      if (g.lane == 0) st.diag[e * 4 + 3] += 1;
+      if (g.lane == 0 && !dummy) st.diag[e * 4 + 3] += 1;
       g.sync();
-      sub = ACTION_REPEAT;
-      last = true;
     }
     forward<T, G>(g, s, md, w);
+    g.phase(3);
+    ti0 = MM_T0(s);
     if (!last) integrate<T, G>(g, s, md);
+
   }
+  if (prof && g.lane == 0 && !dummy) for (int k = 0; k < 8; k++) prof[1 + k] = k < 4 ? (long long)s.tph[k] << 6 : (long long)s.tph[k];
+  if (dummy) return;  // padding warp of a phase-synchronous CTA: took part in every barrier, stores nothing
   bool rc = reward_type == REWARD_STAGED ? any_robot_collision<T, G>(g, s, w) : false;
   for (int i = g.lane; i < 9; i += G) s.tmp6[18 + i / 6][i % 6] = s.qpos[i];
   g.sync();

@@ -11,11 +11,13 @@
 #if defined(__CUDACC__)
 #define MM_HD __host__ __device__ __forceinline__
 #define MM_HDN __host__ __device__
-#define MM_HDX __host__ __device__  // (measured twice: __noinline__ stage functions are 10-15% slower, even with address-space hints)
+#define MM_HDX __host__ __device__  // stage functions stay inline (out-of-line versions measured 10-15% slower)
+#define MM_HDL __host__ __device__ __noinline__  // big leaf functions: ONE copy in the kernel (instruction-cache footprint)
 #else
 #define MM_HD inline
 #define MM_HDN
 #define MM_HDX
+#define MM_HDL
 #endif
 
 // address-space hints for the out-of-line functions (a plain reference would compile to generic loads)
@@ -33,23 +35,56 @@ template <int G>
 struct Grp {
   int lane;       // 0..G-1 inside the group
   unsigned mask;  // lanes of this group inside the warp
+  // G == 32: literal full mask, so that syncs and shuffles compile to single instructions (a run-time
+  // mask makes the compiler emit a MATCH.ANY / vote / divergence-check sequence around every one of them)
+  MM_HD unsigned m() const { return G == 32 ? 0xffffffffu : mask; }
+  // Phase-synchronous execution (ps != 0, G == 32 only): every warp of the CTA passes the same sequence of
+  // phase() calls, so the warps of an SM execute the same region of the (large) kernel at the same time
+  // and share its instruction-cache lines instead of evicting each other's.
+  int ps;  // 0 off | 1 once per substep | 2 + before collision and before the solver | 3 + every stage and Newton iteration
+  // cycles this warp spent working (not waiting at phase barriers): the load estimate used to co-schedule envs
+  // of similar cost in one CTA (mm_set_schedule)
+  mutable long long busy, mark;
+  MM_HD void phase(int level = 3) const {
+#ifdef __CUDA_ARCH__
+    if (ps >= level) {
+      long long t = clock64();
+      busy += t - mark;
+      __syncthreads();
+      mark = clock64();
+    }
+#endif
+  }
+  // true when `done` holds for every env of the CTA (phase-synchronous) / for this env (otherwise)
+  MM_HD bool all_done(bool done) const {
+#ifdef __CUDA_ARCH__
+    if (ps >= 3) {
+      long long t = clock64();
+      busy += t - mark;
+      bool r = __syncthreads_and(done ? 1 : 0) != 0;
+      mark = clock64();
+      return r;
+    }
+#endif
+    return done;
+  }
 
   MM_HD void sync() const {
 #ifdef __CUDA_ARCH__
-    if (G > 1) __syncwarp(mask);
+    if (G > 1) __syncwarp(m());
 #endif
   }
   template <class T>
   MM_HD T sum(T v) const {
 #ifdef __CUDA_ARCH__
 #pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(m(), v, o);
 #endif
     return v;
   }
   MM_HD int any(int pred) const {
 #ifdef __CUDA_ARCH__
-    if (G > 1) return (__ballot_sync(mask, pred) & mask) != 0;
+    if (G > 1) return (__ballot_sync(m(), pred) & mask) != 0;
 #endif
     return pred != 0;
   }
@@ -57,23 +92,53 @@ struct Grp {
   MM_HD unsigned ballot(int pred) const {
 #ifdef __CUDA_ARCH__
     if (G > 1) {
-      unsigned b = __ballot_sync(mask, pred) & mask;
-      return G == 32 ? b : (b >> (__ffs(mask) - 1));
+      unsigned b = __ballot_sync(m(), pred) & mask;
+      return G == 32 ? b : (b >> (__ffs(m()) - 1));
     }
 #endif
     return pred ? 1u : 0u;
   }
+  // (value, index) reductions with the tie rule of a linear scan: among equal values the LOWEST index wins
+  template <class T>
+  MM_HD void argmax(T& v, int& i) const {
+#ifdef __CUDA_ARCH__
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) {
+      T ov = __shfl_xor_sync(m(), v, o);
+      int oi = __shfl_xor_sync(m(), i, o);
+      if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+    }
+#endif
+  }
+  template <class T>
+  MM_HD void argmin(T& v, int& i) const {
+#ifdef __CUDA_ARCH__
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) {
+      T ov = __shfl_xor_sync(m(), v, o);
+      int oi = __shfl_xor_sync(m(), i, o);
+      if (ov < v || (ov == v && oi < i)) { v = ov; i = oi; }
+    }
+#endif
+  }
+  MM_HD int imin(int v) const {
+#ifdef __CUDA_ARCH__
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) { int t = __shfl_xor_sync(m(), v, o); v = t < v ? t : v; }
+#endif
+    return v;
+  }
   MM_HD int isum(int v) const {
 #ifdef __CUDA_ARCH__
 #pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(m(), v, o);
 #endif
     return v;
   }
   MM_HD int imax(int v) const {
 #ifdef __CUDA_ARCH__
 #pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) { int t = __shfl_xor_sync(mask, v, o); v = t > v ? t : v; }
+    for (int o = G / 2; o > 0; o >>= 1) { int t = __shfl_xor_sync(m(), v, o); v = t > v ? t : v; }
 #endif
     return v;
   }
@@ -83,10 +148,10 @@ struct Grp {
 #ifdef __CUDA_ARCH__
 #pragma unroll
     for (int o = 1; o < G; o <<= 1) {
-      int t = __shfl_up_sync(mask, incl, o, G);
+      int t = __shfl_up_sync(m(), incl, o, G);
       if (lane >= o) incl += t;
     }
-    *total = __shfl_sync(mask, incl, G - 1, G);
+    *total = __shfl_sync(m(), incl, G - 1, G);
 #else
     *total = incl;
 #endif
@@ -95,7 +160,7 @@ struct Grp {
   template <class T>
   MM_HD T shfl_up(T v, int o) const {
 #ifdef __CUDA_ARCH__
-    return __shfl_up_sync(mask, v, o, G);
+    return __shfl_up_sync(m(), v, o, G);
 #else
     return v;
 #endif
@@ -103,7 +168,7 @@ struct Grp {
   template <class T>
   MM_HD T shfl_down(T v, int o) const {
 #ifdef __CUDA_ARCH__
-    return __shfl_down_sync(mask, v, o, G);
+    return __shfl_down_sync(m(), v, o, G);
 #else
     return v;
 #endif
@@ -111,7 +176,7 @@ struct Grp {
   template <class T>
   MM_HD T bcast(T v, int src) const {
 #ifdef __CUDA_ARCH__
-    return __shfl_sync(mask, v, src, G);
+    return __shfl_sync(m(), v, src, G);
 #else
     return v;
 #endif
@@ -153,8 +218,15 @@ template <class T> MM_HD T tmax(T a, T b) { return a > b ? a : b; }
 template <class T> MM_HD T tmin(T a, T b) { return a < b ? a : b; }
 template <class T> MM_HD T tabs(T a) { return a < 0 ? -a : a; }
 template <class T> MM_HD T tclamp(T x, T lo, T hi) { return x < lo ? lo : (x > hi ? hi : x); }
+MM_HD int tpopc(int x) {
+#ifdef __CUDA_ARCH__
+  return __popc((unsigned)x);
+#else
+  return __builtin_popcount((unsigned)x);
+#endif
+}
 MM_HD float tsqrt(float x) { return sqrtf(x); }
-MM_HD double tsqrt(double x) { return sqrt(x); }
+MM_HDL inline double tsqrt(double x) { return sqrt(x); }  // ~150 SASS instructions per expansion: keep one copy
 MM_HD void tsincos(float x, float* s, float* c) {
 #ifdef __CUDA_ARCH__
   sincosf(x, s, c);

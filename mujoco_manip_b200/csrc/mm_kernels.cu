@@ -75,7 +75,9 @@ struct mm_handle {
   float* d_reward = nullptr;
   unsigned char* d_flags = nullptr;  // terminated | truncated | success, N each
   long long launches = 0;
-  long long* d_cycles = nullptr;  // optional per-env cycle counts (mm_set_cycle_buffer)
+  long long* d_cycles = nullptr;
+  const int* d_order = nullptr;  // mm_set_schedule
+  int* d_work = nullptr;  // optional per-env cycle counts (mm_set_cycle_buffer)
   size_t smem = 0;
 };
 
@@ -140,8 +142,9 @@ int mm_create(const mm_config* cfg, mm_handle** out) {
   } else {
     if (upload_model<float>(h) != 0) return -1;
   }
-  CK(cudaMalloc(&h->d_work_reals, n * WORK_REALS * real_bytes(cfg)));
-  CK(cudaMalloc(&h->d_work_ints, n * WORK_INTS * sizeof(int)));
+  // + 16 slots: padding warps of the last phase-synchronous CTA
+  CK(cudaMalloc(&h->d_work_reals, (n + 16) * WORK_REALS * real_bytes(cfg)));
+  CK(cudaMalloc(&h->d_work_ints, (n + 16) * WORK_INTS * sizeof(int)));
   CK(cudaMalloc(&h->d_tgt, n * 4 * sizeof(float)));
   CK(cudaMemset(h->d_tgt, 0, n * 4 * sizeof(float)));
   CK(cudaMalloc(&h->d_actions, n * ACTION_STRIDE * sizeof(float)));
@@ -185,6 +188,13 @@ int mm_step(mm_handle* h, const mm_state* st, const float* actions, int action_m
   p.tgt_kp = h->d_tgt; p.n = h->cfg.num_envs; p.mode = action_mode; p.reward_type = h->cfg.reward_type;
   p.max_steps = h->cfg.max_episode_steps;
   p.cycles = h->d_cycles;
+  p.order = h->d_order;
+  p.work = h->d_work;
+  {
+    static int lvl = -1;  // MM_PHASE_LEVEL: tuning knob (default 3)
+    if (lvl < 0) { const char* e = getenv("MM_PHASE_LEVEL"); lvl = e ? atoi(e) : 3; }
+    p.phase_level = lvl;
+  }
   h->launches++;
   CK(LAUNCH[inst_index(h->cfg)](0, p, (cudaStream_t)stream));
   return 0;
@@ -275,6 +285,13 @@ int mm_ops(mm_handle* h, const mm_state* st, int ops, const double* target, void
   p.n = h->cfg.num_envs; p.ops = ops; p.target = target;
   h->launches++;
   CK(LAUNCH[inst_index(h->cfg)](2, p, (cudaStream_t)stream));
+  return 0;
+}
+
+int mm_set_schedule(mm_handle* h, const int32_t* order, int32_t* work) {
+  if (!h) return fail("mm_set_schedule: null handle");
+  h->d_order = order;
+  h->d_work = work;
   return 0;
 }
 

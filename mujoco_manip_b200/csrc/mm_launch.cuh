@@ -10,15 +10,17 @@
 
 namespace mm {
 
-// One warp per CTA (32 / G envs): the number of resident envs per SM is set by the shared-memory
-// scratch, so small CTAs pack the 227 KB best.  MINB = CTAs per SM the register allocation must allow.
+// CTA shape.  The number of resident envs per SM is set by the shared-memory scratch (~17.5 KB per env in
+// FP64).  G == 32: ONE CTA per SM holding as many warps (= envs) as fit, executed phase-synchronously
+// (Grp::phase) so that its warps share the instruction cache.  G < 32: one warp per CTA (32 / G envs).
 template <class T, int G>
 struct BlockCfg {
-  static constexpr int THREADS = 32;
-  static constexpr int ENVS = 32 / G;
-  static constexpr int MINB = (int)((227 * 1024) / (ENVS * sizeof(Scratch<T>) + 1024)) > 16
-                                  ? 16
-                                  : (int)((227 * 1024) / (ENVS * sizeof(Scratch<T>) + 1024));
+  static constexpr int FIT = (int)((227 * 1024 - 2048) / sizeof(Scratch<T>));
+  static constexpr int WARPS = G == 32 ? (FIT > 16 ? 16 : FIT) : 1;
+  static constexpr int THREADS = 32 * WARPS;
+  static constexpr int ENVS = THREADS / G;
+  static constexpr int MINB = G == 32 ? 1 : ((227 * 1024) / (ENVS * (int)sizeof(Scratch<T>) + 1024) > 16
+                                                 ? 16 : (227 * 1024) / (ENVS * (int)sizeof(Scratch<T>) + 1024));
 };
 
 struct StepParams {
@@ -37,7 +39,10 @@ struct StepParams {
   int mode, reward_type, max_steps;
   const double* target;  // [N,3] world EE targets for the IK op, or null
   int ops;
-  long long* cycles;  // [N] or null: SM clock cycles each env's step took (profiling aid)
+  const int* order;      // [N] env processed by each slot (envs of similar cost share a CTA) or null = identity
+  int* work;             // [N] out: busy cycles / 256 of each env's step, or null
+  int phase_level;       // barrier density of the phase-synchronous G == 32 kernel (Grp::ps)
+  long long* cycles;  // [N,9] or null: SM clock cycles of each env's step: total, then per stage (profiling aid)
 };
 
 template <class T, int G>
@@ -47,10 +52,13 @@ __device__ __forceinline__ bool setup(const StepParams& p, unsigned char* smem, 
   constexpr int GPB = BlockCfg<T, G>::ENVS;
   int gi = threadIdx.x / G;
   e = (long)blockIdx.x * GPB + gi;
+  g.busy = 0;
+  g.mark = 0;
   sc = reinterpret_cast<Scratch<T>*>(smem) + gi;
   g.lane = threadIdx.x % G;
   int inwarp = (threadIdx.x % 32) / G;
   g.mask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (inwarp * G));
+  g.ps = 0;
   return e < p.n;
 }
 
@@ -61,11 +69,24 @@ __global__ void __launch_bounds__(BlockCfg<T, G>::THREADS, BlockCfg<T, G>::MINB)
   Scratch<T>* sc;
   Grp<G> g;
   long e;
-  if (!setup<T, G>(p, smem, md, sc, g, e)) return;
-  Work<T> w = make_work(reinterpret_cast<T*>(p.work_reals) + e * WORK_REALS, p.work_ints + e * WORK_INTS);
+  bool valid = setup<T, G>(p, smem, md, sc, g, e);
+  bool dummy = false;
+  if (G == 32) {  // phase-synchronous CTA: padding warps replay the last env without storing
+    g.ps = p.phase_level;
+    if (!valid) { e = p.n - 1; dummy = true; }
+  } else if (!valid) return;
+  if (p.order) e = p.order[e];
+#ifdef __CUDA_ARCH__
+  g.mark = clock64();
+#endif
+  // padding warps get their own workspace slice (allocated past the last env)
+  long wslot = dummy ? p.n + (threadIdx.x / 32) : e;
+  Work<T> w = make_work(reinterpret_cast<T*>(p.work_reals) + wslot * WORK_REALS, p.work_ints + wslot * WORK_INTS);
   long long t0 = p.cycles ? clock64() : 0;
-  env_step<T, G>(g, *sc, *md, w, p.st, e, p.actions, p.mode, p.reward_type, p.max_steps, p.out, p.tgt_kp);
-  if (p.cycles && g.lane == 0) p.cycles[e] = clock64() - t0;
+  env_step<T, G>(g, *sc, *md, w, p.st, e, p.actions, p.mode, p.reward_type, p.max_steps, p.out, p.tgt_kp, dummy,
+                 p.cycles ? p.cycles + 9 * e : nullptr);
+  if (p.cycles && g.lane == 0 && !dummy) p.cycles[9 * e] = clock64() - t0;
+  if (p.work && g.lane == 0 && !dummy) p.work[e] = (int)((g.busy + (clock64() - g.mark)) >> 8);
 }
 
 template <class T, int G>

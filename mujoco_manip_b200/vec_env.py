@@ -65,7 +65,7 @@ class PickPlaceVecEnv:
                  max_episode_steps: int = MAX_EPISODE_STEPS, randomize_objects: bool = False,
                  spawn_x_range=SPAWN_X_RANGE, spawn_y_range=SPAWN_Y_RANGE, seed: int = 0, rng: str = "philox",
                  env_id_offset: int = 0, precision: str = "f64", group: int = 32, auto_reset: bool = True,
-                 task_assignment: str = "random"):
+                 task_assignment: str = "random", load_balance: bool = True):
         if action_mode not in _lib.ACTION_MODES:
             raise ValueError(f"action_mode must be one of {_lib.ACTION_MODES}, got '{action_mode}'")
         if reward_type not in _lib.REWARD_TYPES:
@@ -133,6 +133,12 @@ class PickPlaceVecEnv:
         self._ep_return = torch.zeros(n, dtype=torch.float64, device=dev)
         self._np_rngs: list | None = None
         self._closed = False
+        # load-aware scheduling: envs sorted by the busy time of their previous step share a CTA (mm_set_schedule)
+        self.load_balance = bool(load_balance) and n > 32
+        self._work = torch.zeros(n, dtype=torch.int32, device=dev)
+        self._order = torch.arange(n, dtype=torch.int32, device=dev)
+        if self.load_balance:
+            _lib.check(self._L.mm_set_schedule(self._h, self._order.data_ptr(), self._work.data_ptr()), "mm_set_schedule")
 
     # ------------------------------------------------------------------------------------------
     def _stream(self) -> C.c_void_p:
@@ -242,9 +248,15 @@ class PickPlaceVecEnv:
         else:
             self._actions[:, : a.shape[1]].copy_(a)
             buf = self._actions
+        self._schedule()
         _lib.check(self._L.mm_step(self._h, C.byref(self._st), buf.data_ptr(), _lib.ACTION_MODES.index(self.action_mode),
                                    C.byref(self._out), self._stream()), "mm_step")
         return self._post_step_autoreset()
+
+    def _schedule(self):
+        """Heaviest envs first, envs of similar cost together (the order buffer is read by the next mm_step)."""
+        if self.load_balance:
+            self._order.copy_(torch.argsort(self._work, descending=True).to(torch.int32))
 
     def _post_step_autoreset(self):
         """Bookkeeping after the mm_step launch: episode statistics and (optionally) the reset of

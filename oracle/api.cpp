@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "hotpath.h"
+#include "ccd.h"
 
 using namespace orc;
 
@@ -189,6 +190,11 @@ double orc_bench_random2(int n_envs, int n_steps, int mode, unsigned seed, int n
   }
   for (auto e : envs) delete e;
   return (double)n_envs * n_steps / dt;
+}
+
+void orc_ccd_marks(long long* out) {
+  out[0] = ccd::marks().max_faces; out[1] = ccd::marks().max_iters; out[2] = ccd::marks().calls; out[3] = ccd::marks().iters;
+  out[4] = ccd::marks().gjk_calls; out[5] = ccd::marks().gjk_iters; out[6] = ccd::marks().gjk_hits; out[7] = ccd::marks().gjk_maxed;
 }
 
 double orc_bench_random(int n_envs, int n_steps, int mode, unsigned seed, int nthreads, int flags) {

@@ -10,6 +10,10 @@
 
 namespace ccd {
 
+// high-water marks of the EPA polytope (sizing aid for the GPU workspace; not part of the algorithm)
+struct Marks { int max_faces, max_iters; long long calls, iters, gjk_calls, gjk_iters, gjk_hits, gjk_maxed; };
+inline Marks& marks() { static Marks m = {0, 0, 0, 0, 0, 0, 0, 0}; return m; }
+
 struct Shape {
   int type;            // 5 cylinder, 6 box, 7 convex mesh
   const double* pos;   // world position (3)
@@ -82,7 +86,10 @@ static inline bool gjk(const Shape& s1, const Shape& s2, SP* sx) {
     if (dot(dir, dir) < 1e-24) dir = cross(bc, V3{0, 0, 1});
   }
   int n = 2;
+  marks().gjk_calls++;
   for (int it = 0; it < 64; it++) {
+    marks().gjk_iters++;
+    if (it == 63) marks().gjk_maxed++;
     a = support(s1, s2, dir);
     if (dot(a.v, dir) < 0) return false;
     if (n == 2) {
@@ -110,6 +117,7 @@ static inline bool gjk(const Shape& s1, const Shape& s2, SP* sx) {
     if (dot(acd, ao) > 0) { b = a; dir = acd; continue; }
     if (dot(adb, ao) > 0) { c = d; d = b; b = a; dir = adb; continue; }
     sx[0] = a; sx[1] = b; sx[2] = c; sx[3] = d;
+    marks().gjk_hits++;
     return true;
   }
   return false;
@@ -148,6 +156,9 @@ static inline bool epa(const Shape& s1, const Shape& s2, const SP* sx, double* p
     V3 n = faces[best].n;
     SP p = support(s1, s2, n);
     double dist = dot(p.v, n);
+    if (nf > marks().max_faces) marks().max_faces = nf;
+    if (it > marks().max_iters) marks().max_iters = it;
+    marks().iters++;
     if (dist - faces[best].d < 1e-10 || nf >= MAXF - 8) break;
     // remove faces visible from p, collect the horizon
     struct Edge { SP a, b; };
@@ -179,6 +190,7 @@ static inline bool epa(const Shape& s1, const Shape& s2, const SP* sx, double* p
       faces[nf++] = f;
     }
   }
+  marks().calls++;
   best = 0;
   for (int i = 1; i < nf; i++) if (faces[i].d < faces[best].d) best = i;
   const Face& f = faces[best];

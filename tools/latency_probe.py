@@ -20,8 +20,9 @@ a = ap.parse_args()
 dev = torch.device("cuda:0")
 env = PickPlaceVecEnv(a.envs, device=dev, task=("obj_red", "bin_red"), precision=a.precision, group=a.group, seed=1234)
 env.reset()
-cyc = torch.zeros(a.envs, dtype=torch.int64, device=dev)
-_lib.check(env._L.mm_set_cycle_buffer(env._h, cyc.data_ptr()), "cycles")
+cyc9 = torch.zeros((a.envs, 9), dtype=torch.int64, device=dev)
+cyc = cyc9[:, 0]
+_lib.check(env._L.mm_set_cycle_buffer(env._h, cyc9.data_ptr()), "cycles")
 gen = torch.Generator(device=dev).manual_seed(1234)
 T0 = env.state["tinit"][0]
 p0, R0 = T0[:3], T0[3:].reshape(3, 3)
@@ -46,3 +47,12 @@ for t in range(a.steps):
         print(f"step {t}: launch {e0.elapsed_time(e1):.1f} ms | per-env ms p50 {q[0]:.2f} p90 {q[1]:.2f} p99 {q[2]:.2f} max {q[3]:.2f} "
               f"| sum/SMs {float(c.sum()) / 148:.1f} | ncon mean {float(ncon.mean()):.1f} max {int(ncon.max())} "
               f"| worst env ncon {int(ncon[worst])} iters {int(env.state['diag'][worst, 1])}")
+        names = ["kin+dyn", "broad", "narrow(all)", "narrow-convex", "#gjk", "#gjk-it", "#epa", "#epa-it"]
+        ph = cyc9[:, 1:].double() / 1.965e6
+        ph[:, 4:] = cyc9[:, 5:].double()
+        order = torch.argsort(c)
+        med, slow = order[a.envs // 2 - 50: a.envs // 2 + 50], order[-a.envs // 20:]
+        print("      stage ms   " + "  ".join(f"{n}" for n in names))
+        print("      mean       " + "  ".join(f"{float(ph[:, k].mean()):7.2f}" for k in range(8)))
+        print("      median env " + "  ".join(f"{float(ph[med, k].mean()):7.2f}" for k in range(8)))
+        print("      slowest 5% " + "  ".join(f"{float(ph[slow, k].mean()):7.2f}" for k in range(8)))

@@ -75,6 +75,15 @@ def function_ranges(srcdir):
     return out
 
 
+_FR = {}
+
+
+def function_ranges_cache(srcdir):
+    if srcdir not in _FR:
+        _FR[srcdir] = function_ranges(srcdir)
+    return _FR[srcdir]
+
+
 def func_of(ranges, file, line):
     best = "?"
     for ln, name in ranges.get(file, []):
@@ -101,12 +110,17 @@ def main():
     base = int(rows[0]["Address"], 16)
     by_off = {off: (loc, ins) for off, loc, ins in tab}
     ranges = function_ranges(a.srcdir)
+    agg_loc = collections.defaultdict(lambda: [0, 0])
     agg_f = collections.defaultdict(lambda: [0, 0, 0])
     agg_l = collections.defaultdict(lambda: [0, 0, 0])
     tot = [0, 0, 0]
     for r in rows:
         off = int(r["Address"], 16) - base
-        loc, _ = by_off.get(off, (("?", 0), ""))
+        loc, ins = by_off.get(off, (("?", 0), ""))
+        if ins.startswith(("LDL", "STL")) or " LDL" in ins[:12] or " STL" in ins[:12]:
+            k = f"{loc[0]}:{loc[1]}"
+            agg_loc[k][0] += int(r.get("Instructions Executed", "0") or 0)
+            agg_loc[func_of(function_ranges_cache(a.srcdir), loc[0], loc[1])][1] += int(r.get("Instructions Executed", "0") or 0)
         ie = int(r.get("Instructions Executed", "0") or 0)
         te = int(r.get("Thread Instructions Executed", "0") or 0)
         ss = int(r.get("Warp Stall Sampling (All Samples)", "0") or 0)
@@ -122,6 +136,15 @@ def main():
     print("\n== by source function (share of warp instructions | share of stall samples | active lanes) ==")
     for k, v in sorted(agg_f.items(), key=lambda kv: -kv[1][2])[: a.top]:
         print(f"{100 * v[0] / tot[0]:6.2f}% inst  {100 * v[2] / max(1, tot[2]):6.2f}% samples  {v[1] / max(1, v[0]):5.1f} lanes  {k}")
+    print("\n== local-memory (LDL/STL) warp instructions by function ==")
+    tl = sum(v[1] for v in agg_loc.values())
+    for k, v in sorted(agg_loc.items(), key=lambda kv: -kv[1][1])[:20]:
+        if v[1]:
+            print(f"{v[1]:14,d}  {100 * v[1] / max(1, tl):5.1f}%  {k}")
+    print("\n== local-memory warp instructions by line ==")
+    for k, v in sorted(agg_loc.items(), key=lambda kv: -kv[1][0])[:25]:
+        if v[0]:
+            print(f"{v[0]:14,d}  {k}")
     print("\n== by source line ==")
     for k, v in sorted(agg_l.items(), key=lambda kv: -kv[1][2])[: a.top]:
         print(f"{100 * v[0] / tot[0]:6.2f}% inst  {100 * v[2] / max(1, tot[2]):6.2f}% samples  {v[1] / max(1, v[0]):5.1f} lanes  {k}")
