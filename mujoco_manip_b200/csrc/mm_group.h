@@ -41,7 +41,7 @@ struct Grp {
   // Phase-synchronous execution (ps != 0, G == 32 only): every warp of the CTA passes the same sequence of
   // phase() calls, so the warps of an SM execute the same region of the (large) kernel at the same time
   // and share its instruction-cache lines instead of evicting each other's.
-  int ps;  // 0 off | 1 once per substep | 2 + before collision and before the solver | 3 + every stage and Newton iteration
+  int ps;  // 0 off | 1 once per substep | 2 + before collision and before the solver | 3 + every stage | 4 + every Newton iteration
   // cycles this warp spent working (not waiting at phase barriers): the load estimate used to co-schedule envs
   // of similar cost in one CTA (mm_set_schedule)
   mutable long long busy, mark;
@@ -58,7 +58,7 @@ struct Grp {
   // true when `done` holds for every env of the CTA (phase-synchronous) / for this env (otherwise)
   MM_HD bool all_done(bool done) const {
 #ifdef __CUDA_ARCH__
-    if (ps >= 3) {
+    if (ps >= 4) {
       long long t = clock64();
       busy += t - mark;
       bool r = __syncthreads_and(done ? 1 : 0) != 0;

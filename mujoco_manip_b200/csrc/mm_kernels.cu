@@ -191,8 +191,8 @@ int mm_step(mm_handle* h, const mm_state* st, const float* actions, int action_m
   p.order = h->d_order;
   p.work = h->d_work;
   {
-    static int lvl = -1;  // MM_PHASE_LEVEL: tuning knob (default 3)
-    if (lvl < 0) { const char* e = getenv("MM_PHASE_LEVEL"); lvl = e ? atoi(e) : 3; }
+    static int lvl = -1;  // MM_PHASE_LEVEL: tuning knob (default 4 = all barriers)
+    if (lvl < 0) { const char* e = getenv("MM_PHASE_LEVEL"); lvl = e ? atoi(e) : 4; }
     p.phase_level = lvl;
   }
   h->launches++;
