@@ -65,7 +65,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         src, obj = os.path.join(SRC_DIR, u), os.path.join(BUILD_DIR, u[:-3] + ".o")
         if not force and os.path.exists(obj) and os.path.getmtime(obj) >= max(newest_hdr, os.path.getmtime(src)):
             return obj, False
-        cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+        extra = os.environ.get("MM_NVCC_EXTRA", "").split()
+        cmd = ["nvcc"] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
         subprocess.check_call(cmd)
         return obj, True
 

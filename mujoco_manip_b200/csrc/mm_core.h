@@ -30,7 +30,7 @@ constexpr int MAXCON = 128;   // contacts per env (oracle max: 44 in scripted ep
 constexpr int MAXROW = MAXCON * 6;
 constexpr int MAXPAIR = 16;   // simultaneously touching body pairs
 constexpr int MAXSPEC = 10;   // equality + at most one limit row per robot joint
-constexpr int MAXSURV = 128;  // geom pairs surviving the broad phase
+constexpr int MAXSURV = 256;  // geom pairs surviving the first level of the broad phase
 constexpr double MINVAL_D = 1e-15;
 
 // meta word of a contact
@@ -820,8 +820,6 @@ MM_HDX void collide(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<
         T rs = rb + gm.rbound[a];
         keep = !(dot3(r, r) > rs * rs);
       }
-      // second level (conservative): oriented bounding boxes of the two geoms must overlap
-      if (keep && ta != GT_PLANE) keep = obb_overlap(s, gm, a, b, ident);
     }
     int tot;
     int off = g.scan_excl(keep, &tot);
@@ -830,6 +828,27 @@ MM_HDX void collide(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<
   }
   if (nsurv > MAXSURV) { nsurv = MAXSURV; if (g.lane == 0) s.overflow |= 1; }
   g.sync();
+  // second level (conservative) on the compacted list, so that the lanes stay busy: the oriented bounding boxes
+  // of the two geoms must overlap.  In-place ordered compaction (writes never pass the reads of later chunks).
+  {
+    int kept = 0;
+    for (int base = 0; base < nsurv; base += G) {
+      int si = base + g.lane;
+      int keep = 0, ci = 0;
+      if (si < nsurv) {
+        ci = w.surv[si];
+        int a = gm.pair[ci][0], b = gm.pair[ci][1];
+        keep = gm.type[a] == GT_PLANE ? 1 : (int)obb_overlap(s, gm, a, b, ident);
+      }
+      int tot;
+      int off = g.scan_excl(keep, &tot);
+      g.sync();
+      if (keep) w.surv[kept + off] = ci;
+      kept += tot;
+      g.sync();
+    }
+    nsurv = kept;
+  }
   MM_TICK(s, g, 1, tb0);
   long long tc0 = MM_T0(s);
   g.phase(3);
