@@ -228,6 +228,7 @@ def main():
         ksteps = max(3, args.steps // 3)
 
         def host_step(i):
+            env._schedule()
             _lib.check(env._L.mm_step_host(env._h, C.byref(env._st), h_act[i % len(h_act)].data_ptr(),
                                            _lib.ACTION_MODES.index(MODE), h_obs.data_ptr(), h_rew.data_ptr(),
                                            h_fl[0].data_ptr(), h_fl[1].data_ptr(), h_fl[2].data_ptr(), env._stream()),
@@ -269,6 +270,13 @@ def main():
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": sample + "; FP64 oracle restatement of the reference path (MuJoCo not installable here)"}
         kern_s = kern_ms * 1e-3 / args.steps
+        # DRAM bytes of one launch of the step kernel from the committed `ncu --set full` capture (same config)
+        traffic = None
+        tpath = os.path.join(REPO, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            if tj.get("envs") == n and tj.get("precision") == args.precision:
+                traffic = tj.get("dram_bytes_per_launch")
         peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(REPO, "MEASURED_PEAKS.json")) else {}
         hbm_peak = peaks.get("hbm_gbs", 6548.5)
         state_bytes = 8 * (30 + 27 + 8 + 27) * 2 + 8 * 12 * 2 + 4 * 10 + 4 * 85 + 4 + 3 + 4 * 8  # FP64 state in+out, tinit/eepose, action, obs, reward/flags, ints
@@ -277,7 +285,7 @@ def main():
                 "frac": (flops * n / kern_s * 1e-12 / peak.value) if flops else None,
                 "peak_source": "measured live: dependent-FMA microkernel mm_measure_fma_peak (MEASURED_PEAKS.json has no CUDA-core figure)",
                 "flops_per_env_step": flops, "per_forward_counters": per, "kernel_ms_per_launch": kern_s * 1e3,
-                "traffic": None,
+                "traffic": traffic,
                 "hbm": {"achieved": state_bytes * n / kern_s * 1e-9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": state_bytes * n / kern_s * 1e-9 / hbm_peak, "bytes_per_env_step": state_bytes}}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -18,6 +18,11 @@ constexpr int EPA_INTS = EPA_MAXF + EPA_MAXE + EPA_MAXV;
 constexpr int EPA_VIS = 1 << 30;
 constexpr int SHAPE_LV = 5;  // ceil(152 / 32): the largest hull has 152 vertices
 
+// EPA tolerances: the oracle's values in FP64; scaled to the arithmetic's resolution in FP32 (otherwise the
+// expansion never sees its progress fall below the threshold and runs into the face cap)
+template <class T> MM_HD double epa_tol() { return sizeof(T) == 8 ? 1e-10 : 2e-6; }
+template <class T> MM_HD double epa_vis() { return sizeof(T) == 8 ? 1e-14 : 1e-8; }
+
 template <class T>
 struct Shape {
   int type;       // GT_CYL, GT_BOX, GT_HULL
@@ -242,7 +247,7 @@ MM_HDN bool epa(const Grp<G>& g, const Shape<T>& s1, const Shape<T>& s2, const S
     SP<T> p;
     support<T, G>(g, s1, s2, n, p);
     T dist = dot3(p.v, n);
-    if ((double)(dist - m.face[4 * best + 3]) < 1e-10 || nf >= EPA_MAXF - 8) break;
+    if ((double)(dist - m.face[4 * best + 3]) < epa_tol<T>() || nf >= EPA_MAXF - 8) break;
     int ip = nv++;
     // new vertex, its canonical index, and the visibility flag of every face (spread over the lanes)
     int cn = ip;
@@ -260,7 +265,7 @@ MM_HDN bool epa(const Grp<G>& g, const Shape<T>& s1, const Shape<T>& s2, const S
       const T* F = m.face + 4 * i;
       T r[3];
       sub3(r, p.v, m.vert + 6 * (fi & 1023));
-      if ((double)dot3(F, r) > 1e-14) m.fidx[i] = fi | EPA_VIS;
+      if ((double)dot3(F, r) > epa_vis<T>()) m.fidx[i] = fi | EPA_VIS;
     }
     g.sync();
     // removal of the visible faces and collection of the horizon, in the oracle's order (integer work, one lane)
