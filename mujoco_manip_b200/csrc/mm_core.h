@@ -1551,54 +1551,63 @@ template <class T, int G>
 MM_HDX void ik(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md) {
   MM_IN_SHARED(&s);
   MM_IN_GLOBAL(&md);
-  if (g.lane == 0) {
-    const T* ee = s.bpos[DB_HAND];
-    T J[6][NARM], e[6], z[NARM], b[6];
-    for (int i = 0; i < NARM; i++) {
-      const T* S = s.S[i];
-      T c[3];
-      cross3(c, S, ee);  // a x ee + (p x a)
-      for (int d = 0; d < 3; d++) { J[d][i] = c[d] + S[3 + d]; J[3 + d][i] = S[d]; }
-      z[i] = (T)0.5 * (md.home[i] - s.qpos[i]);
-    }
-    for (int d = 0; d < 3; d++) e[d] = s.target[d] - ee[d];
-    orientation_error(s.bR[DB_HAND], e + 3);
-    T A[36];
-    for (int i = 0; i < 6; i++) {
-      T jz = 0;
-      for (int c = 0; c < NARM; c++) jz += J[i][c] * z[c];
-      b[i] = e[i] - jz;
-      for (int j = 0; j <= i; j++) {
-        T a = 0;
-        for (int c = 0; c < NARM; c++) a += J[i][c] * J[j][c];
-        A[6 * i + j] = a + (i == j ? (T)1e-3 : (T)0);
-      }
-    }
-    // 6x6 Cholesky solve
-    for (int j = 0; j < 6; j++) {
-      T d = A[6 * j + j];
-      for (int k = 0; k < j; k++) d -= A[6 * j + k] * A[6 * j + k];
-      T l = tsqrt(d);
-      A[6 * j + j] = l;
-      for (int i = j + 1; i < 6; i++) {
-        T t = A[6 * i + j];
-        for (int k = 0; k < j; k++) t -= A[6 * i + k] * A[6 * j + k];
-        A[6 * i + j] = t / l;
-      }
-    }
-    for (int i = 0; i < 6; i++) { T t = b[i]; for (int k = 0; k < i; k++) t -= A[6 * i + k] * b[k]; b[i] = t / A[6 * i + i]; }
-    for (int i = 5; i >= 0; i--) { T t = b[i]; for (int k = i + 1; k < 6; k++) t -= A[6 * k + i] * b[k]; b[i] = t / A[6 * i + i]; }
-    T dq[NARM], nn = 0;
-    for (int c = 0; c < NARM; c++) {
-      T a = z[c];
-      for (int i = 0; i < 6; i++) a += J[i][c] * b[i];
-      dq[c] = a;
-      nn += a * a;
-    }
-    nn = tsqrt(nn);
-    T sc = nn > (T)5 ? (T)5 / nn : (T)1;
-    for (int c = 0; c < NARM; c++) s.ctrl[c] = tclamp(s.qpos[c] + dq[c] * sc, md.jnt_lo[c], md.jnt_hi[c]);
+  // spread over the lanes; scratch in the (stale) H region: J [6][7] at 0, z [7] at 42, e / b [6] at 49,
+  // A = J J^T + damping (6x6, row stride NV) at 60, dq [7] at 60 + 6 NV
+  T* J = s.H;
+  T* z = s.H + 42;
+  T* b = s.H + 49;
+  T* A = s.H + 60;
+  T* dq = s.H + 60 + 6 * NV;
+  const T* ee = s.bpos[DB_HAND];
+  for (int e = g.lane; e < 42; e += G) {
+    int d = e / NARM, i = e % NARM;
+    const T* S = s.S[i];
+    T v;
+    if (d < 3) {
+      int d1 = (d + 1) % 3, d2 = (d + 2) % 3;
+      v = S[d1] * ee[d2] - S[d2] * ee[d1] + S[3 + d];  // (a x ee + p x a)_d
+    } else v = S[d - 3];
+    J[e] = v;
   }
+  for (int i = g.lane; i < NARM; i += G) z[i] = (T)0.5 * (md.home[i] - s.qpos[i]);
+  if (g.lane == 0) {
+    T er[6];
+    for (int d = 0; d < 3; d++) er[d] = s.target[d] - ee[d];
+    orientation_error(s.bR[DB_HAND], er + 3);
+    for (int d = 0; d < 6; d++) b[d] = er[d];
+  }
+  g.sync();
+  for (int e = g.lane; e < 21 + 6; e += G) {
+    if (e < 21) {
+      int i, j;
+      tri_rc<T>(e, &i, &j);
+      T a = 0;
+      for (int c = 0; c < NARM; c++) a += J[i * NARM + c] * J[j * NARM + c];
+      A[i * NV + j] = a + (i == j ? (T)1e-3 : (T)0);
+    } else {
+      int i = e - 21;
+      T jz = 0;
+      for (int c = 0; c < NARM; c++) jz += J[i * NARM + c] * z[c];
+      dq[i] = jz;  // J z, subtracted from the error below
+    }
+  }
+  g.sync();
+  if (g.lane == 0) {
+    for (int i = 0; i < 6; i++) b[i] -= dq[i];
+    chol6_local(A);
+    solve6_local(A, b);
+  }
+  g.sync();
+  T mine = 0;
+  for (int c = g.lane; c < NARM; c += G) {
+    T a = z[c];
+    for (int i = 0; i < 6; i++) a += J[i * NARM + c] * b[i];
+    dq[c] = a;
+    mine += a * a;
+  }
+  T nn = tsqrt(g.sum(mine));
+  T sc = nn > (T)5 ? (T)5 / nn : (T)1;
+  for (int c = g.lane; c < NARM; c += G) s.ctrl[c] = tclamp(s.qpos[c] + dq[c] * sc, md.jnt_lo[c], md.jnt_hi[c]);
   g.sync();
 }
 
