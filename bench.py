@@ -41,6 +41,8 @@ def parse():
     ap.add_argument("--envs", type=int, default=4096, help="envs per GPU")
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
     ap.add_argument("--group", type=int, default=32)
+    ap.add_argument("--workload", default="random", choices=["random", "fsm"],
+                    help="random = BASELINE configs[1] (headline); fsm = configs[2] scripted-expert dataset generation (extra)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -130,6 +132,62 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_fsm(args, rank, world, local):
+    """BASELINE.json configs[2] (extra line, not the headline): scripted-FSM expert rollouts, tasks = all (cycled by
+    global env id), randomized objects (device Philox), abs_pos actions, finished episodes are reset in place."""
+    import torch
+    import torch.distributed as dist
+
+    from mujoco_manip_b200 import PickPlaceVecEnv
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.envs
+    env = PickPlaceVecEnv(n, device=dev, tasks="all", action_mode="abs_pos", randomize_objects=True, rng="philox", seed=42,
+                          env_id_offset=rank * n, task_assignment="cycle", auto_reset=False, max_episode_steps=2000,
+                          precision=args.precision, group=args.group)
+    env.reset()
+    episodes = torch.zeros(2, dtype=torch.float64, device=dev)
+
+    def one():
+        a = env.fsm_plan(16)
+        obs, r, te, tr, info = env.step(a)
+        done = env.fsm_state == 11
+        episodes[0] += done.sum()
+        episodes[1] += (done & info["success"]).sum()
+        env.reset(mask=done.to(torch.uint8))
+
+    for _ in range(args.warmup):
+        one()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        one()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(episodes)
+    if rank == 0:
+        ms = float(t[0])
+        print(json.dumps({"metric": METRIC, "value": world * n * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+                          "config": {"workload": f"configs[2]: {n} envs/GPU, tasks=all, randomize_objects seed 42, scripted-FSM "
+                                                 "expert (plan(16) + step), state obs, episodes reset at FSM DONE"},
+                          "episodes_finished": float(episodes[0]), "success_rate": float(episodes[1] / episodes[0].clamp(min=1))}),
+              flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -137,6 +195,9 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.workload == "fsm":
+        run_fsm(args, rank, world, local)
         return
 
     import torch

@@ -127,6 +127,11 @@ int mm_sample_placements(mm_handle* h, uint64_t seed, int64_t env_id_offset, con
  * best of 5 timed launches - the measured denominator of the roofline bench.py reports. */
 int mm_measure_fma_peak(int device, int fp64, double* tflops);
 
+/* replaces get_actions (scripts/generate_dataset.py:56-80): the four action encodings of an expert abs_pos action
+ * [N,10] (x, y, z, gripper): pose (target, TARGET_ORI) in the world frame and relative to the initial EE pose.
+ * encodings [N,36] float32 = pos_quat_g (8) | pos_rot6d_g (10) | pos_quat_g_rel (8) | pos_rot6d_g_rel (10). */
+int mm_expert_actions(mm_handle* h, const mm_state* st, const float* abs_actions, float* encodings, void* stream);
+
 /* Load-aware scheduling of mm_step (no reference counterpart; results do not depend on it).  `work` ([N] int32,
  * device, or NULL) receives each env's busy time of the step (SM cycles / 256); `order` ([N] int32 device permutation,
  * or NULL = identity) tells which env each execution slot processes.  Passing the envs sorted by the previous step's

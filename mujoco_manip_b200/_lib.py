@@ -23,7 +23,7 @@ REWARD_TYPES = ("dense", "sparse", "staged")
 
 # every symbol include/mm_manip.h declares (tests check the built library exports each one)
 EXPORTS = ("mm_create", "mm_destroy", "mm_last_error", "mm_workspace_bytes", "mm_reset", "mm_step", "mm_step_host",
-           "mm_fsm_plan", "mm_launch_count", "mm_sample_placements", "mm_measure_fma_peak", "mm_set_cycle_buffer", "mm_ops", "mm_set_schedule")
+           "mm_fsm_plan", "mm_launch_count", "mm_sample_placements", "mm_measure_fma_peak", "mm_set_cycle_buffer", "mm_ops", "mm_set_schedule", "mm_expert_actions")
 
 
 class MMConfig(C.Structure):
@@ -104,6 +104,7 @@ def lib():
                                        C.c_double, C.c_double, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.mm_measure_fma_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]
     L.mm_ops.argtypes = [C.c_void_p, C.POINTER(MMState), C.c_int, C.c_void_p, C.c_void_p]
+    L.mm_expert_actions.argtypes = [C.c_void_p, C.POINTER(MMState), C.c_void_p, C.c_void_p, C.c_void_p]
     L.mm_set_schedule.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.mm_set_cycle_buffer.argtypes = [C.c_void_p, C.c_void_p]
     L.mm_launch_count.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]

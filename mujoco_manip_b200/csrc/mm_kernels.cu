@@ -30,6 +30,27 @@ __global__ void k_fsm(StatePtrs st, long n, int nsteps, float* actions) {
   if (e < n) fsm_plan_one(st, e, nsteps, actions ? actions + e * ACTION_STRIDE : nullptr);
 }
 
+// The four action encodings of an expert abs_pos action (scripts/generate_dataset.py:56-80): pose = (target
+// position, TARGET_ORI) in the world frame and relative to the episode's initial EE pose.  Thread per env.
+// out [N,36] = pos_quat_g (8) | pos_rot6d_g (10) | pos_quat_g_rel (8) | pos_rot6d_g_rel (10)
+__global__ void k_expert(StatePtrs st, long n, const float* abs_actions, float* out) {
+  long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const float* a = abs_actions + e * ACTION_STRIDE;
+  const double R[9] = {0, 1, 0, 1, 0, 0, 0, 0, -1};  // TARGET_ORI, controller.py:12-18
+  double p[3] = {(double)a[0], (double)a[1], (double)a[2]};
+  float* o = out + e * 36;
+  encode_pose(p, R, a[3], o, o + 8);
+  const double* ti = st.tinit + e * 12;
+  const double* Ri = ti + 3;
+  double Rr[9], pr[3], dp[3] = {p[0] - ti[0], p[1] - ti[1], p[2] - ti[2]};
+  for (int i = 0; i < 3; i++) {
+    pr[i] = Ri[i] * dp[0] + Ri[3 + i] * dp[1] + Ri[6 + i] * dp[2];
+    for (int j = 0; j < 3; j++) Rr[3 * i + j] = Ri[i] * R[j] + Ri[3 + i] * R[3 + j] + Ri[6 + i] * R[6 + j];
+  }
+  encode_pose(pr, Rr, a[3], o + 18, o + 26);
+}
+
 // Philox placement + task draw for every env (mm_rng.h); thread per env
 __global__ void k_sample(unsigned long long seed, long long gid0, const long long* episode, long n, double xlo, double xhi,
                          double ylo, double yhi, double min_sep, int npool, double* xy, int* task_draw, int* attempts) {
@@ -285,6 +306,15 @@ int mm_ops(mm_handle* h, const mm_state* st, int ops, const double* target, void
   p.n = h->cfg.num_envs; p.ops = ops; p.target = target;
   h->launches++;
   CK(LAUNCH[inst_index(h->cfg)](2, p, (cudaStream_t)stream));
+  return 0;
+}
+
+int mm_expert_actions(mm_handle* h, const mm_state* st, const float* abs_actions, float* encodings, void* stream) {
+  if (!h || !st || !abs_actions || !encodings) return fail("mm_expert_actions: null argument");
+  long n = h->cfg.num_envs;
+  k_expert<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(to_ptrs(st), n, abs_actions, encodings);
+  CK(cudaGetLastError());
+  h->launches++;
   return 0;
 }
 

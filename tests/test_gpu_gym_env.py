@@ -316,3 +316,36 @@ def test_expert_success_rate_matches_oracle(cuda_device, oracle_lib):
     assert (gs == ref_s).mean() >= 0.98
     assert (gl == ref_l).mean() >= 0.95, (gl[:10], ref_l[:10])
     assert ref_s.mean() > 0.8
+
+
+def test_expert_action_encodings_match_reference_get_actions(cuda_device):
+    """mm_expert_actions vs the arithmetic of scripts/generate_dataset.py:56-80 (host pose utils, pinned on the
+    reference's own vectors in tests/test_pose_utils.py)."""
+    import torch
+
+    from mujoco_manip_b200 import PickPlaceVecEnv
+    from mujoco_manip_b200 import pose_utils as P
+    from mujoco_manip_b200.features import expert_action_encodings, pack_rows
+    from mujoco_manip_b200.gym_env import TARGET_ORI
+
+    env = PickPlaceVecEnv(5, device=cuda_device, action_mode="abs_pos", reward_type="staged", rng="numpy", auto_reset=False)
+    env.reset()
+    rng = np.random.default_rng(0)
+    a = np.concatenate([rng.uniform([-0.3, 0.3, 0.3], [0.3, 0.65, 0.6], size=(5, 3)), rng.integers(0, 2, size=(5, 1))], axis=1)
+    enc = expert_action_encodings(env, torch.from_numpy(a.astype(np.float32)).to(cuda_device)).cpu().numpy()
+    T0 = env.initial_ee_se3.cpu().numpy()
+    for i in range(5):
+        g = float(np.float32(a[i, 3]))
+        T = P.pos_rotmat_to_se3(a[i, :3].astype(np.float32).astype(np.float64), TARGET_ORI)
+        Tr = np.linalg.inv(T0[i]) @ T
+        ref = np.concatenate([P.se3_to_pos_quat_g(T, g), P.se3_to_pos_rot6d_g(T, g), P.se3_to_pos_quat_g(Tr, g),
+                              P.se3_to_pos_rot6d_g(Tr, g)])
+        np.testing.assert_allclose(enc[i], ref, atol=1e-6)
+    pre = env.obs_packed.clone()
+    obs, r, te, tr, info = env.step(torch.from_numpy(a.astype(np.float32)).to(cuda_device))
+    row = pack_rows(pre, torch.from_numpy(enc).to(cuda_device), env.fsm_state, info["reward_components"])
+    from mujoco_manip_b200.features import FEATURES
+
+    for k, v in row.items():
+        if FEATURES[k]["dtype"] == "float32":
+            assert tuple(v.shape[1:]) == FEATURES[k]["shape"], k
