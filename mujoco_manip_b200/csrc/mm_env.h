@@ -276,7 +276,7 @@ MM_HDN void env_step(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work
     if (!last) integrate<T, G>(g, s, md);
 
   }
-  if (prof && g.lane == 0 && !dummy) for (int k = 0; k < 8; k++) prof[1 + k] = k < 4 ? (long long)s.tph[k] << 6 : (long long)s.tph[k];
+  if (prof && g.lane == 0 && !dummy) for (int k = 0; k < 8; k++) prof[1 + k] = (long long)s.tph[k] << 6;
   if (dummy) return;  // padding warp of a phase-synchronous CTA: took part in every barrier, stores nothing
   bool rc = reward_type == REWARD_STAGED ? any_robot_collision<T, G>(g, s, w) : false;
   for (int i = g.lane; i < 9; i += G) s.tmp6[18 + i / 6][i % 6] = s.qpos[i];
