@@ -26,7 +26,7 @@ namespace mm {
 #define MM_T0(s) 0
 #endif
 
-constexpr int MAXCON = 128;   // contacts per env (oracle max: 44 in scripted episodes, 76 in random-action stress)
+constexpr int MAXCON = 160;   // contacts per env (oracle max: 44 in scripted episodes, 76 in the table-collision stress run, > 128 in rare random-action pile-ups)
 constexpr int MAXROW = MAXCON * 6;
 constexpr int MAXPAIR = 16;   // simultaneously touching body pairs
 constexpr int MAXSPEC = 10;   // equality + at most one limit row per robot joint
@@ -37,6 +37,8 @@ constexpr double MINVAL_D = 1e-15;
 //  bits 0-3 pair slot | 4-7 class A | 8-11 class B | 12 condim-4 (cube) | 13-18 active-row bits | 19 robot-obstacle | 20-28 candidate index
 MM_HD int meta_slot(int m) { return m & 15; }
 MM_HD int meta_dim4(int m) { return (m >> 12) & 1; }
+// candidate pairs (and therefore contacts) are ordered by (class A, class B)
+MM_HD int sort_key(int m) { return (((m >> 4) & 15) << 4) | ((m >> 8) & 15); }
 
 template <class T>
 struct Scratch {
@@ -899,6 +901,7 @@ MM_HDX void collide(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<
     ncon += tot;
     g.sync();
   }
+  int nbox = ncon < MAXCON ? ncon : MAXCON;
   g.phase(3);
   long long tx0 = MM_T0(s);
   // EPA polytope: faces, their index words, horizon edges and canonical vertex ids live in SHARED memory (the H /
@@ -945,6 +948,49 @@ MM_HDX void collide(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<
   }
   if (ncon > MAXCON) { ncon = MAXCON; if (g.lane == 0) s.overflow |= 2; }
   g.sync();
+  // The box contacts [0, nbox) and the appended convex contacts [nbox, ncon) are each ordered by body-pair key;
+  // merge them (stable) so that every body pair owns ONE contiguous run and therefore one pair slot.
+  if (ncon > nbox && nbox > 0) {
+    for (int base = 0; base < ncon; base += G) {
+      int c = base + g.lane;
+      int dst = 0, m = 0;
+      T v[11];
+      if (c < ncon) {
+        m = w.cmeta[c];
+        int key = sort_key(m);
+        if (c < nbox) {  // box contact: stays before convex contacts of the same key
+          int before = 0;
+          for (int j = nbox; j < ncon; j++) before += sort_key(w.cmeta[j]) < key;
+          dst = c + before;
+        } else {
+          int before = 0;
+          for (int j = 0; j < nbox; j++) before += sort_key(w.cmeta[j]) <= key;
+          dst = (c - nbox) + before;
+        }
+        for (int d = 0; d < 3; d++) { v[d] = w.cpos[d * MAXCON + c]; v[3 + d] = w.cn[d * MAXCON + c]; v[6 + d] = w.ct1[d * MAXCON + c]; }
+        v[9] = w.cdist[c]; v[10] = w.cD[c];
+      }
+      // destinations of this chunk may hit sources of later chunks: stage through the row arrays (aref, Jaref, Jv
+      // are contiguous, 18 * MAXCON reals, and not in use before make_constraints)
+      if (c < ncon) {
+#if defined(MM_TRACE) && !defined(__CUDA_ARCH__)
+        printf("merge c %d key %x dst %d (nbox %d ncon %d)\n", c, (m >> 4) & 0xFF, dst, nbox, ncon);
+#endif
+        for (int d = 0; d < 11; d++) w.aref[d * MAXCON + dst] = v[d];
+        reinterpret_cast<int*>(w.aref + 12 * MAXCON)[dst] = m;
+      }
+    }
+    g.sync();
+    for (int c = g.lane; c < ncon; c += G) {
+      for (int d = 0; d < 3; d++) {
+        w.cpos[d * MAXCON + c] = w.aref[d * MAXCON + c]; w.cn[d * MAXCON + c] = w.aref[(3 + d) * MAXCON + c];
+        w.ct1[d * MAXCON + c] = w.aref[(6 + d) * MAXCON + c];
+      }
+      w.cdist[c] = w.aref[9 * MAXCON + c]; w.cD[c] = w.aref[10 * MAXCON + c];
+      w.cmeta[c] = reinterpret_cast<int*>(w.aref + 12 * MAXCON)[c];
+    }
+    g.sync();
+  }
   MM_TICK(s, g, 3, tx0);
   // pair slots: contacts are ordered by (classA, classB); a new slot starts where the key changes
   int npair = 0;
