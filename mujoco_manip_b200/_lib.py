@@ -11,7 +11,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_HERE, "_C", "libmm_manip.so")
+LIB_PATH = os.environ.get("MM_LIB_PATH") or os.path.join(_HERE, "_C", "libmm_manip.so")  # MM_LIB_PATH: A/B builds
 SRC_DIR = os.path.join(_HERE, "csrc")
 
 NQ, NV, NU = 30, 27, 8

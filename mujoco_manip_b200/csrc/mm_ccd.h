@@ -14,7 +14,7 @@ namespace mm {
 
 constexpr int EPA_MAXV = 136, EPA_MAXF = 256, EPA_MAXE = 128, EPA_MAXIT = 128;
 constexpr int EPA_REALS = EPA_MAXV * 6 + EPA_MAXF * 4;
-constexpr int EPA_INTS = EPA_MAXF + EPA_MAXE + EPA_MAXV + 8;
+constexpr int EPA_INTS = EPA_MAXF + EPA_MAXE + EPA_MAXV;
 constexpr int EPA_VIS = 1 << 30;
 constexpr int SHAPE_LV = 5;  // ceil(152 / 32): the largest hull has 152 vertices
 
@@ -126,6 +126,7 @@ MM_HDN bool gjk(const Grp<G>& g, const Shape<T>& s1, const Shape<T>& s2, SP<T>* 
   d = c;
 #pragma unroll 1
   for (int it = 0; it < 64; it++) {
+    if (cnt && g.lane == 0) cnt[1]++;
     support<T, G>(g, s1, s2, dir, a);
     if (dot3(a.v, dir) < 0) return false;
     T ao[3], ab[3], ac[3];
@@ -177,20 +178,13 @@ struct EpaMem {
   T* face;    // [EPA_MAXF][4]  n(3), d
   int* fidx;  // [EPA_MAXF]     three vertex indices packed 10 bits each (+ EPA_VIS while a face is being removed)
   int* edge;  // [EPA_MAXE]     horizon edges: two vertex indices packed 16 bits each
-  T* vs;      // [nvs][3]       shared-memory mirror of the first nvs vertex positions (the hot reads)
-  int nvs;
-  int* canon; // [EPA_MAXV + 8] lowest vertex index with identical coordinates (edge matching compares coordinates);
-              //                the 8 words after it hold the face-visibility bit mask of the current iteration
+  int* canon; // [EPA_MAXV]     lowest vertex index with identical coordinates (edge matching compares coordinates)
 };
-
-// position of vertex i: shared mirror when it is inside the mirrored range, global workspace otherwise
-template <class T>
-MM_HD const T* epa_v(const EpaMem<T>& m, int i) { return i < m.nvs ? m.vs + 3 * i : m.vert + 6 * i; }
 
 // face f from vertices (ia, ib, ic); flip = which two indices swap when the normal points inward
 template <class T>
 MM_HD void epa_mkface(const EpaMem<T>& m, int f, int ia, int ib, int ic, bool initial) {
-  const T *a = epa_v(m, ia), *b = epa_v(m, ib), *c = epa_v(m, ic);
+  const T *a = m.vert + 6 * ia, *b = m.vert + 6 * ib, *c = m.vert + 6 * ic;
   T e1[3], e2[3], n[3];
   sub3(e1, b, a);
   sub3(e2, c, a);
@@ -223,22 +217,14 @@ MM_HD int epa_best(const Grp<G>& g, const EpaMem<T>& m, int nf) {
   return best >= nf ? 0 : best;
 }
 
-// profiling aid: cycles / 64 per EPA stage into cnt[4..7] (best-face search, support, canon + visibility, removal + new faces)
-#ifdef __CUDA_ARCH__
-#define MM_EPA_T(slot) do { if (cnt) { long long t_ = clock64(); if ((slot) && g.lane == 0) cnt[slot] += (unsigned)((t_ - tl_) >> 6); tl_ = t_; } } while (0)
-#else
-#define MM_EPA_T(slot) do { } while (0)
-#endif
-
 // Outputs contact position (mid witness), normal (shape1 -> shape2) and penetration depth (same on every lane).
 template <class T, int G>
 MM_HDN bool epa(const Grp<G>& g, const Shape<T>& s1, const Shape<T>& s2, const SP<T>* sx, const EpaMem<T>& m, T* pos,
                 T* nrm, T* depth, unsigned* cnt = nullptr) {
   int nv = 4, nf = 4;
-  long long tl_ = 0;
   if (g.lane == 0) {
     for (int i = 0; i < 4; i++) {
-      for (int k = 0; k < 3; k++) { m.vert[6 * i + k] = sx[i].v[k]; m.vert[6 * i + 3 + k] = sx[i].a[k]; if (i < m.nvs) m.vs[3 * i + k] = sx[i].v[k]; }
+      for (int k = 0; k < 3; k++) { m.vert[6 * i + k] = sx[i].v[k]; m.vert[6 * i + 3 + k] = sx[i].a[k]; }
       int cn = i;
       for (int j = i - 1; j >= 0; j--)
         if (sx[j].v[0] == sx[i].v[0] && sx[j].v[1] == sx[i].v[1] && sx[j].v[2] == sx[i].v[2]) cn = j;
@@ -255,85 +241,58 @@ MM_HDN bool epa(const Grp<G>& g, const Shape<T>& s1, const Shape<T>& s2, const S
   g.sync();
 #pragma unroll 1
   for (int it = 0; it < EPA_MAXIT; it++) {
-    MM_EPA_T(0);
+    if (cnt && g.lane == 0) cnt[3]++;
     int best = epa_best<T, G>(g, m, nf);
     T n[3] = {m.face[4 * best], m.face[4 * best + 1], m.face[4 * best + 2]};
     SP<T> p;
-    MM_EPA_T(4);
     support<T, G>(g, s1, s2, n, p);
-    MM_EPA_T(5);
     T dist = dot3(p.v, n);
     if ((double)(dist - m.face[4 * best + 3]) < epa_tol<T>() || nf >= EPA_MAXF - 8) break;
     int ip = nv++;
     // new vertex, its canonical index, and the visibility flag of every face (spread over the lanes)
     int cn = ip;
     for (int j = g.lane; j < ip; j += G) {
-      const T* q = epa_v(m, j);
+      const T* q = m.vert + 6 * j;
       if (q[0] == p.v[0] && q[1] == p.v[1] && q[2] == p.v[2] && j < cn) cn = j;
     }
     cn = g.imin(cn);
     if (g.lane == 0) {
-      for (int k = 0; k < 3; k++) { m.vert[6 * ip + k] = p.v[k]; m.vert[6 * ip + 3 + k] = p.a[k]; if (ip < m.nvs) m.vs[3 * ip + k] = p.v[k]; }
+      for (int k = 0; k < 3; k++) { m.vert[6 * ip + k] = p.v[k]; m.vert[6 * ip + 3 + k] = p.a[k]; }
       m.canon[ip] = cn;
     }
-    // visibility of every face from the new vertex, as a bit mask (one ballot per G faces)
-    int* vm = m.canon + EPA_MAXV;
-    if (g.lane < 8) vm[g.lane] = 0;
-    g.sync();
-    for (int base = 0; base < nf; base += G) {
-      int i = base + g.lane;
-      int vis = 0;
-      if (i < nf) {
-        int fi = m.fidx[i];
-        const T* F = m.face + 4 * i;
-        T r[3];
-        sub3(r, p.v, epa_v(m, fi & 1023));
-        vis = (double)dot3(F, r) > epa_vis<T>();
-      }
-      unsigned bits = g.ballot(vis);
-      if (g.lane == 0 && bits) vm[base >> 5] |= (int)(bits << (base & 31));
+    for (int i = g.lane; i < nf; i += G) {
+      int fi = m.fidx[i];
+      const T* F = m.face + 4 * i;
+      T r[3];
+      sub3(r, p.v, m.vert + 6 * (fi & 1023));
+      if ((double)dot3(F, r) > epa_vis<T>()) m.fidx[i] = fi | EPA_VIS;
     }
     g.sync();
-    MM_EPA_T(6);
-    // removal of the visible faces and collection of the horizon in the oracle's order (swap-delete scan from
-    // face 0: a removed face is replaced by the last one, which is then examined in its new place).  Only the
-    // visible faces are visited: the scan jumps from set bit to set bit.
+    // removal of the visible faces and collection of the horizon, in the oracle's order (integer work, one lane)
     int ne = 0;
     if (g.lane == 0) {
-      int i = 0;
-      while (true) {
-        int wd = i >> 5;
-        unsigned word = (unsigned)vm[wd] & (~0u << (i & 31));
-        while (!word && (wd + 1) * 32 < nf) word = (unsigned)vm[++wd];
-        if (!word) break;
-        int pos = wd * 32;
-        while (!(word & 1u)) { word >>= 1; pos++; }
-        if (pos >= nf) break;
-        i = pos;
+      for (int i = 0; i < nf;) {
         int fi = m.fidx[i];
-        int id[3] = {fi & 1023, (fi >> 10) & 1023, (fi >> 20) & 1023};
-        for (int e = 0; e < 3; e++) {
-          int ea = id[e], eb = id[(e + 1) % 3];
-          int ca = m.canon[ea], cb = m.canon[eb];
-          bool found = false;
-          for (int k = 0; k < ne; k++) {
-            int ed = m.edge[k];
-            if (m.canon[ed & 0xFFFF] == cb && m.canon[ed >> 16] == ca) {  // shared edges appear reversed
-              m.edge[k] = m.edge[--ne];
-              found = true;
-              break;
+        if (fi & EPA_VIS) {
+          int id[3] = {fi & 1023, (fi >> 10) & 1023, (fi >> 20) & 1023};
+          for (int e = 0; e < 3; e++) {
+            int ea = id[e], eb = id[(e + 1) % 3];
+            int ca = m.canon[ea], cb = m.canon[eb];
+            bool found = false;
+            for (int k = 0; k < ne; k++) {
+              int ed = m.edge[k];
+              if (m.canon[ed & 0xFFFF] == cb && m.canon[ed >> 16] == ca) {  // shared edges appear reversed
+                m.edge[k] = m.edge[--ne];
+                found = true;
+                break;
+              }
             }
+            if (!found && ne < EPA_MAXE) { m.edge[ne] = ea | (eb << 16); ne++; }
           }
-          if (!found && ne < EPA_MAXE) { m.edge[ne] = ea | (eb << 16); ne++; }
-        }
-        --nf;
-        int lastbit = (vm[nf >> 5] >> (nf & 31)) & 1;
-        vm[nf >> 5] &= ~(1 << (nf & 31));
-        if (i != nf) {
+          --nf;
           m.fidx[i] = m.fidx[nf];
           for (int k = 0; k < 4; k++) m.face[4 * i + k] = m.face[4 * nf + k];
-          if (lastbit) vm[i >> 5] |= 1 << (i & 31); else vm[i >> 5] &= ~(1 << (i & 31));
-        }
+        } else i++;
       }
     }
     ne = g.bcast(ne, 0);
@@ -344,7 +303,6 @@ MM_HDN bool epa(const Grp<G>& g, const Shape<T>& s1, const Shape<T>& s2, const S
     for (int k = g.lane; k < add; k += G) { int ed = m.edge[k]; epa_mkface(m, nf + k, ed & 0xFFFF, ed >> 16, ip, false); }
     nf += add;
     g.sync();
-    MM_EPA_T(7);
   }
   int best = epa_best<T, G>(g, m, nf);
   const T* F = m.face + 4 * best;

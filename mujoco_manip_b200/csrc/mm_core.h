@@ -915,13 +915,6 @@ MM_HDX void collide(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<
   em.fidx = reinterpret_cast<int*>(s.H + EPA_MAXF * 4);
   em.edge = em.fidx + EPA_MAXF;
   em.canon = em.edge + EPA_MAXE;
-  {  // the rest of the dead block mirrors the first vertex positions
-    constexpr size_t blk = sizeof(s.H) + sizeof(s.tmp6) + sizeof(s.pairK) + sizeof(s.pairW) + sizeof(s.pairF) + 6 * sizeof(s.qacc);
-    constexpr size_t used = EPA_MAXF * 4 * sizeof(T) + ((EPA_INTS * sizeof(int) + sizeof(T) - 1) / sizeof(T)) * sizeof(T);
-    constexpr int nvs = (int)((blk - used) / (3 * sizeof(T)));
-    em.vs = s.H + used / sizeof(T);
-    em.nvs = nvs > EPA_MAXV ? EPA_MAXV : nvs;
-  }
   // narrow phase 2: general convex pairs (mesh hulls, cylinders): GJK + EPA by the whole group, one pair at a
   // time (support scans, face searches and face creation are spread over the lanes); contacts are appended
   for (int si = 0; si < nsurv; si++) {
@@ -934,9 +927,8 @@ MM_HDX void collide(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<
     fill_shape<T, G>(g, s, gm, b, ident, s2);
     SP<T> sx[4];
     T pos[3] = {0, 0, 0}, pn[3] = {0, 0, 1}, depth = 0;
-    unsigned* pc = s.prof ? s.tph : nullptr;  // profiling: EPA stage cycles into tph[4..7]
     if (!gjk<T, G>(g, s1, s2, sx)) continue;
-    if (!epa<T, G>(g, s1, s2, sx, em, pos, pn, &depth, pc)) continue;
+    if (!epa<T, G>(g, s1, s2, sx, em, pos, pn, &depth)) continue;
     if (g.lane == 0 && ncon < MAXCON) {
       T t1[3];
       make_tangent(pn, t1);
