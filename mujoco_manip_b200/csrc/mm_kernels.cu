@@ -87,8 +87,10 @@ struct mm_handle {
   mm_config cfg;
   void* d_model = nullptr;
   void* d_geom = nullptr;
-  void* d_work_reals = nullptr;
+  void* d_work_reals = nullptr;  // workspace pool: pool_ctas x envs_per_cta per-env slices
   int* d_work_ints = nullptr;
+  int* d_pool_flags = nullptr;
+  int pool_ctas = 0, envs_per_cta = 0;
   float* d_tgt = nullptr;
   // staging for the host-buffer path
   float* d_actions = nullptr;
@@ -108,8 +110,10 @@ size_t real_bytes(const mm_config* c) { return c->precision ? 4 : 8; }
 
 typedef cudaError_t (*prepare_fn)();
 typedef cudaError_t (*launch_fn)(int, const StepParams&, cudaStream_t);
+typedef cudaError_t (*resident_fn)(int*, int*);
 int inst_index(const mm_config& c) { return (c.precision ? 3 : 0) + (c.group == 32 ? 0 : (c.group == 16 ? 1 : 2)); }
 const prepare_fn PREPARE[6] = {prepare_f64_32, prepare_f64_16, prepare_f64_8, prepare_f32_32, prepare_f32_16, prepare_f32_8};
+const resident_fn RESIDENT[6] = {resident_f64_32, resident_f64_16, resident_f64_8, resident_f32_32, resident_f32_16, resident_f32_8};
 const launch_fn LAUNCH[6] = {launch_f64_32, launch_f64_16, launch_f64_8, launch_f32_32, launch_f32_16, launch_f32_8};
 
 template <class T>
@@ -143,7 +147,9 @@ const char* mm_last_error(void) { return g_err.c_str(); }
 
 size_t mm_workspace_bytes(const mm_config* cfg) {
   size_t n = (size_t)cfg->num_envs;
-  return n * ((size_t)WORK_REALS * real_bytes(cfg) + (size_t)WORK_INTS * 4 + 4 * 4 + (ACTION_STRIDE + OBS_DIM + 1) * 4 + 3);
+  // staging buffers per env + an upper bound of the pooled per-CTA workspaces (2 CTAs x 148 SMs x 16 envs)
+  size_t pool = 4736 < n ? 4736 : n;
+  return n * (4 * 4 + (ACTION_STRIDE + OBS_DIM + 1) * 4 + 3) + pool * ((size_t)WORK_REALS * real_bytes(cfg) + (size_t)WORK_INTS * 4);
 }
 
 int mm_create(const mm_config* cfg, mm_handle** out) {
@@ -163,23 +169,31 @@ int mm_create(const mm_config* cfg, mm_handle** out) {
   } else {
     if (upload_model<float>(h) != 0) return -1;
   }
-  // + 16 slots: padding warps of the last phase-synchronous CTA
-  CK(cudaMalloc(&h->d_work_reals, (n + 16) * WORK_REALS * real_bytes(cfg)));
-  CK(cudaMalloc(&h->d_work_ints, (n + 16) * WORK_INTS * sizeof(int)));
+  if (PREPARE[inst_index(h->cfg)]() != cudaSuccess) return fail("mm_create: kernel attribute set-up failed");
+  CK(RESIDENT[inst_index(h->cfg)](&h->pool_ctas, &h->envs_per_cta));
+  h->pool_ctas += 8;  // margin
+  {
+    size_t slices = (size_t)h->pool_ctas * h->envs_per_cta;
+    size_t need = (n + h->envs_per_cta - 1) / h->envs_per_cta;  // a grid that fits the pool uses blockIdx directly
+    if (need < (size_t)h->pool_ctas) { h->pool_ctas = (int)need; slices = need * h->envs_per_cta; }
+    CK(cudaMalloc(&h->d_work_reals, slices * WORK_REALS * real_bytes(cfg)));
+    CK(cudaMalloc(&h->d_work_ints, slices * WORK_INTS * sizeof(int)));
+    CK(cudaMalloc(&h->d_pool_flags, (size_t)h->pool_ctas * sizeof(int)));
+    CK(cudaMemset(h->d_pool_flags, 0, (size_t)h->pool_ctas * sizeof(int)));
+  }
   CK(cudaMalloc(&h->d_tgt, n * 4 * sizeof(float)));
   CK(cudaMemset(h->d_tgt, 0, n * 4 * sizeof(float)));
   CK(cudaMalloc(&h->d_actions, n * ACTION_STRIDE * sizeof(float)));
   CK(cudaMalloc(&h->d_obs, n * OBS_DIM * sizeof(float)));
   CK(cudaMalloc(&h->d_reward, n * sizeof(float)));
   CK(cudaMalloc(&h->d_flags, n * 3));
-  CK(PREPARE[inst_index(h->cfg)]());
   *out = h;
   return 0;
 }
 
 void mm_destroy(mm_handle* h) {
   if (!h) return;
-  cudaFree(h->d_model); cudaFree(h->d_geom); cudaFree(h->d_work_reals); cudaFree(h->d_work_ints); cudaFree(h->d_tgt);
+  cudaFree(h->d_model); cudaFree(h->d_geom); cudaFree(h->d_work_reals); cudaFree(h->d_work_ints); cudaFree(h->d_pool_flags); cudaFree(h->d_tgt);
   cudaFree(h->d_actions); cudaFree(h->d_obs); cudaFree(h->d_reward); cudaFree(h->d_flags);
   delete h;
 }
@@ -189,7 +203,7 @@ int mm_reset(mm_handle* h, const mm_state* st, const uint8_t* mask, const double
   if (!h || !st || !task) return fail("mm_reset: null argument");
   StepParams p{};
   p.st = to_ptrs(st);
-  p.model = h->d_model; p.work_reals = h->d_work_reals; p.work_ints = h->d_work_ints; p.tgt_kp = h->d_tgt;
+  p.model = h->d_model; p.work_reals = h->d_work_reals; p.work_ints = h->d_work_ints; p.pool_flags = h->d_pool_flags; p.pool_ctas = h->pool_ctas; p.tgt_kp = h->d_tgt;
   p.mask = mask; p.obj_xy = obj_xy; p.task = task; p.obs = obs; p.n = h->cfg.num_envs;
   p.reward_type = h->cfg.reward_type; p.max_steps = h->cfg.max_episode_steps;
   h->launches++;
@@ -205,7 +219,7 @@ int mm_step(mm_handle* h, const mm_state* st, const float* actions, int action_m
   p.st = to_ptrs(st);
   p.out.obs = out->obs; p.out.reward = out->reward; p.out.terminated = out->terminated; p.out.truncated = out->truncated;
   p.out.success = out->success; p.out.reward_components = out->reward_components;
-  p.actions = actions; p.model = h->d_model; p.work_reals = h->d_work_reals; p.work_ints = h->d_work_ints;
+  p.actions = actions; p.model = h->d_model; p.work_reals = h->d_work_reals; p.work_ints = h->d_work_ints; p.pool_flags = h->d_pool_flags; p.pool_ctas = h->pool_ctas;
   p.tgt_kp = h->d_tgt; p.n = h->cfg.num_envs; p.mode = action_mode; p.reward_type = h->cfg.reward_type;
   p.max_steps = h->cfg.max_episode_steps;
   p.cycles = h->d_cycles;
@@ -302,7 +316,7 @@ int mm_ops(mm_handle* h, const mm_state* st, int ops, const double* target, void
   if ((ops & MM_OP_IK) && !target) return fail("mm_ops: MM_OP_IK needs a target array");
   StepParams p{};
   p.st = to_ptrs(st);
-  p.model = h->d_model; p.work_reals = h->d_work_reals; p.work_ints = h->d_work_ints; p.tgt_kp = h->d_tgt;
+  p.model = h->d_model; p.work_reals = h->d_work_reals; p.work_ints = h->d_work_ints; p.pool_flags = h->d_pool_flags; p.pool_ctas = h->pool_ctas; p.tgt_kp = h->d_tgt;
   p.n = h->cfg.num_envs; p.ops = ops; p.target = target;
   h->launches++;
   CK(LAUNCH[inst_index(h->cfg)](2, p, (cudaStream_t)stream));

@@ -32,8 +32,10 @@ struct StepParams {
   StepOut out;
   const float* actions;
   const void* model;
-  void* work_reals;
+  void* work_reals;   // [pool_ctas * ENVS] per-env workspaces, handed out per RESIDENT CTA (see acquire_work)
   int* work_ints;
+  int* pool_flags;    // [pool_ctas] 0 = free
+  int pool_ctas;
   float* tgt_kp;
   const unsigned char* mask;
   const double* obj_xy;
@@ -66,6 +68,29 @@ __device__ __forceinline__ bool setup(const StepParams& p, unsigned char* smem, 
   return e < p.n;
 }
 
+// The per-env workspace (contacts, constraint rows, EPA vertices: ~47 KB) is scratch inside one launch, so it is
+// pooled per RESIDENT CTA instead of per env: a few hundred CTAs are in flight however many envs there are, and
+// their workspaces stay in L2 (N x 47 KB does not).  A CTA claims a free pool entry with a CAS scan that starts at
+// its own index (the pool is at least as large as the number of CTAs that can be resident) and frees it on exit.
+__device__ __forceinline__ int acquire_work(const StepParams& p) {
+  __shared__ int s_slot;
+  if (threadIdx.x == 0) {
+    int slot;
+    if ((int)gridDim.x <= p.pool_ctas) slot = (int)blockIdx.x;
+    else {
+      slot = (int)(blockIdx.x % (unsigned)p.pool_ctas);
+      while (atomicCAS(p.pool_flags + slot, 0, 1) != 0) slot = slot + 1 == p.pool_ctas ? 0 : slot + 1;
+    }
+    s_slot = slot;
+  }
+  __syncthreads();
+  return s_slot;
+}
+__device__ __forceinline__ void release_work(const StepParams& p, int slot) {
+  __syncthreads();
+  if (threadIdx.x == 0 && (int)gridDim.x > p.pool_ctas) { __threadfence(); atomicExch(p.pool_flags + slot, 0); }
+}
+
 template <class T, int G>
 __global__ void __launch_bounds__(BlockCfg<T, G>::THREADS, BlockCfg<T, G>::MINB) k_step(StepParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -73,24 +98,23 @@ __global__ void __launch_bounds__(BlockCfg<T, G>::THREADS, BlockCfg<T, G>::MINB)
   Scratch<T>* sc;
   Grp<G> g;
   long e;
+  int pool = acquire_work(p);
   bool valid = setup<T, G>(p, smem, md, sc, g, e);
   bool dummy = false;
-  if (G == 32) {  // phase-synchronous CTA: padding warps replay the last env without storing
-    g.ps = p.phase_level;
-    if (!valid) { e = p.n - 1; dummy = true; }
-  } else if (!valid) return;
+  if (G == 32) g.ps = p.phase_level;
+  if (!valid) { e = p.n - 1; dummy = true; }  // padding group: replays the last env without storing
   if (p.order) e = p.order[e];
 #ifdef __CUDA_ARCH__
   g.mark = clock64();
 #endif
-  // padding warps get their own workspace slice (allocated past the last env)
-  long wslot = dummy ? p.n + (threadIdx.x / 32) : e;
+  long wslot = (long)pool * BlockCfg<T, G>::ENVS + threadIdx.x / G;
   Work<T> w = make_work(reinterpret_cast<T*>(p.work_reals) + wslot * WORK_REALS, p.work_ints + wslot * WORK_INTS);
   long long t0 = p.cycles ? clock64() : 0;
   env_step<T, G>(g, *sc, *md, w, p.st, e, p.actions, p.mode, p.reward_type, p.max_steps, p.out, p.tgt_kp, dummy,
                  p.cycles ? p.cycles + 9 * e : nullptr);
   if (p.cycles && g.lane == 0 && !dummy) p.cycles[9 * e] = clock64() - t0;
   if (p.work && g.lane == 0 && !dummy) p.work[e] = (int)((g.busy + (clock64() - g.mark)) >> 8);
+  release_work(p, pool);
 }
 
 template <class T, int G>
@@ -100,11 +124,16 @@ __global__ void __launch_bounds__(BlockCfg<T, G>::THREADS, BlockCfg<T, G>::MINB)
   Scratch<T>* sc;
   Grp<G> g;
   long e;
-  if (!setup<T, G>(p, smem, md, sc, g, e)) return;
-  if (p.mask && !p.mask[e]) return;
-  Work<T> w = make_work(reinterpret_cast<T*>(p.work_reals) + e * WORK_REALS, p.work_ints + e * WORK_INTS);
-  env_reset<T, G>(g, *sc, *md, w, p.st, e, p.obj_xy ? p.obj_xy + 6 * e : nullptr, p.task[2 * e], p.task[2 * e + 1], p.obs,
-                  p.tgt_kp);
+  int pool = acquire_work(p);
+  bool valid = setup<T, G>(p, smem, md, sc, g, e);
+  if (valid && p.mask && !p.mask[e]) valid = false;
+  if (valid) {
+    long wslot = (long)pool * BlockCfg<T, G>::ENVS + threadIdx.x / G;
+    Work<T> w = make_work(reinterpret_cast<T*>(p.work_reals) + wslot * WORK_REALS, p.work_ints + wslot * WORK_INTS);
+    env_reset<T, G>(g, *sc, *md, w, p.st, e, p.obj_xy ? p.obj_xy + 6 * e : nullptr, p.task[2 * e], p.task[2 * e + 1], p.obs,
+                    p.tgt_kp);
+  }
+  release_work(p, pool);
 }
 
 
@@ -121,9 +150,13 @@ __global__ void __launch_bounds__(BlockCfg<T, G>::THREADS, BlockCfg<T, G>::MINB)
   Scratch<T>* sc;
   Grp<G> g;
   long e;
-  if (!setup<T, G>(p, smem, md, sc, g, e)) return;
-  Work<T> w = make_work(reinterpret_cast<T*>(p.work_reals) + e * WORK_REALS, p.work_ints + e * WORK_INTS);
-  env_ops<T, G>(g, *sc, *md, w, p.st, e, p.ops, p.target);
+  int pool = acquire_work(p);
+  if (setup<T, G>(p, smem, md, sc, g, e)) {
+    long wslot = (long)pool * BlockCfg<T, G>::ENVS + threadIdx.x / G;
+    Work<T> w = make_work(reinterpret_cast<T*>(p.work_reals) + wslot * WORK_REALS, p.work_ints + wslot * WORK_INTS);
+    env_ops<T, G>(g, *sc, *md, w, p.st, e, p.ops, p.target);
+  }
+  release_work(p, pool);
 }
 
 template <class T, int G>
@@ -137,6 +170,29 @@ cudaError_t inst_prepare() {
   e = cudaFuncSetAttribute(k_ops<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(k_reset<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+}
+
+// CTAs of this instantiation that can be resident on the device (sizes the workspace pool)
+template <class T, int G>
+cudaError_t inst_resident(int* ctas, int* envs_per_cta) {
+  int dev = 0, sms = 0, per = 0, best = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess) return e;
+  size_t sm = smem_bytes<T, G>();
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_step<T, G>, BlockCfg<T, G>::THREADS, sm);
+  if (e != cudaSuccess) return e;
+  best = per;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_reset<T, G>, BlockCfg<T, G>::THREADS, sm);
+  if (e != cudaSuccess) return e;
+  best = per > best ? per : best;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_ops<T, G>, BlockCfg<T, G>::THREADS, sm);
+  if (e != cudaSuccess) return e;
+  best = per > best ? per : best;
+  *ctas = best * sms;
+  *envs_per_cta = BlockCfg<T, G>::ENVS;
+  return cudaSuccess;
 }
 
 template <class T, int G>
@@ -154,6 +210,7 @@ cudaError_t inst_launch(int which, const StepParams& p, cudaStream_t s) {  // wh
 // entry points defined by the mm_inst_*.cu units
 #define MM_DECL_INST(NAME)                 \
   cudaError_t prepare_##NAME();            \
+  cudaError_t resident_##NAME(int* ctas, int* envs_per_cta); \
   cudaError_t launch_##NAME(int which, const StepParams& p, cudaStream_t s);
 MM_DECL_INST(f64_32) MM_DECL_INST(f64_16) MM_DECL_INST(f64_8)
 MM_DECL_INST(f32_32) MM_DECL_INST(f32_16) MM_DECL_INST(f32_8)
@@ -161,6 +218,7 @@ MM_DECL_INST(f32_32) MM_DECL_INST(f32_16) MM_DECL_INST(f32_8)
 #define MM_DEFINE_INST(NAME, T, G)                                                              \
   namespace mm {                                                                                \
   cudaError_t prepare_##NAME() { return inst_prepare<T, G>(); }                                 \
+  cudaError_t resident_##NAME(int* ctas, int* envs_per_cta) { return inst_resident<T, G>(ctas, envs_per_cta); } \
   cudaError_t launch_##NAME(int which, const StepParams& p, cudaStream_t s) { return inst_launch<T, G>(which, p, s); } \
   }
 
