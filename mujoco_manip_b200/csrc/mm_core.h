@@ -858,7 +858,7 @@ MM_HDX void collide(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<
   // live in the shared H region, which is free during collision); ordered compaction of the contacts
   constexpr int KB = G < NARROW_LANES ? G : NARROW_LANES;
   int ncon = 0;
-  for (int base = 0; base < nsurv; base += KB) {
+  for (int base = 0; g.any_more(base < nsurv, 6); base += KB) {
     int si = base + g.lane;
     int cnt = 0, a = 0, b = 0, ci_ = 0;
     T nrm[3] = {0, 0, 1};
@@ -917,11 +917,18 @@ MM_HDX void collide(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<
   em.canon = em.edge + EPA_MAXE;
   // narrow phase 2: general convex pairs (mesh hulls, cylinders): GJK + EPA by the whole group, one pair at a
   // time (support scans, face searches and face creation are spread over the lanes); contacts are appended
-  for (int si = 0; si < nsurv; si++) {
-    int ci = w.surv[si];
-    int a = gm.pair[ci][0], b = gm.pair[ci][1];
-    int ta = gm.type[a], tb = gm.type[b];
-    if (ta == GT_PLANE || (ta == GT_BOX && tb == GT_BOX)) continue;
+  // (the loop advances to the env's next convex pair first, so that a turn of the loop = one GJK / EPA run on
+  // every warp that still has one, and the warps can meet at a barrier per turn)
+  for (int si = 0;; si++) {
+    int ci = 0, a = 0, b = 0;
+    for (; si < nsurv; si++) {
+      ci = w.surv[si];
+      a = gm.pair[ci][0]; b = gm.pair[ci][1];
+      int ta = gm.type[a], tb = gm.type[b];
+      if (!(ta == GT_PLANE || (ta == GT_BOX && tb == GT_BOX))) break;
+    }
+    if (!g.any_more(si < nsurv, 6)) break;
+    if (si >= nsurv) continue;
     Shape<T> s1, s2;
     fill_shape<T, G>(g, s, gm, a, ident, s1);
     fill_shape<T, G>(g, s, gm, b, ident, s2);
@@ -1420,15 +1427,14 @@ MM_HDX void solve(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>
   bool first = true, finished = false;
   g.phase(3);
   long long tn0 = MM_T0(s);
+  // Every warp of a phase-synchronous CTA runs the same number of loop turns and passes the same barriers
+  // (`all_done`, `phase`) in each; a finished env just skips the work between them.
   while (true) {
-   if (!finished) {
-    T oldcost = cost;
-    bool done = false;
-    for (int pass = 0; pass < 2; pass++) {  // pass 1 (per-pair blocks + factorisation) only when the active set changed
+    // (A) constraint update at the current point: active set, cost, forces; convergence test of the last move
+    if (!finished) {
+      T oldcost = cost;
       int chg;
-      T cst = update_constraint<T, G>(g, s, w, pass == 1, &chg);
-      if (pass == 1) { build_factor_H<T, G>(g, s, md); break; }
-      cost = cst;
+      cost = update_constraint<T, G>(g, s, w, false, &chg);
       changed = chg;
       int sb = 0;
       for (int k = 0; k < s.nspec; k++) if (s.specdof[k] < 0 || s.specJaref[k] < 0) sb |= 1 << k;
@@ -1447,56 +1453,61 @@ MM_HDX void solve(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>
 #if defined(MM_TRACE) && !defined(__CUDA_ARCH__)
         printf("  it %d alpha %.6e cost %.12e impr %.3e grad %.3e changed %d\n", iter, (double)a, (double)cost, (double)improvement, (double)gradient, changed);
 #endif
-        if (improvement < tol || gradient < tol || iter >= 100) { done = true; break; }
+        if (improvement < tol || gradient < tol || iter >= 100) finished = true;
       }
-      if (!(first || changed)) break;
     }
-    if (done) finished = true;
-   }
-   if (g.all_done(finished)) break;
-   if (finished) continue;
-   {
+    if (g.all_done(finished)) break;
+    // (B) per-pair blocks + factorisation of H, only when the active set changed
+    if (!finished && (first || changed)) {
+      int dummy;
+      update_constraint<T, G>(g, s, w, true, &dummy);
+      build_factor_H<T, G>(g, s, md);
+    }
     first = false;
-    // gradient and Newton direction
-    for (int i = g.lane; i < NV; i += G) { T gr = s.Ma[i] - s.fs[i] - s.fc[i]; s.grad[i] = gr; s.search[i] = -gr; }
-    g.sync();
-    solve_H<T, G>(g, s, s.search);
-    // line search set-up
+    g.phase(5);
+    // (C) Newton direction and the quantities of the line search
     T sn = 0, qg1 = 0, qg2 = 0;
-    mulM<T, G>(g, s, md, s.search, s.Mv);
-    mulJ<T, G>(g, s, w, s.search, w.Jv, s.specJv);
-    for (int i = g.lane; i < NV; i += G) {
-      sn += s.search[i] * s.search[i];
-      qg1 += s.search[i] * (s.Ma[i] - s.fs[i]);
-      qg2 += (T)0.5 * s.search[i] * s.Mv[i];
-    }
-    sn = tsqrt(g.sum(sn)); qg1 = g.sum(qg1); qg2 = g.sum(qg2);
-    if (sn < (T)MINVAL_D) { finished = true; continue; }
-    T gtol = tol * (T)0.01 * sn * scale_inv;
-    T lo = 0, hi = -1, d1, d2;
-    a = 0;
-    bool flat = false;
-    for (int it = -1; it < 50; it++) {  // it = -1: slope at alpha = 0
-      if (it >= 0) {
-        T an = a - d1 / d2;
-        if (hi > 0 && !(an > lo && an < hi)) an = (T)0.5 * (lo + hi);
-        a = an;
+    if (!finished) {
+      for (int i = g.lane; i < NV; i += G) { T gr = s.Ma[i] - s.fs[i] - s.fc[i]; s.grad[i] = gr; s.search[i] = -gr; }
+      g.sync();
+      solve_H<T, G>(g, s, s.search);
+      mulM<T, G>(g, s, md, s.search, s.Mv);
+      mulJ<T, G>(g, s, w, s.search, w.Jv, s.specJv);
+      for (int i = g.lane; i < NV; i += G) {
+        sn += s.search[i] * s.search[i];
+        qg1 += s.search[i] * (s.Ma[i] - s.fs[i]);
+        qg2 += (T)0.5 * s.search[i] * s.Mv[i];
       }
-      ls_eval<T, G>(g, s, w, a, qg1, qg2, &d1, &d2);
-      if (it < 0) { if (d1 >= 0) { flat = true; break; } continue; }
-      if (tabs(d1) < gtol) break;
-      if (d1 < 0) lo = a; else hi = a;
+      sn = tsqrt(g.sum(sn)); qg1 = g.sum(qg1); qg2 = g.sum(qg2);
+      if (sn < (T)MINVAL_D) finished = true;
     }
-    if (flat) { finished = true; continue; }
-    if (a == 0) { finished = true; continue; }
-    // move
-    for (int i = g.lane; i < NV; i += G) { s.qacc[i] += a * s.search[i]; s.Ma[i] += a * s.Mv[i]; }
-    for (int c = g.lane; c < ncon; c += G) for (int r = 0; r < 6; r++) w.Jaref[c * 6 + r] += a * w.Jv[c * 6 + r];
-    for (int k = g.lane; k < s.nspec; k += G) s.specJaref[k] += a * s.specJv[k];
-    g.sync();
-   }
+    g.phase(5);
+    // (D) exact line search and the move
+    if (!finished) {
+      T gtol = tol * (T)0.01 * sn * scale_inv;
+      T lo = 0, hi = -1, d1, d2;
+      a = 0;
+      bool flat = false;
+      for (int it = -1; it < 50; it++) {  // it = -1: slope at alpha = 0
+        if (it >= 0) {
+          T an = a - d1 / d2;
+          if (hi > 0 && !(an > lo && an < hi)) an = (T)0.5 * (lo + hi);
+          a = an;
+        }
+        ls_eval<T, G>(g, s, w, a, qg1, qg2, &d1, &d2);
+        if (it < 0) { if (d1 >= 0) { flat = true; break; } continue; }
+        if (tabs(d1) < gtol) break;
+        if (d1 < 0) lo = a; else hi = a;
+      }
+      if (flat || a == 0) finished = true;
+      else {
+        for (int i = g.lane; i < NV; i += G) { s.qacc[i] += a * s.search[i]; s.Ma[i] += a * s.Mv[i]; }
+        for (int c = g.lane; c < ncon; c += G) for (int r = 0; r < 6; r++) w.Jaref[c * 6 + r] += a * w.Jv[c * 6 + r];
+        for (int k = g.lane; k < s.nspec; k += G) s.specJaref[k] += a * s.specJv[k];
+        g.sync();
+      }
+    }
   }
-
   if (g.lane == 0) s.niter = iter;
   for (int i = g.lane; i < NV; i += G) s.warm[i] = s.qacc[i];
   g.sync();
@@ -1508,6 +1519,7 @@ MM_HDN void forward(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<
   g.phase(3);
   long long t0 = MM_T0(s);
   fk<T, G>(g, s, md);
+  g.phase(5);
   dyn_smooth<T, G>(g, s, md);
   MM_TICK(s, g, 0, t0);
   g.phase(2);
@@ -1516,6 +1528,7 @@ MM_HDN void forward(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<
   g.phase(2);
   t0 = MM_T0(s);
   make_constraints<T, G>(g, s, md, w);
+  g.phase(5);
   solve<T, G>(g, s, md, w);
 
 }
