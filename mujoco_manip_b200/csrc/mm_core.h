@@ -60,7 +60,8 @@ struct Scratch {
   int specdof[MAXSPEC];  // -1: equality row (e7 - e8); else dof | (negative sign ? 256 : 0)
   int actsat[NU];
   int ncon, npair, nspec, nsurv, overflow, niter, hvalid;
-  unsigned tph[8];  // profiling: cycles/64 spent in fk+dyn | broad | narrow | rows+warmstart | newton | integrate | ik | -
+  unsigned tph[8];  // profiling (mm_set_cycle_buffer): busy cycles / 64 in kinematics+dynamics | broad phase | narrow
+                    // phase | its convex (GJK / EPA) part | constraint rows | solver | IK | integration
   int prof;
   int lone;       // bit c: cube c touches neither the robot nor another cube -> its 6x6 block of H is independent
   int n_il;       // dofs of the coupled part: robot (9) + the cubes that are not `lone`
@@ -1426,7 +1427,6 @@ MM_HDX void solve(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>
   T cost = 0, a = 0;
   bool first = true, finished = false;
   g.phase(3);
-  long long tn0 = MM_T0(s);
   // Every warp of a phase-synchronous CTA runs the same number of loop turns and passes the same barriers
   // (`all_done`, `phase`) in each; a finished env just skips the work between them.
   while (true) {
@@ -1528,8 +1528,11 @@ MM_HDN void forward(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<
   g.phase(2);
   t0 = MM_T0(s);
   make_constraints<T, G>(g, s, md, w);
+  MM_TICK(s, g, 4, t0);
   g.phase(5);
+  t0 = MM_T0(s);
   solve<T, G>(g, s, md, w);
+  MM_TICK(s, g, 5, t0);
 
 }
 

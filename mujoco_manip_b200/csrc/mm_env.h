@@ -263,6 +263,7 @@ MM_HDN void env_step(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work
     g.phase(1);
     long long ti0 = MM_T0(s);
     if (!last) ik<T, G>(g, s, md);
+    MM_TICK(s, g, 6, ti0);
 
     if (state_bad<T, G>(g, s)) {
       for (int i = g.lane; i < NQ; i += G) s.qpos[i] = md.key_qpos[i];
@@ -274,6 +275,7 @@ MM_HDN void env_step(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work
     g.phase(3);
     ti0 = MM_T0(s);
     if (!last) integrate<T, G>(g, s, md);
+    MM_TICK(s, g, 7, ti0);
 
   }
   if (prof && g.lane == 0 && !dummy) for (int k = 0; k < 8; k++) prof[1 + k] = (long long)s.tph[k] << 6;

@@ -47,7 +47,7 @@ for t in range(a.steps):
         print(f"step {t}: launch {e0.elapsed_time(e1):.1f} ms | per-env ms p50 {q[0]:.2f} p90 {q[1]:.2f} p99 {q[2]:.2f} max {q[3]:.2f} "
               f"| sum/SMs {float(c.sum()) / 148:.1f} | ncon mean {float(ncon.mean()):.1f} max {int(ncon.max())} "
               f"| worst env ncon {int(ncon[worst])} iters {int(env.state['diag'][worst, 1])}")
-        names = ["kin+dyn", "broad", "narrow(all)", "narrow-convex", "epa:best", "epa:support", "epa:vis", "epa:remove+new"]
+        names = ["kin+dyn", "broad", "narrow(all)", "narrow-convex", "rows", "solver", "ik", "integrate"]
         ph = cyc9[:, 1:].double() / 1.965e6
         order = torch.argsort(c)
         med, slow = order[a.envs // 2 - 50: a.envs // 2 + 50], order[-a.envs // 20:]
