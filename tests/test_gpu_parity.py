@@ -259,3 +259,90 @@ def test_f64_random_rollout_vs_golden(cuda_device, mode):
         assert reltol(_np(env.state["eepose"])[0][3:], g["ee_R"][t], TOL) < TOL
         assert int(env.state["diag"][0, 0]) == int(g["ncon"][t])
         np.testing.assert_allclose(_np(env.obs_packed)[0], g["obs"][t], rtol=0, atol=2e-5)
+
+
+def test_physics_level_loop_vs_oracle(cuda_device, oracle_lib):
+    """Engine-level ops (mm_ops): compute -> set_arm_ctrl -> mj_step loop of main.py / tests/test_controller.py.
+    The IK of tick k runs on the kinematics of the previous position stage; the oracle's
+    Data keeps that staleness naturally, mm_ops through the `kin` state."""
+    import torch
+
+    from mujoco_manip_b200 import PickPlaceGymEnv
+
+    env = PickPlaceGymEnv(action_mode="abs_pos", task=("obj_red", "bin_red"), device=str(cuda_device))
+    env.reset(seed=0)
+    orc = oracle_lib.OracleEnv(action_mode="abs_pos")
+    orc.reset(None, 0, 0)
+    target = np.array([0.12, 0.5, 0.4])
+    for t in range(60):
+        q = env.controller.compute(target)
+        qo = orc.ik(target)
+        np.testing.assert_allclose(q, qo, rtol=0, atol=1e-9, err_msg=f"IK differs at tick {t}")
+        env.robot.set_arm_ctrl(q)
+        orc.ctrl[:7] = qo
+        if t == 30:
+            env.robot.close_gripper()
+            orc.ctrl[7] = 0.0
+        env.pick_place_env.step()
+        orc.mj_step()
+        qpos = env.pick_place_env._vec.state["qpos"][0].cpu().numpy()
+        assert reltol(qpos, orc.qpos, TOL) < 1e-8, t
+        # robot.ee_pos is the pose of the last position stage (pre-integration), as data.xpos in the reference
+        np.testing.assert_allclose(env.robot.ee_pos, orc.xpos[9], rtol=0, atol=1e-9)
+    env.pick_place_env.forward()
+    orc.mj_forward()
+    np.testing.assert_allclose(env.robot.ee_pos, orc.xpos[9], rtol=0, atol=1e-9)
+    env.close()
+
+
+def test_state_round_trip_is_reproducible(cuda_device):
+    """get_state / set_state (checkpoint of the sim): replaying from a snapshot gives bit-identical results,
+    whatever the env-to-CTA schedule was."""
+    import torch
+
+    env = _make(37, cuda_device, action_mode="abs_pos", randomize_objects=True, rng="philox", seed=3, tasks="cross")
+    env.reset()
+    for _ in range(3):
+        env.step(env.fsm_plan(16).clone())
+    snap = env.get_state()
+    acts = []
+    for _ in range(4):
+        a = env.fsm_plan(16).clone()
+        acts.append(a)
+        env.step(a)
+    end1 = {k: v.clone() for k, v in env.state.items()}
+    env.set_state(snap)
+    env._work.zero_()  # different schedule on the replay
+    for a in acts:
+        env.fsm_plan(16)
+        env.step(a)
+    for k in ("qpos", "qvel", "ctrl", "warm", "fsm_i", "fsm_f", "step_count"):
+        assert torch.equal(env.state[k], end1[k]), k
+
+
+def test_reward_types_and_success_flags_vs_oracle(cuda_device, oracle_lib):
+    """dense / sparse / staged rewards, terminated / success flags for three different tasks in one batch."""
+    import torch
+
+    tasks = [("obj_red", "bin_blue"), ("obj_green", "bin_red"), ("obj_blue", "bin_green")]
+    for rtype in ("dense", "sparse", "staged"):
+        env = _make(3, cuda_device, action_mode="abs_pos", reward_type=rtype)
+        env.reset(options={"task": tasks})
+        orcs = []
+        for o, b in tasks:
+            oc = oracle_lib.OracleEnv(action_mode="abs_pos", reward_type=rtype)
+            oc.reset(None, ["obj_red", "obj_green", "obj_blue"].index(o), ["bin_red", "bin_green", "bin_blue"].index(b))
+            oc.fsm_reset()
+            orcs.append(oc)
+        for t in range(25):
+            a = env.fsm_plan(16).clone()
+            obs, r, te, tr, info = env.step(a)
+            for k, oc in enumerate(orcs):
+                oc.fsm_plan(16)
+                o_obs, o_r, o_te, o_tr, o_info = oc.step(oc.fsm_action())
+                assert abs(float(r[k]) - o_r) < 1e-5, (rtype, t, k)
+                assert bool(te[k]) == o_te and bool(info["success"][k]) == o_info["success"]
+                if rtype == "staged":
+                    np.testing.assert_allclose(info["reward_components"][k].cpu().numpy(), o_info["reward_components"], atol=1e-5)
+                np.testing.assert_allclose(_np(env.obs_packed)[k], o_obs, rtol=0, atol=2e-5)
+        env.close()
