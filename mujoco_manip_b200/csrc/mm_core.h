@@ -9,10 +9,13 @@
 //   * CRBA with compact rigid-body inertias (m, h, Ibar) about the world origin -> 9x9 robot block;
 //     the cube blocks are constant diag(m, I)
 //   * RNEA in the same coordinates for the bias forces
-//   * box-box / plane-box narrow phase, contacts grouped by BODY PAIR
+//   * two-level broad phase, box-box / plane-box / plane-hull narrow phase + GJK / EPA for hulls and cylinders
+//     (mm_ccd.h), contacts grouped by BODY PAIR
 //   * pyramidal soft constraints solved by Newton with exact line search, MATRIX-FREE:
 //     J is never stored; every J*x, J^T*f and J^T D J goes through per-body-pair 6-vectors / 6x6 blocks
+//   * H = M + J^T D J assembled per touching body pair and factored by coupling structure (lone cubes: 6x6 on one lane)
 //   * implicitfast integration (block diagonal: 9x9 robot factor, scalar cube updates)
+// Execution: G = 32 lanes per env, phase-synchronous CTAs (Grp::phase / any_more / all_done), see mm_launch.cuh.
 #pragma once
 #include "mm_ccd.h"
 
@@ -497,7 +500,8 @@ MM_HDN void mulM(const Grp<G>& g, const Scratch<T>& s, const ModelDev<T>& md, co
 }
 
 // ------------------------------------------------------------------------------------------------
-// collision: plane-box and box-box only in this round (robot hulls: see DESIGN.md)
+// collision: all 47 geoms / 780 candidate pairs - plane-box, box-box, plane-hull here, every pair
+// with a mesh hull or a cylinder through GJK + EPA (mm_ccd.h)
 // ------------------------------------------------------------------------------------------------
 template <class T>
 struct BoxRef { const T* c; const T* R; const T* s; };

@@ -1,7 +1,7 @@
 // CUDA kernels (sm_100a) + the C ABI of include/mm_manip.h.
-// One G-lane group per environment (G = 32 warp-per-env, 16 / 8 = two / four envs per warp);
-// per-env matrices live in shared memory, streamed per-contact data in a global workspace that the
-// lanes touch with consecutive indices.  No CPU fallback: every entry point needs a CUDA device.
+// One G-lane group per environment (G = 32 warp-per-env is the tuned, phase-synchronous configuration; 16 / 8 =
+// two / four envs per warp); per-env matrices live in shared memory, streamed per-contact data in a pooled global
+// workspace that the lanes touch with consecutive indices.  No CPU fallback: every entry point needs a CUDA device.
 #define MM_MODEL_HOST_FILL
 #include <cuda_runtime.h>
 

@@ -1,4 +1,4 @@
-// Per-precision model table the kernels read (one copy per CTA in shared memory).
+// Per-precision model tables the kernels read (global memory, read-only, L1 / L2 resident).
 // Filled on the host from the generated double tables (model_gen.h / model_dev_gen.h).
 #pragma once
 #include "mm_group.h"
