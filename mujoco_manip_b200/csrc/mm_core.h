@@ -43,18 +43,28 @@ MM_HD int meta_dim4(int m) { return (m >> 12) & 1; }
 // candidate pairs (and therefore contacts) are ordered by (class A, class B)
 MM_HD int sort_key(int m) { return (((m >> 4) & 15) << 4) | ((m >> 8) & 15); }
 
+// rows of Scratch::S: robot dofs 0..8, then the three rotational dofs of each cube
+constexpr int NSROW = NROB + 9;
+MM_HD int srow(int dof) { return dof < NROB ? dof : NROB + 3 * ((dof - NROB) / 6) + ((dof - NROB) % 6 - 3); }
+MM_HD bool is_cube_translation(int dof) { return dof >= NROB && ((dof - NROB) % 6) < 3; }
+// rows of the 6-vector scratch: 16 suffice (14 dofs of a body pair + 2 rows that park the position-stage qpos);
+// the FP32 build keeps 27 because its EPA workspace (integers are as wide as reals there) needs the room
+template <class T> constexpr int TMP6_ROWS() { return sizeof(T) == 8 ? 16 : 27; }
+constexpr int KIN_ROW = 14;  // tmp6 rows 14, 15: arm + finger qpos of the last position stage (store_state)
+
 template <class T>
 struct Scratch {
-  T qpos[NQ], qvel[NV], ctrl[NU], warm[NV];
+  T qpos[NQ], qvel[NV], ctrl[NU];
+  double* warm_g;  // qacc_warmstart of this env in the global state (read at the start of solve, written at its end)
   T bpos[NDB][3], bR[NDB][9];
-  T S[NV][6];
+  T S[NSROW][6];   // spatial axes of the dofs that have a non-trivial one (see srow); cube translations are unit vectors
   T Mr[NROB * NROB];
   T fs[NV], as[NV];
   // ---- contiguous block that is dead during collision (re-used there as clip scratch and EPA polytope) ----
   T H[NV * NV];
-  T tmp6[NV][6];
+  T tmp6[TMP6_ROWS<T>()][6];
   T pairK[MAXPAIR][21], pairW[MAXPAIR][6], pairF[MAXPAIR][6];
-  T qacc[NV], Ma[NV], grad[NV], search[NV], Mv[NV], fc[NV];
+  T qacc[NV], Ma[NV], search[NV], Mv[NV], fc[NV];
   // -----------------------------------------------------------------------------------------------------------
   T specD[MAXSPEC], specJaref[MAXSPEC], specJv[MAXSPEC], specAref[MAXSPEC];
   T actf[NU];
@@ -84,9 +94,10 @@ struct Work {
   T* Jv;    // [MAXROW]
   int* cmeta;  // [MAXCON]
   int* surv;   // [MAXSURV] geom pairs surviving the broad phase
+  double* warm_pad;  // [NV] private qacc_warmstart of a padding warp (it must not write the real env's)
   EpaMem<T> epa;
 };
-constexpr int WORK_REALS = MAXCON * 11 + MAXROW * 3 + EPA_REALS;
+constexpr int WORK_REALS = MAXCON * 11 + MAXROW * 3 + EPA_REALS + 2 * NV + 2;
 constexpr int WORK_INTS = MAXCON + EPA_INTS + MAXSURV;
 template <class T>
 MM_HD Work<T> make_work(T* reals, int* ints) {
@@ -97,6 +108,10 @@ MM_HD Work<T> make_work(T* reals, int* ints) {
   w.epa.vert = w.Jv + MAXROW; w.epa.face = w.epa.vert + EPA_MAXV * 6;
   w.epa.fidx = ints + MAXCON; w.epa.edge = w.epa.fidx + EPA_MAXF; w.epa.canon = w.epa.edge + EPA_MAXE;
   w.surv = w.epa.canon + EPA_MAXV;
+  {  // 8-byte aligned doubles behind the EPA vertices (the pool slices are 8-byte aligned: WORK_REALS is even)
+    T* tail = w.epa.vert + EPA_REALS;
+    w.warm_pad = reinterpret_cast<double*>((reinterpret_cast<size_t>(tail) + 7) & ~size_t(7));
+  }
   return w;
 }
 
@@ -266,6 +281,23 @@ MM_HDN void solve_H(const Grp<G>& g, const Scratch<T>& s, T* x) {
   }
 }
 
+template <class T>
+MM_HD T S_comp(const Scratch<T>& s, int dof, int c) {
+  if (is_cube_translation(dof)) return c == 3 + (dof - NROB) % 6 ? (T)1 : (T)0;
+  return s.S[srow(dof)][c];
+}
+template <class T>
+MM_HD T S_dot(const Scratch<T>& s, int dof, const T* x) {
+  if (is_cube_translation(dof)) return x[3 + (dof - NROB) % 6];
+  return dot6(s.S[srow(dof)], x);
+}
+template <class T>
+MM_HD void S_get(const Scratch<T>& s, int dof, T* out) {
+  if (is_cube_translation(dof)) { for (int a = 0; a < 6; a++) out[a] = 0; out[3 + (dof - NROB) % 6] = 1; return; }
+  const T* S = s.S[srow(dof)];
+  for (int a = 0; a < 6; a++) out[a] = S[a];
+}
+
 // ------------------------------------------------------------------------------------------------
 // kinematics + world-origin spatial axes (replaces mj_kinematics / mj_comPos / mj_jac data)
 // ------------------------------------------------------------------------------------------------
@@ -324,7 +356,8 @@ MM_HDX void fk(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md) {
   }
   g.sync();
   for (int i = g.lane; i < NV; i += G) {
-    T* S = s.S[i];
+    if (is_cube_translation(i)) continue;
+    T* S = s.S[srow(i)];
     if (i < NARM) {
       T a[3] = {s.bR[i][2], s.bR[i][5], s.bR[i][8]};
       S[0] = a[0]; S[1] = a[1]; S[2] = a[2];
@@ -334,13 +367,10 @@ MM_HDX void fk(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md) {
       S[0] = S[1] = S[2] = 0; S[3] = R[1]; S[4] = R[4]; S[5] = R[7];
     } else {
       int d = i - 9, j = d / 6, k = d % 6;
-      if (k < 3) { for (int a = 0; a < 6; a++) S[a] = 0; S[3 + k] = 1; }
-      else {
-        const T* R = s.bR[DB_CUBE0 + j];
-        T a[3] = {R[k - 3], R[3 + k - 3], R[6 + k - 3]};
-        S[0] = a[0]; S[1] = a[1]; S[2] = a[2];
-        cross3(S + 3, s.bpos[DB_CUBE0 + j], a);
-      }
+      const T* R = s.bR[DB_CUBE0 + j];
+      T a[3] = {R[k - 3], R[3 + k - 3], R[6 + k - 3]};
+      S[0] = a[0]; S[1] = a[1]; S[2] = a[2];
+      cross3(S + 3, s.bpos[DB_CUBE0 + j], a);
     }
   }
   g.sync();
@@ -912,7 +942,7 @@ MM_HDX void collide(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<
   // EPA polytope: faces, their index words, horizon edges and canonical vertex ids live in SHARED memory (the H /
   // tmp6 / pair-block region, free during collision: the sequential face-removal loop must not wait on global
   // memory); vertices stay in the env's global workspace.
-  static_assert(sizeof(s.H) + sizeof(s.tmp6) + sizeof(s.pairK) + sizeof(s.pairW) + sizeof(s.pairF) + 6 * sizeof(s.qacc) >=
+  static_assert(sizeof(s.H) + sizeof(s.tmp6) + sizeof(s.pairK) + sizeof(s.pairW) + sizeof(s.pairF) + 5 * sizeof(s.qacc) >=
                     EPA_MAXF * 4 * sizeof(T) + EPA_INTS * sizeof(int), "EPA workspace does not fit the shared scratch");
   EpaMem<T> em;
   em.vert = w.epa.vert;
@@ -1036,7 +1066,7 @@ MM_HDN void pair_twists(const Grp<G>& g, Scratch<T>& s, const T* x) {
     T acc = 0;
     for (int i = 0; i < NV; i++) {
       int sg = ((mB >> i) & 1) - ((mA >> i) & 1);
-      if (sg) acc += (T)sg * x[i] * s.S[i][c];
+      if (sg) acc += (T)sg * x[i] * S_comp(s, i, c);
     }
     s.pairW[p][c] = acc;
   }
@@ -1242,7 +1272,7 @@ MM_HDN T update_constraint(const Grp<G>& g, Scratch<T>& s, Work<T>& w, bool buil
     for (int p = 0; p < np; p++) {
       int key = s.pairkey[p];
       int sg = ((dofmask((key >> 4) & 15) >> i) & 1) - ((dofmask(key & 15) >> i) & 1);
-      if (sg) acc += (T)sg * dot6(s.S[i], s.pairF[p]);
+      if (sg) acc += (T)sg * S_dot(s, i, s.pairF[p]);
     }
     for (int k = 0; k < s.nspec; k++) {
       int d = s.specdof[k];
@@ -1319,7 +1349,8 @@ MM_HDN void build_factor_H(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md
       if (!((mm_ >> j) & 1)) continue;
       int k = tpopc(mm_ & ((1 << j) - 1));
       s.dl[k] = (signed char)j;
-      const T* S = s.S[j];
+      T S[6];
+      S_get(s, j, S);
       T sg = ((mB >> j) & 1) ? (T)1 : (T)-1;
       // symmetric packed K (lower, row-major): K[a][b] = K[a*(a+1)/2 + b], b <= a
       for (int a = 0; a < 6; a++) {
@@ -1335,7 +1366,7 @@ MM_HDN void build_factor_H(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md
       tri_rc<T>(e, &a, &b);
       int i = s.dl[a], j = s.dl[b];
       T sg = ((mB >> i) & 1) ? (T)1 : (T)-1;
-      s.H[i * NV + j] += sg * dot6(s.S[i], s.tmp6[b]);
+      s.H[i * NV + j] += sg * S_dot(s, i, s.tmp6[b]);
     }
   }
   g.sync();
@@ -1385,7 +1416,11 @@ MM_HDX void solve(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>
   // (which = 1, rows kept in Jaref)
   T cost_sm = 0, cost_ws = 0;
   for (int which = 0; which < 2; which++) {
-    const T* x = which ? s.warm : s.as;
+    if (which) {  // qacc_warmstart arrives from the global state (parked in `search`, free until the Newton loop)
+      for (int i = g.lane; i < NV; i += G) s.search[i] = (T)s.warm_g[i];
+      g.sync();
+    }
+    const T* x = which ? s.search : s.as;
     T* rows = which ? w.Jaref : w.Jv;
     T* srows = which ? s.specJaref : s.specJv;
     mulJ<T, G>(g, s, w, x, rows, srows);
@@ -1405,16 +1440,16 @@ MM_HDX void solve(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>
       if (s.specdof[k] < 0 || ja < 0) cst += (T)0.5 * s.specD[k] * ja * ja;
     }
     if (which) {
-      mulM<T, G>(g, s, md, s.warm, s.Ma);
+      mulM<T, G>(g, s, md, s.search, s.Ma);
       g.sync();
-      for (int i = g.lane; i < NV; i += G) cst += (T)0.5 * (s.Ma[i] - s.fs[i]) * (s.warm[i] - s.as[i]);
+      for (int i = g.lane; i < NV; i += G) cst += (T)0.5 * (s.Ma[i] - s.fs[i]) * (s.search[i] - s.as[i]);
     }
     cst = g.sum(cst);
     if (which) cost_ws = cst; else cost_sm = cst;
     g.sync();
   }
   if (cost_ws < cost_sm) {
-    for (int i = g.lane; i < NV; i += G) s.qacc[i] = s.warm[i];
+    for (int i = g.lane; i < NV; i += G) s.qacc[i] = s.search[i];
   } else {
     for (int i = g.lane; i < NV; i += G) s.qacc[i] = s.as[i];
     for (int c = g.lane; c < ncon; c += G) for (int r = 0; r < 6; r++) w.Jaref[c * 6 + r] = w.Jv[c * 6 + r];
@@ -1472,7 +1507,7 @@ MM_HDX void solve(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>
     // (C) Newton direction and the quantities of the line search
     T sn = 0, qg1 = 0, qg2 = 0;
     if (!finished) {
-      for (int i = g.lane; i < NV; i += G) { T gr = s.Ma[i] - s.fs[i] - s.fc[i]; s.grad[i] = gr; s.search[i] = -gr; }
+      for (int i = g.lane; i < NV; i += G) s.search[i] = -(s.Ma[i] - s.fs[i] - s.fc[i]);
       g.sync();
       solve_H<T, G>(g, s, s.search);
       mulM<T, G>(g, s, md, s.search, s.Mv);
@@ -1513,7 +1548,7 @@ MM_HDX void solve(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>
     }
   }
   if (g.lane == 0) s.niter = iter;
-  for (int i = g.lane; i < NV; i += G) s.warm[i] = s.qacc[i];
+  for (int i = g.lane; i < NV; i += G) s.warm_g[i] = (double)s.qacc[i];
   g.sync();
 }
 
@@ -1549,7 +1584,7 @@ MM_HDX void integrate(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md) {
   MM_IN_GLOBAL(&md);
   const T h = md.timestep;
   T* MH = s.H;
-  T* acc = s.grad;
+  T* acc = s.Mv;
   for (int e = g.lane; e < NROB * NROB; e += G) {
     int i = e / NROB, j = e % NROB;
     T v = s.Mr[e];

@@ -103,7 +103,9 @@ void emul_forward_debug(const double* qpos, const double* qvel, const double* ct
   Scratch<double>& s = c.s;
   Grp<1> g{0, 1u, 0, 0, 0};
   for (int i = 0; i < NQ; i++) s.qpos[i] = qpos[i];
-  for (int i = 0; i < NV; i++) { s.qvel[i] = qvel[i]; s.warm[i] = warm[i]; }
+  static thread_local double warm_buf[NV];
+  for (int i = 0; i < NV; i++) { s.qvel[i] = qvel[i]; warm_buf[i] = warm[i]; }
+  s.warm_g = warm_buf;
   for (int i = 0; i < NU; i++) s.ctrl[i] = ctrl[i];
   s.overflow = 0;
   forward<double, 1>(g, s, c.md, c.w);

@@ -42,7 +42,8 @@ struct StepOut {
 template <class T, int G>
 MM_HDN void load_state(const Grp<G>& g, Scratch<T>& s, const StatePtrs& st, long e) {
   for (int i = g.lane; i < NQ; i += G) s.qpos[i] = (T)st.qpos[e * NQ + i];
-  for (int i = g.lane; i < NV; i += G) { s.qvel[i] = (T)st.qvel[e * NV + i]; s.warm[i] = (T)st.warm[e * NV + i]; }
+  for (int i = g.lane; i < NV; i += G) s.qvel[i] = (T)st.qvel[e * NV + i];
+  if (g.lane == 0) s.warm_g = st.warm + e * NV;
   for (int i = g.lane; i < NU; i += G) s.ctrl[i] = (T)st.ctrl[e * NU + i];
   if (g.lane == 0) { s.overflow = 0; s.ncon = 0; s.npair = 0; s.nspec = 0; s.niter = 0; s.prof = 0; for (int k = 0; k < 8; k++) s.tph[k] = 0; }
   g.sync();
@@ -51,12 +52,12 @@ MM_HDN void load_state(const Grp<G>& g, Scratch<T>& s, const StatePtrs& st, long
 template <class T, int G>
 MM_HDN void store_state(const Grp<G>& g, const Scratch<T>& s, const StatePtrs& st, long e) {
   for (int i = g.lane; i < NQ; i += G) st.qpos[e * NQ + i] = (double)s.qpos[i];
-  for (int i = g.lane; i < NV; i += G) { st.qvel[e * NV + i] = (double)s.qvel[i]; st.warm[e * NV + i] = (double)s.warm[i]; }
+  for (int i = g.lane; i < NV; i += G) st.qvel[e * NV + i] = (double)s.qvel[i];  // (qacc_warmstart is written by solve)
   for (int i = g.lane; i < NU; i += G) st.ctrl[e * NU + i] = (double)s.ctrl[i];
   for (int i = g.lane; i < 12; i += G)
     st.eepose[e * 12 + i] = (double)(i < 3 ? s.bpos[DB_HAND][i] : s.bR[DB_HAND][i - 3]);
   // kinematics of the last position stage (what data.xpos / mj_jac describe in the reference)
-  for (int i = g.lane; i < 18; i += G) st.kin[e * 18 + i] = (double)(i < 9 ? s.tmp6[18 + i / 6][i % 6] : s.bpos[DB_CUBE0 + (i - 9) / 3][(i - 9) % 3]);
+  for (int i = g.lane; i < 18; i += G) st.kin[e * 18 + i] = (double)(i < 9 ? s.tmp6[KIN_ROW + i / 6][i % 6] : s.bpos[DB_CUBE0 + (i - 9) / 3][(i - 9) % 3]);
   if (g.lane == 0) {
     st.diag[e * 4 + 0] = s.ncon; st.diag[e * 4 + 1] = s.niter; st.diag[e * 4 + 2] |= s.overflow;
   }
@@ -240,6 +241,10 @@ MM_HDN void env_step(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work
                      const float* tgt_kp_all, bool dummy = false, long long* prof = nullptr) {
   load_state<T, G>(g, s, st, e);
   if (prof && g.lane == 0) s.prof = 1;
+  if (dummy) {  // padding warp: private copy of the warm start, the real env's state is never written
+    for (int i = g.lane; i < NV; i += G) w.warm_pad[i] = st.warm[e * NV + i];
+    if (g.lane == 0) s.warm_g = w.warm_pad;
+  }
   g.sync();
   fk<T, G>(g, s, md);  // state after reset / the previous step's trailing mj_forward
   if (g.lane == 0) {
@@ -267,7 +272,7 @@ MM_HDN void env_step(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work
 
     if (state_bad<T, G>(g, s)) {
       for (int i = g.lane; i < NQ; i += G) s.qpos[i] = md.key_qpos[i];
-      for (int i = g.lane; i < NV; i += G) { s.qvel[i] = 0; s.warm[i] = 0; }
+      for (int i = g.lane; i < NV; i += G) { s.qvel[i] = 0; s.warm_g[i] = 0; }
       if (g.lane == 0 && !dummy) st.diag[e * 4 + 3] += 1;
       g.sync();
     }
@@ -281,7 +286,7 @@ MM_HDN void env_step(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work
   if (prof && g.lane == 0 && !dummy) for (int k = 0; k < 8; k++) prof[1 + k] = (long long)s.tph[k] << 6;
   if (dummy) return;  // padding warp of a phase-synchronous CTA: took part in every barrier, stores nothing
   bool rc = reward_type == REWARD_STAGED ? any_robot_collision<T, G>(g, s, w) : false;
-  for (int i = g.lane; i < 9; i += G) s.tmp6[18 + i / 6][i % 6] = s.qpos[i];
+  for (int i = g.lane; i < 9; i += G) s.tmp6[KIN_ROW + i / 6][i % 6] = s.qpos[i];
   g.sync();
   store_state<T, G>(g, s, st, e);
   if (g.lane == 0) {
@@ -294,8 +299,10 @@ MM_HDN void env_step(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work
 template <class T, int G>
 MM_HDN void env_reset(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>& w, const StatePtrs& st, long e,
                       const double* obj_xy /*[6] or null*/, int obj, int bin, float* obs, float* tgt_kp_all) {
+  if (g.lane == 0) s.warm_g = st.warm + e * NV;
+  g.sync();
   for (int i = g.lane; i < NQ; i += G) s.qpos[i] = md.key_qpos[i];
-  for (int i = g.lane; i < NV; i += G) { s.qvel[i] = 0; s.warm[i] = 0; }
+  for (int i = g.lane; i < NV; i += G) { s.qvel[i] = 0; s.warm_g[i] = 0; }
   for (int i = g.lane; i < NU; i += G) s.ctrl[i] = md.key_ctrl[i];
   if (g.lane == 0) { s.overflow = 0; s.ncon = 0; s.npair = 0; s.nspec = 0; s.niter = 0; }
   g.sync();
@@ -310,7 +317,7 @@ MM_HDN void env_reset(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Wor
     }
     forward<T, G>(g, s, md, w);  // env.py:116-117
   }
-  for (int i = g.lane; i < 9; i += G) s.tmp6[18 + i / 6][i % 6] = s.qpos[i];
+  for (int i = g.lane; i < 9; i += G) s.tmp6[KIN_ROW + i / 6][i % 6] = s.qpos[i];
   g.sync();
   store_state<T, G>(g, s, st, e);
   if (g.lane == 0) {
@@ -354,16 +361,16 @@ MM_HDN void env_ops(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<
   if (ops & OP_FORWARD) {
     if (state_bad<T, G>(g, s)) {
       for (int i = g.lane; i < NQ; i += G) s.qpos[i] = md.key_qpos[i];
-      for (int i = g.lane; i < NV; i += G) { s.qvel[i] = 0; s.warm[i] = 0; }
+      for (int i = g.lane; i < NV; i += G) { s.qvel[i] = 0; s.warm_g[i] = 0; }
       if (g.lane == 0) st.diag[e * 4 + 3] += 1;
       g.sync();
     }
     forward<T, G>(g, s, md, w);
-    for (int i = g.lane; i < 9; i += G) s.tmp6[18 + i / 6][i % 6] = s.qpos[i];  // position-stage qpos for store_state
+    for (int i = g.lane; i < 9; i += G) s.tmp6[KIN_ROW + i / 6][i % 6] = s.qpos[i];  // position-stage qpos for store_state
     g.sync();
     if (ops & OP_INTEGRATE) integrate<T, G>(g, s, md);
   } else {
-    for (int i = g.lane; i < 9; i += G) s.tmp6[18 + i / 6][i % 6] = (T)st.kin[e * 18 + i];
+    for (int i = g.lane; i < 9; i += G) s.tmp6[KIN_ROW + i / 6][i % 6] = (T)st.kin[e * 18 + i];
     g.sync();
   }
   store_state<T, G>(g, s, st, e);

@@ -20,7 +20,11 @@ namespace mm {
 template <class T, int G>
 struct BlockCfg {
   static constexpr int FIT = (int)((227 * 1024 - 2048) / sizeof(Scratch<T>));
-  static constexpr int WARPS = G == 32 ? ((FIT > 16 ? 16 : FIT) / MM_CTAS_PER_SM) : 1;
+  // 6 warps per CTA measured best in FP64 (7 fit after the scratch diet, but a 7-env CTA takes 40 % longer than a
+  // 6-env one: more members to wait for at every barrier; 4096 envs: 166k vs 138k env-steps/s); the shared memory
+  // left over serves as L1 for the workspace and the local-memory spills
+  static constexpr int WFIT = (FIT > 16 ? 16 : FIT) / MM_CTAS_PER_SM;
+  static constexpr int WARPS = G == 32 ? ((sizeof(T) == 8 && WFIT > 6) ? 6 : WFIT) : 1;
   static constexpr int THREADS = 32 * WARPS;
   static constexpr int ENVS = THREADS / G;
   static constexpr int MINB = G == 32 ? MM_CTAS_PER_SM : ((227 * 1024) / (ENVS * (int)sizeof(Scratch<T>) + 1024) > 16
