@@ -41,16 +41,22 @@ def parse():
     ap.add_argument("--envs", type=int, default=4096, help="envs per GPU")
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
     ap.add_argument("--group", type=int, default=32)
-    ap.add_argument("--workload", default="random", choices=["random", "fsm"],
-                    help="random = BASELINE configs[1] (headline); fsm = configs[2] scripted-expert dataset generation (extra)")
+    ap.add_argument("--workload", default="random", choices=["random", "fsm", "mixed"],
+                    help="random = BASELINE configs[1] (headline); fsm = configs[2] scripted-expert dataset generation (extra); "
+                         "mixed = configs[4] abs_pos + ee_pos_rot6d_g halves, tasks=cross, expert-driven, per-phase report (extra)")
+    ap.add_argument("--mode", default=MODE, choices=["ee_pos_quat_g_rel", "ee_pos_rot6d_g_rel"],
+                    help="action mode of the random workload (configs[3] uses ee_pos_rot6d_g_rel with --randomize)")
+    ap.add_argument("--randomize", action="store_true", help="random workload: randomize_objects=True (device Philox)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
 
 
-def workload(envs):
-    return {"workload": f"configs[1]: {envs} envs/GPU, task (obj_red,bin_red), {MODE} random actions, state obs, "
-                        "500-step episodes, auto-reset", "envs_per_gpu": envs, "action_mode": MODE,
+def workload(envs, mode=MODE, randomize=False):
+    tag = "configs[1]" if (mode == MODE and not randomize) else "configs[3]-style"
+    return {"workload": f"{tag}: {envs} envs/GPU, task (obj_red,bin_red), {mode} random actions, state obs, "
+                        f"500-step episodes, auto-reset{', randomized objects (Philox seed 1234)' if randomize else ''}",
+            "envs_per_gpu": envs, "action_mode": mode,
             "substeps_per_env_step": 16, "l2": "flushed between timed steps (256 MiB write)"}
 
 
@@ -67,7 +73,7 @@ def flops_per_env_step(stats):
     return per_forward * forwards_per_env_step, per
 
 
-def cpu_sample(nthreads, seconds_target=12.0):
+def cpu_sample(nthreads, seconds_target=12.0, mode=MODE):
     """Oracle restatement of the reference path on the host cores, bounded sample."""
     from oracle import oracle
 
@@ -76,7 +82,7 @@ def cpu_sample(nthreads, seconds_target=12.0):
     n_envs = max(nthreads, 8)
     n_steps = max(10, int(seconds_target * 300 * nthreads / n_envs))
     n_steps = min(n_steps, 500)
-    v, st = oracle.bench_random_stats(n_envs, n_steps, mode=MODE, seed=1234, nthreads=nthreads, flags=0)
+    v, st = oracle.bench_random_stats(n_envs, n_steps, mode=mode, seed=1234, nthreads=nthreads, flags=0)
     st["env_steps"] = n_envs * n_steps
     return v, st, f"{n_envs} envs x {n_steps} env-steps of configs[1] (same action distribution), {nthreads} threads"
 
@@ -117,13 +123,13 @@ def run_reference(args, rank, world):
     vals = []
     sample = ""
     for i in range(max(1, min(args.steps, 3)) + (1 if args.warmup else 0)):
-        v, st, sample = cpu_sample(cores, seconds_target=8.0)
+        v, st, sample = cpu_sample(cores, seconds_target=8.0, mode=args.mode)
         if i or not args.warmup:
             vals.append(v)
     v = sum(vals) / len(vals)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * args.envs / v, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload(args.envs),
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload(args.envs, args.mode, args.randomize),
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": sample + " per timed sample; MuJoCo is not installable here, so this is the FP64 "
                                                 "oracle restatement of the reference path"},
@@ -188,6 +194,91 @@ def run_fsm(args, rank, world, local):
         dist.destroy_process_group()
 
 
+PHASES = ("idle", "approaching", "grasping", "lifting", "transporting", "placing", "retreating", "done")
+# FSM state index (1..11) -> phase index, as _STATE_TO_PHASE of pick_and_place.py:46-58
+STATE_PHASE = (0, 0, 1, 2, 2, 3, 4, 4, 5, 5, 6, 7)
+
+
+def run_mixed(args, rank, world, local):
+    """BASELINE.json configs[4] (extra line): half the envs take abs_pos actions, half ee_pos_rot6d_g (absolute EE pose),
+    tasks = cross (cycled by global env id), randomized objects, scripted expert so that grasp / lift contact phases
+    dominate.  Per-phase figures come from the per-env busy cycles the step kernel writes for its scheduler."""
+    import torch
+    import torch.distributed as dist
+
+    from mujoco_manip_b200 import PickPlaceVecEnv
+    from mujoco_manip_b200.features import expert_action_encodings
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.envs
+    half = n // 2
+    envs = []
+    for k, mode in enumerate(("abs_pos", "ee_pos_rot6d_g")):
+        e = PickPlaceVecEnv(half, device=dev, tasks="cross", action_mode=mode, randomize_objects=True, rng="philox", seed=42,
+                            env_id_offset=rank * n + k * half, task_assignment="cycle", auto_reset=False,
+                            max_episode_steps=2000, precision=args.precision, group=args.group)
+        e.reset()
+        envs.append(e)
+    sp = torch.tensor(STATE_PHASE, device=dev)
+    steps_by_phase = torch.zeros(len(PHASES), dtype=torch.float64, device=dev)
+    work_by_phase = torch.zeros(len(PHASES), dtype=torch.float64, device=dev)
+    episodes = torch.zeros(2, dtype=torch.float64, device=dev)
+
+    def one(count):
+        for e in envs:
+            a = e.fsm_plan(16)
+            ph = sp[e.fsm_state.to(torch.int64)]
+            if e.action_mode != "abs_pos":  # the expert's action in the absolute EE-pose encoding (generate_dataset.py:56-80)
+                a = expert_action_encodings(e, a)[:, 8:18]
+            _, _, _, _, info = e.step(a)
+            done = e.fsm_state == 11
+            if count:
+                steps_by_phase.index_add_(0, ph, torch.ones(half, dtype=torch.float64, device=dev))
+                work_by_phase.index_add_(0, ph, e._work.to(torch.float64))
+                episodes[0] += done.sum()
+                episodes[1] += (done & info["success"]).sum()
+            e.reset(mask=done.to(torch.uint8))
+
+    for _ in range(args.warmup):
+        one(False)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        one(True)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        for x in (episodes, steps_by_phase, work_by_phase):
+            dist.all_reduce(x)
+    if rank == 0:
+        ms = float(t[0])
+        value = world * 2 * half * args.steps / (ms * 1e-3)
+        share = (work_by_phase / work_by_phase.sum().clamp(min=1)).tolist()
+        cnt = steps_by_phase.tolist()
+        per_phase = {p: {"env_steps": int(c), "busy_share": round(s, 4),
+                         # env-steps/s the job would reach if every env were in this phase (busy-cycle weighted)
+                         "env_steps_per_s": (c / (s * ms * 1e-3)) if s > 0 else None}
+                     for p, c, s in zip(PHASES, cnt, share)}
+        print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+                          "config": {"workload": f"configs[4]: {n} envs/GPU, half abs_pos + half ee_pos_rot6d_g, tasks=cross, "
+                                                 "randomize_objects seed 42, scripted-FSM expert, episodes reset at FSM DONE"},
+                          "episodes_finished": float(episodes[0]),
+                          "success_rate": float(episodes[1] / episodes[0].clamp(min=1)), "per_phase": per_phase}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -199,6 +290,10 @@ def main():
     if args.workload == "fsm":
         run_fsm(args, rank, world, local)
         return
+    if args.workload == "mixed":
+        run_mixed(args, rank, world, local)
+        return
+    MODE = args.mode
 
     import torch
     import torch.distributed as dist
@@ -215,7 +310,7 @@ def main():
     n = args.envs
     env = PickPlaceVecEnv(n, device=dev, task=("obj_red", "bin_red"), action_mode=MODE, reward_type="dense",
                           max_episode_steps=500, seed=1234, rng="philox", env_id_offset=rank * n, precision=args.precision,
-                          group=args.group, auto_reset=True)
+                          group=args.group, auto_reset=True, randomize_objects=args.randomize)
     env.reset()
     total = args.steps + args.warmup
 
@@ -231,9 +326,13 @@ def main():
         w = lo + (hi - lo) * torch.rand((n, 3), device=dev, dtype=torch.float64, generator=gen)
         a = torch.zeros((n, _lib.ACTION_STRIDE), device=dev, dtype=torch.float32)
         a[:, :3] = ((w - p0) @ R0).float()  # R0^T (w - p0)
-        q = torch.randn((n, 4), device=dev, generator=gen)
-        a[:, 3:7] = q / q.norm(dim=1, keepdim=True)
-        a[:, 7] = (torch.rand(n, device=dev, generator=gen) > 0.5).float()
+        if MODE.startswith("ee_pos_rot6d"):  # any two 3-vectors: rotmat_from_6d orthonormalises them
+            a[:, 3:9] = torch.randn((n, 6), device=dev, generator=gen)
+            a[:, 9] = (torch.rand(n, device=dev, generator=gen) > 0.5).float()
+        else:
+            q = torch.randn((n, 4), device=dev, generator=gen)
+            a[:, 3:7] = q / q.norm(dim=1, keepdim=True)
+            a[:, 7] = (torch.rand(n, device=dev, generator=gen) > 0.5).float()
         return a
 
     pool = [make_actions() for _ in range(min(total, 32))]
@@ -326,7 +425,7 @@ def main():
         per = None
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            v, st, sample = cpu_sample(cores)
+            v, st, sample = cpu_sample(cores, mode=MODE)
             flops, per = flops_per_env_step(st)
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": sample + "; FP64 oracle restatement of the reference path (MuJoCo not installable here)"}
@@ -351,7 +450,7 @@ def main():
                         "frac": state_bytes * n / kern_s * 1e-9 / hbm_peak, "bytes_per_env_step": state_bytes}}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": step_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": args.precision, "data": "synthetic", "config": workload(n), "substeps_per_s": value * 16,
+                "dtype": args.precision, "data": "synthetic", "config": workload(n, MODE, args.randomize), "substeps_per_s": value * 16,
                 "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
                 "wall_s_timed_region": wall, "group": args.group}
         print(json.dumps(line), flush=True)

@@ -123,6 +123,17 @@ int mm_sample_placements(mm_handle* h, uint64_t seed, int64_t env_id_offset, con
                          double x_hi, double y_lo, double y_hi, double min_separation, int32_t npool, double* obj_xy,
                          int32_t* task_draw, int32_t* attempts, void* stream);
 
+/* replaces the `randomize_yaw=True` branch of randomize_object_positions (randomization.py:55-62): the cube
+ * quaternions written with the placement become (cos(theta/2), 0, 0, sin(theta/2)).
+ *   yaw_cs  [N,6] double, device: (cos, sin)(theta/2) of the three cubes, or NULL to switch the option off.
+ * The pointer is kept (caller-owned) and read by every later mm_reset that is given obj_xy. */
+int mm_set_placement_yaw(mm_handle* h, const double* yaw_cs);
+
+/* Philox draw of theta = uniform(0, 2 pi) for the three cubes of every env (csrc/mm_rng.h: words 0,1 of block
+ * 4(o+1)+3 of the (seed, env, episode) stream); theta [N,3] double out or NULL, yaw_cs [N,6] double out. */
+int mm_sample_yaw(mm_handle* h, uint64_t seed, int64_t env_id_offset, const int64_t* episode_index, double* theta,
+                  double* yaw_cs, void* stream);
+
 /* Measurement helper (no reference counterpart): FMA throughput of the CUDA cores in TFLOP/s (FP32 or FP64),
  * best of 5 timed launches - the measured denominator of the roofline bench.py reports. */
 int mm_measure_fma_peak(int device, int fp64, double* tflops);

@@ -23,7 +23,8 @@ REWARD_TYPES = ("dense", "sparse", "staged")
 
 # every symbol include/mm_manip.h declares (tests check the built library exports each one)
 EXPORTS = ("mm_create", "mm_destroy", "mm_last_error", "mm_workspace_bytes", "mm_reset", "mm_step", "mm_step_host",
-           "mm_fsm_plan", "mm_launch_count", "mm_sample_placements", "mm_measure_fma_peak", "mm_set_cycle_buffer", "mm_ops", "mm_set_schedule", "mm_expert_actions")
+           "mm_fsm_plan", "mm_launch_count", "mm_sample_placements", "mm_measure_fma_peak", "mm_set_cycle_buffer", "mm_ops", "mm_set_schedule", "mm_expert_actions",
+           "mm_set_placement_yaw", "mm_sample_yaw")
 
 
 class MMConfig(C.Structure):
@@ -108,6 +109,8 @@ def lib():
     L.mm_expert_actions.argtypes = [C.c_void_p, C.POINTER(MMState), C.c_void_p, C.c_void_p, C.c_void_p]
     L.mm_set_schedule.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.mm_set_cycle_buffer.argtypes = [C.c_void_p, C.c_void_p]
+    L.mm_set_placement_yaw.argtypes = [C.c_void_p, C.c_void_p]
+    L.mm_sample_yaw.argtypes = [C.c_void_p, C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.mm_launch_count.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
     _lib = L
     return L

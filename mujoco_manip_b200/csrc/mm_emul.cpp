@@ -48,13 +48,15 @@ StepOut out_from(void** p) {
 }
 
 template <class T>
-void do_reset(int n, void** sp, const unsigned char* mask, const double* obj_xy, const int* task, float* obs, float* tgt) {
+void do_reset(int n, void** sp, const unsigned char* mask, const double* obj_xy, const double* yaw_cs, const int* task,
+              float* obs, float* tgt) {
   Ctx<T>& c = ctx<T>();
   StatePtrs st = state_from(sp);
   Grp<1> g{0, 1u, 0, 0, 0};
   for (long e = 0; e < n; e++) {
     if (mask && !mask[e]) continue;
-    env_reset<T, 1>(g, c.s, c.md, c.w, st, e, obj_xy ? obj_xy + 6 * e : nullptr, task[2 * e], task[2 * e + 1], obs, tgt);
+    env_reset<T, 1>(g, c.s, c.md, c.w, st, e, obj_xy ? obj_xy + 6 * e : nullptr, yaw_cs ? yaw_cs + 6 * e : nullptr, task[2 * e],
+                    task[2 * e + 1], obs, tgt);
   }
 }
 template <class T>
@@ -69,10 +71,15 @@ void do_step(int n, void** sp, const float* actions, int mode, int reward_type, 
 
 extern "C" {
 
+void emul_reset_yaw(int n, void** state, const unsigned char* mask, const double* obj_xy, const double* yaw_cs,
+                    const int* task, float* obs, float* tgt_kp, int use_float) {
+  if (use_float) do_reset<float>(n, state, mask, obj_xy, yaw_cs, task, obs, tgt_kp);
+  else do_reset<double>(n, state, mask, obj_xy, yaw_cs, task, obs, tgt_kp);
+}
+
 void emul_reset(int n, void** state, const unsigned char* mask, const double* obj_xy, const int* task, float* obs,
                 float* tgt_kp, int use_float) {
-  if (use_float) do_reset<float>(n, state, mask, obj_xy, task, obs, tgt_kp);
-  else do_reset<double>(n, state, mask, obj_xy, task, obs, tgt_kp);
+  emul_reset_yaw(n, state, mask, obj_xy, nullptr, task, obs, tgt_kp, use_float);
 }
 
 void emul_step(int n, void** state, const float* actions, int mode, int reward_type, int max_steps, void** out,

@@ -298,7 +298,8 @@ MM_HDN void env_step(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work
 // Reset env e to the keyframe (+ optional object placement), gym_env.py:477-534.
 template <class T, int G>
 MM_HDN void env_reset(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>& w, const StatePtrs& st, long e,
-                      const double* obj_xy /*[6] or null*/, int obj, int bin, float* obs, float* tgt_kp_all) {
+                      const double* obj_xy /*[6] or null*/, const double* yaw_cs /*[6] or null*/, int obj, int bin, float* obs,
+                      float* tgt_kp_all) {
   if (g.lane == 0) s.warm_g = st.warm + e * NV;
   g.sync();
   for (int i = g.lane; i < NQ; i += G) s.qpos[i] = md.key_qpos[i];
@@ -312,6 +313,7 @@ MM_HDN void env_reset(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Wor
         for (int o = 0; o < 3; o++) {
           T* q = s.qpos + 9 + 7 * o;
           q[0] = (T)obj_xy[2 * o]; q[1] = (T)obj_xy[2 * o + 1]; q[2] = (T)0.26; q[3] = 1; q[4] = q[5] = q[6] = 0;
+          if (yaw_cs) { q[3] = (T)yaw_cs[2 * o]; q[6] = (T)yaw_cs[2 * o + 1]; }  // randomize_yaw, randomization.py:55-62
         }
       g.sync();
     }

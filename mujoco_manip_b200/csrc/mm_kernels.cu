@@ -65,6 +65,19 @@ __global__ void k_sample(unsigned long long seed, long long gid0, const long lon
   if (attempts) attempts[e] = na;
 }
 
+// Philox yaw draw of the three cubes (mm_rng.h): theta [N,3] and (cos, sin)(theta / 2) [N,6]
+__global__ void k_sample_yaw(unsigned long long seed, long long gid0, const long long* episode, long n, double* theta,
+                             double* cs) {
+  long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  for (int o = 0; o < 3; o++) {
+    double th = philox_yaw(seed, (unsigned long long)(gid0 + e), (unsigned)episode[e], o);
+    if (theta) theta[3 * e + o] = th;
+    cs[6 * e + 2 * o] = cos(0.5 * th);
+    cs[6 * e + 2 * o + 1] = sin(0.5 * th);
+  }
+}
+
 // FMA-throughput microbenchmark: the measured denominator of the CUDA-core roofline (bench.py)
 template <class T>
 __global__ void __launch_bounds__(256) k_peak(T* out, int iters, T a, T b) {
@@ -92,6 +105,7 @@ struct mm_handle {
   int* d_pool_flags = nullptr;
   int pool_ctas = 0, envs_per_cta = 0;
   float* d_tgt = nullptr;
+  const double* yaw_cs = nullptr;  // caller-owned, used by mm_reset when placements are given
   // staging for the host-buffer path
   float* d_actions = nullptr;
   float* d_obs = nullptr;
@@ -204,7 +218,7 @@ int mm_reset(mm_handle* h, const mm_state* st, const uint8_t* mask, const double
   StepParams p{};
   p.st = to_ptrs(st);
   p.model = h->d_model; p.work_reals = h->d_work_reals; p.work_ints = h->d_work_ints; p.pool_flags = h->d_pool_flags; p.pool_ctas = h->pool_ctas; p.tgt_kp = h->d_tgt;
-  p.mask = mask; p.obj_xy = obj_xy; p.task = task; p.obs = obs; p.n = h->cfg.num_envs;
+  p.mask = mask; p.obj_xy = obj_xy; p.yaw_cs = obj_xy ? h->yaw_cs : nullptr; p.task = task; p.obs = obs; p.n = h->cfg.num_envs;
   p.reward_type = h->cfg.reward_type; p.max_steps = h->cfg.max_episode_steps;
   h->launches++;
   CK(LAUNCH[inst_index(h->cfg)](1, p, (cudaStream_t)stream));
@@ -273,6 +287,23 @@ int mm_sample_placements(mm_handle* h, uint64_t seed, int64_t env_id_offset, con
   k_sample<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
       (unsigned long long)seed, (long long)env_id_offset, (const long long*)episode_index, n, x_lo, x_hi, y_lo, y_hi,
       min_separation, npool, obj_xy, task_draw, attempts);
+  CK(cudaGetLastError());
+  h->launches++;
+  return 0;
+}
+
+int mm_set_placement_yaw(mm_handle* h, const double* yaw_cs) {
+  if (!h) return fail("mm_set_placement_yaw: null handle");
+  h->yaw_cs = yaw_cs;
+  return 0;
+}
+
+int mm_sample_yaw(mm_handle* h, uint64_t seed, int64_t env_id_offset, const int64_t* episode_index, double* theta,
+                  double* yaw_cs, void* stream) {
+  if (!h || !episode_index || !yaw_cs) return fail("mm_sample_yaw: null argument");
+  long n = h->cfg.num_envs;
+  k_sample_yaw<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      (unsigned long long)seed, (long long)env_id_offset, (const long long*)episode_index, n, theta, yaw_cs);
   CK(cudaGetLastError());
   h->launches++;
   return 0;

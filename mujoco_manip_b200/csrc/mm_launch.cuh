@@ -46,6 +46,7 @@ struct StepParams {
   float* tgt_kp;
   const unsigned char* mask;
   const double* obj_xy;
+  const double* yaw_cs;  // [N,6] cos(theta/2), sin(theta/2) of the three cubes, or null
   const int* task;
   float* obs;
   long n;
@@ -139,8 +140,8 @@ __global__ void __launch_bounds__(BlockCfg<T, G>::THREADS, BlockCfg<T, G>::MINB)
   if (valid) {
     long wslot = (long)pool * BlockCfg<T, G>::ENVS + threadIdx.x / G;
     Work<T> w = make_work(reinterpret_cast<T*>(p.work_reals) + wslot * WORK_REALS, p.work_ints + wslot * WORK_INTS);
-    env_reset<T, G>(g, *sc, *md, w, p.st, e, p.obj_xy ? p.obj_xy + 6 * e : nullptr, p.task[2 * e], p.task[2 * e + 1], p.obs,
-                    p.tgt_kp);
+    env_reset<T, G>(g, *sc, *md, w, p.st, e, p.obj_xy ? p.obj_xy + 6 * e : nullptr, p.yaw_cs ? p.yaw_cs + 6 * e : nullptr, p.task[2 * e],
+                    p.task[2 * e + 1], p.obs, p.tgt_kp);
   }
   release_work(p, pool);
 }

@@ -4,7 +4,7 @@
 // Philox4x32-10, key = 64-bit seed, counter = (global env id lo, hi, episode index, block):
 //   attempt a of the rejection sampler uses blocks 4a+0..4a+2 (12 words -> six 53-bit uniforms:
 //   x of the three cubes, then y of the three cubes - the reference's draw order), block 3 word 0
-//   is the task draw.  The stream depends only on (seed, global env id, episode), never on how envs
+//   is the task draw; with randomize_yaw, cube o takes its yaw uniform from words 0,1 of block 4(o+1)+3.  The stream depends only on (seed, global env id, episode), never on how envs
 //   are sharded over GPUs.  oracle/philox.py is the CPU statement of the same rule (bit-exact).
 #pragma once
 #include "mm_group.h"
@@ -81,6 +81,14 @@ MM_HD int philox_task(uint64_t seed, uint64_t gid, uint32_t episode, int npool) 
   uint32_t w[4];
   ph.block((uint32_t)gid, (uint32_t)(gid >> 32), episode, 3u, w);
   return (int)(((uint64_t)w[0] * (uint64_t)npool) >> 32);
+}
+
+// yaw of cube o (randomization.py:55-62: theta = uniform(0, 2 pi), drawn after the accepted placement)
+MM_HD double philox_yaw(uint64_t seed, uint64_t gid, uint32_t episode, int o) {
+  Philox ph{(uint32_t)seed, (uint32_t)(seed >> 32)};
+  uint32_t w[4];
+  ph.block((uint32_t)gid, (uint32_t)(gid >> 32), episode, (uint32_t)(4 * (o + 1) + 3), w);
+  return affine_rn(0.0, 6.283185307179586, u53(w[0], w[1]));
 }
 
 }  // namespace mm

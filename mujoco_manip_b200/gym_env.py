@@ -131,7 +131,11 @@ class PickPlaceEnv:
         pos = sample_separated_positions(rng, 3, x_range, y_range, kw.get("min_separation", 0.08))
         v = self._vec
         for o, (x, y) in enumerate(pos):
-            v.state["qpos"][0, 9 + 7 * o: 16 + 7 * o] = torch.tensor([x, y, kw.get("obj_z", 0.26), 1.0, 0, 0, 0],
+            quat = [1.0, 0.0, 0.0, 0.0]
+            if kw.get("randomize_yaw", False):  # randomization.py:55-62
+                theta = rng.uniform(0, 2 * np.pi)
+                quat = [np.cos(theta / 2), 0.0, 0.0, np.sin(theta / 2)]
+            v.state["qpos"][0, 9 + 7 * o: 16 + 7 * o] = torch.tensor([x, y, kw.get("obj_z", 0.26)] + quat,
                                                                    dtype=torch.float64, device=v.device)
         _lib.check(v._L.mm_ops(v._h, C.byref(v._st), 2, None, v._stream()), "mm_ops")  # mj_forward
         return {f"{n}_jnt": np.array([x, y, kw.get("obj_z", 0.26)]) for n, (x, y) in zip(OBJECTS, pos)}

@@ -63,7 +63,8 @@ class PickPlaceVecEnv:
     def __init__(self, num_envs: int, device: str | torch.device = "cuda:0", task=None, tasks="all",
                  action_mode: str = "ee_pos_quat_g_rel", reward_type: str = "dense",
                  max_episode_steps: int = MAX_EPISODE_STEPS, randomize_objects: bool = False,
-                 spawn_x_range=SPAWN_X_RANGE, spawn_y_range=SPAWN_Y_RANGE, seed: int = 0, rng: str = "philox",
+                 spawn_x_range=SPAWN_X_RANGE, spawn_y_range=SPAWN_Y_RANGE, randomize_yaw: bool = False, seed: int = 0,
+                 rng: str = "philox",
                  env_id_offset: int = 0, precision: str = "f64", group: int = 32, auto_reset: bool = True,
                  task_assignment: str = "random", load_balance: bool = True):
         if action_mode not in _lib.ACTION_MODES:
@@ -87,6 +88,7 @@ class PickPlaceVecEnv:
         self.reward_type = reward_type
         self.max_episode_steps = int(max_episode_steps)
         self.randomize_objects = bool(randomize_objects)
+        self.randomize_yaw = bool(randomize_yaw)  # randomization.py:19,55-62 (only with randomize_objects)
         self.spawn_x_range = tuple(float(v) for v in spawn_x_range)
         self.spawn_y_range = tuple(float(v) for v in spawn_y_range)
         self.seed = int(seed)
@@ -124,6 +126,9 @@ class PickPlaceVecEnv:
         self._actions = torch.zeros((n, _lib.ACTION_STRIDE), dtype=torch.float32, device=dev)
         self._fsm_actions = torch.zeros((n, _lib.ACTION_STRIDE), dtype=torch.float32, device=dev)
         self._obj_xy = torch.zeros((n, 6), dtype=torch.float64, device=dev)
+        self._yaw_cs = torch.zeros((n, 6), dtype=torch.float64, device=dev)
+        self._yaw_cs[:, 0::2] = 1.0
+        self.last_yaw = torch.zeros((n, 3), dtype=torch.float64, device=dev)
         self._task = torch.zeros((n, 2), dtype=torch.int32, device=dev)
         self._mask = torch.ones(n, dtype=torch.uint8, device=dev)
         self._gid = torch.arange(n, dtype=torch.int64, device=dev) + self.env_id_offset
@@ -156,6 +161,7 @@ class PickPlaceVecEnv:
             if self._np_rngs is None:
                 self._np_rngs = [np.random.default_rng([self.seed, self.env_id_offset + i]) for i in range(n)]
             xy = self._obj_xy.cpu().numpy()
+            yaw = self.last_yaw.cpu().numpy()
             tk = self._task.cpu().numpy()
             pool = self._pool_idx.cpu().numpy()
             for i in sel:
@@ -164,6 +170,8 @@ class PickPlaceVecEnv:
                 g = self._np_rngs[i]
                 if self.randomize_objects:  # placement draws come first (gym_env.py:496-501)
                     xy[i] = np.asarray(sample_separated_positions(g, 3, self.spawn_x_range, self.spawn_y_range)).ravel()
+                    if self.randomize_yaw:  # one theta per cube after the accepted placement (randomization.py:55-56)
+                        yaw[i] = [g.uniform(0, 2 * np.pi) for _ in range(3)]
                 if task_override is not None:
                     tk[i] = task_override[i]
                 elif self._fixed_task is not None:
@@ -173,6 +181,10 @@ class PickPlaceVecEnv:
                 else:  # gym_env.py:516
                     tk[i] = pool[int(g.integers(len(pool)))]
             self._obj_xy.copy_(torch.from_numpy(xy))
+            if self.randomize_yaw:
+                self.last_yaw.copy_(torch.from_numpy(yaw))
+                cs = np.stack([np.cos(yaw / 2), np.sin(yaw / 2)], axis=2).reshape(n, 6)
+                self._yaw_cs.copy_(torch.from_numpy(cs))
             self._task.copy_(torch.from_numpy(tk))
         else:
             xy, tdraw, self.last_attempts = philox_placements(self)
@@ -181,13 +193,25 @@ class PickPlaceVecEnv:
             tk = self._pool_idx[tdraw.to(torch.int64)]
             if task_override is not None:
                 tk = torch.as_tensor(np.asarray(task_override), dtype=torch.int32, device=self.device)
+            if self.randomize_yaw:
+                th = torch.empty_like(self.last_yaw)
+                cs = torch.empty_like(self._yaw_cs)
+                _lib.check(self._L.mm_sample_yaw(self._h, C.c_uint64(self.seed & 0xFFFFFFFFFFFFFFFF), self.env_id_offset,
+                                                 self.episode_index.data_ptr(), th.data_ptr(), cs.data_ptr(),
+                                                 self._stream()), "mm_sample_yaw")
             if mask is None:
                 self._obj_xy.copy_(xy)
                 self._task.copy_(tk)
+                if self.randomize_yaw:
+                    self.last_yaw.copy_(th)
+                    self._yaw_cs.copy_(cs)
             else:
                 m = mask.bool()
                 self._obj_xy[m] = xy[m]
                 self._task[m] = tk[m]
+                if self.randomize_yaw:
+                    self.last_yaw[m] = th[m]
+                    self._yaw_cs[m] = cs[m]
 
     def reset(self, *, seed=None, options: dict | None = None, mask: torch.Tensor | None = None):
         """Reset all envs (or those where `mask` is non-zero).
@@ -195,7 +219,8 @@ class PickPlaceVecEnv:
         seed: None, an int (new base seed) or a sequence of N per-env seeds (rng="numpy": each env is
             reseeded with `np.random.default_rng(seed_i)` exactly as `PickPlaceGymEnv.reset(seed=seed_i)`).
         options: {"task": (obj, bin)} for all envs or {"task": [N pairs]} per env (gym_env.py:511-512),
-            {"obj_xy": [N,3,2]} to place the cubes explicitly.
+            {"obj_xy": [N,3,2]} to place the cubes explicitly, {"obj_yaw": [N,3]} (with obj_xy or
+            randomize_objects) to set their yaw angles.
         """
         seeds = None
         if seed is not None:
@@ -224,6 +249,14 @@ class PickPlaceVecEnv:
                                  device=self.device)
             self._obj_xy.copy_(xy)
             use_xy = True
+        use_yaw = self.randomize_objects and self.randomize_yaw
+        if options and "obj_yaw" in options:
+            th = np.asarray(options["obj_yaw"], dtype=np.float64).reshape(self.num_envs, 3)
+            self.last_yaw.copy_(torch.from_numpy(th))
+            self._yaw_cs.copy_(torch.from_numpy(np.stack([np.cos(th / 2), np.sin(th / 2)], axis=2).reshape(-1, 6)))
+            use_yaw = True
+        _lib.check(self._L.mm_set_placement_yaw(self._h, self._yaw_cs.data_ptr() if use_yaw else None),
+                   "mm_set_placement_yaw")
         m = None if mask is None else mask.to(torch.uint8).contiguous()
         _lib.check(self._L.mm_reset(self._h, C.byref(self._st), None if m is None else m.data_ptr(),
                                     self._obj_xy.data_ptr() if use_xy else None, self._task.data_ptr(),

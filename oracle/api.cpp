@@ -75,6 +75,9 @@ void orc_mj_reset_keyframe(void* h) { reset_keyframe(((Env*)h)->d); }
 void orc_mj_jac(void* h, double* jp, double* jr, const double* point, int body) { jac(((Env*)h)->d, jp, jr, point, body); }
 
 void orc_env_reset(void* h, const double* obj_xy, int obj_idx, int bin_idx) { env_reset(*(Env*)h, obj_xy, obj_idx, bin_idx); }
+void orc_env_reset_yaw(void* h, const double* obj_xy, const double* yaw_cs, int obj_idx, int bin_idx) {
+  env_reset(*(Env*)h, obj_xy, obj_idx, bin_idx, yaw_cs);
+}
 void orc_env_step(void* h, const float* action, float* obs, double* reward, int* term, int* trunc, int* succ, float* rc) {
   env_step(*(Env*)h, action, obs, reward, term, trunc, succ, rc);
 }

@@ -182,7 +182,7 @@ void env_obs(const Env& e, float* o) {
 }
 
 // gym_env.py:477-534 (placement drawn on the host with numpy's PCG64 and passed in as obj_xy)
-void env_reset(Env& e, const double* obj_xy, int obj_idx, int bin_idx) {
+void env_reset(Env& e, const double* obj_xy, int obj_idx, int bin_idx, const double* yaw_cs) {
   reset_keyframe(e.d);
   forward(e.d);
   e.step_count = 0;
@@ -190,6 +190,7 @@ void env_reset(Env& e, const double* obj_xy, int obj_idx, int bin_idx) {
     for (int o = 0; o < 3; o++) {
       double* q = e.d.qpos + 9 + 7 * o;
       q[0] = obj_xy[2 * o]; q[1] = obj_xy[2 * o + 1]; q[2] = 0.26; q[3] = 1; q[4] = q[5] = q[6] = 0;
+      if (yaw_cs) { q[3] = yaw_cs[2 * o]; q[6] = yaw_cs[2 * o + 1]; }  // randomize_yaw=True, randomization.py:55-62
     }
     forward(e.d);
   }

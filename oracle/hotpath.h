@@ -26,7 +26,8 @@ struct Env {
   double target[3] = {0, 0, 0}, transit_end[3] = {0, 0, 0};
 };
 
-void env_reset(Env& e, const double* obj_xy /*6 or null*/, int obj_idx, int bin_idx);
+void env_reset(Env& e, const double* obj_xy /*6 or null*/, int obj_idx, int bin_idx,
+               const double* yaw_cs = nullptr /*6: (cos, sin)(theta/2) per cube, randomization.py:55-62*/);
 void decode_action(const Env& e, const float* action, double target[3], float* gripper);
 void ik_compute(const Data& d, const double target[3], double q_target[7]);
 bool ik_reached(const Data& d, const double target[3]);

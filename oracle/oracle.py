@@ -56,6 +56,7 @@ def lib():
             getattr(L, n).argtypes = [C.c_void_p]
         L.orc_mj_jac.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.orc_env_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.orc_env_reset_yaw.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.orc_env_step.argtypes = [C.c_void_p] + [C.c_void_p] * 7
         L.orc_env_obs.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_ik.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -145,12 +146,18 @@ class OracleEnv:
         return out
 
     # hot path -----------------------------------------------------------------------------
-    def reset(self, obj_xy=None, obj_idx=0, bin_idx=0):
+    def reset(self, obj_xy=None, obj_idx=0, bin_idx=0, yaw=None):
+        """yaw: three angles theta (randomize_yaw=True of randomization.py:55-62) or None."""
         p = None
         if obj_xy is not None:
             xy = np.ascontiguousarray(obj_xy, dtype=np.float64).reshape(6)
             p = xy.ctypes.data
-        self.L.orc_env_reset(self.h, p, int(obj_idx), int(bin_idx))
+        if yaw is not None:
+            th = np.asarray(yaw, dtype=np.float64).reshape(3)
+            cs = np.ascontiguousarray(np.stack([np.cos(th / 2), np.sin(th / 2)], axis=1).reshape(6))
+            self.L.orc_env_reset_yaw(self.h, p, cs.ctypes.data, int(obj_idx), int(bin_idx))
+        else:
+            self.L.orc_env_reset(self.h, p, int(obj_idx), int(bin_idx))
         return self.obs()
 
     def obs(self):

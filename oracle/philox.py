@@ -52,3 +52,10 @@ def task_draw(seed, gid, episode, npool):
     key = (seed & MASK, (seed >> 32) & MASK)
     w = philox4x32((gid & MASK, (gid >> 32) & MASK, episode & MASK, 3), key)
     return (w[0] * npool) >> 32
+
+
+def yaw(seed, gid, episode, o):
+    """theta of cube o: uniform(0, 2 pi) from words 0,1 of block 4(o+1)+3 (randomization.py:55-62)."""
+    key = (seed & MASK, (seed >> 32) & MASK)
+    w = philox4x32((gid & MASK, (gid >> 32) & MASK, episode & MASK, 4 * (o + 1) + 3), key)
+    return np.float64(0.0) + np.float64(6.283185307179586) * np.float64(u53(w[0], w[1]))

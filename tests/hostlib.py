@@ -49,13 +49,18 @@ class EmulEnv:
         self._op = (C.c_void_p * 6)(self.obs.ctypes.data, self.reward_buf.ctypes.data, self.term.ctypes.data,
                                     self.trunc.ctypes.data, self.succ.ctypes.data, self.rc.ctypes.data)
 
-    def reset(self, obj_xy=None, task=None, mask=None):
+    def reset(self, obj_xy=None, task=None, mask=None, yaw=None):
         task = np.ascontiguousarray(np.zeros((self.n, 2)) if task is None else task, dtype=np.int32)
         xy = None if obj_xy is None else np.ascontiguousarray(obj_xy, dtype=np.float64).reshape(self.n, 6)
         m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
-        self.L.emul_reset(self.n, self._sp, None if m is None else m.ctypes.data_as(C.c_void_p),
-                          None if xy is None else xy.ctypes.data_as(C.c_void_p), task.ctypes.data_as(C.c_void_p),
-                          self.obs.ctypes.data_as(C.c_void_p), self.tgt.ctypes.data_as(C.c_void_p), self.use_float)
+        cs = None
+        if yaw is not None:  # [n,3] angles -> (cos, sin)(theta / 2)
+            th = np.asarray(yaw, dtype=np.float64).reshape(self.n, 3)
+            cs = np.ascontiguousarray(np.stack([np.cos(th / 2), np.sin(th / 2)], axis=2).reshape(self.n, 6))
+        self.L.emul_reset_yaw(self.n, self._sp, None if m is None else m.ctypes.data_as(C.c_void_p),
+                              None if xy is None else xy.ctypes.data_as(C.c_void_p),
+                              None if cs is None else cs.ctypes.data_as(C.c_void_p), task.ctypes.data_as(C.c_void_p),
+                              self.obs.ctypes.data_as(C.c_void_p), self.tgt.ctypes.data_as(C.c_void_p), self.use_float)
         return self.obs.copy()
 
     def step(self, actions):

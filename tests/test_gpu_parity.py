@@ -346,3 +346,68 @@ def test_reward_types_and_success_flags_vs_oracle(cuda_device, oracle_lib):
                     np.testing.assert_allclose(info["reward_components"][k].cpu().numpy(), o_info["reward_components"], atol=1e-5)
                 np.testing.assert_allclose(_np(env.obs_packed)[k], o_obs, rtol=0, atol=2e-5)
         env.close()
+
+
+def test_philox_yaw_draw_and_placement(cuda_device):
+    """randomize_yaw (randomization.py:55-62) on the device stream: theta bit-exact with oracle/philox.py,
+    the cube quaternions (cos, 0, 0, sin)(theta/2) to the last bits (device cos/sin vs libm)."""
+    from oracle import philox
+
+    env = _make(32, cuda_device, randomize_objects=True, randomize_yaw=True, rng="philox", seed=9, env_id_offset=77)
+    env.reset()
+    th = _np(env.last_yaw)
+    q = _np(env.state["qpos"])[:, 9:30].reshape(32, 3, 7)
+    for i in range(32):
+        exp = np.array([philox.yaw(9, 77 + i, 0, o) for o in range(3)])
+        assert np.array_equal(th[i], exp), i
+        assert np.all((exp >= 0) & (exp < 2 * np.pi))
+        np.testing.assert_allclose(q[i, :, 3], np.cos(exp / 2), rtol=0, atol=4e-16)
+        np.testing.assert_allclose(q[i, :, 6], np.sin(exp / 2), rtol=0, atol=4e-16)
+        assert np.all(q[i, :, 4:6] == 0)
+        assert np.array_equal(q[i, :, :2], philox.place(9, 77 + i, 0)[0])
+    # option off again: identity quaternions
+    env2 = _make(4, cuda_device, randomize_objects=True, rng="philox", seed=9, env_id_offset=77)
+    env2.reset()
+    assert np.all(_np(env2.state["qpos"])[:, 9:30].reshape(4, 3, 7)[:, :, 3] == 1.0)
+
+
+def test_yawed_cubes_fsm_episode_vs_oracle(cuda_device, oracle_lib):
+    """Scripted expert on cubes that are not axis-aligned, several envs with different yaw / placement:
+    FSM states bit-exact, qpos within TOL at every step, all episodes succeed."""
+    n = 6
+    rng = np.random.default_rng(11)
+    xy = np.stack([oracle_lib.sample_placement(100 + i)[0] for i in range(n)])
+    yaw = rng.uniform(0, 2 * np.pi, size=(n, 3))
+    tasks = [(i % 3, (i + 1) % 3) for i in range(n)]
+    from mujoco_manip_b200.constants import BINS, OBJECTS
+
+    env = _make(n, cuda_device, action_mode="abs_pos")
+    env.reset(options={"obj_xy": xy, "obj_yaw": yaw, "task": [(OBJECTS[o], BINS[b]) for o, b in tasks]})
+    orcs = []
+    for i in range(n):
+        o = oracle_lib.OracleEnv(action_mode="abs_pos", flags=0)
+        o.reset(xy[i], tasks[i][0], tasks[i][1], yaw=yaw[i])
+        o.fsm_reset()
+        orcs.append(o)
+    assert reltol(_np(env.state["qpos"]), np.stack([o.qpos for o in orcs]), TOL) < 1e-9
+    done = np.zeros(n, dtype=bool)
+    succ = np.zeros(n, dtype=bool)
+    for t in range(400):
+        a = env.fsm_plan(16).clone()
+        fs = _np(env.fsm_state)
+        for i, o in enumerate(orcs):
+            if not done[i]:
+                o.fsm_plan(16)
+                assert int(fs[i]) == o.fsm_get()["state"], (t, i)
+        done |= fs == 11
+        if done.all():
+            break
+        _, _, _, _, info = env.step(a)
+        q = _np(env.state["qpos"])
+        s = _np(info["success"])
+        for i, o in enumerate(orcs):
+            if not done[i]:
+                o.step(o.fsm_action())
+                assert reltol(q[i], o.qpos, TOL) < TOL, (t, i)
+                succ[i] = s[i]
+    assert done.all() and succ.all()

@@ -124,3 +124,31 @@ def test_oracle_agrees_on_fresh_random_inputs(oracle_lib):
         env.step(a[None])
         assert reltol(env.st["qpos"][0], orc.qpos, 1e-5) < 1e-6
         assert reltol(env.st["qvel"][0], orc.qvel, 1e-5) < 1e-5
+
+
+def test_yawed_cubes_fsm_episode_vs_oracle(oracle_lib):
+    """randomize_yaw=True (randomization.py:55-62): the gripper closes on a cube that is not axis-aligned,
+    so the pad / cube and cube / bin contacts go through the general box-box and hull code."""
+    rng = np.random.default_rng(5)
+    xy, _ = oracle_lib.sample_placement(23)
+    yaw = rng.uniform(0, 2 * np.pi, size=3)
+    orc = oracle_lib.OracleEnv(action_mode="abs_pos", flags=0)
+    env = EmulEnv(1, mode="abs_pos")
+    orc.reset(xy, 1, 2, yaw=yaw)
+    env.reset(obj_xy=xy.reshape(1, 6), task=np.array([[1, 2]]), yaw=yaw[None])
+    np.testing.assert_allclose(env.st["qpos"][0, 9:30].reshape(3, 7)[:, 3], np.cos(yaw / 2), rtol=0, atol=1e-15)
+    np.testing.assert_allclose(env.st["qpos"][0, 9:30].reshape(3, 7)[:, 6], np.sin(yaw / 2), rtol=0, atol=1e-15)
+    assert reltol(env.st["qpos"][0], orc.qpos, 1e-5) < 1e-9
+    orc.fsm_reset()
+    for t in range(2000):
+        orc.fsm_plan(16)
+        a = env.fsm_plan(16)
+        assert int(env.st["fsm_i"][0, 0]) == orc.fsm_get()["state"], t
+        if int(env.st["fsm_i"][0, 0]) == 11:
+            break
+        np.testing.assert_allclose(a[0, :4], orc.fsm_action(), rtol=0, atol=1e-6)
+        orc.step(orc.fsm_action())
+        env.step(a)
+        assert reltol(env.st["qpos"][0], orc.qpos, 1e-5) < 1e-5, t
+    assert 50 < t < 2000
+    assert bool(env.succ[0])
