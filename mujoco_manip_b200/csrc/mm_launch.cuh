@@ -101,8 +101,11 @@ __device__ __forceinline__ void release_work(const StepParams& p, int slot) {
 // W = warps per CTA.  Two variants of the G == 32 kernel are built: W = BlockCfg::WARPS (6 in FP64) for large
 // batches and W = MM_WARPS_SMALL (4) for small ones, where shorter CTAs fill the tail of the launch better
 // (4096 envs: 186k vs 170k env-steps/s; 16384 envs: 228k vs 238k).
+#ifndef MM_MINB_SMALL
+#define MM_MINB_SMALL MM_CTAS_PER_SM  // CTAs per SM the short-CTA variant is compiled for (sets its register budget)
+#endif
 template <class T, int G, int W>
-__global__ void __launch_bounds__(32 * W, BlockCfg<T, G>::MINB) k_step(StepParams p) {
+__global__ void __launch_bounds__(32 * W, W == BlockCfg<T, G>::WARPS ? BlockCfg<T, G>::MINB : MM_MINB_SMALL) k_step(StepParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   const ModelDev<T>* md;
   Scratch<T>* sc;
@@ -175,6 +178,11 @@ __global__ void __launch_bounds__(BlockCfg<T, G>::THREADS, BlockCfg<T, G>::MINB)
 #ifndef MM_SMALL_BATCH
 #define MM_SMALL_BATCH 8192  // envs per GPU below which the short-CTA variant of the step kernel is launched
 #endif
+inline long small_batch() {  // MM_SMALL_BATCH (environment variable) overrides the compiled threshold: tuning aid
+  static long v = -1;
+  if (v < 0) { const char* e = getenv("MM_SMALL_BATCH"); v = e ? atol(e) : MM_SMALL_BATCH; }
+  return v;
+}
 template <class T, int G>
 constexpr int small_warps() { return G == 32 ? (BlockCfg<T, G>::WARPS < MM_WARPS_SMALL ? BlockCfg<T, G>::WARPS : MM_WARPS_SMALL) : 1; }
 
@@ -228,7 +236,7 @@ cudaError_t inst_launch(int which, const StepParams& p, cudaStream_t s) {  // wh
   size_t sm = smem_bytes<T, G>();
   if (which == 1) k_reset<T, G><<<grid, BLOCK, sm, s>>>(p);
   else if (which == 2) k_ops<T, G><<<grid, BLOCK, sm, s>>>(p);
-  else if (G == 32 && p.n < MM_SMALL_BATCH) {
+  else if (G == 32 && p.n < small_batch()) {
     constexpr int W = small_warps<T, G>();
     unsigned g2 = (unsigned)((p.n + W - 1) / W);
     k_step<T, G, W><<<g2, 32 * W, W * sizeof(Scratch<T>) + extra_smem(), s>>>(p);

@@ -373,7 +373,8 @@ def test_philox_yaw_draw_and_placement(cuda_device):
 
 def test_yawed_cubes_fsm_episode_vs_oracle(cuda_device, oracle_lib):
     """Scripted expert on cubes that are not axis-aligned, several envs with different yaw / placement:
-    FSM states bit-exact, qpos within TOL at every step, all episodes succeed."""
+    FSM states bit-exact, qpos within TOL at every step, success flags equal (a cube turned ~45 degrees can slip
+    out of the expert's grasp - in the oracle and on the GPU alike)."""
     n = 6
     rng = np.random.default_rng(11)
     xy = np.stack([oracle_lib.sample_placement(100 + i)[0] for i in range(n)])
@@ -392,6 +393,7 @@ def test_yawed_cubes_fsm_episode_vs_oracle(cuda_device, oracle_lib):
     assert reltol(_np(env.state["qpos"]), np.stack([o.qpos for o in orcs]), TOL) < 1e-9
     done = np.zeros(n, dtype=bool)
     succ = np.zeros(n, dtype=bool)
+    osucc = np.zeros(n, dtype=bool)
     for t in range(400):
         a = env.fsm_plan(16).clone()
         fs = _np(env.fsm_state)
@@ -407,7 +409,7 @@ def test_yawed_cubes_fsm_episode_vs_oracle(cuda_device, oracle_lib):
         s = _np(info["success"])
         for i, o in enumerate(orcs):
             if not done[i]:
-                o.step(o.fsm_action())
+                osucc[i] = o.step(o.fsm_action())[4]["success"]
                 assert reltol(q[i], o.qpos, TOL) < TOL, (t, i)
                 succ[i] = s[i]
-    assert done.all() and succ.all()
+    assert done.all() and np.array_equal(succ, osucc) and succ.sum() >= n - 2
