@@ -48,3 +48,18 @@ def test_sampler_failure_raises():
 
     with pytest.raises(RuntimeError):
         sample_separated_positions(np.random.default_rng(0), 3, (0.0, 0.01), (0.0, 0.01), 0.08)
+
+
+def test_philox_yaw_stream():
+    """randomize_yaw draws: words 0,1 of block 4(o+1)+3 of the (seed, env, episode) stream, theta = 2 pi u
+    (values pinned from the first implementation; the device sampler is compared bit-exactly in the gpu tests)."""
+    from oracle import philox
+
+    got = [float(philox.yaw(42, 1000, 0, o)) for o in range(3)]
+    assert got == [0.5236206822210825, 1.3999901980488791, 3.2421176688892728]
+    assert float(philox.yaw(7, 2 ** 33 + 5, 3, 1)) == 1.0779784660538425
+    # the yaw blocks are not the blocks of the first placement attempt or the task draw
+    w = philox.philox4x32((1000, 0, 0, 7), (42, 0))
+    assert got[0] == 6.283185307179586 * philox.u53(w[0], w[1])
+    th = np.array([philox.yaw(1, e, 0, o) for e in range(200) for o in range(3)])
+    assert th.min() >= 0 and th.max() < 2 * np.pi and abs(th.mean() - np.pi) < 0.3
