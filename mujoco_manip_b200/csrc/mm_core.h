@@ -22,11 +22,23 @@
 namespace mm {
 
 #ifdef __CUDA_ARCH__
-#define MM_TICK(s, g, slot, t0) do { if ((s).prof) { long long t1_ = clock64(); if ((g).lane == 0) (s).tph[slot] += (unsigned)((t1_ - (t0)) >> 6); (t0) = t1_; } } while (0)
+#define MM_TICK_(s, g, slot, t0) do { if ((s).prof) { long long t1_ = clock64(); if ((g).lane == 0) (s).tph[slot] += (unsigned)((t1_ - (t0)) >> 6); (t0) = t1_; } } while (0)
 #define MM_T0(s) ((s).prof ? clock64() : 0)
 #else
-#define MM_TICK(s, g, slot, t0) do { } while (0)
+#define MM_TICK_(s, g, slot, t0) do { } while (0)
 #define MM_T0(s) 0
+#endif
+// -DMM_PROF_CONVEX (tools/build_variant.sh prof -DMM_PROF_CONVEX, read with tools/convex_probe.py): the eight profiling
+// slots then split the convex narrow phase instead of the stages: 0 barrier wait + list advance | 1 shape load |
+// 2 GJK | 3 EPA | 4 GJK calls | 5 EPA calls | 6 EPA iterations (counts are stored << 6 like the timers) | 7 whole section
+#ifdef MM_PROF_CONVEX
+#define MM_TICK(s, g, slot, t0) do { } while (0)
+#define MM_TICKX(s, g, slot, t0) MM_TICK_(s, g, slot, t0)
+#define MM_CNTX(s, g, slot, n) do { if ((s).prof && (g).lane == 0) (s).tph[slot] += (unsigned)(n); } while (0)
+#else
+#define MM_TICK(s, g, slot, t0) MM_TICK_(s, g, slot, t0)
+#define MM_TICKX(s, g, slot, t0) do { } while (0)
+#define MM_CNTX(s, g, slot, n) do { } while (0)
 #endif
 
 constexpr int MAXCON = 160;   // contacts per env (oracle max: 44 in scripted episodes, 76 in the table-collision stress run, > 128 in rare random-action pile-ups)
@@ -962,15 +974,33 @@ MM_HDX void collide(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<
       int ta = gm.type[a], tb = gm.type[b];
       if (!(ta == GT_PLANE || (ta == GT_BOX && tb == GT_BOX))) break;
     }
-    if (!g.any_more(si < nsurv, 6)) break;
+#ifdef MM_PROF_CONVEX
+    long long tq = MM_T0(s);
+    unsigned cnt_[4] = {0, 0, 0, 0};
+#endif
+    bool more = g.any_more(si < nsurv, 6);
+    MM_TICKX(s, g, 0, tq);
+    if (!more) break;
     if (si >= nsurv) continue;
     Shape<T> s1, s2;
     fill_shape<T, G>(g, s, gm, a, ident, s1);
     fill_shape<T, G>(g, s, gm, b, ident, s2);
+    MM_TICKX(s, g, 1, tq);
     SP<T> sx[4];
     T pos[3] = {0, 0, 0}, pn[3] = {0, 0, 1}, depth = 0;
-    if (!gjk<T, G>(g, s1, s2, sx)) continue;
-    if (!epa<T, G>(g, s1, s2, sx, em, pos, pn, &depth)) continue;
+    MM_CNTX(s, g, 4, 1);
+    bool hit = gjk<T, G>(g, s1, s2, sx);
+    MM_TICKX(s, g, 2, tq);
+    if (!hit) continue;
+    MM_CNTX(s, g, 5, 1);
+#ifdef MM_PROF_CONVEX
+    hit = epa<T, G>(g, s1, s2, sx, em, pos, pn, &depth, cnt_);
+#else
+    hit = epa<T, G>(g, s1, s2, sx, em, pos, pn, &depth);
+#endif
+    MM_CNTX(s, g, 6, cnt_[3]);
+    MM_TICKX(s, g, 3, tq);
+    if (!hit) continue;
     if (g.lane == 0 && ncon < MAXCON) {
       T t1[3];
       make_tangent(pn, t1);
@@ -1026,6 +1056,7 @@ MM_HDX void collide(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<
     g.sync();
   }
   MM_TICK(s, g, 3, tx0);
+  MM_TICKX(s, g, 7, tx0);
   // pair slots: contacts are ordered by (classA, classB); a new slot starts where the key changes
   int npair = 0;
   for (int base = 0; base < ncon; base += G) {
