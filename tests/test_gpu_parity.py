@@ -413,3 +413,34 @@ def test_yawed_cubes_fsm_episode_vs_oracle(cuda_device, oracle_lib):
                 assert reltol(q[i], o.qpos, TOL) < TOL, (t, i)
                 succ[i] = s[i]
     assert done.all() and np.array_equal(succ, osucc) and succ.sum() >= n - 2
+
+
+def test_large_batch_kernel_variant_vs_oracle(cuda_device, oracle_lib):
+    """Batches of 8,192 envs and more run the 6-warp CTA shape of the step kernel (csrc/mm_launch.cuh); a ragged batch
+    of 9,001 scripted-expert envs (Philox placements, cycled tasks, load-aware scheduling on) is compared with the
+    oracle on a handful of its envs, first and last slots included."""
+    n = 9001
+    env = _make(n, cuda_device, action_mode="abs_pos", tasks="all", randomize_objects=True, rng="philox", seed=5,
+                task_assignment="cycle")
+    env.reset()
+    xy = _np(env._obj_xy).reshape(n, 3, 2)
+    tk = _np(env._task)
+    idx = [0, 1, 4500, 8191, 8999, 9000]
+    orcs = []
+    for i in idx:
+        o = oracle_lib.OracleEnv(action_mode="abs_pos", flags=0)
+        o.reset(xy[i], int(tk[i, 0]), int(tk[i, 1]))
+        o.fsm_reset()
+        orcs.append(o)
+    for t in range(45):
+        a = env.fsm_plan(16).clone()
+        fs = _np(env.fsm_state)
+        env.step(a)
+        q = _np(env.state["qpos"][idx])
+        for k, o in enumerate(orcs):
+            o.fsm_plan(16)
+            assert int(fs[idx[k]]) == o.fsm_get()["state"], (t, k)
+            o.step(o.fsm_action())
+            assert reltol(q[k], o.qpos, TOL) < TOL, (t, k)
+    assert int(env.state["diag"][:, 2].max()) == 0
+    assert bool((env.state["step_count"] == 45).all())
