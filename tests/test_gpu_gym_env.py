@@ -349,3 +349,39 @@ def test_expert_action_encodings_match_reference_get_actions(cuda_device):
     for k, v in row.items():
         if FEATURES[k]["dtype"] == "float32":
             assert tuple(v.shape[1:]) == FEATURES[k]["shape"], k
+
+
+def test_randomize_yaw_draw_order_and_quaternions(cuda_device):
+    """randomize_yaw=True (randomization.py:19,55-62): positions are drawn first (rejection sampler), then one
+    theta = uniform(0, 2 pi) per cube in order; the cube quaternion becomes (cos(theta/2), 0, 0, sin(theta/2))."""
+    from mujoco_manip_b200 import PickPlaceVecEnv
+    from mujoco_manip_b200.randomization import sample_separated_positions
+
+    # engine-level call of the N = 1 facade, as PickPlaceEnv.randomize_objects(rng, randomize_yaw=True)
+    env = make(cuda_device)
+    env.reset(seed=0)
+    out = env.pick_place_env.randomize_objects(np.random.default_rng(123), randomize_yaw=True)
+    ref = np.random.default_rng(123)
+    pos = sample_separated_positions(ref, 3, (-0.20, 0.20), (0.30, 0.45))
+    theta = [ref.uniform(0, 2 * np.pi) for _ in range(3)]
+    q = env.pick_place_env._vec.state["qpos"][0].cpu().numpy()
+    for o, name in enumerate(("obj_red", "obj_green", "obj_blue")):
+        np.testing.assert_array_equal(out[f"{name}_jnt"], [pos[o][0], pos[o][1], 0.26])
+        np.testing.assert_allclose(q[9 + 7 * o: 12 + 7 * o], [pos[o][0], pos[o][1], 0.26], rtol=0, atol=0)
+        np.testing.assert_allclose(q[12 + 7 * o: 16 + 7 * o], [np.cos(theta[o] / 2), 0, 0, np.sin(theta[o] / 2)], rtol=0, atol=1e-15)
+        R = env.pick_place_env.get_body_xmat(name)
+        np.testing.assert_allclose(R[:2, :2], [[np.cos(theta[o]), -np.sin(theta[o])], [np.sin(theta[o]), np.cos(theta[o])]], atol=1e-12)
+    # vectorised env with per-env numpy generators: same draw order, then the task draw
+    v = PickPlaceVecEnv(3, device=cuda_device, tasks="all", randomize_objects=True, randomize_yaw=True, rng="numpy", auto_reset=False)
+    v.reset(seed=[7, 8, 9])
+    qv = v.state["qpos"].cpu().numpy()
+    for i, sd in enumerate((7, 8, 9)):
+        ref = np.random.default_rng(sd)
+        pos = sample_separated_positions(ref, 3, (-0.20, 0.20), (0.30, 0.45))
+        theta = np.array([ref.uniform(0, 2 * np.pi) for _ in range(3)])
+        task = int(ref.integers(9))
+        np.testing.assert_array_equal(v.last_yaw[i].cpu().numpy(), theta)
+        np.testing.assert_array_equal(qv[i, 9:30].reshape(3, 7)[:, :2], np.asarray(pos))
+        np.testing.assert_allclose(qv[i, 9:30].reshape(3, 7)[:, 3], np.cos(theta / 2), rtol=0, atol=1e-15)
+        np.testing.assert_allclose(qv[i, 9:30].reshape(3, 7)[:, 6], np.sin(theta / 2), rtol=0, atol=1e-15)
+        assert tuple(v._task[i].cpu().numpy()) == tuple(v._pool_idx[task].cpu().numpy())
