@@ -143,7 +143,8 @@ MM_HDN void chol_factor(const Grp<G>& g, T* A, int n) {
   for (int j = 0; j < n; j++) {
     T d = A[j * n + j];
     if (d < (T)MINVAL_D) d = (T)MINVAL_D;
-    T l = tsqrt(d), inv = (T)1 / l;
+    T l, inv;
+    tsqrt_inv(d, &l, &inv);
     g.sync();
     for (int i = j + 1 + g.lane; i < n; i += G) A[i * n + j] *= inv;
     if (g.lane == 0) A[j * n + j] = l;
@@ -190,7 +191,8 @@ MM_HD void chol6_local(T* A) {  // A -> H[b][b], row stride NV; lower triangle i
   for (int j = 0; j < 6; j++) {
     T d = a[j * (j + 1) / 2 + j];
     if (d < (T)MINVAL_D) d = (T)MINVAL_D;
-    T l = tsqrt(d), inv = (T)1 / l;
+    T l, inv;
+    tsqrt_inv(d, &l, &inv);
     a[j * (j + 1) / 2 + j] = l;
 #pragma unroll
     for (int i = j + 1; i < 6; i++) a[i * (i + 1) / 2 + j] *= inv;
@@ -233,7 +235,8 @@ MM_HDN void chol_factor_list(const Grp<G>& g, T* A, const signed char* il, int n
     int j = il[jj];
     T d = A[j * NV + j];
     if (d < (T)MINVAL_D) d = (T)MINVAL_D;
-    T l = tsqrt(d), inv = (T)1 / l;
+    T l, inv;
+    tsqrt_inv(d, &l, &inv);
     g.sync();
     for (int ii = jj + 1 + g.lane; ii < n; ii += G) A[il[ii] * NV + j] *= inv;
     if (g.lane == 0) A[j * NV + j] = l;
