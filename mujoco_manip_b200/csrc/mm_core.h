@@ -136,18 +136,18 @@ MM_HD int dofmask(int cls) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// group Cholesky (lower, in place, row-major ld = n) and solve
+// group Cholesky (lower, in place, row-major ld = n) and solve.  Every factor routine below leaves the RECIPROCAL
+// of the pivot on the diagonal: the triangular solves multiply instead of dividing on their sequential chain.
 // ------------------------------------------------------------------------------------------------
 template <class T, int G>
 MM_HDN void chol_factor(const Grp<G>& g, T* A, int n) {
   for (int j = 0; j < n; j++) {
     T d = A[j * n + j];
     if (d < (T)MINVAL_D) d = (T)MINVAL_D;
-    T l, inv;
-    tsqrt_inv(d, &l, &inv);
+    T inv = trsqrt(d);
     g.sync();
     for (int i = j + 1 + g.lane; i < n; i += G) A[i * n + j] *= inv;
-    if (g.lane == 0) A[j * n + j] = l;
+    if (g.lane == 0) A[j * n + j] = inv;
     g.sync();
     for (int i = j + 1 + g.lane; i < n; i += G) {
       T lij = A[i * n + j];
@@ -160,14 +160,14 @@ MM_HDN void chol_factor(const Grp<G>& g, T* A, int n) {
 template <class T, int G>
 MM_HDN void chol_solve(const Grp<G>& g, const T* L, int n, T* x) {
   for (int k = 0; k < n; k++) {
-    T xk = x[k] / L[k * n + k];
+    T xk = x[k] * L[k * n + k];
     g.sync();
     if (g.lane == 0) x[k] = xk;
     for (int i = k + 1 + g.lane; i < n; i += G) x[i] -= L[i * n + k] * xk;
     g.sync();
   }
   for (int k = n - 1; k >= 0; k--) {
-    T xk = x[k] / L[k * n + k];
+    T xk = x[k] * L[k * n + k];
     g.sync();
     if (g.lane == 0) x[k] = xk;
     for (int i = g.lane; i < k; i += G) x[i] -= L[k * n + i] * xk;
@@ -191,9 +191,8 @@ MM_HD void chol6_local(T* A) {  // A -> H[b][b], row stride NV; lower triangle i
   for (int j = 0; j < 6; j++) {
     T d = a[j * (j + 1) / 2 + j];
     if (d < (T)MINVAL_D) d = (T)MINVAL_D;
-    T l, inv;
-    tsqrt_inv(d, &l, &inv);
-    a[j * (j + 1) / 2 + j] = l;
+    T inv = trsqrt(d);
+    a[j * (j + 1) / 2 + j] = inv;
 #pragma unroll
     for (int i = j + 1; i < 6; i++) a[i * (i + 1) / 2 + j] *= inv;
 #pragma unroll
@@ -216,13 +215,13 @@ MM_HD void solve6_local(const T* L, T* x) {  // L -> H[b][b] (factor), x -> vect
   for (int i = 0; i < 6; i++) {
 #pragma unroll
     for (int k = 0; k < i; k++) v[i] -= L[i * NV + k] * v[k];
-    v[i] /= L[i * NV + i];
+    v[i] *= L[i * NV + i];
   }
 #pragma unroll
   for (int i = 5; i >= 0; i--) {
 #pragma unroll
     for (int k = i + 1; k < 6; k++) v[i] -= L[k * NV + i] * v[k];
-    v[i] /= L[i * NV + i];
+    v[i] *= L[i * NV + i];
   }
 #pragma unroll
   for (int i = 0; i < 6; i++) x[i] = v[i];
@@ -235,11 +234,10 @@ MM_HDN void chol_factor_list(const Grp<G>& g, T* A, const signed char* il, int n
     int j = il[jj];
     T d = A[j * NV + j];
     if (d < (T)MINVAL_D) d = (T)MINVAL_D;
-    T l, inv;
-    tsqrt_inv(d, &l, &inv);
+    T inv = trsqrt(d);
     g.sync();
     for (int ii = jj + 1 + g.lane; ii < n; ii += G) A[il[ii] * NV + j] *= inv;
-    if (g.lane == 0) A[j * NV + j] = l;
+    if (g.lane == 0) A[j * NV + j] = inv;
     g.sync();
     for (int ii = jj + 1 + g.lane; ii < n; ii += G) {
       int i = il[ii];
@@ -266,12 +264,12 @@ MM_HDN void solve_H(const Grp<G>& g, const Scratch<T>& s, T* x) {
       for (int i = 0; i < NROB; i++) {
         T v = x[i];
         for (int k = 0; k < i; k++) v -= L[i * NV + k] * x[k];
-        x[i] = v / L[i * NV + i];
+        x[i] = v * L[i * NV + i];
       }
       for (int i = NROB - 1; i >= 0; i--) {
         T v = x[i];
         for (int k = i + 1; k < NROB; k++) v -= L[k * NV + i] * x[k];
-        x[i] = v / L[i * NV + i];
+        x[i] = v * L[i * NV + i];
       }
     }
     g.sync();
@@ -280,7 +278,7 @@ MM_HDN void solve_H(const Grp<G>& g, const Scratch<T>& s, T* x) {
   const signed char* il = s.il;
   for (int kk = 0; kk < n; kk++) {
     int k = il[kk];
-    T xk = x[k] / L[k * NV + k];
+    T xk = x[k] * L[k * NV + k];
     g.sync();
     if (g.lane == 0) x[k] = xk;
     for (int ii = kk + 1 + g.lane; ii < n; ii += G) { int i = il[ii]; x[i] -= L[i * NV + k] * xk; }
@@ -288,7 +286,7 @@ MM_HDN void solve_H(const Grp<G>& g, const Scratch<T>& s, T* x) {
   }
   for (int kk = n - 1; kk >= 0; kk--) {
     int k = il[kk];
-    T xk = x[k] / L[k * NV + k];
+    T xk = x[k] * L[k * NV + k];
     g.sync();
     if (g.lane == 0) x[k] = xk;
     for (int ii = g.lane; ii < kk; ii += G) { int i = il[ii]; x[i] -= L[k * NV + i] * xk; }

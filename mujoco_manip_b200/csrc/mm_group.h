@@ -241,17 +241,16 @@ MM_HD int tpopc(int x) {
 }
 MM_HD float tsqrt(float x) { return sqrtf(x); }
 MM_HDL inline double tsqrt(double x) { return sqrt(x); }  // ~150 SASS instructions per expansion: keep one copy
-// Cholesky pivot: l = sqrt(d) and 1 / l.  On the device one reciprocal square root (1 ulp) replaces the square root
-// and the division; d >= MINVAL_D > 0 at every call.
-MM_HD void tsqrt_inv(double d, double* l, double* inv) {
+// Cholesky pivot: 1 / sqrt(d).  On the device one reciprocal square root (1 ulp) replaces the square root and the
+// division; d >= MINVAL_D > 0 at every call.
+MM_HD double trsqrt(double d) {
 #ifdef __CUDA_ARCH__
-  double r = rsqrt(d);
-  *inv = r; *l = d * r;
+  return rsqrt(d);
 #else
-  *l = sqrt(d); *inv = 1.0 / *l;
+  return 1.0 / sqrt(d);
 #endif
 }
-MM_HD void tsqrt_inv(float d, float* l, float* inv) { *l = sqrtf(d); *inv = 1.0f / *l; }
+MM_HD float trsqrt(float d) { return 1.0f / sqrtf(d); }
 MM_HD void tsincos(float x, float* s, float* c) {
 #ifdef __CUDA_ARCH__
   sincosf(x, s, c);
