@@ -844,6 +844,12 @@ MM_HDX void collide(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<
   const T ident[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
   const GeomDev<T>& gm = *md.geom;
   long long tb0 = MM_T0(s);
+  // bounding-sphere centres of all geoms, once per forward pass (the H region is free during collision; the
+  // narrow-phase scratch takes it over after the broad phase)
+  T* bcen = s.H;
+  static_assert(3 * NGEOM <= NV * NV, "bounding-sphere centres do not fit the H region");
+  for (int gi = g.lane; gi < NGEOM; gi += G) geom_bcenter(s, gm, gi, bcen + 3 * gi);
+  g.sync();
   // broad phase: ordered compaction of the surviving candidates
   int nsurv = 0;
   for (int base = 0; base < NPAIRC; base += G) {
@@ -852,8 +858,7 @@ MM_HDX void collide(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<
     if (ci < NPAIRC) {
       int a = gm.pair[ci][0], b = gm.pair[ci][1];
       int ta = gm.type[a];
-      T cb[3];
-      geom_bcenter(s, gm, b, cb);
+      const T* cb = bcen + 3 * b;
       T rb = gm.rbound[b];
       if (ta == GT_PLANE) keep = gm.type[b] != GT_CYL && !(cb[2] > rb);
       else if (ta == GT_BOX && gm.body[a] < 0) {  // axis-aligned static box vs bounding sphere
@@ -864,8 +869,7 @@ MM_HDX void collide(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<
         }
         keep = !(d2 > rb * rb);
       } else {
-        T ca[3];
-        geom_bcenter(s, gm, a, ca);
+        const T* ca = bcen + 3 * a;
         T r[3] = {cb[0] - ca[0], cb[1] - ca[1], cb[2] - ca[2]};
         T rs = rb + gm.rbound[a];
         keep = !(dot3(r, r) > rs * rs);
