@@ -82,6 +82,7 @@ struct Scratch {
   T actf[NU];
   T target[3];
   int pairkey[MAXPAIR];
+  int pairmd[MAXPAIR], pairmb[MAXPAIR];  // dof masks of the pair: dofs of exactly one of the two bodies | dofs of body B
   int specdof[MAXSPEC];  // -1: equality row (e7 - e8); else dof | (negative sign ? 256 : 0)
   int actsat[NU];
   int ncon, npair, nspec, nsurv, overflow, niter, hvalid;
@@ -1079,7 +1080,10 @@ MM_HDX void collide(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<
       int slot = npair + off + head - 1;
       if (slot >= MAXPAIR) slot = MAXPAIR - 1;
       w.cmeta[c] = (m & ~15) | slot;
-      if (head && npair + off < MAXPAIR) s.pairkey[npair + off] = key;
+      if (head && npair + off < MAXPAIR) {
+        int mA = dofmask(key & 15), mB = dofmask((key >> 4) & 15);
+        s.pairkey[npair + off] = key; s.pairmd[npair + off] = mA ^ mB; s.pairmb[npair + off] = mB;
+      }
     }
     npair += tot;
   }
@@ -1097,12 +1101,14 @@ MM_HDN void pair_twists(const Grp<G>& g, Scratch<T>& s, const T* x) {
   int np = s.npair;
   for (int idx = g.lane; idx < np * 6; idx += G) {
     int p = idx / 6, c = idx % 6;
-    int key = s.pairkey[p];
-    int mA = dofmask(key & 15), mB = dofmask((key >> 4) & 15);
+    unsigned md = (unsigned)s.pairmd[p];  // dofs shared by both bodies cancel
+    int mB = s.pairmb[p];
     T acc = 0;
-    for (int i = 0; i < NV; i++) {
-      int sg = ((mB >> i) & 1) - ((mA >> i) & 1);
-      if (sg) acc += (T)sg * x[i] * S_comp(s, i, c);
+    while (md) {  // ascending dof order
+      int i = tctz(md);
+      md &= md - 1;
+      T sg = ((mB >> i) & 1) ? (T)1 : (T)-1;
+      acc += sg * x[i] * S_comp(s, i, c);
     }
     s.pairW[p][c] = acc;
   }
@@ -1306,9 +1312,7 @@ MM_HDN T update_constraint(const Grp<G>& g, Scratch<T>& s, Work<T>& w, bool buil
   for (int i = g.lane; i < NV; i += G) {
     T acc = 0;
     for (int p = 0; p < np; p++) {
-      int key = s.pairkey[p];
-      int sg = ((dofmask((key >> 4) & 15) >> i) & 1) - ((dofmask(key & 15) >> i) & 1);
-      if (sg) acc += (T)sg * S_dot(s, i, s.pairF[p]);
+      if ((s.pairmd[p] >> i) & 1) acc += (((s.pairmb[p] >> i) & 1) ? (T)1 : (T)-1) * S_dot(s, i, s.pairF[p]);
     }
     for (int k = 0; k < s.nspec; k++) {
       int d = s.specdof[k];
@@ -1375,9 +1379,8 @@ MM_HDN void build_factor_H(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md
     }
   }
   for (int p = 0; p < s.npair; p++) {
-    int key = s.pairkey[p];
-    int mA = dofmask(key & 15), mB = dofmask((key >> 4) & 15);
-    int mm_ = mA ^ mB;  // dofs shared by both bodies cancel (sigma = 0)
+    int mB = s.pairmb[p];
+    int mm_ = s.pairmd[p];  // dofs shared by both bodies cancel (sigma = 0)
     const T* K = s.pairK[p];
     g.sync();
     // dofs of this pair in ascending order (rank = number of lower set bits), and u_k = sigma K S

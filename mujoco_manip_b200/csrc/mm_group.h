@@ -239,6 +239,14 @@ MM_HD int tpopc(int x) {
   return __builtin_popcount((unsigned)x);
 #endif
 }
+// index of the lowest set bit (x != 0)
+MM_HD int tctz(unsigned x) {
+#ifdef __CUDA_ARCH__
+  return __ffs((int)x) - 1;
+#else
+  return __builtin_ctz(x);
+#endif
+}
 MM_HD float tsqrt(float x) { return sqrtf(x); }
 MM_HDL inline double tsqrt(double x) { return sqrt(x); }  // ~150 SASS instructions per expansion: keep one copy
 // Cholesky pivot: 1 / sqrt(d).  On the device one reciprocal square root (1 ulp) replaces the square root and the
