@@ -1,14 +1,23 @@
 #!/usr/bin/env python3
-"""Generate tests/golden/*.npz by running the UNMODIFIED reference package (imported read-only from
-/root/reference) on top of the CPU oracle engine through oracle/fake_mujoco.py.
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference package on an engine, and compare two such sets.
 
-What these fixtures pin: everything the reference implements in Python above the engine boundary -
+    python tools/make_golden.py                          # here: reference (read-only, /root/reference) on the CPU oracle
+                                                         # engine through oracle/fake_mujoco.py -> tests/golden/
+    python tools/make_golden.py --engine mujoco --reference /path/to/mujoco-manip --out /tmp/golden_mujoco --compare
+                                                         # on a machine WITH MuJoCo 3.5: same rollouts on the real engine,
+                                                         # then the deviation of tests/golden/ (oracle engine) from them
+
+What the committed fixtures pin: everything the reference implements in Python above the engine boundary -
 action decode, DLS IK, the pick-and-place FSM, rewards, observation packing, reset/RNG order - as
 executed by the reference's own code.  The engine underneath is the oracle restatement (MuJoCo is
-not installable here), so engine-level trajectories remain "parity unpinned" against real MuJoCo.
+not installable in the build container), so engine-level trajectories remain "parity unpinned" against real
+MuJoCo until someone runs the second command; its report (largest relative deviation of qpos / qvel / EE pose per
+file and the first step above 1e-5, FSM-state disagreements) is what would pin the oracle.
+Rendering is stubbed in both modes (no GL needed; image observations are off the hot path).
 
-Run here only (the GPU box has no /root/reference):  python tools/make_golden.py
+The first form runs here only (the GPU box has no /root/reference).
 """
+import argparse
 import os
 import sys
 
@@ -18,18 +27,47 @@ sys.path.insert(0, REPO)
 
 import numpy as np  # noqa: E402
 
-from oracle import fake_mujoco  # noqa: E402
+_ap = argparse.ArgumentParser()
+_ap.add_argument("--engine", default="oracle", choices=["oracle", "mujoco"])
+_ap.add_argument("--reference", default="/root/reference", help="checkout of the reference package")
+_ap.add_argument("--out", default=None, help="output directory (default tests/golden for the oracle engine)")
+_ap.add_argument("--compare", action="store_true", help="after generating, compare tests/golden/ with the new set")
+_ap.add_argument("--compare-only", nargs=2, metavar=("A", "B"), help="only compare two existing directories")
+ARGS = _ap.parse_args()
 
-fake_mujoco.install("/root/reference")
+if ARGS.compare_only is None:
+    if ARGS.engine == "oracle":
+        from oracle import fake_mujoco  # noqa: E402
 
-from mujoco_manip import pose_utils as P  # noqa: E402
-from mujoco_manip.constants import ACTION_REPEAT, TASK_SETS  # noqa: E402
-from mujoco_manip.controller import TARGET_ORI  # noqa: E402
-from mujoco_manip.gym_env import PickPlaceGymEnv  # noqa: E402
-from mujoco_manip.pick_and_place import PickAndPlaceTask  # noqa: E402
-from mujoco_manip.randomization import _sample_separated_positions  # noqa: E402
+        fake_mujoco.install(ARGS.reference)
+    else:
+        import mujoco  # noqa: E402  (the real engine)
 
-OUT = os.path.join(REPO, "tests", "golden")
+        class _NoRenderer:  # physics does not depend on the renderer; avoids the GL context
+            def __init__(self, model, height=224, width=224):
+                self._h, self._w = height, width
+
+            def update_scene(self, data, camera=None):
+                pass
+
+            def render(self):
+                return np.zeros((self._h, self._w, 3), dtype=np.uint8)
+
+            def close(self):
+                pass
+
+        mujoco.Renderer = _NoRenderer
+        sys.path.insert(0, ARGS.reference)
+
+    from mujoco_manip import pose_utils as P  # noqa: E402
+    from mujoco_manip.constants import ACTION_REPEAT, TASK_SETS  # noqa: E402
+    from mujoco_manip.controller import TARGET_ORI  # noqa: E402
+    from mujoco_manip.gym_env import PickPlaceGymEnv  # noqa: E402
+    from mujoco_manip.pick_and_place import PickAndPlaceTask  # noqa: E402
+    from mujoco_manip.randomization import _sample_separated_positions  # noqa: E402
+
+GOLDEN = os.path.join(REPO, "tests", "golden")
+OUT = ARGS.out or (GOLDEN if ARGS.engine == "oracle" else os.path.join(REPO, "tests", "golden_mujoco"))
 OBS_KEYS = ["state", "state.ee.pos_quat_g", "state.ee.pos_rot6d_g", "state.ee.pos_quat_g_rel",
             "state.ee.pos_rot6d_g_rel", "target_bin_onehot", "target_obj_onehot"]
 KP_KEYS = ["keypoints_overhead", "keypoints_wrist", "target_obj_keypoints_overhead", "target_bin_keypoints_overhead"]
@@ -210,5 +248,48 @@ def main():
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
 
+def compare_dirs(a, b, tol=1e-5):
+    """Deviation of the trajectories in directory `a` from those in `b` (same file names): |x_a - x_b| <= tol * max(|x_b|, 1)
+    is the bar of BASELINE.json's north_star.  Returns the number of files above the bar."""
+    bad = 0
+    for f in sorted(os.listdir(b)):
+        if not f.endswith(".npz") or not os.path.exists(os.path.join(a, f)):
+            continue
+        A, B = np.load(os.path.join(a, f)), np.load(os.path.join(b, f))
+        line, worst = [], 0.0
+        for k in ("qpos", "qvel", "ee_pos", "ee_R", "obs", "reward"):
+            if k not in A.files or k not in B.files:
+                continue
+            x, y = np.asarray(A[k], dtype=np.float64), np.asarray(B[k], dtype=np.float64)
+            n = min(len(x), len(y))
+            if n == 0:
+                continue
+            x, y = x[:n].reshape(n, -1), y[:n].reshape(n, -1)
+            rel = (np.abs(x - y) / np.maximum(np.abs(y), 1.0)).max(axis=1)
+            first = int(np.argmax(rel > tol)) if (rel > tol).any() else -1
+            at50 = float(rel[: min(n, 50)].max())
+            worst = max(worst, at50 if k in ("qpos", "qvel", "ee_pos", "ee_R") else 0.0)
+            line.append(f"{k} max {rel.max():.2e} (first 50 steps {at50:.2e}, first step above {tol:g}: {first})")
+        for k in ("fsm_state", "terminated", "truncated", "success"):
+            if k in A.files and k in B.files:
+                n = min(len(A[k]), len(B[k]))
+                mism = int((np.asarray(A[k][:n]) != np.asarray(B[k][:n])).sum()) + abs(len(A[k]) - len(B[k]))
+                if mism:
+                    line.append(f"{k}: {mism} steps differ (lengths {len(A[k])} / {len(B[k])})")
+        if f in ("pose_utils.npz", "reset_seeds.npz"):
+            same = all(np.array_equal(A[k], B[k]) for k in B.files if k in A.files)
+            line.append("identical" if same else "DIFFERENT")
+            worst = 0.0 if same else 1.0
+        ok = worst <= tol
+        bad += 0 if ok else 1
+        print(("ok   " if ok else "ABOVE") + f" {f}: " + "; ".join(line))
+    return bad
+
+
 if __name__ == "__main__":
+    if ARGS.compare_only:
+        sys.exit(1 if compare_dirs(*ARGS.compare_only) else 0)
     main()
+    if ARGS.compare and os.path.abspath(OUT) != os.path.abspath(GOLDEN):
+        print(f"\n== tests/golden (oracle engine) against {OUT} ({ARGS.engine} engine) ==")
+        sys.exit(1 if compare_dirs(GOLDEN, OUT) else 0)
