@@ -150,9 +150,24 @@ MM_HDN void chol_factor(const Grp<G>& g, T* A, int n) {
     for (int i = j + 1 + g.lane; i < n; i += G) A[i * n + j] *= inv;
     if (g.lane == 0) A[j * n + j] = inv;
     g.sync();
-    for (int i = j + 1 + g.lane; i < n; i += G) {
-      T lij = A[i * n + j];
-      for (int k = j + 1; k <= i; k++) A[i * n + k] -= lij * A[k * n + j];
+    // trailing update: one lane per row, or 2 / 4 lanes per row (each a contiguous share of the row) while the
+    // rows left are few - every entry is still updated once per pivot by exactly one lane, so the result is the same
+    int m = n - j - 1;
+    int P = G >= 4 * m ? 4 : (G >= 2 * m ? 2 : 1);
+    if (G < 32) P = 1;
+    if (P == 1) {
+      for (int i = j + 1 + g.lane; i < n; i += G) {
+        T lij = A[i * n + j];
+        for (int k = j + 1; k <= i; k++) A[i * n + k] -= lij * A[k * n + j];
+      }
+    } else {
+      int r = g.lane / P, h = g.lane % P;
+      if (r < m) {
+        int i = j + 1 + r, len = i - j;
+        T lij = A[i * n + j];
+        int k0 = j + 1 + (len * h) / P, k1 = j + 1 + (len * (h + 1)) / P;
+        for (int k = k0; k < k1; k++) A[i * n + k] -= lij * A[k * n + j];
+      }
     }
     g.sync();
   }
@@ -240,11 +255,27 @@ MM_HDN void chol_factor_list(const Grp<G>& g, T* A, const signed char* il, int n
     for (int ii = jj + 1 + g.lane; ii < n; ii += G) A[il[ii] * NV + j] *= inv;
     if (g.lane == 0) A[j * NV + j] = inv;
     g.sync();
-    for (int ii = jj + 1 + g.lane; ii < n; ii += G) {
-      int i = il[ii];
-      T lij = A[i * NV + j];
-      if (lij == 0) continue;
-      for (int kk = jj + 1; kk <= ii; kk++) { int k = il[kk]; A[i * NV + k] -= lij * A[k * NV + j]; }
+    int m = n - jj - 1;  // trailing update, 1 / 2 / 4 lanes per row as in chol_factor
+    int P = G >= 4 * m ? 4 : (G >= 2 * m ? 2 : 1);
+    if (G < 32) P = 1;
+    if (P == 1) {
+      for (int ii = jj + 1 + g.lane; ii < n; ii += G) {
+        int i = il[ii];
+        T lij = A[i * NV + j];
+        if (lij == 0) continue;
+        for (int kk = jj + 1; kk <= ii; kk++) { int k = il[kk]; A[i * NV + k] -= lij * A[k * NV + j]; }
+      }
+    } else {
+      int r = g.lane / P, h = g.lane % P;
+      if (r < m) {
+        int ii = jj + 1 + r, len = ii - jj;
+        int i = il[ii];
+        T lij = A[i * NV + j];
+        if (lij != 0) {
+          int c0 = jj + 1 + (len * h) / P, c1 = jj + 1 + (len * (h + 1)) / P;
+          for (int kk = c0; kk < c1; kk++) { int k = il[kk]; A[i * NV + k] -= lij * A[k * NV + j]; }
+        }
+      }
     }
     g.sync();
   }
