@@ -76,7 +76,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         res = list(ex.map(compile_one, units))
     objs = [o for o, _ in res]
     if force or any(c for _, c in res) or not os.path.exists(LIB_PATH):
-        subprocess.check_call(["nvcc", "--shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + objs)
+        subprocess.check_call(["nvcc", "--shared", "-cudart", "shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + objs)
     return LIB_PATH
 
 
