@@ -41,19 +41,23 @@ namespace mm {
 #define MM_CNTX(s, g, slot, n) do { } while (0)
 #endif
 
-constexpr int MAXCON = 160;   // contacts per env (oracle max: 44 in scripted episodes, 76 in the table-collision stress run, > 128 in rare random-action pile-ups)
+constexpr int MAXCON = 256;   // contacts per env (oracle max: 44 in scripted episodes, 76 in the table-collision stress run, 143 in random-action pile-ups)
 constexpr int MAXROW = MAXCON * 6;
-constexpr int MAXPAIR = 16;   // simultaneously touching body pairs
+constexpr int MAXPAIR_S = 16; // simultaneously touching body pairs whose tables live in shared memory (the common case)
+constexpr int MAXPAIR = 96;   // every ordered (class, class) key of the 780 candidate pairs (94, tools/modelc.py): exact, no cap;
+                              // envs with more than MAXPAIR_S touching pairs keep their pair tables in the global workspace
 constexpr int MAXSPEC = 10;   // equality + at most one limit row per robot joint
-constexpr int MAXSURV = 256;  // geom pairs surviving the first level of the broad phase
+constexpr int MAXSURV = 384;  // geom pairs surviving the first level of the broad phase
 constexpr double MINVAL_D = 1e-15;
 
 // meta word of a contact
-//  bits 0-3 pair slot | 4-7 class A | 8-11 class B | 12 condim-4 (cube) | 13-18 active-row bits | 19 robot-obstacle | 20-28 candidate index
-MM_HD int meta_slot(int m) { return m & 15; }
-MM_HD int meta_dim4(int m) { return (m >> 12) & 1; }
+//  bits 0-6 pair slot | 7-10 class A | 11-14 class B | 15 condim-4 (cube) | 16-21 active-row bits | 22 robot-obstacle
+constexpr int META_KEY_SHIFT = 7, META_DIM4_BIT = 15, META_ACT_SHIFT = 16, META_ROBOBS_BIT = 22;
+MM_HD int meta_slot(int m) { return m & 127; }
+MM_HD int meta_dim4(int m) { return (m >> META_DIM4_BIT) & 1; }
+MM_HD int meta_key(int m) { return (m >> META_KEY_SHIFT) & 0xFF; }  // class A | class B << 4
 // candidate pairs (and therefore contacts) are ordered by (class A, class B)
-MM_HD int sort_key(int m) { return (((m >> 4) & 15) << 4) | ((m >> 8) & 15); }
+MM_HD int sort_key(int m) { return (((m >> META_KEY_SHIFT) & 15) << 4) | ((m >> (META_KEY_SHIFT + 4)) & 15); }
 
 // rows of Scratch::S: robot dofs 0..8, then the three rotational dofs of each cube
 constexpr int NSROW = NROB + 9;
@@ -66,65 +70,91 @@ constexpr int KIN_ROW = 14;  // tmp6 rows 14, 15: arm + finger qpos of the last 
 
 template <class T>
 struct Scratch {
+  // ---- persistent part: the image of an env that travels between the stage kernels of one control step
+  //      (mm_stage.h: ctx_load / ctx_store copy [0, SCRATCH_PERSIST) to / from global memory) ----
   T qpos[NQ], qvel[NV], ctrl[NU];
-  double* warm_g;  // qacc_warmstart of this env in the global state (read at the start of solve, written at its end)
   T bpos[NDB][3], bR[NDB][9];
   T S[NSROW][6];   // spatial axes of the dofs that have a non-trivial one (see srow); cube translations are unit vectors
   T Mr[NROB * NROB];
   T fs[NV], as[NV];
-  // ---- contiguous block that is dead during collision (re-used there as clip scratch and EPA polytope) ----
+  T actf[NU];
+  T target[3];
+  int actsat[NU];
+  int ncon, nbox, nsurv, overflow, niter, prof;
+  int qbase, ncvx;  // this env's slice of the convex-pair queue: items / results [qbase, qbase + ncvx)
+  unsigned tph[8];  // profiling (mm_set_cycle_buffer): busy cycles / 64 in kinematics+dynamics | broad phase | narrow
+                    // phase | its convex (GJK / EPA) part | constraint rows | solver | IK | integration
+  // ---- stage temporaries ----
+  double* warm_g;  // qacc_warmstart of this env in the global state (read at the start of solve, written at its end)
+  // contiguous block that is dead during collision (re-used there as clip scratch and EPA polytope)
   T H[NV * NV];
   T tmp6[TMP6_ROWS<T>()][6];
-  T pairK[MAXPAIR][21], pairW[MAXPAIR][6], pairF[MAXPAIR][6];
+  T pairK_s[MAXPAIR_S][21], pairW_s[MAXPAIR_S][6], pairF_s[MAXPAIR_S][6];
   T qacc[NV], Ma[NV], search[NV], Mv[NV], fc[NV];
   // -----------------------------------------------------------------------------------------------------------
   T specD[MAXSPEC], specJaref[MAXSPEC], specJv[MAXSPEC], specAref[MAXSPEC];
-  T actf[NU];
-  T target[3];
-  int pairkey[MAXPAIR];
-  int pairmd[MAXPAIR], pairmb[MAXPAIR];  // dof masks of the pair: dofs of exactly one of the two bodies | dofs of body B
+  int pairkey_s[MAXPAIR_S];
+  int pairmd_s[MAXPAIR_S], pairmb_s[MAXPAIR_S];  // dof masks of the pair: dofs of exactly one of the two bodies | dofs of body B
+  // pair tables of this forward pass: the shared arrays above, or (more than MAXPAIR_S touching pairs) the global workspace
+  T (*pairK)[21];
+  T (*pairW)[6];
+  T (*pairF)[6];
+  int *pairkey, *pairmd, *pairmb;
   int specdof[MAXSPEC];  // -1: equality row (e7 - e8); else dof | (negative sign ? 256 : 0)
-  int actsat[NU];
-  int ncon, npair, nspec, nsurv, overflow, niter, hvalid;
-  unsigned tph[8];  // profiling (mm_set_cycle_buffer): busy cycles / 64 in kinematics+dynamics | broad phase | narrow
-                    // phase | its convex (GJK / EPA) part | constraint rows | solver | IK | integration
-  int prof;
+  int npair, nspec, hvalid;
   int lone;       // bit c: cube c touches neither the robot nor another cube -> its 6x6 block of H is independent
   int n_il;       // dofs of the coupled part: robot (9) + the cubes that are not `lone`
   signed char il[NV], dl[16];
 };
+#define SCRATCH_PERSIST(T) (offsetof(Scratch<T>, warm_g))
+
+// result of the general convex test of one queued geom pair (mm_ccd.h), consumed in candidate order by assemble_contacts
+template <class T>
+struct CvxRes { T pos[3], nrm[3], depth; int hit, ci; };
 
 // per-env slice of the global workspace (streamed, coalesced across lanes: index = contact / row)
 template <class T>
 struct Work {
+  // contact list of the env (lives from the narrow phase to the end of the solver)
   T* cpos;  // [3][MAXCON]
   T* cn;    // [3][MAXCON]
   T* ct1;   // [3][MAXCON]
   T* cdist; // [MAXCON]
   T* cD;    // [MAXCON]
+  int* cmeta;  // [MAXCON]
+  int* surv;   // [MAXSURV] geom pairs surviving the broad phase
+  // solver rows + spill space (only alive inside one kernel: pooled per resident CTA)
   T* aref;  // [MAXROW]
   T* Jaref; // [MAXROW]
   T* Jv;    // [MAXROW]
-  int* cmeta;  // [MAXCON]
-  int* surv;   // [MAXSURV] geom pairs surviving the broad phase
-  double* warm_pad;  // [NV] private qacc_warmstart of a padding warp (it must not write the real env's)
-  EpaMem<T> epa;
+  T* pairbig;    // [MAXPAIR][33] pair tables of an env with more than MAXPAIR_S touching body pairs
+  int* pairbig_i;  // [3][MAXPAIR]
+  double* warm_pad;  // [NV] spare qacc_warmstart
+  CvxRes<T>* cvx;  // results of this env's convex pairs (global queue slice, or [MAXSURV] pooled for the fused forward)
+  EpaMem<T> epa;   // fused forward only (the convex kernel has its own per-warp polytope)
 };
-constexpr int WORK_REALS = MAXCON * 11 + MAXROW * 3 + EPA_REALS + 2 * NV + 2;
-constexpr int WORK_INTS = MAXCON + EPA_INTS + MAXSURV;
+// per-env part (contacts + survivors) and pooled part (rows, pair spill, EPA, convex results of the fused forward)
+constexpr int WORKE_REALS = MAXCON * 11;
+constexpr int WORKE_INTS = MAXCON + MAXSURV;
+constexpr int WORKP_REALS = MAXROW * 3 + MAXPAIR * 33 + EPA_REALS + 2 * NV + 2 + MAXSURV * 10;
+constexpr int WORKP_INTS = EPA_INTS + 3 * MAXPAIR;
 template <class T>
-MM_HD Work<T> make_work(T* reals, int* ints) {
+MM_HD Work<T> make_work(T* ereals, int* eints, T* preals, int* pints) {
   Work<T> w;
-  w.cpos = reals; w.cn = reals + 3 * MAXCON; w.ct1 = reals + 6 * MAXCON; w.cdist = reals + 9 * MAXCON;
-  w.cD = reals + 10 * MAXCON; w.aref = reals + 11 * MAXCON; w.Jaref = w.aref + MAXROW; w.Jv = w.Jaref + MAXROW;
-  w.cmeta = ints;
-  w.epa.vert = w.Jv + MAXROW; w.epa.face = w.epa.vert + EPA_MAXV * 6;
-  w.epa.fidx = ints + MAXCON; w.epa.edge = w.epa.fidx + EPA_MAXF; w.epa.canon = w.epa.edge + EPA_MAXE;
-  w.surv = w.epa.canon + EPA_MAXV;
-  {  // 8-byte aligned doubles behind the EPA vertices (the pool slices are 8-byte aligned: WORK_REALS is even)
+  w.cpos = ereals; w.cn = ereals + 3 * MAXCON; w.ct1 = ereals + 6 * MAXCON; w.cdist = ereals + 9 * MAXCON;
+  w.cD = ereals + 10 * MAXCON;
+  w.cmeta = eints; w.surv = eints + MAXCON;
+  w.aref = preals; w.Jaref = w.aref + MAXROW; w.Jv = w.Jaref + MAXROW;
+  w.pairbig = w.Jv + MAXROW;
+  w.epa.vert = w.pairbig + MAXPAIR * 33; w.epa.face = w.epa.vert + EPA_MAXV * 6;
+  {  // 8-byte aligned doubles behind the EPA block (pool slices are 8-byte aligned: WORKP_REALS is even)
     T* tail = w.epa.vert + EPA_REALS;
     w.warm_pad = reinterpret_cast<double*>((reinterpret_cast<size_t>(tail) + 7) & ~size_t(7));
   }
+  w.epa.fidx = pints; w.epa.edge = w.epa.fidx + EPA_MAXF; w.epa.canon = w.epa.edge + EPA_MAXE;
+  w.pairbig_i = w.epa.canon + EPA_MAXV;
+  w.cvx = reinterpret_cast<CvxRes<T>*>(w.warm_pad + NV + 1);  // [MAXSURV] (the stage kernels point it at the queue instead)
+  static_assert(sizeof(CvxRes<T>) <= 10 * sizeof(T), "CvxRes does not fit its pool slot");
   return w;
 }
 
@@ -826,10 +856,19 @@ MM_HDL int plane_hull(const T* gpos, const T* R, const T* V, int nvert, T* nrm, 
   return 0;
 }
 
+// shape of geom `gi` for the general convex test; body poses come as plain arrays (shared scratch or a global context)
 template <class T, int G>
-MM_HD void fill_shape(const Grp<G>& g, const Scratch<T>& s, const GeomDev<T>& gm, int gi, const T* ident, Shape<T>& sh) {
+MM_HD void fill_shape(const Grp<G>& g, const T (*bpos)[3], const T (*bR)[9], const GeomDev<T>& gm, int gi, const T* ident, Shape<T>& sh) {
   sh.type = gm.type[gi];
-  sh.R = geom_pose(s, gm, gi, ident, sh.pos);
+  int body = gm.body[gi];
+  if (body < 0) { sh.pos[0] = gm.pos[gi][0]; sh.pos[1] = gm.pos[gi][1]; sh.pos[2] = gm.pos[gi][2]; sh.R = ident; }
+  else {
+    const T* R = bR[body];
+    T v[3];
+    rot(v, R, gm.pos[gi]);
+    for (int k = 0; k < 3; k++) sh.pos[k] = bpos[body][k] + v[k];
+    sh.R = R;
+  }
   sh.size[0] = gm.size[gi][0]; sh.size[1] = gm.size[gi][1]; sh.size[2] = gm.size[gi][2];
   sh.verts = &gm.hull[gm.vadr[gi]][0];
   sh.nvert = gm.vnum[gi];
@@ -857,22 +896,29 @@ MM_HD void store_contact(Work<T>& w, int c, const T* pos, const T* nrm, const T*
   w.cmeta[c] = meta;
 }
 
-// meta word of a contact between geoms a and b (candidate ci)
+// meta word of a contact between geoms a and b
 template <class T>
-MM_HD int contact_meta(const GeomDev<T>& gm, int a, int b, int ci) {
+MM_HD int contact_meta(const GeomDev<T>& gm, int a, int b) {
   int ca = gm.cls[a], cb = gm.cls[b];
   int cube = gm.cube[a] || gm.cube[b];
   // robot geom against an obstacle geom (table / bins; the floor does not count, gym_env.py:137-152,341-350)
   int robobs = (ca >= 1 && ca <= 9 && gm.obst[b]) || (cb >= 1 && cb <= 9 && gm.obst[a]);
-  return (ca << 4) | (cb << 8) | (cube << 12) | (robobs << 19) | (ci << 20);
+  return (ca << META_KEY_SHIFT) | (cb << (META_KEY_SHIFT + 4)) | (cube << META_DIM4_BIT) | (robobs << META_ROBOBS_BIT);
 }
 
+// true when candidate pair (a, b) goes through the general convex test (a mesh hull or a cylinder is involved)
+template <class T>
+MM_HD bool is_convex_pair(const GeomDev<T>& gm, int a, int b) {
+  int ta = gm.type[a], tb = gm.type[b];
+  return !(ta == GT_PLANE || (ta == GT_BOX && tb == GT_BOX));
+}
+
+// Broad phase: two levels over the 780 candidates -> w.surv[0, s.nsurv) in candidate order
 template <class T, int G>
-MM_HDX void collide(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>& w) {
+MM_HDX void broad_phase(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>& w) {
   MM_IN_SHARED(&s);
   MM_IN_GLOBAL(&md);
-  MM_IN_GLOBAL(w.cpos); MM_IN_GLOBAL(w.cn); MM_IN_GLOBAL(w.ct1); MM_IN_GLOBAL(w.cdist); MM_IN_GLOBAL(w.cD); MM_IN_GLOBAL(w.aref);
-  MM_IN_GLOBAL(w.Jaref); MM_IN_GLOBAL(w.Jv); MM_IN_GLOBAL(w.cmeta); MM_IN_GLOBAL(w.surv);
+  MM_IN_GLOBAL(w.surv);
   const T ident[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
   const GeomDev<T>& gm = *md.geom;
   long long tb0 = MM_T0(s);
@@ -882,7 +928,7 @@ MM_HDX void collide(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<
   static_assert(3 * NGEOM <= NV * NV, "bounding-sphere centres do not fit the H region");
   for (int gi = g.lane; gi < NGEOM; gi += G) geom_bcenter(s, gm, gi, bcen + 3 * gi);
   g.sync();
-  // broad phase: ordered compaction of the surviving candidates
+  // first level: ordered compaction of the surviving candidates
   int nsurv = 0;
   for (int base = 0; base < NPAIRC; base += G) {
     int ci = base + g.lane;
@@ -935,21 +981,32 @@ MM_HDX void collide(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<
     }
     nsurv = kept;
   }
+  if (g.lane == 0) s.nsurv = nsurv;
+  g.sync();
   MM_TICK(s, g, 1, tb0);
+}
+
+// Narrow phase 1: box / plane pairs, one pair per lane, NARROW_LANES lanes at a time (their clip polygons live in
+// the shared H region, which is free during collision); ordered compaction of the contacts -> s.ncon (raw count), s.nbox
+template <class T, int G>
+MM_HDX void narrow_box(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>& w) {
+  MM_IN_SHARED(&s);
+  MM_IN_GLOBAL(&md);
+  MM_IN_GLOBAL(w.cpos); MM_IN_GLOBAL(w.cn); MM_IN_GLOBAL(w.ct1); MM_IN_GLOBAL(w.cdist); MM_IN_GLOBAL(w.cD);
+  MM_IN_GLOBAL(w.cmeta); MM_IN_GLOBAL(w.surv);
+  const T ident[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  const GeomDev<T>& gm = *md.geom;
   long long tc0 = MM_T0(s);
-  g.phase(3);
-  // narrow phase 1: box / plane pairs, one pair per lane, NARROW_LANES lanes at a time (their clip polygons
-  // live in the shared H region, which is free during collision); ordered compaction of the contacts
+  const int nsurv = s.nsurv;
   constexpr int KB = G < NARROW_LANES ? G : NARROW_LANES;
   int ncon = 0;
-  for (int base = 0; g.any_more(base < nsurv, 6); base += KB) {
+  for (int base = 0; base < nsurv; base += KB) {
     int si = base + g.lane;
-    int cnt = 0, a = 0, b = 0, ci_ = 0;
+    int cnt = 0, a = 0, b = 0;
     T nrm[3] = {0, 0, 1};
     T* scr = s.H + (g.lane < KB ? g.lane : 0) * NARROW_SCR;
     if (g.lane < KB && si < nsurv) {
       int ci = w.surv[si];
-      ci_ = ci;
       a = gm.pair[ci][0]; b = gm.pair[ci][1];
       int ta = gm.type[a], tb = gm.type[b];
       if (tb == GT_BOX && (ta == GT_PLANE || ta == GT_BOX)) {
@@ -975,7 +1032,7 @@ MM_HDX void collide(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<
       make_tangent(nrm, t1);
       int cube = gm.cube[a] || gm.cube[b];
       T tran = gm.invw[a] + gm.invw[b];
-      int meta = contact_meta(gm, a, b, ci_);
+      int meta = contact_meta(gm, a, b);
       for (int k = 0; k < cnt; k++) {
         int c = ncon + off + k;
         if (c >= MAXCON) break;
@@ -985,72 +1042,84 @@ MM_HDX void collide(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<
     ncon += tot;
     g.sync();
   }
-  int nbox = ncon < MAXCON ? ncon : MAXCON;
-  g.phase(3);
-  long long tx0 = MM_T0(s);
-  // EPA polytope: faces, their index words, horizon edges and canonical vertex ids live in SHARED memory (the H /
-  // tmp6 / pair-block region, free during collision: the sequential face-removal loop must not wait on global
-  // memory); vertices stay in the env's global workspace.
-  static_assert(sizeof(s.H) + sizeof(s.tmp6) + sizeof(s.pairK) + sizeof(s.pairW) + sizeof(s.pairF) + 5 * sizeof(s.qacc) >=
-                    EPA_MAXF * 4 * sizeof(T) + EPA_INTS * sizeof(int), "EPA workspace does not fit the shared scratch");
-  EpaMem<T> em;
-  em.vert = w.epa.vert;
-  em.face = s.H;
-  em.fidx = reinterpret_cast<int*>(s.H + EPA_MAXF * 4);
-  em.edge = em.fidx + EPA_MAXF;
-  em.canon = em.edge + EPA_MAXE;
-  // narrow phase 2: general convex pairs (mesh hulls, cylinders): GJK + EPA by the whole group, one pair at a
-  // time (support scans, face searches and face creation are spread over the lanes); contacts are appended
-  // (the loop advances to the env's next convex pair first, so that a turn of the loop = one GJK / EPA run on
-  // every warp that still has one, and the warps can meet at a barrier per turn)
-  for (int si = 0;; si++) {
-    int ci = 0, a = 0, b = 0;
-    for (; si < nsurv; si++) {
+  if (g.lane == 0) { s.ncon = ncon; s.nbox = ncon < MAXCON ? ncon : MAXCON; }
+  g.sync();
+  MM_TICK(s, g, 2, tc0);
+}
+
+// Convex candidates of the env (survivors with a mesh hull or a cylinder), in candidate order.  Returns their number;
+// item k (candidate index) goes to emit(k, ci).
+template <class T, int G, class Emit>
+MM_HD int list_convex(const Grp<G>& g, const Scratch<T>& s, const GeomDev<T>& gm, const Work<T>& w, Emit emit) {
+  const int nsurv = s.nsurv;
+  int n = 0;
+  for (int base = 0; base < nsurv; base += G) {
+    int si = base + g.lane;
+    int is = 0, ci = 0;
+    if (si < nsurv) {
       ci = w.surv[si];
-      a = gm.pair[ci][0]; b = gm.pair[ci][1];
-      int ta = gm.type[a], tb = gm.type[b];
-      if (!(ta == GT_PLANE || (ta == GT_BOX && tb == GT_BOX))) break;
+      is = is_convex_pair(gm, gm.pair[ci][0], gm.pair[ci][1]) ? 1 : 0;
     }
-#ifdef MM_PROF_CONVEX
-    long long tq = MM_T0(s);
-    unsigned cnt_[4] = {0, 0, 0, 0};
-#endif
-    bool more = g.any_more(si < nsurv, 6);
-    MM_TICKX(s, g, 0, tq);
-    if (!more) break;
-    if (si >= nsurv) continue;
-    Shape<T> s1, s2;
-    fill_shape<T, G>(g, s, gm, a, ident, s1);
-    fill_shape<T, G>(g, s, gm, b, ident, s2);
-    MM_TICKX(s, g, 1, tq);
-    SP<T> sx[4];
-    T pos[3] = {0, 0, 0}, pn[3] = {0, 0, 1}, depth = 0;
-    MM_CNTX(s, g, 4, 1);
-    bool hit = gjk<T, G>(g, s1, s2, sx);
-    MM_TICKX(s, g, 2, tq);
-    if (!hit) continue;
-    MM_CNTX(s, g, 5, 1);
-#ifdef MM_PROF_CONVEX
-    hit = epa<T, G>(g, s1, s2, sx, em, pos, pn, &depth, cnt_);
-#else
-    hit = epa<T, G>(g, s1, s2, sx, em, pos, pn, &depth);
-#endif
-    MM_CNTX(s, g, 6, cnt_[3]);
-    MM_TICKX(s, g, 3, tq);
-    if (!hit) continue;
-    if (g.lane == 0 && ncon < MAXCON) {
-      T t1[3];
+    int tot;
+    int off = g.scan_excl(is, &tot);
+    if (is) emit(n + off, ci);
+    n += tot;
+  }
+  return n;
+}
+
+// Narrow phase 2 of ONE geom pair with a mesh hull or a cylinder: GJK + EPA by the whole group (support scans, face
+// searches and face creation are spread over the lanes).  Body poses from bpos / bR; result (same on every lane) -> out.
+template <class T, int G>
+MM_HDN void convex_pair(const Grp<G>& g, const T (*bpos)[3], const T (*bR)[9], const GeomDev<T>& gm, int ci,
+                        const EpaMem<T>& em, CvxRes<T>* out) {
+  const T ident[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  int a = gm.pair[ci][0], b = gm.pair[ci][1];
+  Shape<T> s1, s2;
+  fill_shape<T, G>(g, bpos, bR, gm, a, ident, s1);
+  fill_shape<T, G>(g, bpos, bR, gm, b, ident, s2);
+  SP<T> sx[4];
+  T pos[3] = {0, 0, 0}, pn[3] = {0, 0, 1}, depth = 0;
+  bool hit = gjk<T, G>(g, s1, s2, sx);
+  if (hit) hit = epa<T, G>(g, s1, s2, sx, em, pos, pn, &depth);
+  if (g.lane == 0) {
+    for (int k = 0; k < 3; k++) { out->pos[k] = pos[k]; out->nrm[k] = pn[k]; }
+    out->depth = depth; out->hit = hit ? 1 : 0; out->ci = ci;
+  }
+  g.sync();
+}
+
+// The convex results w.cvx[0, s.ncvx) (candidate order) are appended to the box contacts; then the box contacts
+// [0, nbox) and the convex contacts [nbox, ncon) - each ordered by body-pair key - are merged (stable) so that every
+// body pair owns ONE contiguous run of contacts and therefore one pair slot; finally the pair tables.
+template <class T, int G>
+MM_HDX void assemble_contacts(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>& w) {
+  MM_IN_SHARED(&s);
+  MM_IN_GLOBAL(&md);
+  MM_IN_GLOBAL(w.cpos); MM_IN_GLOBAL(w.cn); MM_IN_GLOBAL(w.ct1); MM_IN_GLOBAL(w.cdist); MM_IN_GLOBAL(w.cD); MM_IN_GLOBAL(w.aref);
+  MM_IN_GLOBAL(w.cmeta);
+  const GeomDev<T>& gm = *md.geom;
+  long long tx0 = MM_T0(s);
+  int ncon = s.ncon;
+  const int nbox = s.nbox, ncvx = s.ncvx;
+  for (int base = 0; base < ncvx; base += G) {
+    int k = base + g.lane;
+    int hit = 0;
+    if (k < ncvx) hit = w.cvx[k].hit;
+    int tot;
+    int off = g.scan_excl(hit, &tot);
+    if (hit && ncon + off < MAXCON) {
+      const CvxRes<T>& r = w.cvx[k];
+      int a = gm.pair[r.ci][0], b = gm.pair[r.ci][1];
+      T pos[3] = {r.pos[0], r.pos[1], r.pos[2]}, pn[3] = {r.nrm[0], r.nrm[1], r.nrm[2]}, t1[3];
       make_tangent(pn, t1);
       int cube = gm.cube[a] || gm.cube[b];
-      store_contact(w, ncon, pos, pn, t1, -depth, gm.invw[a] + gm.invw[b], cube ? (T)2 : (T)1, contact_meta(gm, a, b, ci));
+      store_contact(w, ncon + off, pos, pn, t1, -r.depth, gm.invw[a] + gm.invw[b], cube ? (T)2 : (T)1, contact_meta(gm, a, b));
     }
-    ncon++;
-    g.sync();
+    ncon += tot;
   }
   if (ncon > MAXCON) { ncon = MAXCON; if (g.lane == 0) s.overflow |= 2; }
   g.sync();
-  // The box contacts [0, nbox) and the appended convex contacts [nbox, ncon) are each ordered by body-pair key;
-  // merge them (stable) so that every body pair owns ONE contiguous run and therefore one pair slot.
   if (ncon > nbox && nbox > 0) {
     for (int base = 0; base < ncon; base += G) {
       int c = base + g.lane;
@@ -1074,9 +1143,6 @@ MM_HDX void collide(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<
       // destinations of this chunk may hit sources of later chunks: stage through the row arrays (aref, Jaref, Jv
       // are contiguous, 18 * MAXCON reals, and not in use before make_constraints)
       if (c < ncon) {
-#if defined(MM_TRACE) && !defined(__CUDA_ARCH__)
-        printf("merge c %d key %x dst %d (nbox %d ncon %d)\n", c, (m >> 4) & 0xFF, dst, nbox, ncon);
-#endif
         for (int d = 0; d < 11; d++) w.aref[d * MAXCON + dst] = v[d];
         reinterpret_cast<int*>(w.aref + 12 * MAXCON)[dst] = m;
       }
@@ -1093,24 +1159,42 @@ MM_HDX void collide(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<
     g.sync();
   }
   MM_TICK(s, g, 3, tx0);
-  MM_TICKX(s, g, 7, tx0);
-  // pair slots: contacts are ordered by (classA, classB); a new slot starts where the key changes
+  // pair slots: contacts are ordered by (classA, classB); a new slot starts where the key changes.  First the number of
+  // touching body pairs, which decides where this pass keeps its pair tables (shared memory / global spill, same layout).
   int npair = 0;
+  for (int base = 0; base < ncon; base += G) {
+    int c = base + g.lane;
+    int head = c < ncon && ((c == 0) || (meta_key(w.cmeta[c - 1]) != meta_key(w.cmeta[c])));
+    npair += tpopc((int)g.ballot(head));
+  }
+  if (g.lane == 0) {
+    if (npair <= MAXPAIR_S) {
+      s.pairK = s.pairK_s; s.pairW = s.pairW_s; s.pairF = s.pairF_s;
+      s.pairkey = s.pairkey_s; s.pairmd = s.pairmd_s; s.pairmb = s.pairmb_s;
+    } else {
+      s.pairK = reinterpret_cast<T (*)[21]>(w.pairbig);
+      s.pairW = reinterpret_cast<T (*)[6]>(w.pairbig + 21 * MAXPAIR);
+      s.pairF = reinterpret_cast<T (*)[6]>(w.pairbig + 27 * MAXPAIR);
+      s.pairkey = w.pairbig_i; s.pairmd = w.pairbig_i + MAXPAIR; s.pairmb = w.pairbig_i + 2 * MAXPAIR;
+    }
+  }
+  g.sync();
+  npair = 0;
   for (int base = 0; base < ncon; base += G) {
     int c = base + g.lane;
     int head = 0, key = 0, m = 0;
     if (c < ncon) {
       m = w.cmeta[c];
-      key = (m >> 4) & 0xFF;
-      head = (c == 0) || (((w.cmeta[c - 1] >> 4) & 0xFF) != key);
+      key = meta_key(m);
+      head = (c == 0) || (meta_key(w.cmeta[c - 1]) != key);
     }
     int tot;
     int off = g.scan_excl(head, &tot);
     g.sync();  // every lane has read its neighbour's meta word before any is rewritten
     if (c < ncon) {
       int slot = npair + off + head - 1;
-      if (slot >= MAXPAIR) slot = MAXPAIR - 1;
-      w.cmeta[c] = (m & ~15) | slot;
+      if (slot >= MAXPAIR) slot = MAXPAIR - 1;  // unreachable: MAXPAIR covers every (class, class) key of the model
+      w.cmeta[c] = (m & ~127) | slot;
       if (head && npair + off < MAXPAIR) {
         int mA = dofmask(key & 15), mB = dofmask((key >> 4) & 15);
         s.pairkey[npair + off] = key; s.pairmd[npair + off] = mA ^ mB; s.pairmb[npair + off] = mB;
@@ -1119,9 +1203,37 @@ MM_HDX void collide(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<
     npair += tot;
   }
   if (npair > MAXPAIR) { npair = MAXPAIR; if (g.lane == 0) s.overflow |= 4; }
-  if (g.lane == 0) { s.ncon = ncon; s.npair = npair; s.nsurv = nsurv; }
+  if (g.lane == 0) { s.ncon = ncon; s.npair = npair; }
   g.sync();
-  MM_TICK(s, g, 2, tc0);
+}
+
+// Fused collision of one env by its own group (reset / engine-level ops / host emulation): the convex pairs are
+// tested one after the other by the whole group; results are identical to the staged path (mm_stage.h), where a
+// batch-wide kernel tests every queued pair with its own warp.
+template <class T, int G>
+MM_HDX void collide(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>& w) {
+  const GeomDev<T>& gm = *md.geom;
+  broad_phase<T, G>(g, s, md, w);
+  narrow_box<T, G>(g, s, md, w);
+  // candidate indices first (the EPA polytope takes over the shared H region below)
+  CvxRes<T>* res = w.cvx;
+  int ncvx = list_convex<T, G>(g, s, gm, w, [&](int k, int ci) { res[k].ci = ci; });
+  if (g.lane == 0) s.ncvx = ncvx;
+  g.sync();
+  // EPA polytope: faces, their index words, horizon edges and canonical vertex ids live in SHARED memory (the H /
+  // tmp6 / pair-block region, free during collision); vertices stay in the global workspace.
+  static_assert(sizeof(s.H) + sizeof(s.tmp6) + sizeof(s.pairK_s) + sizeof(s.pairW_s) + sizeof(s.pairF_s) + 5 * sizeof(s.qacc) >=
+                    EPA_MAXF * 4 * sizeof(T) + EPA_INTS * sizeof(int), "EPA workspace does not fit the shared scratch");
+  EpaMem<T> em;
+  em.vert = w.epa.vert;
+  em.face = s.H;
+  em.fidx = reinterpret_cast<int*>(s.H + EPA_MAXF * 4);
+  em.edge = em.fidx + EPA_MAXF;
+  em.canon = em.edge + EPA_MAXE;
+  long long tx0 = MM_T0(s);
+  for (int k = 0; k < ncvx; k++) convex_pair<T, G>(g, s.bpos, s.bR, gm, res[k].ci, em, res + k);
+  MM_TICK(s, g, 3, tx0);
+  assemble_contacts<T, G>(g, s, md, w);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1310,8 +1422,8 @@ MM_HDN T update_constraint(const Grp<G>& g, Scratch<T>& s, Work<T>& w, bool buil
           }
         }
       }
-      int old = (m >> 13) & 63;
-      if (old != bits) { chg = 1; w.cmeta[c] = (m & ~(63 << 13)) | (bits << 13); }
+      int old = (m >> META_ACT_SHIFT) & 63;
+      if (old != bits) { chg = 1; w.cmeta[c] = (m & ~(63 << META_ACT_SHIFT)) | (bits << META_ACT_SHIFT); }
     }
     // segmented inclusive scan over lanes (keys are non-decreasing); segment tails commit
     if (G > 1) {
@@ -1535,9 +1647,6 @@ MM_HDX void solve(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>
   int iter = 0;
   T cost = 0, a = 0;
   bool first = true, finished = false;
-  g.phase(3);
-  // Every warp of a phase-synchronous CTA runs the same number of loop turns and passes the same barriers
-  // (`all_done`, `phase`) in each; a finished env just skips the work between them.
   while (true) {
     // (A) constraint update at the current point: active set, cost, forces; convergence test of the last move
     if (!finished) {
@@ -1565,7 +1674,7 @@ MM_HDX void solve(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>
         if (improvement < tol || gradient < tol || iter >= 100) finished = true;
       }
     }
-    if (g.all_done(finished)) break;
+    if (finished) break;
     // (B) per-pair blocks + factorisation of H, only when the active set changed
     if (!finished && (first || changed)) {
       int dummy;
@@ -1573,7 +1682,6 @@ MM_HDX void solve(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>
       build_factor_H<T, G>(g, s, md);
     }
     first = false;
-    g.phase(5);
     // (C) Newton direction and the quantities of the line search
     T sn = 0, qg1 = 0, qg2 = 0;
     if (!finished) {
@@ -1590,7 +1698,6 @@ MM_HDX void solve(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>
       sn = tsqrt(g.sum(sn)); qg1 = g.sum(qg1); qg2 = g.sum(qg2);
       if (sn < (T)MINVAL_D) finished = true;
     }
-    g.phase(5);
     // (D) exact line search and the move
     if (!finished) {
       T gtol = tol * (T)0.01 * sn * scale_inv;
@@ -1625,20 +1732,15 @@ MM_HDX void solve(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>
 // full forward at the current (qpos, qvel, ctrl): everything mj_forward computes that the path needs
 template <class T, int G>
 MM_HDN void forward(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>& w) {
-  g.phase(3);
   long long t0 = MM_T0(s);
   fk<T, G>(g, s, md);
-  g.phase(5);
   dyn_smooth<T, G>(g, s, md);
   MM_TICK(s, g, 0, t0);
-  g.phase(2);
   t0 = MM_T0(s);
   collide<T, G>(g, s, md, w);
-  g.phase(2);
   t0 = MM_T0(s);
   make_constraints<T, G>(g, s, md, w);
   MM_TICK(s, g, 4, t0);
-  g.phase(5);
   t0 = MM_T0(s);
   solve<T, G>(g, s, md, w);
   MM_TICK(s, g, 5, t0);

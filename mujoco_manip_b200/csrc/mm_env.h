@@ -222,7 +222,7 @@ MM_HDN void write_reward(const Scratch<T>& s, const StatePtrs& st, long e, int r
 template <class T, int G>
 MM_HDN bool any_robot_collision(const Grp<G>& g, const Scratch<T>& s, const Work<T>& w) {
   int hit = 0;
-  for (int c = g.lane; c < s.ncon; c += G) hit |= (w.cmeta[c] >> 19) & 1;
+  for (int c = g.lane; c < s.ncon; c += G) hit |= (w.cmeta[c] >> META_ROBOBS_BIT) & 1;
   return g.any(hit);
 }
 
@@ -234,57 +234,128 @@ MM_HDN bool state_bad(const Grp<G>& g, const Scratch<T>& s) {
   return g.any(bad);
 }
 
-// One PickPlaceGymEnv.step for env e (gym_env.py:536-581).
+// ------------------------------------------------------------------------------------------------
+// One PickPlaceGymEnv.step (gym_env.py:536-581) as a sequence of batch-wide STAGES.  The 16 x (IK, mj_step) +
+// trailing mj_forward of an env are 17 rounds of
+//   stage A  (group per env)   [first round: load state, decode action]  IK -> position + velocity stage
+//                              (kinematics, CRBA, RNEA, actuation, qacc_smooth) -> broad phase -> box / plane
+//                              narrow phase -> the env's convex candidates are pushed on the batch-wide queue
+//   convex   (warp per PAIR)   GJK + EPA of every queued (env, geom pair): a pile-up env's 25 hull pairs run on 25
+//                              warps instead of one after the other on the env's own warp
+//   stage C  (group per env)   contact list assembly (candidate order: results do not depend on the schedule) ->
+//                              constraint rows -> Newton solver -> implicitfast integration
+//                              [last round: reward, termination, observation, state store]
+// The env's image between stages (Scratch<T>[0, SCRATCH_PERSIST)) lives in global memory (L2 resident).
+// ------------------------------------------------------------------------------------------------
+struct CvxItem { int env, ci; };
+
+template <class T>
+struct CvxQueue {
+  CvxItem* items;    // [cap]
+  CvxRes<T>* res;    // [cap]
+  int* count;        // items pushed in this round
+  int* head;         // next item to be taken (convex kernel)
+  int cap;
+};
+
+#ifdef __CUDA_ARCH__
+#define MM_ATOMIC_ADD(p, v) atomicAdd((p), (v))
+#else
+#define MM_ATOMIC_ADD(p, v) ([&]() { int old_ = *(p); *(p) += (v); return old_; }())
+#endif
+
+template <class T> MM_HDN constexpr int ctx_stride() { return (int)((SCRATCH_PERSIST(T) + 15) / 16 * 16); }
+
 template <class T, int G>
-MM_HDN void env_step(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>& w, const StatePtrs& st, long e,
-                     const float* action, int mode, int reward_type, int max_steps, const StepOut& out,
-                     const float* tgt_kp_all, bool dummy = false, long long* prof = nullptr) {
-  load_state<T, G>(g, s, st, e);
-  if (prof && g.lane == 0) s.prof = 1;
-  if (dummy) {  // padding warp: private copy of the warm start, the real env's state is never written
-    for (int i = g.lane; i < NV; i += G) w.warm_pad[i] = st.warm[e * NV + i];
-    if (g.lane == 0) s.warm_g = w.warm_pad;
-  }
+MM_HD void ctx_copy(const Grp<G>& g, void* dst, const void* src) {
+  constexpr int NW = ctx_stride<T>() / 16;
+  struct alignas(16) W16 { unsigned x, y, z, w; };
+  const W16* s_ = reinterpret_cast<const W16*>(src);
+  W16* d_ = reinterpret_cast<W16*>(dst);
+  for (int i = g.lane; i < NW; i += G) d_[i] = s_[i];
   g.sync();
-  fk<T, G>(g, s, md);  // state after reset / the previous step's trailing mj_forward
-  if (g.lane == 0) {
-    // decode_action (gym_env.py:252-281): only the translation reaches the controller; rotation is
-    // decoded and dropped by the reference, so it is not computed here.
-    const float* a = action + e * ACTION_STRIDE;
-    float gr = mode == MODE_ABS_POS ? a[3] : ((mode == MODE_QUAT || mode == MODE_QUAT_REL) ? a[7] : a[9]);
-    if (mode == MODE_QUAT_REL || mode == MODE_ROT6D_REL) {
-      const double* ti = st.tinit + e * 12;
-      for (int r = 0; r < 3; r++)
-        s.target[r] = (T)(ti[3 + 3 * r] * (double)a[0] + ti[3 + 3 * r + 1] * (double)a[1] + ti[3 + 3 * r + 2] * (double)a[2] + ti[r]);
-    } else for (int r = 0; r < 3; r++) s.target[r] = (T)(double)a[r];
-    s.ctrl[7] = gr > 0.5f ? (T)255 : (T)0;
-  }
-  g.sync();
-  // 16 x (IK, forward, integrate) then the trailing mj_forward (gym_env.py:555-560) - one forward site.
+}
+
+template <class T, int G>
+MM_HDN void reset_bad_state(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, const StatePtrs& st, long e) {
   // Non-finite state: mj_checkPos / mj_checkVel would warn and reset the data; here the env is put back on
   // the keyframe, flagged (diag[3]) so the host can count it, and stepping continues (as mj_step does).
-  for (int sub = 0; sub <= ACTION_REPEAT; sub++) {
-    bool last = sub == ACTION_REPEAT;
-    g.phase(1);
-    long long ti0 = MM_T0(s);
-    if (!last) ik<T, G>(g, s, md);
-    MM_TICK(s, g, 6, ti0);
-
-    if (state_bad<T, G>(g, s)) {
-      for (int i = g.lane; i < NQ; i += G) s.qpos[i] = md.key_qpos[i];
-      for (int i = g.lane; i < NV; i += G) { s.qvel[i] = 0; s.warm_g[i] = 0; }
-      if (g.lane == 0 && !dummy) st.diag[e * 4 + 3] += 1;
-      g.sync();
-    }
-    forward<T, G>(g, s, md, w);
-    g.phase(3);
-    ti0 = MM_T0(s);
-    if (!last) integrate<T, G>(g, s, md);
-    MM_TICK(s, g, 7, ti0);
-
+  if (state_bad<T, G>(g, s)) {
+    for (int i = g.lane; i < NQ; i += G) s.qpos[i] = md.key_qpos[i];
+    for (int i = g.lane; i < NV; i += G) { s.qvel[i] = 0; s.warm_g[i] = 0; }
+    if (g.lane == 0) st.diag[e * 4 + 3] += 1;
+    g.sync();
   }
-  if (prof && g.lane == 0 && !dummy) for (int k = 0; k < 8; k++) prof[1 + k] = (long long)s.tph[k] << 6;
-  if (dummy) return;  // padding warp of a phase-synchronous CTA: took part in every barrier, stores nothing
+}
+
+// decode_action (gym_env.py:252-281): only the translation reaches the controller; rotation is decoded and
+// dropped by the reference, so it is not computed here.
+template <class T>
+MM_HD void decode_action(Scratch<T>& s, const StatePtrs& st, long e, const float* a, int mode) {
+  float gr = mode == MODE_ABS_POS ? a[3] : ((mode == MODE_QUAT || mode == MODE_QUAT_REL) ? a[7] : a[9]);
+  if (mode == MODE_QUAT_REL || mode == MODE_ROT6D_REL) {
+    const double* ti = st.tinit + e * 12;
+    for (int r = 0; r < 3; r++)
+      s.target[r] = (T)(ti[3 + 3 * r] * (double)a[0] + ti[3 + 3 * r + 1] * (double)a[1] + ti[3 + 3 * r + 2] * (double)a[2] + ti[r]);
+  } else for (int r = 0; r < 3; r++) s.target[r] = (T)(double)a[r];
+  s.ctrl[7] = gr > 0.5f ? (T)255 : (T)0;
+}
+
+template <class T, int G>
+MM_HDN void stage_a(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>& w, const StatePtrs& st, long e, int sub,
+                    const float* action, int mode, char* ctx_base, const CvxQueue<T>& q) {
+  void* ctx = ctx_base + (size_t)e * ctx_stride<T>();
+  if (sub == 0) {
+    load_state<T, G>(g, s, st, e);
+    fk<T, G>(g, s, md);  // state after reset / the previous step's trailing mj_forward
+    if (g.lane == 0) decode_action(s, st, e, action + e * ACTION_STRIDE, mode);
+    g.sync();
+  } else {
+    ctx_copy<T, G>(g, &s, ctx);
+    if (g.lane == 0) s.warm_g = st.warm + e * NV;
+    g.sync();
+  }
+  if (sub != ACTION_REPEAT) ik<T, G>(g, s, md);
+  reset_bad_state<T, G>(g, s, md, st, e);
+  fk<T, G>(g, s, md);
+  dyn_smooth<T, G>(g, s, md);
+  broad_phase<T, G>(g, s, md, w);
+  narrow_box<T, G>(g, s, md, w);
+  // convex candidates -> batch-wide queue (the slice [qbase, qbase + ncvx) keeps them in candidate order)
+  const GeomDev<T>& gm = *md.geom;
+  int ncvx = list_convex<T, G>(g, s, gm, w, [](int, int) {});
+  int qbase = 0;
+  if (g.lane == 0 && ncvx > 0) qbase = MM_ATOMIC_ADD(q.count, ncvx);
+  qbase = g.bcast(qbase, 0);
+  if (qbase + ncvx > q.cap) {  // queue full (sized for 64 convex pairs per env on average): flagged, never silent
+    ncvx = q.cap - qbase < 0 ? 0 : q.cap - qbase;
+    if (g.lane == 0) s.overflow |= 8;
+  }
+  CvxItem* items = q.items + qbase;
+  const int lim = ncvx, env = (int)e;
+  list_convex<T, G>(g, s, gm, w, [=](int k, int ci) { if (k < lim) { items[k].env = env; items[k].ci = ci; } });
+  if (g.lane == 0) { s.qbase = qbase; s.ncvx = ncvx; }
+  g.sync();
+  ctx_copy<T, G>(g, ctx, &s);
+}
+
+template <class T, int G>
+MM_HDN void stage_c(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>& w, const StatePtrs& st, long e, int sub,
+                    char* ctx_base, const CvxQueue<T>& q, int reward_type, int max_steps, const StepOut& out,
+                    const float* tgt_kp_all) {
+  void* ctx = ctx_base + (size_t)e * ctx_stride<T>();
+  ctx_copy<T, G>(g, &s, ctx);
+  if (g.lane == 0) s.warm_g = st.warm + e * NV;
+  g.sync();
+  w.cvx = q.res + s.qbase;
+  assemble_contacts<T, G>(g, s, md, w);
+  make_constraints<T, G>(g, s, md, w);
+  solve<T, G>(g, s, md, w);
+  if (sub != ACTION_REPEAT) {
+    integrate<T, G>(g, s, md);
+    ctx_copy<T, G>(g, ctx, &s);
+    return;
+  }
   bool rc = reward_type == REWARD_STAGED ? any_robot_collision<T, G>(g, s, w) : false;
   for (int i = g.lane; i < 9; i += G) s.tmp6[KIN_ROW + i / 6][i % 6] = s.qpos[i];
   g.sync();
@@ -293,6 +364,18 @@ MM_HDN void env_step(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work
     write_reward<T>(s, st, e, reward_type, max_steps, rc, out);
     write_obs<T>(s, st, e, out.obs + e * OBS_DIM, tgt_kp_all + e * 4);
   }
+}
+
+// convex stage: item i of the queue by one group; body poses from the env's global image
+template <class T, int G>
+MM_HDN void stage_convex(const Grp<G>& g, const GeomDev<T>& gm, const CvxQueue<T>& q, int i, const char* ctx_base,
+                         T (*bpos)[3], T (*bR)[9], const EpaMem<T>& em) {
+  CvxItem it = q.items[i];
+  const Scratch<T>* cs = reinterpret_cast<const Scratch<T>*>(ctx_base + (size_t)it.env * ctx_stride<T>());
+  for (int k = g.lane; k < NDB * 3; k += G) bpos[k / 3][k % 3] = cs->bpos[k / 3][k % 3];
+  for (int k = g.lane; k < NDB * 9; k += G) bR[k / 9][k % 9] = cs->bR[k / 9][k % 9];
+  g.sync();
+  convex_pair<T, G>(g, bpos, bR, gm, it.ci, em, q.res + i);
 }
 
 // Reset env e to the keyframe (+ optional object placement), gym_env.py:477-534.

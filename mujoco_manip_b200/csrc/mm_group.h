@@ -38,51 +38,6 @@ struct Grp {
   // G == 32: literal full mask, so that syncs and shuffles compile to single instructions (a run-time
   // mask makes the compiler emit a MATCH.ANY / vote / divergence-check sequence around every one of them)
   MM_HD unsigned m() const { return G == 32 ? 0xffffffffu : mask; }
-  // Phase-synchronous execution (ps != 0, G == 32 only): every warp of the CTA passes the same sequence of
-  // phase() calls, so the warps of an SM execute the same region of the (large) kernel at the same time
-  // and share its instruction-cache lines instead of evicting each other's.
-  int ps;  // 0 off | 1 once per substep | 2 + before collision and before the solver | 3 + every stage | 4 + every Newton iteration | 5 + sub-stages of the Newton iteration and of the forward pass | 6 + every narrow-phase batch / convex pair
-  // cycles this warp spent working (not waiting at phase barriers): the load estimate used to co-schedule envs
-  // of similar cost in one CTA (mm_set_schedule)
-  mutable long long busy, mark;
-  MM_HD void phase(int level = 3) const {
-#ifdef __CUDA_ARCH__
-    if (ps >= level) {
-      long long t = clock64();
-      busy += t - mark;
-      __syncthreads();
-      mark = clock64();
-    }
-#endif
-  }
-  // loop guard for data-dependent trip counts: true while ANY env of the CTA still has work (phase-synchronous at
-  // `level`), so that all warps take the same number of turns and meet at this barrier in each; otherwise `more`
-  MM_HD bool any_more(bool more, int level) const {
-#ifdef __CUDA_ARCH__
-    if (ps >= level) {
-      long long t = clock64();
-      busy += t - mark;
-      bool r = __syncthreads_or(more ? 1 : 0) != 0;
-      mark = clock64();
-      return r;
-    }
-#endif
-    return more;
-  }
-  // true when `done` holds for every env of the CTA (phase-synchronous) / for this env (otherwise)
-  MM_HD bool all_done(bool done) const {
-#ifdef __CUDA_ARCH__
-    if (ps >= 4) {
-      long long t = clock64();
-      busy += t - mark;
-      bool r = __syncthreads_and(done ? 1 : 0) != 0;
-      mark = clock64();
-      return r;
-    }
-#endif
-    return done;
-  }
-
   MM_HD void sync() const {
 #ifdef __CUDA_ARCH__
     if (G > 1) __syncwarp(m());

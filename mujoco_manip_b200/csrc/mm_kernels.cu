@@ -1,7 +1,7 @@
 // CUDA kernels (sm_100a) + the C ABI of include/mm_manip.h.
-// One G-lane group per environment (G = 32 warp-per-env is the tuned, phase-synchronous configuration; 16 / 8 =
-// two / four envs per warp); per-env matrices live in shared memory, streamed per-contact data in a pooled global
-// workspace that the lanes touch with consecutive indices.  No CPU fallback: every entry point needs a CUDA device.
+// A control step is a sequence of batch-wide stage kernels (mm_launch.cuh); inside a stage one G-lane group works on
+// one environment (G = 32 warp per env; 16 / 8 = two / four envs per warp) with its matrices in shared memory, and one
+// warp on one convex geom pair.  No CPU fallback: every entry point needs a CUDA device.
 #define MM_MODEL_HOST_FILL
 #include <cuda_runtime.h>
 
@@ -100,10 +100,23 @@ struct mm_handle {
   mm_config cfg;
   void* d_model = nullptr;
   void* d_geom = nullptr;
-  void* d_work_reals = nullptr;  // workspace pool: pool_ctas x envs_per_cta per-env slices
-  int* d_work_ints = nullptr;
+  void* d_worke_reals = nullptr;  // per-env workspace: contacts, survivors
+  int* d_worke_ints = nullptr;
+  char* d_ctx = nullptr;          // env images between the stage kernels
+  void* d_workp_reals = nullptr;  // pooled workspace: pool_ctas x envs_per_cta slices
+  int* d_workp_ints = nullptr;
   int* d_pool_flags = nullptr;
-  int pool_ctas = 0, envs_per_cta = 0;
+  int pool_ctas = 0, envs_per_cta = 0, convex_grid = 0;
+  // chunks of the batch and their convex-pair queues
+  long chunk = 0;
+  int nchunk = 0, nstream = 0;
+  void* d_q_items = nullptr;   // [nchunk][q_cap]
+  void* d_q_res = nullptr;
+  int* d_q_ctr = nullptr;      // [nchunk][2][NROUND] counts, heads
+  int q_cap = 0;
+  void* d_epa_verts = nullptr; // [nstream][convex_grid * MM_WX][EPA_MAXV * 6]
+  cudaStream_t side[8] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[8] = {};
   float* d_tgt = nullptr;
   const double* yaw_cs = nullptr;  // caller-owned, used by mm_reset when placements are given
   // staging for the host-buffer path
@@ -114,17 +127,30 @@ struct mm_handle {
   long long launches = 0;
   long long* d_cycles = nullptr;
   const int* d_order = nullptr;  // mm_set_schedule
-  int* d_work = nullptr;  // optional per-env cycle counts (mm_set_cycle_buffer)
-  size_t smem = 0;
+  int* d_work = nullptr;  // optional per-env cycle counts (mm_set_schedule)
 };
+
+// every entry point runs on the handle's device whatever the caller's current device is
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define GUARD(h)                                                     \
+  DeviceGuard guard_((h)->cfg.device);                               \
+  if (!guard_.ok) return fail("cannot select the handle's CUDA device")
 
 namespace {
 
 size_t real_bytes(const mm_config* c) { return c->precision ? 4 : 8; }
 
 typedef cudaError_t (*prepare_fn)();
-typedef cudaError_t (*launch_fn)(int, const StepParams&, cudaStream_t);
-typedef cudaError_t (*resident_fn)(int*, int*);
+typedef cudaError_t (*launch_fn)(int, const StepParams&, int, int, cudaStream_t);
+typedef cudaError_t (*resident_fn)(int*, int*, int*);
 int inst_index(const mm_config& c) { return (c.precision ? 3 : 0) + (c.group == 32 ? 0 : (c.group == 16 ? 1 : 2)); }
 const prepare_fn PREPARE[6] = {prepare_f64_32, prepare_f64_16, prepare_f64_8, prepare_f32_32, prepare_f32_16, prepare_f32_8};
 const resident_fn RESIDENT[6] = {resident_f64_32, resident_f64_16, resident_f64_8, resident_f32_32, resident_f32_16, resident_f32_8};
@@ -160,10 +186,13 @@ extern "C" {
 const char* mm_last_error(void) { return g_err.c_str(); }
 
 size_t mm_workspace_bytes(const mm_config* cfg) {
-  size_t n = (size_t)cfg->num_envs;
-  // staging buffers per env + an upper bound of the pooled per-CTA workspaces (2 CTAs x 148 SMs x 16 envs)
-  size_t pool = 4736 < n ? 4736 : n;
-  return n * (4 * 4 + (ACTION_STRIDE + OBS_DIM + 1) * 4 + 3) + pool * ((size_t)WORK_REALS * real_bytes(cfg) + (size_t)WORK_INTS * 4);
+  size_t n = (size_t)cfg->num_envs, rb = real_bytes(cfg);
+  // staging buffers, per-env contact lists + stage images + convex queue, and an upper bound of the pooled workspaces
+  size_t per_env = 4 * 4 + (ACTION_STRIDE + OBS_DIM + 1) * 4 + 3 + (size_t)WORKE_REALS * rb + (size_t)WORKE_INTS * 4 +
+                   (cfg->precision ? ctx_stride<float>() : ctx_stride<double>()) +
+                   64 * (sizeof(CvxItem) + (cfg->precision ? sizeof(CvxRes<float>) : sizeof(CvxRes<double>)));
+  size_t pool = (size_t)148 * 4 * 16;
+  return n * per_env + pool * ((size_t)WORKP_REALS * rb + (size_t)WORKP_INTS * 4);
 }
 
 int mm_create(const mm_config* cfg, mm_handle** out) {
@@ -174,27 +203,59 @@ int mm_create(const mm_config* cfg, mm_handle** out) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail("mm_create: no CUDA device (this library has no CPU path)");
-  CK(cudaSetDevice(cfg->device));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail("mm_create: no such CUDA device");
   mm_handle* h = new mm_handle();
   h->cfg = *cfg;
-  size_t n = (size_t)cfg->num_envs;
+  GUARD(h);
+  size_t n = (size_t)cfg->num_envs, rb = real_bytes(cfg);
   if (cfg->precision == 0) {
     if (upload_model<double>(h) != 0) return -1;
   } else {
     if (upload_model<float>(h) != 0) return -1;
   }
   if (PREPARE[inst_index(h->cfg)]() != cudaSuccess) return fail("mm_create: kernel attribute set-up failed");
-  CK(RESIDENT[inst_index(h->cfg)](&h->pool_ctas, &h->envs_per_cta));
+  CK(RESIDENT[inst_index(h->cfg)](&h->pool_ctas, &h->envs_per_cta, &h->convex_grid));
   h->pool_ctas += 8;  // margin
   {
+    // never more pool entries than CTAs a launch can have (one entry per CTA is then free without contention)
+    size_t need = (n + h->envs_per_cta - 1) / h->envs_per_cta;
+    if (need < (size_t)h->pool_ctas) h->pool_ctas = (int)need;
     size_t slices = (size_t)h->pool_ctas * h->envs_per_cta;
-    size_t need = (n + h->envs_per_cta - 1) / h->envs_per_cta;  // a grid that fits the pool uses blockIdx directly
-    if (need < (size_t)h->pool_ctas) { h->pool_ctas = (int)need; slices = need * h->envs_per_cta; }
-    CK(cudaMalloc(&h->d_work_reals, slices * WORK_REALS * real_bytes(cfg)));
-    CK(cudaMalloc(&h->d_work_ints, slices * WORK_INTS * sizeof(int)));
+    CK(cudaMalloc(&h->d_workp_reals, slices * WORKP_REALS * rb));
+    CK(cudaMalloc(&h->d_workp_ints, slices * WORKP_INTS * sizeof(int)));
     CK(cudaMalloc(&h->d_pool_flags, (size_t)h->pool_ctas * sizeof(int)));
     CK(cudaMemset(h->d_pool_flags, 0, (size_t)h->pool_ctas * sizeof(int)));
   }
+  CK(cudaMalloc(&h->d_worke_reals, n * WORKE_REALS * rb));
+  CK(cudaMalloc(&h->d_worke_ints, n * WORKE_INTS * sizeof(int)));
+  size_t cstride = cfg->precision ? ctx_stride<float>() : ctx_stride<double>();
+  CK(cudaMalloc(&h->d_ctx, n * cstride));
+  CK(cudaMemset(h->d_ctx, 0, n * cstride));
+  // chunks: MM_CHUNK envs each (default: the batch in MM_STREAMS pieces, at most 4096 envs per piece)
+  h->nstream = (int)env_long("MM_STREAMS", 2);
+  if (h->nstream < 1) h->nstream = 1;
+  if (h->nstream > 8) h->nstream = 8;
+  long chunk = env_long("MM_CHUNK", 0);
+  if (chunk <= 0) {
+    chunk = ((long)n + h->nstream - 1) / h->nstream;
+    if (chunk > 4096) chunk = 4096;
+    if (chunk < 256) chunk = 256;
+  }
+  if (((long)n + chunk - 1) / chunk > MAX_CHUNKS) chunk = ((long)n + MAX_CHUNKS - 1) / MAX_CHUNKS;
+  h->chunk = chunk;
+  h->nchunk = (int)(((long)n + chunk - 1) / chunk);
+  if (h->nstream > h->nchunk) h->nstream = h->nchunk;
+  h->q_cap = (int)(chunk * 64);
+  size_t res_bytes = cfg->precision ? sizeof(CvxRes<float>) : sizeof(CvxRes<double>);
+  CK(cudaMalloc(&h->d_q_items, (size_t)h->nchunk * h->q_cap * sizeof(CvxItem)));
+  CK(cudaMalloc(&h->d_q_res, (size_t)h->nchunk * h->q_cap * res_bytes));
+  CK(cudaMalloc(&h->d_q_ctr, (size_t)h->nchunk * 2 * NROUND * sizeof(int)));
+  CK(cudaMalloc(&h->d_epa_verts, (size_t)h->nstream * h->convex_grid * MM_WX * EPA_MAXV * 6 * rb));
+  for (int i = 0; i < h->nstream; i++) {
+    CK(cudaStreamCreateWithFlags(&h->side[i], cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming));
+  }
+  CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
   CK(cudaMalloc(&h->d_tgt, n * 4 * sizeof(float)));
   CK(cudaMemset(h->d_tgt, 0, n * 4 * sizeof(float)));
   CK(cudaMalloc(&h->d_actions, n * ACTION_STRIDE * sizeof(float)));
@@ -207,21 +268,40 @@ int mm_create(const mm_config* cfg, mm_handle** out) {
 
 void mm_destroy(mm_handle* h) {
   if (!h) return;
-  cudaFree(h->d_model); cudaFree(h->d_geom); cudaFree(h->d_work_reals); cudaFree(h->d_work_ints); cudaFree(h->d_pool_flags); cudaFree(h->d_tgt);
+  DeviceGuard guard_(h->cfg.device);
+  for (int i = 0; i < h->nstream; i++) {
+    if (h->side[i]) cudaStreamDestroy(h->side[i]);
+    if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
+  }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  cudaFree(h->d_model); cudaFree(h->d_geom); cudaFree(h->d_worke_reals); cudaFree(h->d_worke_ints); cudaFree(h->d_ctx);
+  cudaFree(h->d_workp_reals); cudaFree(h->d_workp_ints); cudaFree(h->d_pool_flags); cudaFree(h->d_q_items); cudaFree(h->d_q_res);
+  cudaFree(h->d_q_ctr); cudaFree(h->d_epa_verts); cudaFree(h->d_tgt);
   cudaFree(h->d_actions); cudaFree(h->d_obs); cudaFree(h->d_reward); cudaFree(h->d_flags);
   delete h;
 }
 
+namespace {
+void base_params(mm_handle* h, const mm_state* st, StepParams& p) {
+  p.st = to_ptrs(st);
+  p.model = h->d_model;
+  p.worke_reals = h->d_worke_reals; p.worke_ints = h->d_worke_ints; p.ctx = h->d_ctx;
+  p.workp_reals = h->d_workp_reals; p.workp_ints = h->d_workp_ints; p.pool_flags = h->d_pool_flags; p.pool_ctas = h->pool_ctas;
+  p.tgt_kp = h->d_tgt; p.n = h->cfg.num_envs; p.slot0 = 0; p.nslot = h->cfg.num_envs;
+  p.reward_type = h->cfg.reward_type; p.max_steps = h->cfg.max_episode_steps;
+  p.q_cap = h->q_cap;
+}
+}  // namespace
+
 int mm_reset(mm_handle* h, const mm_state* st, const uint8_t* mask, const double* obj_xy, const int32_t* task,
              float* obs, void* stream) {
   if (!h || !st || !task) return fail("mm_reset: null argument");
+  GUARD(h);
   StepParams p{};
-  p.st = to_ptrs(st);
-  p.model = h->d_model; p.work_reals = h->d_work_reals; p.work_ints = h->d_work_ints; p.pool_flags = h->d_pool_flags; p.pool_ctas = h->pool_ctas; p.tgt_kp = h->d_tgt;
-  p.mask = mask; p.obj_xy = obj_xy; p.yaw_cs = obj_xy ? h->yaw_cs : nullptr; p.task = task; p.obs = obs; p.n = h->cfg.num_envs;
-  p.reward_type = h->cfg.reward_type; p.max_steps = h->cfg.max_episode_steps;
+  base_params(h, st, p);
+  p.mask = mask; p.obj_xy = obj_xy; p.yaw_cs = obj_xy ? h->yaw_cs : nullptr; p.task = task; p.obs = obs;
   h->launches++;
-  CK(LAUNCH[inst_index(h->cfg)](1, p, (cudaStream_t)stream));
+  CK(LAUNCH[inst_index(h->cfg)](3, p, 0, 0, (cudaStream_t)stream));
   return 0;
 }
 
@@ -229,29 +309,56 @@ int mm_step(mm_handle* h, const mm_state* st, const float* actions, int action_m
             void* stream) {
   if (!h || !st || !actions || !out) return fail("mm_step: null argument");
   if (action_mode < 0 || action_mode > 4) return fail("mm_step: bad action_mode");
+  GUARD(h);
+  cudaStream_t main = (cudaStream_t)stream;
   StepParams p{};
-  p.st = to_ptrs(st);
+  base_params(h, st, p);
   p.out.obs = out->obs; p.out.reward = out->reward; p.out.terminated = out->terminated; p.out.truncated = out->truncated;
   p.out.success = out->success; p.out.reward_components = out->reward_components;
-  p.actions = actions; p.model = h->d_model; p.work_reals = h->d_work_reals; p.work_ints = h->d_work_ints; p.pool_flags = h->d_pool_flags; p.pool_ctas = h->pool_ctas;
-  p.tgt_kp = h->d_tgt; p.n = h->cfg.num_envs; p.mode = action_mode; p.reward_type = h->cfg.reward_type;
-  p.max_steps = h->cfg.max_episode_steps;
+  p.actions = actions; p.mode = action_mode;
   p.cycles = h->d_cycles;
   p.order = h->d_order;
   p.work = h->d_work;
-  {
-    static int lvl = -1;  // MM_PHASE_LEVEL: tuning knob (default 6 = all barriers; measured 2: 129k, 3: 138k, 4: 148k, 5: 165k, 6: 165k env-steps/s at 4096 envs, 234k at 16384)
-    if (lvl < 0) { const char* e = getenv("MM_PHASE_LEVEL"); lvl = e ? atoi(e) : 6; }
-    p.phase_level = lvl;
+  const launch_fn launch = LAUNCH[inst_index(h->cfg)];
+  const size_t rb = real_bytes(&h->cfg);
+  const size_t res_bytes = h->cfg.precision ? sizeof(CvxRes<float>) : sizeof(CvxRes<double>);
+  CK(cudaMemsetAsync(h->d_q_ctr, 0, (size_t)h->nchunk * 2 * NROUND * sizeof(int), main));
+  const bool forked = h->nstream > 1;
+  if (forked) {
+    CK(cudaEventRecord(h->ev_fork, main));
+    for (int i = 0; i < h->nstream; i++) CK(cudaStreamWaitEvent(h->side[i], h->ev_fork, 0));
   }
-  h->launches++;
-  CK(LAUNCH[inst_index(h->cfg)](0, p, (cudaStream_t)stream));
+  // the chunks of a stream run one after the other; rounds are issued chunk-interleaved so that the streams advance together
+  for (int c = 0; c < h->nchunk; c++) {
+    int si = c % h->nstream;
+    cudaStream_t s = forked ? h->side[si] : main;
+    StepParams pc = p;
+    pc.slot0 = (long)c * h->chunk;
+    pc.nslot = pc.slot0 + h->chunk <= p.n ? h->chunk : p.n - pc.slot0;
+    pc.q_items = (char*)h->d_q_items + (size_t)c * h->q_cap * sizeof(CvxItem);
+    pc.q_res = (char*)h->d_q_res + (size_t)c * h->q_cap * res_bytes;
+    pc.q_count = h->d_q_ctr + (size_t)c * 2 * NROUND;
+    pc.q_head = pc.q_count + NROUND;
+    pc.epa_verts = (char*)h->d_epa_verts + (size_t)si * h->convex_grid * MM_WX * EPA_MAXV * 6 * rb;
+    for (int sub = 0; sub < NROUND; sub++) {
+      CK(launch(0, pc, sub, 0, s));
+      CK(launch(1, pc, sub, h->convex_grid, s));
+      CK(launch(2, pc, sub, 0, s));
+    }
+    h->launches += 3 * NROUND;
+  }
+  if (forked)
+    for (int i = 0; i < h->nstream; i++) {
+      CK(cudaEventRecord(h->ev_join[i], h->side[i]));
+      CK(cudaStreamWaitEvent(main, h->ev_join[i], 0));
+    }
   return 0;
 }
 
 int mm_step_host(mm_handle* h, const mm_state* st, const float* h_actions, int action_mode, float* h_obs,
                  float* h_reward, uint8_t* h_terminated, uint8_t* h_truncated, uint8_t* h_success, void* stream) {
   if (!h || !st || !h_actions) return fail("mm_step_host: null argument");
+  GUARD(h);
   cudaStream_t s = (cudaStream_t)stream;
   size_t n = (size_t)h->cfg.num_envs;
   CK(cudaMemcpyAsync(h->d_actions, h_actions, n * ACTION_STRIDE * sizeof(float), cudaMemcpyHostToDevice, s));
@@ -271,6 +378,7 @@ int mm_step_host(mm_handle* h, const mm_state* st, const float* h_actions, int a
 
 int mm_fsm_plan(mm_handle* h, const mm_state* st, int n_steps, float* actions_out, void* stream) {
   if (!h || !st) return fail("mm_fsm_plan: null argument");
+  GUARD(h);
   long n = h->cfg.num_envs;
   k_fsm<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(to_ptrs(st), n, n_steps, actions_out);
   CK(cudaGetLastError());
@@ -282,6 +390,7 @@ int mm_sample_placements(mm_handle* h, uint64_t seed, int64_t env_id_offset, con
                          double x_hi, double y_lo, double y_hi, double min_separation, int32_t npool, double* obj_xy,
                          int32_t* task_draw, int32_t* attempts, void* stream) {
   if (!h || !episode_index || !obj_xy) return fail("mm_sample_placements: null argument");
+  GUARD(h);
   if (npool <= 0) return fail("mm_sample_placements: npool must be positive");
   long n = h->cfg.num_envs;
   k_sample<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
@@ -301,6 +410,7 @@ int mm_set_placement_yaw(mm_handle* h, const double* yaw_cs) {
 int mm_sample_yaw(mm_handle* h, uint64_t seed, int64_t env_id_offset, const int64_t* episode_index, double* theta,
                   double* yaw_cs, void* stream) {
   if (!h || !episode_index || !yaw_cs) return fail("mm_sample_yaw: null argument");
+  GUARD(h);
   long n = h->cfg.num_envs;
   k_sample_yaw<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
       (unsigned long long)seed, (long long)env_id_offset, (const long long*)episode_index, n, theta, yaw_cs);
@@ -313,7 +423,8 @@ int mm_measure_fma_peak(int device, int fp64, double* tflops) {
   if (!tflops) return fail("mm_measure_fma_peak: null argument");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail("mm_measure_fma_peak: no CUDA device");
-  CK(cudaSetDevice(device));
+  DeviceGuard guard_(device);
+  if (!guard_.ok) return fail("mm_measure_fma_peak: cannot select the device");
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
   void* buf;
@@ -345,17 +456,18 @@ int mm_ops(mm_handle* h, const mm_state* st, int ops, const double* target, void
   if (ops <= 0 || ops > 7) return fail("mm_ops: ops must be a combination of MM_OP_IK, MM_OP_FORWARD, MM_OP_INTEGRATE");
   if ((ops & MM_OP_INTEGRATE) && !(ops & MM_OP_FORWARD)) return fail("mm_ops: MM_OP_INTEGRATE needs MM_OP_FORWARD");
   if ((ops & MM_OP_IK) && !target) return fail("mm_ops: MM_OP_IK needs a target array");
+  GUARD(h);
   StepParams p{};
-  p.st = to_ptrs(st);
-  p.model = h->d_model; p.work_reals = h->d_work_reals; p.work_ints = h->d_work_ints; p.pool_flags = h->d_pool_flags; p.pool_ctas = h->pool_ctas; p.tgt_kp = h->d_tgt;
-  p.n = h->cfg.num_envs; p.ops = ops; p.target = target;
+  base_params(h, st, p);
+  p.ops = ops; p.target = target;
   h->launches++;
-  CK(LAUNCH[inst_index(h->cfg)](2, p, (cudaStream_t)stream));
+  CK(LAUNCH[inst_index(h->cfg)](4, p, 0, 0, (cudaStream_t)stream));
   return 0;
 }
 
 int mm_expert_actions(mm_handle* h, const mm_state* st, const float* abs_actions, float* encodings, void* stream) {
   if (!h || !st || !abs_actions || !encodings) return fail("mm_expert_actions: null argument");
+  GUARD(h);
   long n = h->cfg.num_envs;
   k_expert<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(to_ptrs(st), n, abs_actions, encodings);
   CK(cudaGetLastError());

@@ -8,6 +8,7 @@ library behind include/mm_manip.h; torch only owns the memory and the stream.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -102,7 +103,7 @@ class PickPlaceVecEnv:
         self._pool_idx = torch.tensor([task_indices(t) for t in pool], dtype=torch.int32, device=self.device)
 
         self._L = _lib.lib()
-        cfg = _lib.MMConfig(self.num_envs, self.device.index or 0, 0 if precision == "f64" else 1, int(group),
+        cfg = _lib.MMConfig(self.num_envs, self.device.index if self.device.index is not None else torch.cuda.current_device(), 0 if precision == "f64" else 1, int(group),
                             _lib.REWARD_TYPES.index(reward_type), self.max_episode_steps)
         self._cfg = cfg
         h = C.c_void_p()
@@ -139,7 +140,7 @@ class PickPlaceVecEnv:
         self._np_rngs: list | None = None
         self._closed = False
         # load-aware scheduling: envs sorted by the busy time of their previous step share a CTA (mm_set_schedule)
-        self.load_balance = bool(load_balance) and n > 32
+        self.load_balance = bool(load_balance) and n > 32 and os.environ.get("MM_LOAD_BALANCE", "1") != "0"
         self._work = torch.zeros(n, dtype=torch.int32, device=dev)
         self._order = torch.arange(n, dtype=torch.int32, device=dev)
         if self.load_balance:

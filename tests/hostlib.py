@@ -1,5 +1,5 @@
 """Test helpers: state allocation + ctypes access to the 1-lane host emulation of the kernel source
-(tests/_build/libmm_emul.so, built from mujoco_manip_b200/csrc/mm_emul.cpp with g++).  Test-only."""
+(tests/_build/libmm_emul.so, built from tests/mm_emul.cpp + the kernel headers with g++).  Test-only."""
 import ctypes as C
 import os
 import subprocess
@@ -22,12 +22,12 @@ STATE_FIELDS = [("qpos", 30, np.float64), ("qvel", 27, np.float64), ("ctrl", 8, 
 
 def build_emul():
     srcdir = os.path.join(REPO, "mujoco_manip_b200", "csrc")
-    srcs = [os.path.join(srcdir, f) for f in os.listdir(srcdir) if f.endswith((".h", ".cpp"))]
+    srcs = [os.path.join(srcdir, f) for f in os.listdir(srcdir) if f.endswith(".h")] + [os.path.join(REPO, "tests", "mm_emul.cpp")]
     if os.path.exists(_EMUL) and all(os.path.getmtime(s) <= os.path.getmtime(_EMUL) for s in srcs):
         return _EMUL
     os.makedirs(os.path.dirname(_EMUL), exist_ok=True)
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-w", "-o", _EMUL,
-                           os.path.join(srcdir, "mm_emul.cpp")])
+                           os.path.join(REPO, "tests", "mm_emul.cpp")])
     return _EMUL
 
 

@@ -1,12 +1,12 @@
 // TEST-ONLY host build of the kernel source with a 1-lane group (G = 1).
-// Built by tests/ (g++) into tests/_build/libmm_emul.so so that the kernel LOGIC can be checked
+// Lives in tests/ and is built by tests/hostlib.py (g++) into tests/_build/libmm_emul.so so that the kernel LOGIC can be checked
 // against the oracle on machines without a GPU (`-m "not gpu"` tests).  It is never loaded by the
 // mujoco_manip_b200 package: the product path is the CUDA library and fails loudly without it.
 #define MM_MODEL_HOST_FILL
 #include <cstring>
 #include <vector>
 
-#include "mm_env.h"
+#include "../mujoco_manip_b200/csrc/mm_env.h"
 
 using namespace mm;
 
@@ -16,14 +16,14 @@ struct Ctx {
   ModelDev<T> md;
   GeomDev<T> gm;
   Scratch<T> s;
-  std::vector<T> wr;
-  std::vector<int> wi;
+  std::vector<T> wr, wp;
+  std::vector<int> wi, wpi;
   Work<T> w;
-  Ctx() : wr(WORK_REALS), wi(WORK_INTS) {
+  Ctx() : wr(WORKE_REALS), wp(WORKP_REALS), wi(WORKE_INTS), wpi(WORKP_INTS) {
     fill_model(md);
     fill_geom(gm);
     md.geom = &gm;
-    w = make_work(wr.data(), wi.data());
+    w = make_work(wr.data(), wi.data(), wp.data(), wpi.data());
     std::memset(&s, 0, sizeof s);
   }
 };
@@ -52,20 +52,47 @@ void do_reset(int n, void** sp, const unsigned char* mask, const double* obj_xy,
               float* obs, float* tgt) {
   Ctx<T>& c = ctx<T>();
   StatePtrs st = state_from(sp);
-  Grp<1> g{0, 1u, 0, 0, 0};
+  Grp<1> g{0, 1u};
   for (long e = 0; e < n; e++) {
     if (mask && !mask[e]) continue;
     env_reset<T, 1>(g, c.s, c.md, c.w, st, e, obj_xy ? obj_xy + 6 * e : nullptr, yaw_cs ? yaw_cs + 6 * e : nullptr, task[2 * e],
                     task[2 * e + 1], obs, tgt);
   }
 }
+// One control step of n envs through the STAGE functions the CUDA kernels run (mm_env.h): 17 rounds of stage A for
+// every env, the batch-wide convex queue, stage C for every env - with per-env contact lists and images as on the device.
 template <class T>
 void do_step(int n, void** sp, const float* actions, int mode, int reward_type, int max_steps, void** op, const float* tgt) {
   Ctx<T>& c = ctx<T>();
   StatePtrs st = state_from(sp);
   StepOut out = out_from(op);
-  Grp<1> g{0, 1u, 0, 0, 0};
-  for (long e = 0; e < n; e++) env_step<T, 1>(g, c.s, c.md, c.w, st, e, actions, mode, reward_type, max_steps, out, tgt);
+  Grp<1> g{0, 1u};
+  std::vector<T> wer((size_t)n * WORKE_REALS);
+  std::vector<int> wei((size_t)n * WORKE_INTS);
+  std::vector<char> image((size_t)n * ctx_stride<T>());
+  const int cap = n * 64;
+  std::vector<CvxItem> items(cap);
+  std::vector<CvxRes<T>> res(cap);
+  std::vector<T> everts(EPA_MAXV * 6), eface(EPA_MAXF * 4);
+  std::vector<int> eints(EPA_INTS);
+  static T bpos[NDB][3], bR[NDB][9];
+  for (int sub = 0; sub <= ACTION_REPEAT; sub++) {
+    int count = 0, head = 0;
+    CvxQueue<T> q{items.data(), res.data(), &count, &head, cap};
+    for (long e = 0; e < n; e++) {
+      Work<T> w = make_work(wer.data() + e * WORKE_REALS, wei.data() + e * WORKE_INTS, c.wp.data(), c.wpi.data());
+      stage_a<T, 1>(g, c.s, c.md, w, st, e, sub, actions, mode, image.data(), q);
+    }
+    EpaMem<T> em;
+    em.vert = everts.data(); em.face = eface.data(); em.fidx = eints.data(); em.edge = em.fidx + EPA_MAXF; em.canon = em.edge + EPA_MAXE;
+    int cnt = count < cap ? count : cap;
+    for (int i = cnt - 1; i >= 0; i--)  // any order: results are addressed by queue position
+      stage_convex<T, 1>(g, c.gm, q, i, image.data(), bpos, bR, em);
+    for (long e = 0; e < n; e++) {
+      Work<T> w = make_work(wer.data() + e * WORKE_REALS, wei.data() + e * WORKE_INTS, c.wp.data(), c.wpi.data());
+      stage_c<T, 1>(g, c.s, c.md, w, st, e, sub, image.data(), q, reward_type, max_steps, out, tgt);
+    }
+  }
 }
 }  // namespace
 
@@ -90,7 +117,7 @@ void emul_step(int n, void** state, const float* actions, int mode, int reward_t
 
 void emul_ops(int n, void** state, int ops, const double* target, int use_float) {
   StatePtrs st = state_from(state);
-  Grp<1> g{0, 1u, 0, 0, 0};
+  Grp<1> g{0, 1u};
   for (long e = 0; e < n; e++) {
     if (use_float) { Ctx<float>& c = ctx<float>(); env_ops<float, 1>(g, c.s, c.md, c.w, st, e, ops, target); }
     else { Ctx<double>& c = ctx<double>(); env_ops<double, 1>(g, c.s, c.md, c.w, st, e, ops, target); }
@@ -108,7 +135,7 @@ void emul_forward_debug(const double* qpos, const double* qvel, const double* ct
                         double* cpos, double* cn, double* cdist, int* cmeta, int* niter) {
   Ctx<double>& c = ctx<double>();
   Scratch<double>& s = c.s;
-  Grp<1> g{0, 1u, 0, 0, 0};
+  Grp<1> g{0, 1u};
   for (int i = 0; i < NQ; i++) s.qpos[i] = qpos[i];
   static thread_local double warm_buf[NV];
   for (int i = 0; i < NV; i++) { s.qvel[i] = qvel[i]; warm_buf[i] = warm[i]; }
