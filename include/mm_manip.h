@@ -60,6 +60,8 @@ typedef struct {
   int32_t* step_count; /* [N]    gym_env.py:111                                */
   int32_t* task;       /* [N,2]  object index, bin index (constants.py:3-4)    */
   int32_t* fsm_i;      /* [N,5]  state 1..11, task_index, settle_counter, gripper_open, has_target */
+  int32_t* fsm_tasks;  /* [N,20] the FSM's own task list (pick_and_place.py:91, independent of `task`): count, then up to 9
+                                 (object index, bin index) pairs; mm_reset arms it with the env's single task */
   int32_t* flags;      /* [N]    staged stickies bits0-3, hwm-set bit4 (gym_env.py:129-132) */
   int32_t* diag;       /* [N,4]  ncon, newton iters (last forward), overflow bits, non-finite resets */
 } mm_state;
@@ -146,12 +148,13 @@ int mm_expert_actions(mm_handle* h, const mm_state* st, const float* abs_actions
 /* Load-aware scheduling of mm_step (no reference counterpart; results do not depend on it).  `work` ([N] int32,
  * device, or NULL) receives each env's busy time of the step (SM cycles / 256); `order` ([N] int32 device permutation,
  * or NULL = identity) tells which env each execution slot processes.  Passing the envs sorted by the previous step's
- * `work` (descending) puts envs of similar cost into the same CTA, so the phase barriers of the step kernel wait less. */
+ * `work` (descending) starts the most expensive envs first, which shortens the tail of the stage launches of large batches. */
 int mm_set_schedule(mm_handle* h, const int32_t* order, int32_t* work);
 
-/* Profiling aid: when `cycles` ([N,9] int64, device) is non-NULL every mm_step stores the SM clock cycles each env's
- * step took: total, then kinematics+dynamics, broad phase, narrow phase, constraint rows + warm start, (unused),
- * Newton iterations, IK, integration.  NULL switches it off. */
+/* Profiling aid: when `cycles` ([N,9] int64, device) is non-NULL every mm_step ADDS the SM clock cycles each env spent
+ * in the stage kernels: [0] total, [1] stage A (IK, kinematics, dynamics, broad + box narrow phase), [2] convex stage
+ * (GJK / EPA of the env's queued pairs, summed over the warps that ran them), [3] stage C (contact assembly, constraint
+ * rows, Newton solver, integration); [4..8] unused.  NULL switches it off. */
 int mm_set_cycle_buffer(mm_handle* h, long long* cycles);
 
 /* number of kernels this handle has launched so far */

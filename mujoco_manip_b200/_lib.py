@@ -35,7 +35,8 @@ class MMConfig(C.Structure):
 # (name, width, is_double) in the order of struct mm_state
 STATE_FIELDS = (("qpos", 30, True), ("qvel", 27, True), ("ctrl", 8, True), ("warm", 27, True), ("tinit", 12, True),
                 ("eepose", 12, True), ("fsm_f", 6, True), ("hwm", 5, True), ("kin", 18, True), ("step_count", 1, False),
-                ("task", 2, False), ("fsm_i", 5, False), ("flags", 1, False), ("diag", 4, False))
+                ("task", 2, False), ("fsm_i", 5, False), ("fsm_tasks", 20, False),
+                ("flags", 1, False), ("diag", 4, False))
 
 
 class MMState(C.Structure):

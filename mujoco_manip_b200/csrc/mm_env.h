@@ -10,6 +10,7 @@ enum { REWARD_DENSE = 0, REWARD_SPARSE = 1, REWARD_STAGED = 2 };
 constexpr int OBS_DIM = 85;      // 53 state floats + 32 keypoint floats (layout: oracle/hotpath.cpp env_obs)
 constexpr int ACTION_STRIDE = 10;
 constexpr int ACTION_REPEAT = 16;  // constants.py:26
+constexpr int FSM_TASKS_STRIDE = 20, FSM_MAX_TASKS = 9;
 
 // Env-major state arrays in HBM (FP64 storage regardless of the compute type; a G-lane group reads
 // one env's contiguous rows with consecutive lanes -> coalesced).
@@ -26,6 +27,7 @@ struct StatePtrs {
   int* step_count;   // [N]
   int* task;         // [N,2]   object index, bin index
   int* fsm_i;        // [N,5]   state(1..11), task_index, settle_counter, gripper_open, has_target
+  int* fsm_tasks;    // [N,20]  the FSM's task list: count, then (object, bin) index pairs (pick_and_place.py:91)
   int* flags;        // [N]     bits 0..3 staged stickies, bit 4 hwm initialised
   int* diag;         // [N,4]   ncon, newton iterations (last forward), overflow bits, non-finite resets
 };
@@ -45,7 +47,8 @@ MM_HDN void load_state(const Grp<G>& g, Scratch<T>& s, const StatePtrs& st, long
   for (int i = g.lane; i < NV; i += G) s.qvel[i] = (T)st.qvel[e * NV + i];
   if (g.lane == 0) s.warm_g = st.warm + e * NV;
   for (int i = g.lane; i < NU; i += G) s.ctrl[i] = (T)st.ctrl[e * NU + i];
-  if (g.lane == 0) { s.overflow = 0; s.ncon = 0; s.npair = 0; s.nspec = 0; s.niter = 0; s.prof = 0; for (int k = 0; k < 8; k++) s.tph[k] = 0; }
+  // (only members of the persistent part: stage A runs on a shared-memory slice that ends before the solver's temporaries)
+  if (g.lane == 0) { s.overflow = 0; s.ncon = 0; s.nbox = 0; s.ncvx = 0; s.qbase = 0; s.nsurv = 0; s.niter = 0; s.prof = 0; for (int k = 0; k < 8; k++) s.tph[k] = 0; }
   g.sync();
 }
 
@@ -264,6 +267,8 @@ struct CvxQueue {
 #define MM_ATOMIC_ADD(p, v) ([&]() { int old_ = *(p); *(p) += (v); return old_; }())
 #endif
 
+// bytes of Scratch<T> stage A may touch: the persistent image + the H / tmp6 scratch (kinematics, dynamics, clip polygons)
+template <class T> MM_HDN constexpr size_t scratch_a_bytes() { return (offsetof(Scratch<T>, pairK_s) + 15) / 16 * 16; }
 template <class T> MM_HDN constexpr int ctx_stride() { return (int)((SCRATCH_PERSIST(T) + 15) / 16 * 16); }
 
 template <class T, int G>
@@ -388,7 +393,7 @@ MM_HDN void env_reset(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Wor
   for (int i = g.lane; i < NQ; i += G) s.qpos[i] = md.key_qpos[i];
   for (int i = g.lane; i < NV; i += G) { s.qvel[i] = 0; s.warm_g[i] = 0; }
   for (int i = g.lane; i < NU; i += G) s.ctrl[i] = md.key_ctrl[i];
-  if (g.lane == 0) { s.overflow = 0; s.ncon = 0; s.npair = 0; s.nspec = 0; s.niter = 0; }
+  if (g.lane == 0) { s.overflow = 0; s.ncon = 0; s.npair = 0; s.nspec = 0; s.niter = 0; s.prof = 0; }
   g.sync();
   for (int pass = 0; pass < (obj_xy ? 2 : 1); pass++) {
     if (pass == 1) {  // randomization.py:52-65 + env.py:160-161
@@ -413,6 +418,8 @@ MM_HDN void env_reset(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Wor
     for (int k = 0; k < 5; k++) st.hwm[e * 5 + k] = 0;
     int* fi = st.fsm_i + e * 5;
     fi[0] = 1; fi[1] = 0; fi[2] = 0; fi[3] = 1; fi[4] = 0;
+    int* ft = st.fsm_tasks + e * FSM_TASKS_STRIDE;  // the expert of this episode works on the env's own task
+    ft[0] = 1; ft[1] = obj; ft[2] = bin;
     for (int k = 0; k < 6; k++) st.fsm_f[e * 6 + k] = 0;
     st.diag[e * 4 + 2] = 0;
     // target keypoints frozen at reset (gym_env.py:519-531)
@@ -468,7 +475,11 @@ MM_HDN inline void fsm_plan_one(const StatePtrs& st, long e, int n, float* actio
   double* tg = st.fsm_f + e * 6;
   double* te = tg + 3;
   const double* ee = st.eepose + e * 12;
-  int obj = st.task[e * 2], bin = st.task[e * 2 + 1];
+  // the FSM's own task list (pick_and_place.py:91,151-165); task_index >= count only while IDLE -> DONE
+  const int* ft = st.fsm_tasks + e * FSM_TASKS_STRIDE;
+  int ntask = ft[0] < FSM_MAX_TASKS ? ft[0] : FSM_MAX_TASKS;
+  int ti = fi[1] < ntask ? fi[1] : (ntask > 0 ? ntask - 1 : 0);
+  int obj = ntask > 0 ? ft[1 + 2 * ti] : 0, bin = ntask > 0 ? ft[2 + 2 * ti] : 0;
   const double* op = st.kin + e * 18 + 9 + 3 * obj;  // data.xpos of the object at the last position stage
   double bp[3];
   bin_pos(bin, bp);
@@ -476,7 +487,7 @@ MM_HDN inline void fsm_plan_one(const StatePtrs& st, long e, int n, float* actio
   bool reached = dd < 0.02;
   switch (fi[0]) {
     case 1:
-      if (fi[1] >= 1) { fi[0] = 11; break; }
+      if (fi[1] >= ntask) { fi[0] = 11; break; }
       fi[3] = 1; tg[0] = op[0]; tg[1] = op[1]; tg[2] = 0.44; fi[4] = 1; fi[0] = 2;
       break;
     case 2:

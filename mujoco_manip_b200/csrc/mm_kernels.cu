@@ -174,7 +174,7 @@ int upload_model(mm_handle* h) {
 StatePtrs to_ptrs(const mm_state* s) {
   StatePtrs st;
   st.qpos = s->qpos; st.qvel = s->qvel; st.ctrl = s->ctrl; st.warm = s->warm; st.tinit = s->tinit; st.eepose = s->eepose;
-  st.fsm_f = s->fsm_f; st.hwm = s->hwm; st.kin = s->kin; st.step_count = s->step_count; st.task = s->task; st.fsm_i = s->fsm_i;
+  st.fsm_f = s->fsm_f; st.hwm = s->hwm; st.kin = s->kin; st.step_count = s->step_count; st.task = s->task; st.fsm_i = s->fsm_i; st.fsm_tasks = s->fsm_tasks;
   st.flags = s->flags; st.diag = s->diag;
   return st;
 }

@@ -122,8 +122,6 @@ __device__ __forceinline__ Work<T> work_of(const StepParams& p, long e, long psl
                    reinterpret_cast<T*>(p.workp_reals) + pslot * WORKP_REALS, p.workp_ints + pslot * WORKP_INTS);
 }
 
-// shared-memory bytes per env of stage A: the persistent image + the H / tmp6 scratch (kinematics, dynamics, clip polygons)
-template <class T> MM_HDN constexpr size_t scratch_a_bytes() { return (offsetof(Scratch<T>, pairK_s) + 15) / 16 * 16; }
 template <class T> MM_HDN constexpr size_t scratch_c_bytes() { return (sizeof(Scratch<T>) + 15) / 16 * 16; }
 
 template <class T, int G, int W>

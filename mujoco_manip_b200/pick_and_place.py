@@ -56,30 +56,29 @@ GRIPPER_SETTLE_STEPS, BIN_SETTLE_STEPS, TRANSIT_SPEED = 150, 100, 0.001
 class PickAndPlaceTask:
     """FSM view bound to env 0 of the PickPlaceVecEnv behind a PickPlaceGymEnv.
 
-    `tasks` lists the (object, bin) pairs to execute in order; the device FSM handles one pair per
-    episode (scripts/generate_dataset.py:112-117 builds it with a single task), so longer lists are
-    run pair after pair by re-arming the device FSM when it reaches DONE.
+    `tasks` lists the (object, bin) pairs to execute in order (default TASKS, pick_and_place.py:91); the list is the
+    FSM's own (device field `fsm_tasks`) and does not touch the env's task (reward, success test, one-hot observations),
+    exactly as in the reference.  All transitions, including IDLE -> PRE_GRASP of the next pair, happen on the device.
     """
 
-    def __init__(self, env, robot, controller, tasks=None):
-        self.env, self.robot, self.controller = env, robot, controller
-        self._tasks = list(tasks or TASKS)
-        self._vec = env._vec
-        self.task_index = 0
-        self._arm(0)
+    MAX_TASKS = 9
 
-    def _arm(self, idx):
+    def __init__(self, env, robot, controller, tasks=None):
         import torch
 
+        self.env, self.robot, self.controller = env, robot, controller
+        self._tasks = list(tasks or TASKS)
+        if len(self._tasks) > self.MAX_TASKS:
+            raise ValueError(f"at most {self.MAX_TASKS} tasks")
+        self._vec = env._vec
         v = self._vec
+        row = [len(self._tasks)]
+        for o, b in self._tasks:
+            row += [OBJECTS.index(o), BINS.index(b)]
+        row += [0] * (20 - len(row))
+        v.state["fsm_tasks"][0] = torch.tensor(row, dtype=torch.int32, device=v.device)
         v.state["fsm_i"][0] = torch.tensor([1, 0, 0, 1, 0], dtype=torch.int32, device=v.device)
         v.state["fsm_f"][0].zero_()
-        if idx < len(self._tasks):
-            o, b = self._tasks[idx]
-            v.state["task"][0] = torch.tensor([OBJECTS.index(o), BINS.index(b)], dtype=torch.int32, device=v.device)
-            v._task[0] = v.state["task"][0]
-        else:
-            v.state["fsm_i"][0, 0] = 11
 
     def _fsm(self):
         return self._vec.state["fsm_i"][0].cpu().numpy()
@@ -87,6 +86,10 @@ class PickAndPlaceTask:
     @property
     def state(self) -> State:
         return State(int(self._fsm()[0]))
+
+    @property
+    def task_index(self) -> int:
+        return int(self._fsm()[1])
 
     @property
     def settle_counter(self) -> int:
@@ -125,6 +128,7 @@ class PickAndPlaceTask:
 
     @property
     def phase_description(self) -> str:
+        """pick_and_place.py:127-149"""
         ph = self.phase
         if ph in (Phase.IDLE, Phase.DONE):
             return "idle"
@@ -137,13 +141,29 @@ class PickAndPlaceTask:
                 Phase.PLACING: f"placing the {oc} cube in the {bc} bin"}.get(ph, "idle")
 
     def plan(self, n_steps: int = 1) -> str:
-        """One FSM tick covering n_steps physics steps (at most one transition), pick_and_place.py:167-277."""
+        """One FSM tick covering n_steps physics steps (at most one transition), pick_and_place.py:167-277.
+        Returns the reference's status string, derived from the transition the device FSM made."""
+        s0, ti = self.state, self.task_index
         self._vec.fsm_plan(n_steps)
-        if int(self._fsm()[0]) == 11 and self.task_index < len(self._tasks):
-            self.task_index += 1
-            if self.task_index < len(self._tasks):
-                self._arm(self.task_index)
-        return self.phase_description
+        s1, cnt = self.state, self.settle_counter
+        if s0 == State.DONE or (s0 == State.IDLE and s1 == State.DONE):
+            return "All objects placed!"
+        if s0 == State.RETREAT:
+            return "Ready for next object" if s1 == State.IDLE else "Retreating"
+        if s0 == State.RELEASE:
+            return "Retreating to neutral position" if s1 == State.RETREAT else f"Releasing ({cnt})"
+        obj, bn = self._tasks[min(ti, len(self._tasks) - 1)]
+        moved = s1 != s0
+        return {
+            State.IDLE: (f"Moving to pre-grasp above {obj}",) * 2,
+            State.PRE_GRASP: (f"Descending to grasp {obj}", f"Approaching pre-grasp for {obj}"),
+            State.GRASP: (f"Closing gripper on {obj}", f"Descending to {obj}"),
+            State.CLOSE_GRIPPER: (f"Lifting {obj}", f"Gripping {obj} ({cnt})"),
+            State.LIFT: (f"Moving {obj} to {bn}", f"Lifting {obj}"),
+            State.MOVE_TO_BIN: (f"Settling above {bn}", f"Transporting {obj}"),
+            State.SETTLE_AT_BIN: (f"Lowering {obj} into {bn}", f"Settling above {bn} ({cnt})"),
+            State.LOWER_TO_BIN: (f"Releasing {obj} into {bn}", f"Lowering to {bn}"),
+        }[s0][0 if moved else 1]
 
     def _actuate(self) -> None:
         if self._gripper_open:

@@ -16,7 +16,7 @@ REWARDS = ("dense", "sparse", "staged")
 STATE_FIELDS = [("qpos", 30, np.float64), ("qvel", 27, np.float64), ("ctrl", 8, np.float64), ("warm", 27, np.float64),
                 ("tinit", 12, np.float64), ("eepose", 12, np.float64), ("fsm_f", 6, np.float64), ("hwm", 5, np.float64),
                 ("kin", 18, np.float64),
-                ("step_count", 1, np.int32), ("task", 2, np.int32), ("fsm_i", 5, np.int32), ("flags", 1, np.int32),
+                ("step_count", 1, np.int32), ("task", 2, np.int32), ("fsm_i", 5, np.int32), ("fsm_tasks", 20, np.int32), ("flags", 1, np.int32),
                 ("diag", 4, np.int32)]
 
 

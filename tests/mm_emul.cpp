@@ -3,6 +3,8 @@
 // against the oracle on machines without a GPU (`-m "not gpu"` tests).  It is never loaded by the
 // mujoco_manip_b200 package: the product path is the CUDA library and fails loudly without it.
 #define MM_MODEL_HOST_FILL
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -37,7 +39,7 @@ StatePtrs state_from(void** p) {
   StatePtrs st;
   st.qpos = (double*)p[0]; st.qvel = (double*)p[1]; st.ctrl = (double*)p[2]; st.warm = (double*)p[3];
   st.tinit = (double*)p[4]; st.eepose = (double*)p[5]; st.fsm_f = (double*)p[6]; st.hwm = (double*)p[7]; st.kin = (double*)p[8];
-  st.step_count = (int*)p[9]; st.task = (int*)p[10]; st.fsm_i = (int*)p[11]; st.flags = (int*)p[12]; st.diag = (int*)p[13];
+  st.step_count = (int*)p[9]; st.task = (int*)p[10]; st.fsm_i = (int*)p[11]; st.fsm_tasks = (int*)p[12]; st.flags = (int*)p[13]; st.diag = (int*)p[14];
   return st;
 }
 StepOut out_from(void** p) {
@@ -81,7 +83,13 @@ void do_step(int n, void** sp, const float* actions, int mode, int reward_type, 
     CvxQueue<T> q{items.data(), res.data(), &count, &head, cap};
     for (long e = 0; e < n; e++) {
       Work<T> w = make_work(wer.data() + e * WORKE_REALS, wei.data() + e * WORKE_INTS, c.wp.data(), c.wpi.data());
+      // stage A owns only the first scratch_a_bytes of the scratch on the device: everything behind must stay untouched
+      unsigned char* tail = reinterpret_cast<unsigned char*>(&c.s) + scratch_a_bytes<T>();
+      size_t ntail = sizeof(Scratch<T>) - scratch_a_bytes<T>();
+      std::memset(tail, 0xA5, ntail);
       stage_a<T, 1>(g, c.s, c.md, w, st, e, sub, actions, mode, image.data(), q);
+      for (size_t k = 0; k < ntail; k++)
+        if (tail[k] != 0xA5) { std::fprintf(stderr, "stage A wrote outside its scratch slice (byte %zu)\n", scratch_a_bytes<T>() + k); std::abort(); }
     }
     EpaMem<T> em;
     em.vert = everts.data(); em.face = eface.data(); em.fidx = eints.data(); em.edge = em.fidx + EPA_MAXF; em.canon = em.edge + EPA_MAXE;

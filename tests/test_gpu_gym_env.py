@@ -1,8 +1,12 @@
 """Behavioural tests of the single-env API on the CUDA path, following the reference's own test-suite
 (tests/test_gym_env.py, test_controller.py, test_pick_and_place.py, test_randomization.py: same
 scenarios and tolerances), plus scripted-expert success parity with the oracle."""
+import os
+
 import numpy as np
 import pytest
+
+from hostlib import GOLDEN, reltol
 
 pytestmark = pytest.mark.gpu
 
@@ -270,6 +274,36 @@ def test_fsm_class_surface_and_expert_episode(cuda_device):
     p = env.pick_place_env.get_body_pos("obj_red")
     assert np.linalg.norm(p[:2] - [-0.3, 0.55]) < 0.05 and p[2] < 0.30
     assert fsm.phase_description == "idle"
+    env.close()
+
+
+@pytest.mark.parametrize("fname", ["fsm_multi3_seed5.npz", "fsm_multi2_cross_seed11.npz"])
+def test_multi_task_fsm_matches_reference_fsm(cuda_device, fname):
+    """PickAndPlaceTask with a task LIST (default TASKS has three pairs, pick_and_place.py:91): state, task index, timer
+    and the status string of every plan(16) call equal the reference FSM's (golden produced by the reference's own
+    class), and the FSM's list leaves the env's own task alone."""
+    from mujoco_manip_b200.constants import BINS, OBJECTS
+    from mujoco_manip_b200.pick_and_place import PickAndPlaceTask
+
+    g = np.load(os.path.join(GOLDEN, fname))
+    env = make(cuda_device, action_mode="abs_pos", task=("obj_red", "bin_red"), max_episode_steps=2000, randomize_objects=True)
+    seed = int(fname.split("seed")[1].split(".")[0])
+    env.reset(seed=seed)
+    np.testing.assert_allclose(env.pick_place_env._vec.state["qpos"][0].cpu().numpy(), g["init_qpos"], atol=1e-12)
+    tasks = [(OBJECTS[o], BINS[b]) for o, b in g["tasks"]]
+    fsm = PickAndPlaceTask(env.pick_place_env, env.robot, env.controller, tasks=tasks)
+    assert (env.obj_name, env.bin_name) == ("obj_red", "bin_red")
+    for t in range(len(g["fsm_state"])):
+        status = fsm.plan(16)
+        assert status == str(g["status"][t]), (t, status, str(g["status"][t]))
+        assert fsm.state.value == int(g["fsm_state"][t]) and fsm.task_index == int(g["task_index"][t]), t
+        assert fsm.settle_counter == int(g["counter"][t])
+        tp = fsm.target_pos if fsm.target_pos is not None else env.robot.ee_pos
+        np.testing.assert_allclose(tp, g["target"][t], atol=1e-7)
+        obs, r, te, tr, info = env.step(np.array([*tp, fsm.gripper_val], dtype=np.float32))
+        assert reltol(env.pick_place_env._vec.state["qpos"][0].cpu().numpy(), g["qpos"][t], 1e-5) < 1e-5, t
+        assert bool(info["success"]) == bool(g["success"][t])
+    assert fsm.is_done and (env.obj_name, env.bin_name) == ("obj_red", "bin_red")
     env.close()
 
 

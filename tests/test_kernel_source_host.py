@@ -75,6 +75,31 @@ def test_f64_stress_rollout_with_table_collisions():
     assert g["reward"].min() == -1.0
 
 
+@pytest.mark.parametrize("fname", ["fsm_multi3_seed5.npz", "fsm_multi2_cross_seed11.npz"])
+def test_f64_multi_task_fsm_vs_reference_fsm(fname):
+    """Task LIST on the device FSM (pick_and_place.py:184-192, 267-272): state, task index and timer of every plan()
+    call bit-exact against the reference's own FSM run over the same list (golden), no extra tick between tasks."""
+    g = _load(fname)
+    env = EmulEnv(1, mode="abs_pos", max_steps=2000)
+    q = g["init_qpos"]
+    env.reset(obj_xy=np.array([q[9:11], q[16:18], q[23:25]]).reshape(1, 6), task=np.array([[0, 0]]))
+    tasks = g["tasks"]
+    env.st["fsm_tasks"][0, 0] = len(tasks)
+    env.st["fsm_tasks"][0, 1:1 + 2 * len(tasks)] = tasks.ravel()
+    n = g["fsm_state"].shape[0]
+    for t in range(n):
+        a = env.fsm_plan(16)
+        assert int(env.st["fsm_i"][0, 0]) == int(g["fsm_state"][t]), f"FSM state differs at step {t}"
+        assert int(env.st["fsm_i"][0, 1]) == int(g["task_index"][t]), f"task index differs at step {t}"
+        assert int(env.st["fsm_i"][0, 2]) == int(g["counter"][t])
+        np.testing.assert_allclose(a[0, :3], g["target"][t].astype(np.float32), rtol=0, atol=1e-6)
+        assert a[0, 3] == g["gripper"][t]
+        obs, r, te, tr, su = env.step(a)
+        assert reltol(env.st["qpos"][0], g["qpos"][t], 1e-5) < 1e-5, t
+        assert bool(su[0]) == bool(g["success"][t])
+    assert int(env.st["fsm_i"][0, 0]) == 11 == int(g["final_fsm_state"])
+
+
 def test_f32_arm_tracks_f64_over_50_steps(oracle_lib):
     """FP32 arithmetic against the FP64 oracle: report-style bound (FP32 is the optional fast mode;
     the stated 1e-5 parity bar is met by the FP64 path)."""

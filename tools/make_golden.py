@@ -133,6 +133,38 @@ def fsm_episode(mode, task, randomize, seed, reward_type="dense", max_steps=400)
     return out
 
 
+def fsm_multi_episode(tasks, seed, max_steps=900):
+    """The reference FSM run over a LIST of tasks at gym-step level (plan(16) -> abs_pos action -> env.step), as
+    tests/test_pick_and_place.py:274-289 and scripts/generate_dataset.py:140-196 drive it.  The env's own task (reward,
+    one-hots) stays (obj_red, bin_red): the FSM's list is independent of it (pick_and_place.py:91 vs gym_env.py:511-517)."""
+    env = PickPlaceGymEnv(task=("obj_red", "bin_red"), action_mode="abs_pos", randomize_objects=True, max_episode_steps=2000)
+    env.reset(seed=seed)
+    fsm = PickAndPlaceTask(env.pick_place_env, env.robot, env.controller, tasks=list(tasks))
+    rec = {k: [] for k in ("fsm_state", "task_index", "counter", "target", "gripper", "qpos", "status", "reward", "success")}
+    init = snapshot(env)
+    n = 0
+    while not fsm.is_done and n < max_steps:
+        status = fsm.plan(n_steps=ACTION_REPEAT)
+        tp = fsm.target_pos if fsm.target_pos is not None else env.robot.ee_pos
+        rec["status"].append(status)
+        rec["fsm_state"].append(fsm.state.value)
+        rec["task_index"].append(fsm.task_index)
+        rec["counter"].append(fsm.settle_counter)
+        rec["target"].append(np.array(tp, dtype=np.float64))
+        rec["gripper"].append(fsm.gripper_val)
+        obs, r, te, tr, info = env.step(np.array([*tp, fsm.gripper_val], dtype=np.float32))
+        rec["qpos"].append(env.pick_place_env.data.qpos.copy())
+        rec["reward"].append(r)
+        rec["success"].append(info["success"])
+        n += 1
+    out = {k: np.array(v) for k, v in rec.items()}
+    names_o, names_b = ["obj_red", "obj_green", "obj_blue"], ["bin_red", "bin_green", "bin_blue"]
+    out.update(init_qpos=init["qpos"], final_fsm_state=fsm.state.value,
+               tasks=np.array([[names_o.index(o), names_b.index(b)] for o, b in tasks]))
+    env.close()
+    return out
+
+
 def random_rollout(mode, seed, n_steps=50, reward_type="dense", stress=False):
     env = PickPlaceGymEnv(task=("obj_red", "bin_red"), action_mode=mode, reward_type=reward_type)
     obs, _ = env.reset(seed=seed)
@@ -240,6 +272,10 @@ def main():
                         **fsm_episode("abs_pos", ("obj_green", "bin_blue"), True, 42, reward_type="staged"))
     np.savez_compressed(os.path.join(OUT, "fsm_rot6d_rel_blue_red_seed7.npz"),
                         **fsm_episode("ee_pos_rot6d_g_rel", ("obj_blue", "bin_red"), True, 7))
+    np.savez_compressed(os.path.join(OUT, "fsm_multi3_seed5.npz"),
+                        **fsm_multi_episode([("obj_red", "bin_red"), ("obj_green", "bin_green"), ("obj_blue", "bin_blue")], 5))
+    np.savez_compressed(os.path.join(OUT, "fsm_multi2_cross_seed11.npz"),
+                        **fsm_multi_episode([("obj_blue", "bin_red"), ("obj_red", "bin_green")], 11))
     for mode in ("abs_pos", "ee_pos_quat_g", "ee_pos_rot6d_g", "ee_pos_quat_g_rel", "ee_pos_rot6d_g_rel"):
         np.savez_compressed(os.path.join(OUT, f"random50_{mode}.npz"), **random_rollout(mode, 1234, 50))
     np.savez_compressed(os.path.join(OUT, "stress30_abs_pos_staged.npz"),
