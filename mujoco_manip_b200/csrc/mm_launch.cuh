@@ -38,6 +38,8 @@ namespace mm {
 #ifndef MM_MINB_X
 #define MM_MINB_X 4
 #endif
+// stage C / fused kernels: G = 8 packs four envs into a warp, so fewer warps fit the shared memory of a CTA
+template <int G> constexpr int warps_c() { return G == 8 ? (MM_WC > 2 ? 2 : MM_WC) : MM_WC; }
 constexpr int MAX_CHUNKS = 64;
 constexpr int NROUND = ACTION_REPEAT + 1;
 
@@ -211,7 +213,7 @@ __global__ void __launch_bounds__(32 * W, MM_MINB_X) k_convex(StepParams p, int 
 
 template <class T, int G>
 struct FusedCfg {  // reset / engine-level ops: the fused forward of an env by its own group
-  static constexpr int W = MM_WC;
+  static constexpr int W = warps_c<G>();
   static constexpr int THREADS = 32 * W;
   static constexpr int ENVS = THREADS / G;
 };
@@ -257,14 +259,14 @@ inline long env_long(const char* name, long dflt) {
 }
 
 template <class T, int G> size_t smem_a() { return (32 * MM_WA / G) * scratch_a_bytes<T>(); }
-template <class T, int G> size_t smem_c() { return (32 * MM_WC / G) * scratch_c_bytes<T>(); }
+template <class T, int G> size_t smem_c() { return (32 * warps_c<G>() / G) * scratch_c_bytes<T>(); }
 template <class T> size_t smem_x() { return MM_WX * sizeof(ConvexSmem<T>); }
 
 template <class T, int G>
 cudaError_t inst_prepare() {
   cudaError_t e = cudaFuncSetAttribute(k_stage_a<T, G, MM_WA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a<T, G>());
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(k_stage_c<T, G, MM_WC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c<T, G>());
+  e = cudaFuncSetAttribute(k_stage_c<T, G, warps_c<G>()>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c<T, G>());
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_convex<T, MM_WX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x<T>());
   if (e != cudaSuccess) return e;
@@ -282,17 +284,17 @@ cudaError_t inst_resident(int* ctas, int* envs_per_cta, int* convex_grid) {
   if (e != cudaSuccess) return e;
   e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (e != cudaSuccess) return e;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_stage_c<T, G, MM_WC>, 32 * MM_WC, smem_c<T, G>());
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_stage_c<T, G, warps_c<G>()>, 32 * warps_c<G>(), smem_c<T, G>());
   if (e != cudaSuccess) return e;
   best = per;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_reset<T, G>, 32 * MM_WC, smem_c<T, G>());
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_reset<T, G>, 32 * warps_c<G>(), smem_c<T, G>());
   if (e != cudaSuccess) return e;
   best = per > best ? per : best;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_ops<T, G>, 32 * MM_WC, smem_c<T, G>());
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_ops<T, G>, 32 * warps_c<G>(), smem_c<T, G>());
   if (e != cudaSuccess) return e;
   best = per > best ? per : best;
   *ctas = best * sms;
-  *envs_per_cta = 32 * MM_WC / G;
+  *envs_per_cta = 32 * warps_c<G>() / G;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_convex<T, MM_WX>, 32 * MM_WX, smem_x<T>());
   if (e != cudaSuccess) return e;
   *convex_grid = (per > 0 ? per : 1) * sms;
@@ -308,8 +310,8 @@ cudaError_t inst_launch(int which, const StepParams& p, int sub, int grid_x, cud
   } else if (which == 1) {
     k_convex<T, MM_WX><<<(unsigned)grid_x, 32 * MM_WX, smem_x<T>(), s>>>(p, sub);
   } else if (which == 2) {
-    constexpr int EPB = 32 * MM_WC / G;
-    k_stage_c<T, G, MM_WC><<<(unsigned)((p.nslot + EPB - 1) / EPB), 32 * MM_WC, smem_c<T, G>(), s>>>(p, sub);
+    constexpr int EPB = 32 * warps_c<G>() / G;
+    k_stage_c<T, G, warps_c<G>()><<<(unsigned)((p.nslot + EPB - 1) / EPB), 32 * warps_c<G>(), smem_c<T, G>(), s>>>(p, sub);
   } else {
     constexpr int EPB = FusedCfg<T, G>::ENVS;
     unsigned grid = (unsigned)((p.n + EPB - 1) / EPB);

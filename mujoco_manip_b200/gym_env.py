@@ -10,7 +10,7 @@ import numpy as np
 
 from . import _lib, pose_utils
 from .constants import (BINS, IMAGE_SIZE, KEYPOINT_BODIES, MAX_EPISODE_STEPS, OBJECTS, SPAWN_X_RANGE, SPAWN_Y_RANGE,
-                        TASK_SETS)
+                        TASK_SETS, check_scene_xml)
 from .randomization import sample_separated_positions
 from .spaces import Box, Dict, Env
 
@@ -166,8 +166,7 @@ class PickPlaceGymEnv(Env):
                  precision: str = "f64"):
         if action_mode not in ACTION_MODES:
             raise ValueError(f"action_mode must be one of {ACTION_MODES}, got '{action_mode}'")
-        if xml_path is not None:
-            raise ValueError("the CUDA kernels are compiled for the bundled pick-and-place scene; custom xml_path is not supported")
+        check_scene_xml(xml_path)  # the bundled scene (or None) is accepted, gym_env.py:64
         from .vec_env import PickPlaceVecEnv
 
         self._fixed_task = task

@@ -21,3 +21,23 @@ def test_phase_strings():
     assert F.phase_description(1, "obj_red", "bin_blue") == "idle"
     assert F.phase_description(6, "obj_red", "bin_blue") == "transporting the red cube to the blue bin"
     assert F.phase_description(10, "obj_red", "bin_blue") == "retreating to neutral position"
+
+
+def test_xml_path_accepts_only_the_bundled_scene(tmp_path):
+    """gym_env.py:64 / env.py:15-69: the reference's default xml_path must be accepted; other scenes are refused loudly."""
+    import os
+
+    import pytest
+
+    from mujoco_manip_b200.constants import check_scene_xml
+
+    check_scene_xml(None)
+    ref = "/root/reference/mujoco_manip/data/pick_and_place_scene.xml"
+    if os.path.exists(ref):  # only in the build container
+        check_scene_xml(ref)
+        other = tmp_path / "scene.xml"
+        other.write_text(open(ref).read().replace('timestep="0.002"', 'timestep="0.004"'))
+        with pytest.raises(ValueError):
+            check_scene_xml(str(other))
+    with pytest.raises(FileNotFoundError):
+        check_scene_xml(str(tmp_path / "missing.xml"))
