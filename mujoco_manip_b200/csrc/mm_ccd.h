@@ -10,11 +10,14 @@
 #pragma once
 #include "mm_model.h"
 
+#if defined(MM_DEBUG_EPA) && !defined(__CUDA_ARCH__)
+static long mm_debug_epa_iters = 0;
+#endif
 namespace mm {
 
 constexpr int EPA_MAXV = 136, EPA_MAXF = 256, EPA_MAXE = 128, EPA_MAXIT = 128;
 constexpr int EPA_REALS = EPA_MAXV * 6 + EPA_MAXF * 4;
-constexpr int EPA_INTS = EPA_MAXF + EPA_MAXE + EPA_MAXV;
+constexpr int EPA_INTS = EPA_MAXF + 2 * EPA_MAXE + EPA_MAXV;
 constexpr int EPA_VIS = 1 << 30;
 constexpr int SHAPE_LV = 5;  // ceil(152 / 32): the largest hull has 152 vertices
 
@@ -179,6 +182,7 @@ struct EpaMem {
   int* fidx;  // [EPA_MAXF]     three vertex indices packed 10 bits each (+ EPA_VIS while a face is being removed)
   int* edge;  // [EPA_MAXE]     horizon edges: two vertex indices packed 16 bits each
   int* canon; // [EPA_MAXV]     lowest vertex index with identical coordinates (edge matching compares coordinates)
+  int* ecan;  // [EPA_MAXE]     canonical ids of the horizon edges' end points, packed like `edge`
 };
 
 // face f from vertices (ia, ib, ic); flip = which two indices swap when the normal points inward
@@ -242,6 +246,9 @@ MM_HDN bool epa(const Grp<G>& g, const Shape<T>& s1, const Shape<T>& s2, const S
 #pragma unroll 1
   for (int it = 0; it < EPA_MAXIT; it++) {
     if (cnt && g.lane == 0) cnt[3]++;
+#if defined(MM_DEBUG_EPA) && !defined(__CUDA_ARCH__)
+    mm_debug_epa_iters++;
+#endif
     int best = epa_best<T, G>(g, m, nf);
     T n[3] = {m.face[4 * best], m.face[4 * best + 1], m.face[4 * best + 2]};
     SP<T> p;
@@ -268,36 +275,47 @@ MM_HDN bool epa(const Grp<G>& g, const Shape<T>& s1, const Shape<T>& s2, const S
       if ((double)dot3(F, r) > epa_vis<T>()) m.fidx[i] = fi | EPA_VIS;
     }
     g.sync();
-    // removal of the visible faces and collection of the horizon, in the oracle's order (integer work, one lane)
+    // Removal of the visible faces and collection of the horizon.  The SEQUENCE of removals (face i is replaced by the
+    // last face and examined again) and of edge insertions / cancellations is the oracle's - it fixes the order of the
+    // new faces and therefore every later tie - but each step is done by all lanes: the next visible face and the
+    // matching reversed edge are found with a ballot instead of a scan by one lane.
     int ne = 0;
-    if (g.lane == 0) {
-      for (int i = 0; i < nf;) {
-        int fi = m.fidx[i];
-        if (fi & EPA_VIS) {
-          int id[3] = {fi & 1023, (fi >> 10) & 1023, (fi >> 20) & 1023};
-          for (int e = 0; e < 3; e++) {
-            int ea = id[e], eb = id[(e + 1) % 3];
-            int ca = m.canon[ea], cb = m.canon[eb];
-            bool found = false;
-            for (int k = 0; k < ne; k++) {
-              int ed = m.edge[k];
-              if (m.canon[ed & 0xFFFF] == cb && m.canon[ed >> 16] == ca) {  // shared edges appear reversed
-                m.edge[k] = m.edge[--ne];
-                found = true;
-                break;
-              }
-            }
-            if (!found && ne < EPA_MAXE) { m.edge[ne] = ea | (eb << 16); ne++; }
-          }
-          --nf;
-          m.fidx[i] = m.fidx[nf];
-          for (int k = 0; k < 4; k++) m.face[4 * i + k] = m.face[4 * nf + k];
-        } else i++;
+    for (int i = 0;;) {
+      // next visible face at or after i
+      int found_face = -1;
+      for (int base = i; base < nf; base += G) {
+        int idx = base + g.lane;
+        unsigned b = g.ballot(idx < nf && (m.fidx[idx] & EPA_VIS));
+        if (b) { found_face = base + tctz(b); break; }
       }
+      if (found_face < 0) break;
+      i = found_face;
+      int fi = m.fidx[i];
+      int id[3] = {fi & 1023, (fi >> 10) & 1023, (fi >> 20) & 1023};
+#pragma unroll 1
+      for (int e = 0; e < 3; e++) {
+        int ea = id[e], eb = id[e == 2 ? 0 : e + 1];
+        int rev = m.canon[eb] | (m.canon[ea] << 16);  // shared edges appear reversed
+        int hit = -1;
+        for (int base = 0; base < ne; base += G) {
+          int k = base + g.lane;
+          unsigned b = g.ballot(k < ne && m.ecan[k] == rev);
+          if (b) { hit = base + tctz(b); break; }
+        }
+        if (hit >= 0) {
+          --ne;
+          if (g.lane == 0) { m.edge[hit] = m.edge[ne]; m.ecan[hit] = m.ecan[ne]; }
+        } else if (ne < EPA_MAXE) {
+          if (g.lane == 0) { m.edge[ne] = ea | (eb << 16); m.ecan[ne] = m.canon[ea] | (m.canon[eb] << 16); }
+          ne++;
+        }
+        g.sync();
+      }
+      --nf;
+      for (int k = g.lane; k < 4; k += G) m.face[4 * i + k] = m.face[4 * nf + k];
+      if (g.lane == G - 1) m.fidx[i] = m.fidx[nf];
+      g.sync();
     }
-    ne = g.bcast(ne, 0);
-    nf = g.bcast(nf, 0);
-    g.sync();
     if (ne == 0) break;
     int add = ne < EPA_MAXF - nf ? ne : EPA_MAXF - nf;
     for (int k = g.lane; k < add; k += G) { int ed = m.edge[k]; epa_mkface(m, nf + k, ed & 0xFFFF, ed >> 16, ip, false); }

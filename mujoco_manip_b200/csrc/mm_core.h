@@ -65,7 +65,7 @@ MM_HD int srow(int dof) { return dof < NROB ? dof : NROB + 3 * ((dof - NROB) / 6
 MM_HD bool is_cube_translation(int dof) { return dof >= NROB && ((dof - NROB) % 6) < 3; }
 // rows of the 6-vector scratch: 16 suffice (14 dofs of a body pair + 2 rows that park the position-stage qpos);
 // the FP32 build keeps 27 because its EPA workspace (integers are as wide as reals there) needs the room
-template <class T> constexpr int TMP6_ROWS() { return sizeof(T) == 8 ? 16 : 27; }
+template <class T> constexpr int TMP6_ROWS() { return sizeof(T) == 8 ? 16 : 48; }
 constexpr int KIN_ROW = 14;  // tmp6 rows 14, 15: arm + finger qpos of the last position stage (store_state)
 
 template <class T>
@@ -123,38 +123,31 @@ struct Work {
   T* cD;    // [MAXCON]
   int* cmeta;  // [MAXCON]
   int* surv;   // [MAXSURV] geom pairs surviving the broad phase
-  // solver rows + spill space (only alive inside one kernel: pooled per resident CTA)
+  // solver rows (alive inside stage C only) + spill space
   T* aref;  // [MAXROW]
   T* Jaref; // [MAXROW]
   T* Jv;    // [MAXROW]
   T* pairbig;    // [MAXPAIR][33] pair tables of an env with more than MAXPAIR_S touching body pairs
   int* pairbig_i;  // [3][MAXPAIR]
-  double* warm_pad;  // [NV] spare qacc_warmstart
-  CvxRes<T>* cvx;  // results of this env's convex pairs (global queue slice, or [MAXSURV] pooled for the fused forward)
-  EpaMem<T> epa;   // fused forward only (the convex kernel has its own per-warp polytope)
+  CvxRes<T>* cvx;  // results of this env's convex pairs: its slice of the batch-wide queue (stage kernels), or - fused
+                   // forward - the head of the row arrays, which are idle until the constraint rows are made
+  EpaMem<T> epa;   // fused forward only: vertices at the tail of the row arrays (the convex kernel has its own polytope)
 };
-// per-env part (contacts + survivors) and pooled part (rows, pair spill, EPA, convex results of the fused forward)
-constexpr int WORKE_REALS = MAXCON * 11;
-constexpr int WORKE_INTS = MAXCON + MAXSURV;
-constexpr int WORKP_REALS = MAXROW * 3 + MAXPAIR * 33 + EPA_REALS + 2 * NV + 2 + MAXSURV * 10;
-constexpr int WORKP_INTS = EPA_INTS + 3 * MAXPAIR;
+constexpr int WORK_REALS = MAXCON * 11 + MAXROW * 3 + MAXPAIR * 33;
+constexpr int WORK_INTS = MAXCON + MAXSURV + 3 * MAXPAIR;
 template <class T>
-MM_HD Work<T> make_work(T* ereals, int* eints, T* preals, int* pints) {
+MM_HD Work<T> make_work(T* reals, int* ints) {
   Work<T> w;
-  w.cpos = ereals; w.cn = ereals + 3 * MAXCON; w.ct1 = ereals + 6 * MAXCON; w.cdist = ereals + 9 * MAXCON;
-  w.cD = ereals + 10 * MAXCON;
-  w.cmeta = eints; w.surv = eints + MAXCON;
-  w.aref = preals; w.Jaref = w.aref + MAXROW; w.Jv = w.Jaref + MAXROW;
+  w.cpos = reals; w.cn = reals + 3 * MAXCON; w.ct1 = reals + 6 * MAXCON; w.cdist = reals + 9 * MAXCON;
+  w.cD = reals + 10 * MAXCON;
+  w.aref = reals + 11 * MAXCON; w.Jaref = w.aref + MAXROW; w.Jv = w.Jaref + MAXROW;
   w.pairbig = w.Jv + MAXROW;
-  w.epa.vert = w.pairbig + MAXPAIR * 33; w.epa.face = w.epa.vert + EPA_MAXV * 6;
-  {  // 8-byte aligned doubles behind the EPA block (pool slices are 8-byte aligned: WORKP_REALS is even)
-    T* tail = w.epa.vert + EPA_REALS;
-    w.warm_pad = reinterpret_cast<double*>((reinterpret_cast<size_t>(tail) + 7) & ~size_t(7));
-  }
-  w.epa.fidx = pints; w.epa.edge = w.epa.fidx + EPA_MAXF; w.epa.canon = w.epa.edge + EPA_MAXE;
-  w.pairbig_i = w.epa.canon + EPA_MAXV;
-  w.cvx = reinterpret_cast<CvxRes<T>*>(w.warm_pad + NV + 1);  // [MAXSURV] (the stage kernels point it at the queue instead)
-  static_assert(sizeof(CvxRes<T>) <= 10 * sizeof(T), "CvxRes does not fit its pool slot");
+  w.cmeta = ints; w.surv = ints + MAXCON; w.pairbig_i = w.surv + MAXSURV;
+  w.cvx = reinterpret_cast<CvxRes<T>*>(w.aref);
+  w.epa.vert = w.aref + 3 * MAXROW - EPA_MAXV * 6;
+  w.epa.face = nullptr; w.epa.fidx = nullptr; w.epa.edge = nullptr; w.epa.canon = nullptr; w.epa.ecan = nullptr;  // shared memory (collide)
+  static_assert(MAXSURV * sizeof(CvxRes<T>) + EPA_MAXV * 6 * sizeof(T) <= 3 * MAXROW * sizeof(T), "fused convex scratch does not fit the row arrays");
+  static_assert((MAXCON * 11) % 2 == 0 && WORK_REALS % 2 == 0, "8-byte alignment of the slices");
   return w;
 }
 
@@ -1230,6 +1223,7 @@ MM_HDX void collide(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<
   em.fidx = reinterpret_cast<int*>(s.H + EPA_MAXF * 4);
   em.edge = em.fidx + EPA_MAXF;
   em.canon = em.edge + EPA_MAXE;
+  em.ecan = em.canon + EPA_MAXV;
   long long tx0 = MM_T0(s);
   for (int k = 0; k < ncvx; k++) convex_pair<T, G>(g, s.bpos, s.bR, gm, res[k].ci, em, res + k);
   MM_TICK(s, g, 3, tx0);

@@ -100,13 +100,10 @@ struct mm_handle {
   mm_config cfg;
   void* d_model = nullptr;
   void* d_geom = nullptr;
-  void* d_worke_reals = nullptr;  // per-env workspace: contacts, survivors
-  int* d_worke_ints = nullptr;
-  char* d_ctx = nullptr;          // env images between the stage kernels
-  void* d_workp_reals = nullptr;  // pooled workspace: pool_ctas x envs_per_cta slices
-  int* d_workp_ints = nullptr;
-  int* d_pool_flags = nullptr;
-  int pool_ctas = 0, envs_per_cta = 0, convex_grid = 0;
+  void* d_work_reals = nullptr;  // per-env workspace: contacts, survivors, solver rows
+  int* d_work_ints = nullptr;
+  char* d_ctx = nullptr;         // env images between the stage kernels
+  int convex_grid = 0;
   // chunks of the batch and their convex-pair queues
   long chunk = 0;
   int nchunk = 0, nstream = 0;
@@ -150,7 +147,7 @@ size_t real_bytes(const mm_config* c) { return c->precision ? 4 : 8; }
 
 typedef cudaError_t (*prepare_fn)();
 typedef cudaError_t (*launch_fn)(int, const StepParams&, int, int, cudaStream_t);
-typedef cudaError_t (*resident_fn)(int*, int*, int*);
+typedef cudaError_t (*resident_fn)(int*);
 int inst_index(const mm_config& c) { return (c.precision ? 3 : 0) + (c.group == 32 ? 0 : (c.group == 16 ? 1 : 2)); }
 const prepare_fn PREPARE[6] = {prepare_f64_32, prepare_f64_16, prepare_f64_8, prepare_f32_32, prepare_f32_16, prepare_f32_8};
 const resident_fn RESIDENT[6] = {resident_f64_32, resident_f64_16, resident_f64_8, resident_f32_32, resident_f32_16, resident_f32_8};
@@ -187,12 +184,11 @@ const char* mm_last_error(void) { return g_err.c_str(); }
 
 size_t mm_workspace_bytes(const mm_config* cfg) {
   size_t n = (size_t)cfg->num_envs, rb = real_bytes(cfg);
-  // staging buffers, per-env contact lists + stage images + convex queue, and an upper bound of the pooled workspaces
-  size_t per_env = 4 * 4 + (ACTION_STRIDE + OBS_DIM + 1) * 4 + 3 + (size_t)WORKE_REALS * rb + (size_t)WORKE_INTS * 4 +
+  // per env: staging buffers, contact list + solver rows, stage image, share of the convex queue
+  size_t per_env = 4 * 4 + (ACTION_STRIDE + OBS_DIM + 1) * 4 + 3 + (size_t)WORK_REALS * rb + (size_t)WORK_INTS * 4 +
                    (cfg->precision ? ctx_stride<float>() : ctx_stride<double>()) +
                    64 * (sizeof(CvxItem) + (cfg->precision ? sizeof(CvxRes<float>) : sizeof(CvxRes<double>)));
-  size_t pool = (size_t)148 * 4 * 16;
-  return n * per_env + pool * ((size_t)WORKP_REALS * rb + (size_t)WORKP_INTS * 4);
+  return n * per_env + (size_t)8 * 148 * 8 * MM_WX * EPA_MAXV * 6 * rb;
 }
 
 int mm_create(const mm_config* cfg, mm_handle** out) {
@@ -214,20 +210,9 @@ int mm_create(const mm_config* cfg, mm_handle** out) {
     if (upload_model<float>(h) != 0) return -1;
   }
   if (PREPARE[inst_index(h->cfg)]() != cudaSuccess) return fail("mm_create: kernel attribute set-up failed");
-  CK(RESIDENT[inst_index(h->cfg)](&h->pool_ctas, &h->envs_per_cta, &h->convex_grid));
-  h->pool_ctas += 8;  // margin
-  {
-    // never more pool entries than CTAs a launch can have (one entry per CTA is then free without contention)
-    size_t need = (n + h->envs_per_cta - 1) / h->envs_per_cta;
-    if (need < (size_t)h->pool_ctas) h->pool_ctas = (int)need;
-    size_t slices = (size_t)h->pool_ctas * h->envs_per_cta;
-    CK(cudaMalloc(&h->d_workp_reals, slices * WORKP_REALS * rb));
-    CK(cudaMalloc(&h->d_workp_ints, slices * WORKP_INTS * sizeof(int)));
-    CK(cudaMalloc(&h->d_pool_flags, (size_t)h->pool_ctas * sizeof(int)));
-    CK(cudaMemset(h->d_pool_flags, 0, (size_t)h->pool_ctas * sizeof(int)));
-  }
-  CK(cudaMalloc(&h->d_worke_reals, n * WORKE_REALS * rb));
-  CK(cudaMalloc(&h->d_worke_ints, n * WORKE_INTS * sizeof(int)));
+  CK(RESIDENT[inst_index(h->cfg)](&h->convex_grid));
+  CK(cudaMalloc(&h->d_work_reals, n * WORK_REALS * rb));
+  CK(cudaMalloc(&h->d_work_ints, n * WORK_INTS * sizeof(int)));
   size_t cstride = cfg->precision ? ctx_stride<float>() : ctx_stride<double>();
   CK(cudaMalloc(&h->d_ctx, n * cstride));
   CK(cudaMemset(h->d_ctx, 0, n * cstride));
@@ -274,8 +259,8 @@ void mm_destroy(mm_handle* h) {
     if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
   }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
-  cudaFree(h->d_model); cudaFree(h->d_geom); cudaFree(h->d_worke_reals); cudaFree(h->d_worke_ints); cudaFree(h->d_ctx);
-  cudaFree(h->d_workp_reals); cudaFree(h->d_workp_ints); cudaFree(h->d_pool_flags); cudaFree(h->d_q_items); cudaFree(h->d_q_res);
+  cudaFree(h->d_model); cudaFree(h->d_geom); cudaFree(h->d_work_reals); cudaFree(h->d_work_ints); cudaFree(h->d_ctx);
+  cudaFree(h->d_q_items); cudaFree(h->d_q_res);
   cudaFree(h->d_q_ctr); cudaFree(h->d_epa_verts); cudaFree(h->d_tgt);
   cudaFree(h->d_actions); cudaFree(h->d_obs); cudaFree(h->d_reward); cudaFree(h->d_flags);
   delete h;
@@ -285,8 +270,7 @@ namespace {
 void base_params(mm_handle* h, const mm_state* st, StepParams& p) {
   p.st = to_ptrs(st);
   p.model = h->d_model;
-  p.worke_reals = h->d_worke_reals; p.worke_ints = h->d_worke_ints; p.ctx = h->d_ctx;
-  p.workp_reals = h->d_workp_reals; p.workp_ints = h->d_workp_ints; p.pool_flags = h->d_pool_flags; p.pool_ctas = h->pool_ctas;
+  p.work_reals = h->d_work_reals; p.work_ints = h->d_work_ints; p.ctx = h->d_ctx;
   p.tgt_kp = h->d_tgt; p.n = h->cfg.num_envs; p.slot0 = 0; p.nslot = h->cfg.num_envs;
   p.reward_type = h->cfg.reward_type; p.max_steps = h->cfg.max_episode_steps;
   p.q_cap = h->q_cap;

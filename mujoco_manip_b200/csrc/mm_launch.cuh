@@ -48,15 +48,10 @@ struct StepParams {
   StepOut out;
   const float* actions;
   const void* model;
-  // per-env workspace (contacts, survivors) and env images between the stages
-  void* worke_reals;  // [N][WORKE_REALS]
-  int* worke_ints;    // [N][WORKE_INTS]
+  // per-env workspace (contacts, survivors, solver rows) and env images between the stages
+  void* work_reals;   // [N][WORK_REALS]
+  int* work_ints;     // [N][WORK_INTS]
   char* ctx;          // [N][ctx_stride]
-  // pooled workspace (solver rows, pair spill, fused-forward extras), handed out per RESIDENT CTA (see acquire_work)
-  void* workp_reals;  // [pool_ctas * envs_per_cta][WORKP_REALS]
-  int* workp_ints;
-  int* pool_flags;    // [pool_ctas] 0 = free
-  int pool_ctas;
   // convex-pair queue of this chunk
   void* q_items;
   void* q_res;
@@ -99,29 +94,9 @@ __device__ __forceinline__ CvxQueue<T> queue_of(const StepParams& p, int sub) {
   return q;
 }
 
-// The pooled workspace (solver rows ...) is scratch inside one kernel, so it is pooled per RESIDENT CTA instead of per
-// env: a few hundred CTAs are in flight however many envs there are.  A CTA claims a free pool entry with a CAS scan
-// that starts at its own index (the pool is at least as large as the number of CTAs that can be resident) and frees
-// it on exit.
-__device__ __forceinline__ int acquire_work(const StepParams& p) {
-  __shared__ int s_slot;
-  if (threadIdx.x == 0) {
-    int slot = (int)(blockIdx.x % (unsigned)p.pool_ctas);
-    while (atomicCAS(p.pool_flags + slot, 0, 1) != 0) slot = slot + 1 == p.pool_ctas ? 0 : slot + 1;
-    s_slot = slot;
-  }
-  __syncthreads();
-  return s_slot;
-}
-__device__ __forceinline__ void release_work(const StepParams& p, int slot) {
-  __syncthreads();
-  if (threadIdx.x == 0) { __threadfence(); atomicExch(p.pool_flags + slot, 0); }
-}
-
 template <class T>
-__device__ __forceinline__ Work<T> work_of(const StepParams& p, long e, long pslot) {
-  return make_work(reinterpret_cast<T*>(p.worke_reals) + e * WORKE_REALS, p.worke_ints + e * WORKE_INTS,
-                   reinterpret_cast<T*>(p.workp_reals) + pslot * WORKP_REALS, p.workp_ints + pslot * WORKP_INTS);
+__device__ __forceinline__ Work<T> work_of(const StepParams& p, long e) {
+  return make_work(reinterpret_cast<T*>(p.work_reals) + e * WORK_REALS, p.work_ints + e * WORK_INTS);
 }
 
 template <class T> MM_HDN constexpr size_t scratch_c_bytes() { return (sizeof(Scratch<T>) + 15) / 16 * 16; }
@@ -139,7 +114,7 @@ __global__ void __launch_bounds__(32 * W, MM_MINB_A) k_stage_a(StepParams p, int
   long e = p.order ? p.order[slot] : slot;
   long long t0 = clock64();
   Scratch<T>& s = *reinterpret_cast<Scratch<T>*>(smem + gi * scratch_a_bytes<T>());
-  Work<T> w = work_of<T>(p, e, 0);  // stage A touches the per-env part only
+  Work<T> w = work_of<T>(p, e);
   stage_a<T, G>(g, s, *md, w, p.st, e, sub, p.actions, p.mode, p.ctx, queue_of<T>(p, sub));
   if (g.lane == 0) {
     long long dt = clock64() - t0;
@@ -154,23 +129,20 @@ __global__ void __launch_bounds__(32 * W, MM_MINB_C) k_stage_c(StepParams p, int
   Grp<G> g;
   setup_group<T, G>(g);
   const ModelDev<T>* md = reinterpret_cast<const ModelDev<T>*>(p.model);
-  int pool = acquire_work(p);
   int gi = threadIdx.x / G;
   long slot = (long)blockIdx.x * (32 * W / G) + gi;
-  if (slot < p.nslot) {
-    slot += p.slot0;
-    long e = p.order ? p.order[slot] : slot;
-    long long t0 = clock64();
-    Scratch<T>& s = *reinterpret_cast<Scratch<T>*>(smem + gi * scratch_c_bytes<T>());
-    Work<T> w = work_of<T>(p, e, (long)pool * (32 * W / G) + gi);
-    stage_c<T, G>(g, s, *md, w, p.st, e, sub, p.ctx, queue_of<T>(p, sub), p.reward_type, p.max_steps, p.out, p.tgt_kp);
-    if (g.lane == 0) {
-      long long dt = clock64() - t0;
-      if (p.work) p.work[e] += (int)(dt >> 8);
-      if (p.cycles) { p.cycles[9 * e + 3] += dt; p.cycles[9 * e] += dt; }
-    }
+  if (slot >= p.nslot) return;
+  slot += p.slot0;
+  long e = p.order ? p.order[slot] : slot;
+  long long t0 = clock64();
+  Scratch<T>& s = *reinterpret_cast<Scratch<T>*>(smem + gi * scratch_c_bytes<T>());
+  Work<T> w = work_of<T>(p, e);
+  stage_c<T, G>(g, s, *md, w, p.st, e, sub, p.ctx, queue_of<T>(p, sub), p.reward_type, p.max_steps, p.out, p.tgt_kp);
+  if (g.lane == 0) {
+    long long dt = clock64() - t0;
+    if (p.work) p.work[e] += (int)(dt >> 8);
+    if (p.cycles) { p.cycles[9 * e + 3] += dt; p.cycles[9 * e] += dt; }
   }
-  release_work(p, pool);
 }
 
 // convex stage: persistent warps take (env, geom pair) items off the queue of this round
@@ -178,7 +150,7 @@ template <class T>
 struct ConvexSmem {
   T face[EPA_MAXF * 4];
   T bpos[NDB][3], bR[NDB][9];
-  int fidx[EPA_MAXF], edge[EPA_MAXE], canon[EPA_MAXV];
+  int fidx[EPA_MAXF], edge[EPA_MAXE], canon[EPA_MAXV], ecan[EPA_MAXE];
 };
 template <class T, int W>
 __global__ void __launch_bounds__(32 * W, MM_MINB_X) k_convex(StepParams p, int sub) {
@@ -194,7 +166,7 @@ __global__ void __launch_bounds__(32 * W, MM_MINB_X) k_convex(StepParams p, int 
   if (count > q.cap) count = q.cap;
   EpaMem<T> em;
   em.vert = reinterpret_cast<T*>(p.epa_verts) + ((size_t)blockIdx.x * W + wi) * (EPA_MAXV * 6);
-  em.face = cs.face; em.fidx = cs.fidx; em.edge = cs.edge; em.canon = cs.canon;
+  em.face = cs.face; em.fidx = cs.fidx; em.edge = cs.edge; em.canon = cs.canon; em.ecan = cs.ecan;
   while (true) {
     int i = 0;
     if (g.lane == 0) i = atomicAdd(q.head, 1);
@@ -224,16 +196,14 @@ __global__ void __launch_bounds__(FusedCfg<T, G>::THREADS, MM_MINB_C) k_reset(St
   Grp<G> g;
   setup_group<T, G>(g);
   const ModelDev<T>* md = reinterpret_cast<const ModelDev<T>*>(p.model);
-  int pool = acquire_work(p);
   int gi = threadIdx.x / G;
   long e = (long)blockIdx.x * FusedCfg<T, G>::ENVS + gi;
   if (e < p.n && !(p.mask && !p.mask[e])) {
     Scratch<T>& s = *reinterpret_cast<Scratch<T>*>(smem + gi * scratch_c_bytes<T>());
-    Work<T> w = work_of<T>(p, e, (long)pool * FusedCfg<T, G>::ENVS + gi);
+    Work<T> w = work_of<T>(p, e);
     env_reset<T, G>(g, s, *md, w, p.st, e, p.obj_xy ? p.obj_xy + 6 * e : nullptr, p.yaw_cs ? p.yaw_cs + 6 * e : nullptr, p.task[2 * e],
                     p.task[2 * e + 1], p.obs, p.tgt_kp);
   }
-  release_work(p, pool);
 }
 
 template <class T, int G>
@@ -242,15 +212,13 @@ __global__ void __launch_bounds__(FusedCfg<T, G>::THREADS, MM_MINB_C) k_ops(Step
   Grp<G> g;
   setup_group<T, G>(g);
   const ModelDev<T>* md = reinterpret_cast<const ModelDev<T>*>(p.model);
-  int pool = acquire_work(p);
   int gi = threadIdx.x / G;
   long e = (long)blockIdx.x * FusedCfg<T, G>::ENVS + gi;
   if (e < p.n) {
     Scratch<T>& s = *reinterpret_cast<Scratch<T>*>(smem + gi * scratch_c_bytes<T>());
-    Work<T> w = work_of<T>(p, e, (long)pool * FusedCfg<T, G>::ENVS + gi);
+    Work<T> w = work_of<T>(p, e);
     env_ops<T, G>(g, s, *md, w, p.st, e, p.ops, p.target);
   }
-  release_work(p, pool);
 }
 
 inline long env_long(const char* name, long dflt) {
@@ -275,26 +243,14 @@ cudaError_t inst_prepare() {
   return cudaFuncSetAttribute(k_reset<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c<T, G>());
 }
 
-// launch geometry of this instantiation: CTAs of the pooled-workspace kernels that can be resident on the device
-// (sizes the pool), their envs per CTA, and the grid of the persistent convex kernel
+// grid of the persistent convex kernel of this instantiation: every CTA that can be resident
 template <class T, int G>
-cudaError_t inst_resident(int* ctas, int* envs_per_cta, int* convex_grid) {
-  int dev = 0, sms = 0, per = 0, best = 0;
+cudaError_t inst_resident(int* convex_grid) {
+  int dev = 0, sms = 0, per = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (e != cudaSuccess) return e;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_stage_c<T, G, warps_c<G>()>, 32 * warps_c<G>(), smem_c<T, G>());
-  if (e != cudaSuccess) return e;
-  best = per;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_reset<T, G>, 32 * warps_c<G>(), smem_c<T, G>());
-  if (e != cudaSuccess) return e;
-  best = per > best ? per : best;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_ops<T, G>, 32 * warps_c<G>(), smem_c<T, G>());
-  if (e != cudaSuccess) return e;
-  best = per > best ? per : best;
-  *ctas = best * sms;
-  *envs_per_cta = 32 * warps_c<G>() / G;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_convex<T, MM_WX>, 32 * MM_WX, smem_x<T>());
   if (e != cudaSuccess) return e;
   *convex_grid = (per > 0 ? per : 1) * sms;
@@ -324,7 +280,7 @@ cudaError_t inst_launch(int which, const StepParams& p, int sub, int grid_x, cud
 // entry points defined by the mm_inst_*.cu units
 #define MM_DECL_INST(NAME)                 \
   cudaError_t prepare_##NAME();            \
-  cudaError_t resident_##NAME(int* ctas, int* envs_per_cta, int* convex_grid); \
+  cudaError_t resident_##NAME(int* convex_grid); \
   cudaError_t launch_##NAME(int which, const StepParams& p, int sub, int grid_x, cudaStream_t s);
 MM_DECL_INST(f64_32) MM_DECL_INST(f64_16) MM_DECL_INST(f64_8)
 MM_DECL_INST(f32_32) MM_DECL_INST(f32_16) MM_DECL_INST(f32_8)
@@ -332,7 +288,7 @@ MM_DECL_INST(f32_32) MM_DECL_INST(f32_16) MM_DECL_INST(f32_8)
 #define MM_DEFINE_INST(NAME, T, G)                                                              \
   namespace mm {                                                                                \
   cudaError_t prepare_##NAME() { return inst_prepare<T, G>(); }                                 \
-  cudaError_t resident_##NAME(int* ctas, int* envs_per_cta, int* convex_grid) { return inst_resident<T, G>(ctas, envs_per_cta, convex_grid); } \
+  cudaError_t resident_##NAME(int* convex_grid) { return inst_resident<T, G>(convex_grid); } \
   cudaError_t launch_##NAME(int which, const StepParams& p, int sub, int grid_x, cudaStream_t s) { return inst_launch<T, G>(which, p, sub, grid_x, s); } \
   }
 

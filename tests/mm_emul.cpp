@@ -18,14 +18,14 @@ struct Ctx {
   ModelDev<T> md;
   GeomDev<T> gm;
   Scratch<T> s;
-  std::vector<T> wr, wp;
-  std::vector<int> wi, wpi;
+  std::vector<T> wr;
+  std::vector<int> wi;
   Work<T> w;
-  Ctx() : wr(WORKE_REALS), wp(WORKP_REALS), wi(WORKE_INTS), wpi(WORKP_INTS) {
+  Ctx() : wr(WORK_REALS), wi(WORK_INTS) {
     fill_model(md);
     fill_geom(gm);
     md.geom = &gm;
-    w = make_work(wr.data(), wi.data(), wp.data(), wpi.data());
+    w = make_work(wr.data(), wi.data());
     std::memset(&s, 0, sizeof s);
   }
 };
@@ -69,8 +69,8 @@ void do_step(int n, void** sp, const float* actions, int mode, int reward_type, 
   StatePtrs st = state_from(sp);
   StepOut out = out_from(op);
   Grp<1> g{0, 1u};
-  std::vector<T> wer((size_t)n * WORKE_REALS);
-  std::vector<int> wei((size_t)n * WORKE_INTS);
+  std::vector<T> wer((size_t)n * WORK_REALS);
+  std::vector<int> wei((size_t)n * WORK_INTS);
   std::vector<char> image((size_t)n * ctx_stride<T>());
   const int cap = n * 64;
   std::vector<CvxItem> items(cap);
@@ -82,7 +82,7 @@ void do_step(int n, void** sp, const float* actions, int mode, int reward_type, 
     int count = 0, head = 0;
     CvxQueue<T> q{items.data(), res.data(), &count, &head, cap};
     for (long e = 0; e < n; e++) {
-      Work<T> w = make_work(wer.data() + e * WORKE_REALS, wei.data() + e * WORKE_INTS, c.wp.data(), c.wpi.data());
+      Work<T> w = make_work(wer.data() + e * WORK_REALS, wei.data() + e * WORK_INTS);
       // stage A owns only the first scratch_a_bytes of the scratch on the device: everything behind must stay untouched
       unsigned char* tail = reinterpret_cast<unsigned char*>(&c.s) + scratch_a_bytes<T>();
       size_t ntail = sizeof(Scratch<T>) - scratch_a_bytes<T>();
@@ -92,12 +92,25 @@ void do_step(int n, void** sp, const float* actions, int mode, int reward_type, 
         if (tail[k] != 0xA5) { std::fprintf(stderr, "stage A wrote outside its scratch slice (byte %zu)\n", scratch_a_bytes<T>() + k); std::abort(); }
     }
     EpaMem<T> em;
-    em.vert = everts.data(); em.face = eface.data(); em.fidx = eints.data(); em.edge = em.fidx + EPA_MAXF; em.canon = em.edge + EPA_MAXE;
+    em.vert = everts.data(); em.face = eface.data(); em.fidx = eints.data(); em.edge = em.fidx + EPA_MAXF; em.canon = em.edge + EPA_MAXE; em.ecan = em.canon + EPA_MAXV;
     int cnt = count < cap ? count : cap;
     for (int i = cnt - 1; i >= 0; i--)  // any order: results are addressed by queue position
+#ifdef MM_DEBUG_EPA
+    {
+      long before = mm_debug_epa_iters;
       stage_convex<T, 1>(g, c.gm, q, i, image.data(), bpos, bR, em);
+      long it = mm_debug_epa_iters - before;
+      if (it >= 40) {
+        int ci = items[i].ci, a = c.gm.pair[ci][0], b = c.gm.pair[ci][1];
+        std::fprintf(stderr, "EPA %ld iterations: env %d pair %d (geom %d type %d body %d | geom %d type %d body %d) hit %d depth %g\n", it,
+                     items[i].env, ci, a, c.gm.type[a], c.gm.body[a], b, c.gm.type[b], c.gm.body[b], res[i].hit, (double)res[i].depth);
+      }
+    }
+#else
+      stage_convex<T, 1>(g, c.gm, q, i, image.data(), bpos, bR, em);
+#endif
     for (long e = 0; e < n; e++) {
-      Work<T> w = make_work(wer.data() + e * WORKE_REALS, wei.data() + e * WORKE_INTS, c.wp.data(), c.wpi.data());
+      Work<T> w = make_work(wer.data() + e * WORK_REALS, wei.data() + e * WORK_INTS);
       stage_c<T, 1>(g, c.s, c.md, w, st, e, sub, image.data(), q, reward_type, max_steps, out, tgt);
     }
   }

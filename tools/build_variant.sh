@@ -1,6 +1,6 @@
 #!/bin/bash
 # Build a variant of the FP64 / 32-lane kernel unit with extra -D flags and link it with the other (default) objects:
-#   tools/build_variant.sh NAME -DMM_WARPS_SMALL=2 -DMM_MINB_SMALL=4
+#   tools/build_variant.sh NAME -DMM_WA=1 -DMM_MINB_A=16
 # -> mujoco_manip_b200/_C/variants/libmm_NAME.so   (use with MM_LIB_PATH=... python bench.py)
 set -e
 name=$1; shift
@@ -11,5 +11,5 @@ mkdir -p $out
 nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -diag-suppress=170 "$@" \
   -Xptxas -v -c -o $out/mm_inst_f64_32_$name.o $root/mujoco_manip_b200/csrc/mm_inst_f64_32.cu 2> $out/ptxas_$name.log
 others=$(ls $obj/*.o | grep -v mm_inst_f64_32.o)
-nvcc --shared -gencode arch=compute_100a,code=sm_100a -o $out/libmm_$name.so $out/mm_inst_f64_32_$name.o $others
-grep -A1 "k_stepIdLi32E" $out/ptxas_$name.log | grep -o "Used [0-9]* registers\|[0-9]* bytes spill stores" | paste -sd' '
+nvcc --shared -cudart shared -gencode arch=compute_100a,code=sm_100a -o $out/libmm_$name.so $out/mm_inst_f64_32_$name.o $others
+grep -A2 "Compiling entry function" $out/ptxas_$name.log | grep -o "k_[a-z_]*I\|Used [0-9]* registers\|[0-9]* bytes spill stores" | paste -sd' '
