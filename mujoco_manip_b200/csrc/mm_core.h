@@ -108,6 +108,7 @@ struct Scratch {
   short* inc;
   int specdof[MAXSPEC];  // -1: equality row (e7 - e8); else dof | (negative sign ? 256 : 0)
   int npair, nspec, hvalid;
+  int bodyact;    // bit b (1..12): body b has touching pairs; bit 0: the robot has
   int lone;       // bit c: cube c touches neither the robot nor another cube -> its 6x6 block of H is independent
   int n_il;       // dofs of the coupled part: robot (9) + the cubes that are not `lone`
   signed char il[NV], dl[16], dla[16];
@@ -290,6 +291,16 @@ MM_HDN void chol_factor_list(const Grp<G>& g, T* A, const signed char* il, int n
     g.sync();
     const int m = n - jj - 1;
     if (m <= 0) break;
+    if (m <= 8) {  // few rows left (and always the robot-only system): one row per lane
+      for (int ii = jj + 1 + g.lane; ii < n; ii += G) {
+        int i = il[ii];
+        T lij = A[i * NV + j];
+        if (lij == 0) continue;
+        for (int kk = jj + 1; kk <= ii; kk++) { int k = il[kk]; A[i * NV + k] -= lij * A[k * NV + j]; }
+      }
+      g.sync();
+      continue;
+    }
     const int F = (m + 1) / 2;                 // folded items
     const int P = G >= F ? G / F : 1;          // lanes per item
     for (int f = g.lane / P; f < F; f += (G / P > 0 ? G / P : 1)) {
@@ -1217,6 +1228,12 @@ MM_HDX void assemble_contacts(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>&
     for (int k = 0; k < b; k++) st += cnt[k];
     s.incst[b] = (unsigned char)st;
   }
+  if (g.lane == 0) {  // bodies with at least one touching pair; bit 0: some robot body (classes 1 .. 9) is among them
+    int act = 0;
+    for (int b = 1; b < NCLS; b++) if (cnt[b]) act |= 1 << b;
+    if (act & 0x3FE) act |= 1;
+    s.bodyact = act;
+  }
   g.sync();
   for (int b = g.lane; b < NCLS; b += G) {
     if (b == 0) continue;
@@ -1267,17 +1284,20 @@ MM_HDX void collide(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<
 // branch off the hand, the cubes are free.  s.bodyV[0] (static bodies) stays zero.
 template <class T, int G>
 MM_HDN void body_twists(const Grp<G>& g, Scratch<T>& s, const T* x) {
+  const int act = s.bodyact;
   for (int it = g.lane; it < 6 + 18; it += G) {
     if (it < 6) {
       int c = it;
       T acc = 0;
       s.bodyV[0][c] = 0;
+      if (!(act & 1)) continue;
 #pragma unroll
       for (int k = 0; k < NARM; k++) { acc += s.S[k][c] * x[k]; s.bodyV[k + 1][c] = acc; }
       s.bodyV[8][c] = acc + s.S[7][c] * x[7];
       s.bodyV[9][c] = acc + s.S[8][c] * x[8];
     } else {
       int j = (it - 6) / 6, c = (it - 6) % 6;
+      if (!((act >> (CLS_CUBE0 + j)) & 1)) continue;
       const T* xq = x + NROB + 6 * j;
       T acc = c >= 3 ? xq[c - 3] : (T)0;  // translational dofs: unit axes
 #pragma unroll
@@ -1486,8 +1506,10 @@ MM_HDN T update_constraint(const Grp<G>& g, Scratch<T>& s, Work<T>& w, bool buil
   cost = g.sum(cost);
   *changed = g.any(chg);
   // qfrc_constraint = J^T f through the bodies: pair p pushes body B with +F_p and body A with -F_p ...
+  const int act = s.bodyact;
   for (int it = g.lane; it < (NCLS - 1) * 6; it += G) {
     int b = 1 + it / 6, c = it % 6;
+    if (!((act >> b) & 1)) { if (b < CLS_CUBE0 && (act & 1)) s.bodyF[b][c] = 0; continue; }
     T acc = 0;
     for (int k = s.incst[b]; k < s.incst[b + 1]; k++) {
       int e = s.inc[k];
@@ -1498,15 +1520,19 @@ MM_HDN T update_constraint(const Grp<G>& g, Scratch<T>& s, Work<T>& w, bool buil
   }
   g.sync();
   // ... dof i of the arm carries every body behind it: subtree sums (bodyF[i + 1] <- bodies i + 1 .. 9)
-  for (int c = g.lane; c < 6; c += G) {
-    T acc = s.bodyF[7][c] + s.bodyF[8][c] + s.bodyF[9][c];
-    s.bodyF[7][c] = acc;
+  if (act & 1) {
+    for (int c = g.lane; c < 6; c += G) {
+      T acc = s.bodyF[7][c] + s.bodyF[8][c] + s.bodyF[9][c];
+      s.bodyF[7][c] = acc;
 #pragma unroll
-    for (int k = 6; k >= 1; k--) { acc += s.bodyF[k][c]; s.bodyF[k][c] = acc; }
+      for (int k = 6; k >= 1; k--) { acc += s.bodyF[k][c]; s.bodyF[k][c] = acc; }
+    }
+    g.sync();
   }
-  g.sync();
   for (int i = g.lane; i < NV; i += G) {
-    T acc = i < NROB ? dot6(s.S[i], s.bodyF[i + 1]) : S_dot(s, i, s.bodyF[CLS_CUBE0 + (i - NROB) / 6]);
+    T acc = 0;
+    if (i < NROB) { if (act & 1) acc = dot6(s.S[i], s.bodyF[i + 1]); }
+    else if ((act >> (CLS_CUBE0 + (i - NROB) / 6)) & 1) acc = S_dot(s, i, s.bodyF[CLS_CUBE0 + (i - NROB) / 6]);
     for (int k = 0; k < s.nspec; k++) {
       int d = s.specdof[k];
       T ja = s.specJaref[k];
@@ -1563,8 +1589,10 @@ MM_HD T ksym(const T* K, int a, int b) { return a >= b ? K[a * (a + 1) / 2 + b] 
 // (finger - cube, cube - cube, link - link), which are few.  Static - moving pairs, the many, cost nothing per pair.
 template <class T, int G>
 MM_HDN void build_factor_H(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md) {
+  const int act = s.bodyact;  // bodies without a touching pair (and the whole arm, when it touches nothing) are skipped
   for (int it = g.lane; it < (NCLS - 1) * 21; it += G) {
     int b = 1 + it / 21, k = it % 21;
+    if (!((act >> b) & 1)) { if (b < CLS_CUBE0 && (act & 1)) s.bodyK[b][k] = 0; continue; }
     T acc = 0;
     for (int q = s.incst[b]; q < s.incst[b + 1]; q++) acc += s.pairK[s.inc[q] & 255][k];
     s.bodyK[b][k] = acc;
@@ -1587,17 +1615,21 @@ MM_HDN void build_factor_H(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md
     }
   }
   // composite blocks along the arm: bodyK[i + 1] <- bodies i + 1 .. 9 (the block dof i sees); fingers keep their own
-  for (int k = g.lane; k < 21; k += G) {
-    T acc = s.bodyK[7][k] + s.bodyK[8][k] + s.bodyK[9][k];
-    s.bodyK[7][k] = acc;
+  if (act & 1) {
+    for (int k = g.lane; k < 21; k += G) {
+      T acc = s.bodyK[7][k] + s.bodyK[8][k] + s.bodyK[9][k];
+      s.bodyK[7][k] = acc;
 #pragma unroll
-    for (int b = 6; b >= 1; b--) { acc += s.bodyK[b][k]; s.bodyK[b][k] = acc; }
+      for (int b = 6; b >= 1; b--) { acc += s.bodyK[b][k]; s.bodyK[b][k] = acc; }
+    }
+    g.sync();
   }
-  g.sync();
-  // T_j = Kc(j) S_j for every dof
+  // T_j = Kc(j) S_j for every dof of a touching body
   for (int it = g.lane; it < NV * 6; it += G) {
     int j = it / 6, a = it - 6 * j;
-    const T* K = s.bodyK[j < NROB ? j + 1 : CLS_CUBE0 + (j - NROB) / 6];
+    int body = j < NROB ? j + 1 : CLS_CUBE0 + (j - NROB) / 6;
+    if (!((act >> (j < NROB ? 0 : body)) & 1)) continue;
+    const T* K = s.bodyK[body];
     T acc = 0;
 #pragma unroll
     for (int b = 0; b < 6; b++) acc += ksym(K, a, b) * S_comp(s, j, b);
@@ -1607,10 +1639,12 @@ MM_HDN void build_factor_H(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md
   for (int e = g.lane; e < NROB * NROB + 3 * 36; e += G) {
     int i, j;
     if (e < NROB * NROB) {  // robot block: the deeper dof's composite block; the two fingers do not see each other
+      if (!(act & 1)) continue;
       i = e / NROB; j = e - i * NROB;
       if (j > i || (i == 8 && j == 7)) continue;
     } else {
       int r = e - NROB * NROB, c = r / 36;
+      if (!((act >> (CLS_CUBE0 + c)) & 1)) continue;
       r -= 36 * c;
       int k = r / 6, l = r - 6 * k;
       if (l > k) continue;

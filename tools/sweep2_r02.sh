@@ -11,7 +11,7 @@ for v in $VARIANTS; do
     for cfg in "$@"; do
       if [ $v = new ]; then unset MM_LIB_PATH; else export MM_LIB_PATH=$PWD/mujoco_manip_b200/_C/variants/libmm_$v.so; fi
       steps=20; [ $n -gt 20000 ] && steps=8
-      r=$(env $cfg python bench.py --envs $n --steps $steps --warmup 5 --no-cpu-baseline --no-e2e 2>>gpurun_out/sweep2_$TAG.err | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(round(d['value']), round(d['ms_per_step'],2))")
+      r=$(env $cfg python bench.py --envs $n --steps $steps --warmup 5 --no-cpu-baseline --no-e2e $BENCH_EXTRA 2>>gpurun_out/sweep2_$TAG.err | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(round(d['value']), round(d['ms_per_step'],2))")
       echo "$v $n [$cfg] $r" >> $OUT
     done
   done
