@@ -46,7 +46,6 @@ constexpr int MAXROW = MAXCON * 6;
 constexpr int MAXPAIR_S = 16; // simultaneously touching body pairs whose tables live in shared memory (the common case)
 constexpr int MAXPAIR = 96;   // every ordered (class, class) key of the 780 candidate pairs (94, tools/modelc.py): exact, no cap;
                               // envs with more than MAXPAIR_S touching pairs keep their pair tables in the global workspace
-constexpr int NCLS = 13;      // collision classes = bodies of the matrix-free Jacobian
 constexpr int MAXSPEC = 10;   // equality + at most one limit row per robot joint
 constexpr int MAXSURV = 384;  // geom pairs surviving the first level of the broad phase
 constexpr double MINVAL_D = 1e-15;
@@ -66,7 +65,7 @@ MM_HD int srow(int dof) { return dof < NROB ? dof : NROB + 3 * ((dof - NROB) / 6
 MM_HD bool is_cube_translation(int dof) { return dof >= NROB && ((dof - NROB) % 6) < 3; }
 // rows of the 6-vector scratch: 16 suffice (14 dofs of a body pair + 2 rows that park the position-stage qpos);
 // the FP32 build keeps 27 because its EPA workspace (integers are as wide as reals there) needs the room
-template <class T> constexpr int TMP6_ROWS() { return sizeof(T) == 8 ? 27 : 48; }  // one row per dof (K S products)
+template <class T> constexpr int TMP6_ROWS() { return sizeof(T) == 8 ? 16 : 48; }
 constexpr int KIN_ROW = 14;  // tmp6 rows 14, 15: arm + finger qpos of the last position stage (store_state)
 
 template <class T>
@@ -90,28 +89,22 @@ struct Scratch {
   // contiguous block that is dead during collision (re-used there as clip scratch and EPA polytope)
   T H[NV * NV];
   T tmp6[TMP6_ROWS<T>()][6];
-  T pairK_s[MAXPAIR_S][21], pairF_s[MAXPAIR_S][6];
-  // per-BODY quantities of the matrix-free Jacobian (body = collision class: 0 static, 1..7 links (hand = 7), 8 / 9
-  // fingers, 10..12 cubes): twist of the body under a dof vector, wrench on the body (subtree sums for the chain), and
-  // the 6x6 blocks sum_p K_p of the pairs that touch the body (composite sums for the chain, like CRBA inertias)
-  T bodyV[NCLS][6], bodyF[NCLS][6], bodyK[NCLS][21];
+  T pairK_s[MAXPAIR_S][21], pairW_s[MAXPAIR_S][6], pairF_s[MAXPAIR_S][6];
   T qacc[NV], Ma[NV], search[NV], Mv[NV], fc[NV];
   // -----------------------------------------------------------------------------------------------------------
   T specD[MAXSPEC], specJaref[MAXSPEC], specJv[MAXSPEC], specAref[MAXSPEC];
   int pairkey_s[MAXPAIR_S];
-  short inc_s[2 * MAXPAIR_S];  // incidence lists body -> pairs: pair index | 256 when the body is body B of the pair
-  unsigned char incst[NCLS + 1];  // list of body b = inc[incst[b] .. incst[b + 1])
+  int pairmd_s[MAXPAIR_S], pairmb_s[MAXPAIR_S];  // dof masks of the pair: dofs of exactly one of the two bodies | dofs of body B
   // pair tables of this forward pass: the shared arrays above, or (more than MAXPAIR_S touching pairs) the global workspace
   T (*pairK)[21];
+  T (*pairW)[6];
   T (*pairF)[6];
-  int* pairkey;
-  short* inc;
+  int *pairkey, *pairmd, *pairmb;
   int specdof[MAXSPEC];  // -1: equality row (e7 - e8); else dof | (negative sign ? 256 : 0)
   int npair, nspec, hvalid;
-  int bodyact;    // bit b (1..12): body b has touching pairs; bit 0: the robot has
   int lone;       // bit c: cube c touches neither the robot nor another cube -> its 6x6 block of H is independent
   int n_il;       // dofs of the coupled part: robot (9) + the cubes that are not `lone`
-  signed char il[NV], dl[16], dla[16];
+  signed char il[NV], dl[16];
 };
 #define SCRATCH_PERSIST(T) (offsetof(Scratch<T>, warm_g))
 
@@ -134,14 +127,14 @@ struct Work {
   T* aref;  // [MAXROW]
   T* Jaref; // [MAXROW]
   T* Jv;    // [MAXROW]
-  T* pairbig;    // [MAXPAIR][27] pair tables (K 21, F 6) of an env with more than MAXPAIR_S touching body pairs
-  int* pairbig_i;  // [MAXPAIR] keys + [2 * MAXPAIR] shorts of incidence lists
+  T* pairbig;    // [MAXPAIR][33] pair tables of an env with more than MAXPAIR_S touching body pairs
+  int* pairbig_i;  // [3][MAXPAIR]
   CvxRes<T>* cvx;  // results of this env's convex pairs: its slice of the batch-wide queue (stage kernels), or - fused
                    // forward - the head of the row arrays, which are idle until the constraint rows are made
   EpaMem<T> epa;   // fused forward only: vertices at the tail of the row arrays (the convex kernel has its own polytope)
 };
-constexpr int WORK_REALS = MAXCON * 11 + MAXROW * 3 + MAXPAIR * 28;
-constexpr int WORK_INTS = MAXCON + MAXSURV + 2 * MAXPAIR;
+constexpr int WORK_REALS = MAXCON * 11 + MAXROW * 3 + MAXPAIR * 33;
+constexpr int WORK_INTS = MAXCON + MAXSURV + 3 * MAXPAIR;
 template <class T>
 MM_HD Work<T> make_work(T* reals, int* ints) {
   Work<T> w;
@@ -273,11 +266,7 @@ MM_HD void solve6_local(const T* L, T* x) {  // L -> H[b][b] (factor), x -> vect
   for (int i = 0; i < 6; i++) x[i] = v[i];
 }
 
-// cooperative Cholesky of the rows / columns listed in il[0..n) of the NV x NV matrix A (zero entries skipped).
-// Trailing update of pivot jj: the m = n - jj - 1 remaining rows have 1 .. m entries to update; row r and row m - 1 - r
-// are folded into one work item of m + 1 entries, and each item is cut into P equal shares for P lanes, so that all
-// lanes carry the same load (m^2 / 2G entries instead of the m of the longest row).  Every entry is updated once per
-// pivot by exactly one lane, whatever the split.
+// cooperative Cholesky of the rows / columns listed in il[0..n) of the NV x NV matrix A (zero entries skipped)
 template <class T, int G>
 MM_HDN void chol_factor_list(const Grp<G>& g, T* A, const signed char* il, int n) {
   for (int jj = 0; jj < n; jj++) {
@@ -289,36 +278,26 @@ MM_HDN void chol_factor_list(const Grp<G>& g, T* A, const signed char* il, int n
     for (int ii = jj + 1 + g.lane; ii < n; ii += G) A[il[ii] * NV + j] *= inv;
     if (g.lane == 0) A[j * NV + j] = inv;
     g.sync();
-    const int m = n - jj - 1;
-    if (m <= 0) break;
-    if (m <= 8) {  // few rows left (and always the robot-only system): one row per lane
+    int m = n - jj - 1;  // trailing update, 1 / 2 / 4 lanes per row as in chol_factor
+    int P = G >= 4 * m ? 4 : (G >= 2 * m ? 2 : 1);
+    if (G < 32) P = 1;
+    if (P == 1) {
       for (int ii = jj + 1 + g.lane; ii < n; ii += G) {
         int i = il[ii];
         T lij = A[i * NV + j];
         if (lij == 0) continue;
         for (int kk = jj + 1; kk <= ii; kk++) { int k = il[kk]; A[i * NV + k] -= lij * A[k * NV + j]; }
       }
-      g.sync();
-      continue;
-    }
-    const int F = (m + 1) / 2;                 // folded items
-    const int P = G >= F ? G / F : 1;          // lanes per item
-    for (int f = g.lane / P; f < F; f += (G / P > 0 ? G / P : 1)) {
-      const int h = g.lane % P;
-      const int ra = f, rb = m - 1 - f;        // rows (relative to jj + 1) of this item; ra == rb in the middle
-      const int la = ra + 1, ltot = ra == rb ? la : la + rb + 1;
-      int t0 = (ltot * h) / P, t1 = (ltot * (h + 1)) / P;
-      // share [t0, t1) of the item: positions below la belong to row ra, the others to row rb
-      for (int part = 0; part < 2; part++) {
-        int r = part ? rb : ra;
-        int c0 = part ? (t0 > la ? t0 - la : 0) : t0;
-        int c1 = part ? (t1 > la ? t1 - la : 0) : (t1 < la ? t1 : la);
-        if (part && ra == rb) break;
-        if (c1 <= c0) continue;
-        int ii = jj + 1 + r, i = il[ii];
+    } else {
+      int r = g.lane / P, h = g.lane % P;
+      if (r < m) {
+        int ii = jj + 1 + r, len = ii - jj;
+        int i = il[ii];
         T lij = A[i * NV + j];
-        if (lij == 0) continue;
-        for (int kk = jj + 1 + c0; kk < jj + 1 + c1; kk++) { int k = il[kk]; A[i * NV + k] -= lij * A[k * NV + j]; }
+        if (lij != 0) {
+          int c0 = jj + 1 + (len * h) / P, c1 = jj + 1 + (len * (h + 1)) / P;
+          for (int kk = c0; kk < c1; kk++) { int k = il[kk]; A[i * NV + k] -= lij * A[k * NV + j]; }
+        }
       }
     }
     g.sync();
@@ -1179,15 +1158,17 @@ MM_HDX void assemble_contacts(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>&
   for (int base = 0; base < ncon; base += G) {
     int c = base + g.lane;
     int head = c < ncon && ((c == 0) || (meta_key(w.cmeta[c - 1]) != meta_key(w.cmeta[c])));
-    npair += tpopc((int)g.ballot(head));
+    npair += g.isum(head);
   }
   if (g.lane == 0) {
     if (npair <= MAXPAIR_S) {
-      s.pairK = s.pairK_s; s.pairF = s.pairF_s; s.pairkey = s.pairkey_s; s.inc = s.inc_s;
+      s.pairK = s.pairK_s; s.pairW = s.pairW_s; s.pairF = s.pairF_s;
+      s.pairkey = s.pairkey_s; s.pairmd = s.pairmd_s; s.pairmb = s.pairmb_s;
     } else {
       s.pairK = reinterpret_cast<T (*)[21]>(w.pairbig);
-      s.pairF = reinterpret_cast<T (*)[6]>(w.pairbig + 21 * MAXPAIR);
-      s.pairkey = w.pairbig_i; s.inc = reinterpret_cast<short*>(w.pairbig_i + MAXPAIR);
+      s.pairW = reinterpret_cast<T (*)[6]>(w.pairbig + 21 * MAXPAIR);
+      s.pairF = reinterpret_cast<T (*)[6]>(w.pairbig + 27 * MAXPAIR);
+      s.pairkey = w.pairbig_i; s.pairmd = w.pairbig_i + MAXPAIR; s.pairmb = w.pairbig_i + 2 * MAXPAIR;
     }
   }
   g.sync();
@@ -1207,43 +1188,15 @@ MM_HDX void assemble_contacts(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>&
       int slot = npair + off + head - 1;
       if (slot >= MAXPAIR) slot = MAXPAIR - 1;  // unreachable: MAXPAIR covers every (class, class) key of the model
       w.cmeta[c] = (m & ~127) | slot;
-      if (head && npair + off < MAXPAIR) s.pairkey[npair + off] = key;
+      if (head && npair + off < MAXPAIR) {
+        int mA = dofmask(key & 15), mB = dofmask((key >> 4) & 15);
+        s.pairkey[npair + off] = key; s.pairmd[npair + off] = mA ^ mB; s.pairmb[npair + off] = mB;
+      }
     }
     npair += tot;
   }
   if (npair > MAXPAIR) { npair = MAXPAIR; if (g.lane == 0) s.overflow |= 4; }
   if (g.lane == 0) { s.ncon = ncon; s.npair = npair; }
-  g.sync();
-  // incidence lists body -> touching pairs (pair order kept inside a list): count, offsets, fill.  The counts are
-  // parked in the (not yet used) body-wrench rows.
-  int* cnt = reinterpret_cast<int*>(&s.bodyF[0][0]);
-  for (int b = g.lane; b < NCLS; b += G) {
-    int c = 0;
-    if (b > 0) for (int p = 0; p < npair; p++) { int key = s.pairkey[p]; c += ((key & 15) == b) + (((key >> 4) & 15) == b); }
-    cnt[b] = c;
-  }
-  g.sync();
-  for (int b = g.lane; b <= NCLS; b += G) {
-    int st = 0;
-    for (int k = 0; k < b; k++) st += cnt[k];
-    s.incst[b] = (unsigned char)st;
-  }
-  if (g.lane == 0) {  // bodies with at least one touching pair; bit 0: some robot body (classes 1 .. 9) is among them
-    int act = 0;
-    for (int b = 1; b < NCLS; b++) if (cnt[b]) act |= 1 << b;
-    if (act & 0x3FE) act |= 1;
-    s.bodyact = act;
-  }
-  g.sync();
-  for (int b = g.lane; b < NCLS; b += G) {
-    if (b == 0) continue;
-    int o = s.incst[b];
-    for (int p = 0; p < npair; p++) {
-      int key = s.pairkey[p];
-      if ((key & 15) == b) s.inc[o++] = (short)p;
-      if (((key >> 4) & 15) == b) s.inc[o++] = (short)(p | 256);
-    }
-  }
   g.sync();
 }
 
@@ -1262,7 +1215,7 @@ MM_HDX void collide(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<
   g.sync();
   // EPA polytope: faces, their index words, horizon edges and canonical vertex ids live in SHARED memory (the H /
   // tmp6 / pair-block region, free during collision); vertices stay in the global workspace.
-  static_assert(sizeof(s.H) + sizeof(s.tmp6) + sizeof(s.pairK_s) + sizeof(s.pairF_s) + sizeof(s.bodyV) + sizeof(s.bodyF) + sizeof(s.bodyK) >=
+  static_assert(sizeof(s.H) + sizeof(s.tmp6) + sizeof(s.pairK_s) + sizeof(s.pairW_s) + sizeof(s.pairF_s) + 5 * sizeof(s.qacc) >=
                     EPA_MAXF * 4 * sizeof(T) + EPA_INTS * sizeof(int), "EPA workspace does not fit the shared scratch");
   EpaMem<T> em;
   em.vert = w.epa.vert;
@@ -1280,30 +1233,21 @@ MM_HDX void collide(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<
 // ------------------------------------------------------------------------------------------------
 // matrix-free Jacobian products through body-pair twists / wrenches
 // ------------------------------------------------------------------------------------------------
-// twist of every body under the dof vector x (world origin coordinates): prefix sums along the arm, the two fingers
-// branch off the hand, the cubes are free.  s.bodyV[0] (static bodies) stays zero.
 template <class T, int G>
-MM_HDN void body_twists(const Grp<G>& g, Scratch<T>& s, const T* x) {
-  const int act = s.bodyact;
-  for (int it = g.lane; it < 6 + 18; it += G) {
-    if (it < 6) {
-      int c = it;
-      T acc = 0;
-      s.bodyV[0][c] = 0;
-      if (!(act & 1)) continue;
-#pragma unroll
-      for (int k = 0; k < NARM; k++) { acc += s.S[k][c] * x[k]; s.bodyV[k + 1][c] = acc; }
-      s.bodyV[8][c] = acc + s.S[7][c] * x[7];
-      s.bodyV[9][c] = acc + s.S[8][c] * x[8];
-    } else {
-      int j = (it - 6) / 6, c = (it - 6) % 6;
-      if (!((act >> (CLS_CUBE0 + j)) & 1)) continue;
-      const T* xq = x + NROB + 6 * j;
-      T acc = c >= 3 ? xq[c - 3] : (T)0;  // translational dofs: unit axes
-#pragma unroll
-      for (int k = 0; k < 3; k++) acc += s.S[NROB + 3 * j + k][c] * xq[3 + k];
-      s.bodyV[CLS_CUBE0 + j][c] = acc;
+MM_HDN void pair_twists(const Grp<G>& g, Scratch<T>& s, const T* x) {
+  int np = s.npair;
+  for (int idx = g.lane; idx < np * 6; idx += G) {
+    int p = idx / 6, c = idx % 6;
+    unsigned md = (unsigned)s.pairmd[p];  // dofs shared by both bodies cancel
+    int mB = s.pairmb[p];
+    T acc = 0;
+    while (md) {  // ascending dof order
+      int i = tctz(md);
+      md &= md - 1;
+      T sg = ((mB >> i) & 1) ? (T)1 : (T)-1;
+      acc += sg * x[i] * S_comp(s, i, c);
     }
+    s.pairW[p][c] = acc;
   }
   g.sync();
 }
@@ -1319,17 +1263,13 @@ MM_HD void load_con(const Work<T>& w, int c, ConGeom<T>& q) {
 // rows of J*x for every contact (out[c*6 + r]) and special row (outspec[k])
 template <class T, int G>
 MM_HDN void mulJ(const Grp<G>& g, Scratch<T>& s, const Work<T>& w, const T* x, T* out, T* outspec) {
-  body_twists<T, G>(g, s, x);
+  pair_twists<T, G>(g, s, x);
   int ncon = s.ncon;
   for (int c = g.lane; c < ncon; c += G) {
     ConGeom<T> q;
     load_con(w, c, q);
     int m = w.cmeta[c];
-    const T* VA = s.bodyV[(m >> META_KEY_SHIFT) & 15];
-    const T* VB = s.bodyV[(m >> (META_KEY_SHIFT + 4)) & 15];
-    T W[6];
-#pragma unroll
-    for (int d = 0; d < 6; d++) W[d] = VB[d] - VA[d];  // relative twist of the pair: body B against body A
+    const T* W = s.pairW[meta_slot(m)];
     T u[3];
     cross3(u, W, q.pos);
     for (int d = 0; d < 3; d++) u[d] += W[3 + d];
@@ -1479,24 +1419,28 @@ MM_HDN T update_constraint(const Grp<G>& g, Scratch<T>& s, Work<T>& w, bool buil
       int old = (m >> META_ACT_SHIFT) & 63;
       if (old != bits) { chg = 1; w.cmeta[c] = (m & ~(63 << META_ACT_SHIFT)) | (bits << META_ACT_SHIFT); }
     }
-    // segmented inclusive scan over lanes (keys are non-decreasing); segment tails commit
-    if (G > 1) {
+    // segmented inclusive scan over the lanes of a warp (keys are non-decreasing); segment tails commit.  A group that
+    // spans several warps (Grp<128>) commits warp after warp, so that a run cut by a warp boundary adds up in order.
+    constexpr int WL = Grp<G>::WL;
+    if (WL > 1) {
 #pragma unroll 1
-      for (int o = 1; o < G; o <<= 1) {
-        int ks = g.shfl_up(slot, o);
-        bool take = g.lane >= o && ks == slot;
-        if (!g.any(take)) break;  // slots are sorted: no run is longer than o
-        for (int d = 0; d < 6; d++) { T t = g.shfl_up(F[d], o); if (take) F[d] += t; }
-        if (buildK) for (int k = 0; k < 21; k++) { T t = g.shfl_up(Kc[k], o); if (take) Kc[k] += t; }
+      for (int o = 1; o < WL; o <<= 1) {
+        int ks = g.wshfl_up(slot, o);
+        bool take = g.wlane() >= o && ks == slot;
+        if (!g.wany(take)) break;  // slots are sorted: no run is longer than o
+        for (int d = 0; d < 6; d++) { T t = g.wshfl_up(F[d], o); if (take) F[d] += t; }
+        if (buildK) for (int k = 0; k < 21; k++) { T t = g.wshfl_up(Kc[k], o); if (take) Kc[k] += t; }
       }
     }
-    int nxt = g.shfl_down(slot, 1);
-    bool tail = valid && (G == 1 || g.lane == G - 1 || nxt != slot);
-    if (tail) {
-      for (int d = 0; d < 6; d++) s.pairF[slot][d] += F[d];
-      if (buildK) for (int k = 0; k < 21; k++) s.pairK[slot][k] += Kc[k];
+    int nxt = g.wshfl_down(slot, 1);
+    bool tail = valid && (WL == 1 || g.wlane() == WL - 1 || nxt != slot);
+    for (int wq = 0; wq < Grp<G>::nwarps(); wq++) {
+      if (tail && g.warp() == wq) {
+        for (int d = 0; d < 6; d++) s.pairF[slot][d] += F[d];
+        if (buildK) for (int k = 0; k < 21; k++) s.pairK[slot][k] += Kc[k];
+      }
+      g.sync();
     }
-    g.sync();
   }
   // special rows
   for (int k = g.lane; k < s.nspec; k += G) {
@@ -1505,34 +1449,12 @@ MM_HDN T update_constraint(const Grp<G>& g, Scratch<T>& s, Work<T>& w, bool buil
   }
   cost = g.sum(cost);
   *changed = g.any(chg);
-  // qfrc_constraint = J^T f through the bodies: pair p pushes body B with +F_p and body A with -F_p ...
-  const int act = s.bodyact;
-  for (int it = g.lane; it < (NCLS - 1) * 6; it += G) {
-    int b = 1 + it / 6, c = it % 6;
-    if (!((act >> b) & 1)) { if (b < CLS_CUBE0 && (act & 1)) s.bodyF[b][c] = 0; continue; }
-    T acc = 0;
-    for (int k = s.incst[b]; k < s.incst[b + 1]; k++) {
-      int e = s.inc[k];
-      T f = s.pairF[e & 255][c];
-      acc += (e & 256) ? f : -f;
-    }
-    s.bodyF[b][c] = acc;
-  }
-  g.sync();
-  // ... dof i of the arm carries every body behind it: subtree sums (bodyF[i + 1] <- bodies i + 1 .. 9)
-  if (act & 1) {
-    for (int c = g.lane; c < 6; c += G) {
-      T acc = s.bodyF[7][c] + s.bodyF[8][c] + s.bodyF[9][c];
-      s.bodyF[7][c] = acc;
-#pragma unroll
-      for (int k = 6; k >= 1; k--) { acc += s.bodyF[k][c]; s.bodyF[k][c] = acc; }
-    }
-    g.sync();
-  }
+  // qfrc_constraint
   for (int i = g.lane; i < NV; i += G) {
     T acc = 0;
-    if (i < NROB) { if (act & 1) acc = dot6(s.S[i], s.bodyF[i + 1]); }
-    else if ((act >> (CLS_CUBE0 + (i - NROB) / 6)) & 1) acc = S_dot(s, i, s.bodyF[CLS_CUBE0 + (i - NROB) / 6]);
+    for (int p = 0; p < np; p++) {
+      if ((s.pairmd[p] >> i) & 1) acc += (((s.pairmb[p] >> i) & 1) ? (T)1 : (T)-1) * S_dot(s, i, s.pairF[p]);
+    }
     for (int k = 0; k < s.nspec; k++) {
       int d = s.specdof[k];
       T ja = s.specJaref[k];
@@ -1577,33 +1499,16 @@ MM_HDN void analyse_coupling(const Grp<G>& g, Scratch<T>& s) {
   g.sync();
 }
 
-// symmetric packed 6x6 (lower, row-major): K[a][b] = K[a (a + 1) / 2 + b], b <= a
-template <class T>
-MM_HD T ksym(const T* K, int a, int b) { return a >= b ? K[a * (a + 1) / 2 + b] : K[b * (b + 1) / 2 + a]; }
-
-// H = M + J^T D J over the active rows; then factor in place.  J^T D J is assembled BODY-wise, the way CRBA assembles
-// the mass matrix: with V_b the twist of body b, a pair p = (A, B) adds (V_B - V_A)^T K_p (V_B - V_A)
-//   = V_B^T K_p V_B + V_A^T K_p V_A - 2 V_A^T K_p V_B.
-// The first two terms of all pairs are one block per body (bodyK), composite along the arm (dof i moves every body
-// behind it), so the robot block is S_i^T Kc_max(i,j) S_j; the cross term exists only for pairs of two MOVING bodies
-// (finger - cube, cube - cube, link - link), which are few.  Static - moving pairs, the many, cost nothing per pair.
+// H = M + J^T D J over the active rows, assembled from the per-pair blocks; then factor in place
 template <class T, int G>
 MM_HDN void build_factor_H(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md) {
-  const int act = s.bodyact;  // bodies without a touching pair (and the whole arm, when it touches nothing) are skipped
-  for (int it = g.lane; it < (NCLS - 1) * 21; it += G) {
-    int b = 1 + it / 21, k = it % 21;
-    if (!((act >> b) & 1)) { if (b < CLS_CUBE0 && (act & 1)) s.bodyK[b][k] = 0; continue; }
-    T acc = 0;
-    for (int q = s.incst[b]; q < s.incst[b + 1]; q++) acc += s.pairK[s.inc[q] & 255][k];
-    s.bodyK[b][k] = acc;
-  }
-  for (int e = g.lane; e < NV * NV; e += G) {
-    int i = e / NV, j = e - i * NV;
-    if (j > i) continue;
+  for (int e = g.lane; e < NV * (NV + 1) / 2; e += G) {
+    int i, j;
+    tri_rc<T>(e, &i, &j);
     T v = 0;
     if (i < NROB) v = s.Mr[i * NROB + j];
     else if (i == j) v = ((i - 9) % 6) < 3 ? md.cube_mass : md.cube_inertia;
-    s.H[e] = v;
+    s.H[i * NV + j] = v;
   }
   g.sync();
   if (g.lane == 0) {
@@ -1614,74 +1519,34 @@ MM_HDN void build_factor_H(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md
       else if (s.specJaref[k] < 0) s.H[(d & 255) * (NV + 1)] += D;
     }
   }
-  // composite blocks along the arm: bodyK[i + 1] <- bodies i + 1 .. 9 (the block dof i sees); fingers keep their own
-  if (act & 1) {
-    for (int k = g.lane; k < 21; k += G) {
-      T acc = s.bodyK[7][k] + s.bodyK[8][k] + s.bodyK[9][k];
-      s.bodyK[7][k] = acc;
-#pragma unroll
-      for (int b = 6; b >= 1; b--) { acc += s.bodyK[b][k]; s.bodyK[b][k] = acc; }
-    }
-    g.sync();
-  }
-  // T_j = Kc(j) S_j for every dof of a touching body
-  for (int it = g.lane; it < NV * 6; it += G) {
-    int j = it / 6, a = it - 6 * j;
-    int body = j < NROB ? j + 1 : CLS_CUBE0 + (j - NROB) / 6;
-    if (!((act >> (j < NROB ? 0 : body)) & 1)) continue;
-    const T* K = s.bodyK[body];
-    T acc = 0;
-#pragma unroll
-    for (int b = 0; b < 6; b++) acc += ksym(K, a, b) * S_comp(s, j, b);
-    s.tmp6[j][a] = acc;
-  }
-  g.sync();
-  for (int e = g.lane; e < NROB * NROB + 3 * 36; e += G) {
-    int i, j;
-    if (e < NROB * NROB) {  // robot block: the deeper dof's composite block; the two fingers do not see each other
-      if (!(act & 1)) continue;
-      i = e / NROB; j = e - i * NROB;
-      if (j > i || (i == 8 && j == 7)) continue;
-    } else {
-      int r = e - NROB * NROB, c = r / 36;
-      if (!((act >> (CLS_CUBE0 + c)) & 1)) continue;
-      r -= 36 * c;
-      int k = r / 6, l = r - 6 * k;
-      if (l > k) continue;
-      i = NROB + 6 * c + k; j = NROB + 6 * c + l;
-    }
-    s.H[i * NV + j] += S_dot(s, j, s.tmp6[i]);
-  }
-  // cross terms of the pairs between two moving bodies, one pair at a time
   for (int p = 0; p < s.npair; p++) {
-    int key = s.pairkey[p], ca = key & 15, cb = (key >> 4) & 15;
-    if (ca == 0 || cb == 0) continue;
-    const int mA = dofmask(ca), mB = dofmask(cb);
+    int mB = s.pairmb[p];
+    int mm_ = s.pairmd[p];  // dofs shared by both bodies cancel (sigma = 0)
     const T* K = s.pairK[p];
     g.sync();
+    // dofs of this pair in ascending order (rank = number of lower set bits), and u_k = sigma K S
     for (int j = g.lane; j < NV; j += G) {
-      if ((mA >> j) & 1) s.dla[tpopc(mA & ((1 << j) - 1))] = (signed char)j;
-      if (!((mB >> j) & 1)) continue;
-      int k = tpopc(mB & ((1 << j) - 1));
+      if (!((mm_ >> j) & 1)) continue;
+      int k = tpopc(mm_ & ((1 << j) - 1));
       s.dl[k] = (signed char)j;
-#pragma unroll
+      T S[6];
+      S_get(s, j, S);
+      T sg = ((mB >> j) & 1) ? (T)1 : (T)-1;
+      // symmetric packed K (lower, row-major): K[a][b] = K[a*(a+1)/2 + b], b <= a
       for (int a = 0; a < 6; a++) {
         T acc = 0;
-#pragma unroll
-        for (int b = 0; b < 6; b++) acc += ksym(K, a, b) * S_comp(s, j, b);
-        s.tmp6[k][a] = acc;
+        for (int b = 0; b < 6; b++) acc += (a >= b ? K[a * (a + 1) / 2 + b] : K[b * (b + 1) / 2 + a]) * S[b];
+        s.tmp6[k][a] = sg * acc;
       }
     }
     g.sync();
-    const int nA = tpopc(mA), nB = tpopc(mB), both = mA & mB;
-    for (int it = g.lane; it < nA * nB; it += G) {
-      int ia = it / nB, kb = it - ia * nB;
-      int i = s.dla[ia], j = s.dl[kb];
-      bool twice = ((both >> i) & 1) && ((both >> j) & 1);  // (i, j) and (j, i) meet in one entry: taken once, doubled
-      if (twice && i < j) continue;
-      T v = S_dot(s, i, s.tmp6[kb]);
-      int hi = i > j ? i : j, lo = i > j ? j : i;
-      s.H[hi * NV + lo] -= twice ? 2 * v : v;
+    int nd = tpopc(mm_);
+    for (int e = g.lane; e < nd * (nd + 1) / 2; e += G) {
+      int a, b;
+      tri_rc<T>(e, &a, &b);
+      int i = s.dl[a], j = s.dl[b];
+      T sg = ((mB >> i) & 1) ? (T)1 : (T)-1;
+      s.H[i * NV + j] += sg * S_dot(s, i, s.tmp6[b]);
     }
   }
   g.sync();

@@ -240,7 +240,8 @@ MM_HDN bool state_bad(const Grp<G>& g, const Scratch<T>& s) {
 // ------------------------------------------------------------------------------------------------
 // One PickPlaceGymEnv.step (gym_env.py:536-581) as a sequence of batch-wide STAGES.  The 16 x (IK, mj_step) +
 // trailing mj_forward of an env are 17 rounds of
-//   stage A  (group per env)   [first round: load state, decode action]  IK -> position + velocity stage
+//   stage A  (group per env)   [first round: load state, decode action; later rounds: fused behind stage C of the
+//                              round before, same kernel]  IK -> position + velocity stage
 //                              (kinematics, CRBA, RNEA, actuation, qacc_smooth) -> broad phase -> box / plane
 //                              narrow phase -> the env's convex candidates are pushed on the batch-wide queue
 //   convex   (warp per PAIR)   GJK + EPA of every queued (env, geom pair): a pile-up env's 25 hull pairs run on 25
@@ -259,6 +260,15 @@ struct CvxQueue {
   int* count;        // items pushed in this round
   int* head;         // next item to be taken (convex kernel)
   int cap;
+};
+
+// contact-rich envs of a round: stage A lists them, and stage C runs them with a whole CTA each (Grp<128>) next to the
+// warp-per-env launch of the others
+struct HeavyList {
+  unsigned char* flag;  // [N] 1 = listed this round (the warp-per-env stage C skips it); null = feature off
+  int* items;           // [cap] env ids
+  int* count;           // listed this round
+  int min_load;         // box contacts + convex candidates from which an env counts as contact-rich
 };
 
 #ifdef __CUDA_ARCH__
@@ -306,20 +316,10 @@ MM_HD void decode_action(Scratch<T>& s, const StatePtrs& st, long e, const float
   s.ctrl[7] = gr > 0.5f ? (T)255 : (T)0;
 }
 
+// stage A on a loaded scratch: IK .. queue push of round `sub`
 template <class T, int G>
-MM_HDN void stage_a(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>& w, const StatePtrs& st, long e, int sub,
-                    const float* action, int mode, char* ctx_base, const CvxQueue<T>& q) {
-  void* ctx = ctx_base + (size_t)e * ctx_stride<T>();
-  if (sub == 0) {
-    load_state<T, G>(g, s, st, e);
-    fk<T, G>(g, s, md);  // state after reset / the previous step's trailing mj_forward
-    if (g.lane == 0) decode_action(s, st, e, action + e * ACTION_STRIDE, mode);
-    g.sync();
-  } else {
-    ctx_copy<T, G>(g, &s, ctx);
-    if (g.lane == 0) s.warm_g = st.warm + e * NV;
-    g.sync();
-  }
+MM_HDN void stage_a_body(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>& w, const StatePtrs& st, long e, int sub,
+                         const CvxQueue<T>& q, const HeavyList& hv) {
   if (sub != ACTION_REPEAT) ik<T, G>(g, s, md);
   reset_bad_state<T, G>(g, s, md, st, e);
   fk<T, G>(g, s, md);
@@ -339,15 +339,43 @@ MM_HDN void stage_a(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<
   CvxItem* items = q.items + qbase;
   const int lim = ncvx, env = (int)e;
   list_convex<T, G>(g, s, gm, w, [=](int k, int ci) { if (k < lim) { items[k].env = env; items[k].ci = ci; } });
-  if (g.lane == 0) { s.qbase = qbase; s.ncvx = ncvx; }
+  if (g.lane == 0) {
+    s.qbase = qbase; s.ncvx = ncvx;
+    if (hv.flag) {
+      int heavy = s.ncon + ncvx >= hv.min_load;
+      hv.flag[e] = (unsigned char)heavy;
+      if (heavy) { int at = MM_ATOMIC_ADD(hv.count, 1); hv.items[at] = (int)e; }
+    }
+  }
   g.sync();
+}
+
+// stage A of round 0 (the later rounds' stage A runs fused behind stage C of the round before, see stage_c)
+template <class T, int G>
+MM_HDN void stage_a(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>& w, const StatePtrs& st, long e, int sub,
+                    const float* action, int mode, char* ctx_base, const CvxQueue<T>& q, const HeavyList& hv) {
+  void* ctx = ctx_base + (size_t)e * ctx_stride<T>();
+  if (sub == 0) {
+    load_state<T, G>(g, s, st, e);
+    fk<T, G>(g, s, md);  // state after reset / the previous step's trailing mj_forward
+    if (g.lane == 0) decode_action(s, st, e, action + e * ACTION_STRIDE, mode);
+    g.sync();
+  } else {
+    ctx_copy<T, G>(g, &s, ctx);
+    if (g.lane == 0) s.warm_g = st.warm + e * NV;
+    g.sync();
+  }
+  stage_a_body<T, G>(g, s, md, w, st, e, sub, q, hv);
   ctx_copy<T, G>(g, ctx, &s);
 }
 
+// Stage C of round `sub`; unless it is the last round, stage A of round sub + 1 follows at once for the same env (no
+// batch-wide barrier and no image round trip between them: `qn` / `hvn` are the NEXT round's queue and list, which
+// alternate between two buffers so that this round's results stay readable for the envs still in stage C).
 template <class T, int G>
 MM_HDN void stage_c(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>& w, const StatePtrs& st, long e, int sub,
-                    char* ctx_base, const CvxQueue<T>& q, int reward_type, int max_steps, const StepOut& out,
-                    const float* tgt_kp_all) {
+                    char* ctx_base, const CvxQueue<T>& q, const CvxQueue<T>& qn, const HeavyList& hvn, int reward_type,
+                    int max_steps, const StepOut& out, const float* tgt_kp_all) {
   void* ctx = ctx_base + (size_t)e * ctx_stride<T>();
   ctx_copy<T, G>(g, &s, ctx);
   if (g.lane == 0) s.warm_g = st.warm + e * NV;
@@ -358,6 +386,7 @@ MM_HDN void stage_c(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<
   solve<T, G>(g, s, md, w);
   if (sub != ACTION_REPEAT) {
     integrate<T, G>(g, s, md);
+    stage_a_body<T, G>(g, s, md, w, st, e, sub + 1, qn, hvn);
     ctx_copy<T, G>(g, ctx, &s);
     return;
   }

@@ -38,6 +38,15 @@ struct Grp {
   // G == 32: literal full mask, so that syncs and shuffles compile to single instructions (a run-time
   // mask makes the compiler emit a MATCH.ANY / vote / divergence-check sequence around every one of them)
   MM_HD unsigned m() const { return G == 32 ? 0xffffffffu : mask; }
+  // warp-scope view of the group (a group never spans warps here; Grp<128> below does)
+  static constexpr int WL = G;  // lanes of the group inside one warp
+  MM_HD int wlane() const { return lane; }
+  MM_HD int warp() const { return 0; }
+  MM_HD static constexpr int nwarps() { return 1; }
+  template <class T> MM_HD T wshfl_up(T v, int o) const { return shfl_up(v, o); }
+  template <class T> MM_HD T wshfl_down(T v, int o) const { return shfl_down(v, o); }
+  MM_HD int wany(int pred) const { return any(pred); }
+
   MM_HD void sync() const {
 #ifdef __CUDA_ARCH__
     if (G > 1) __syncwarp(m());
@@ -151,6 +160,67 @@ struct Grp {
 #endif
   }
 };
+
+// A whole 128-thread CTA on ONE environment (stage C of contact-rich envs, mm_launch.cuh k_stage_c_heavy): loops over
+// contacts / rows / matrix entries spread over four warps, group syncs are CTA barriers, reductions go through a small
+// shared scratch (fixed combination order: deterministic).  Only what stage C uses is provided.
+#if defined(__CUDACC__)
+template <>
+struct Grp<128> {
+  int lane;
+  unsigned mask;
+  double* xs;        // shared scratch of the CTA: [2][4] reduction slots, then [128] exchange slots
+  mutable int par;   // alternating reduction slot set (every thread calls the reductions in the same order)
+  static constexpr int WL = 32;
+  __device__ __forceinline__ unsigned m() const { return 0xffffffffu; }
+  __device__ __forceinline__ int wlane() const { return lane & 31; }
+  __device__ __forceinline__ int warp() const { return lane >> 5; }
+  __device__ __forceinline__ static constexpr int nwarps() { return 4; }
+  __device__ __forceinline__ void sync() const { __syncthreads(); }
+  template <class T> __device__ __forceinline__ T wshfl_up(T v, int o) const { return __shfl_up_sync(0xffffffffu, v, o); }
+  template <class T> __device__ __forceinline__ T wshfl_down(T v, int o) const { return __shfl_down_sync(0xffffffffu, v, o); }
+  __device__ __forceinline__ int wany(int pred) const { return __any_sync(0xffffffffu, pred); }
+  __device__ __forceinline__ int any(int pred) const { return __syncthreads_or(pred) != 0; }
+  template <class T>
+  __device__ __forceinline__ T sum(T v) const {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    T* slot = reinterpret_cast<T*>(xs + 4 * par);
+    if ((lane & 31) == 0) slot[lane >> 5] = v;
+    __syncthreads();
+    T r = (slot[0] + slot[1]) + (slot[2] + slot[3]);
+    par ^= 1;
+    return r;
+  }
+  __device__ __forceinline__ int isum(int v) const { return sum<int>(v); }
+  __device__ __forceinline__ int bcast(int v, int src) const {
+    int* slot = reinterpret_cast<int*>(xs + 4 * par);
+    if (lane == src) slot[0] = v;
+    __syncthreads();
+    int r = slot[0];
+    par ^= 1;
+    return r;
+  }
+  // exclusive prefix sum over the 128 lanes; *total receives the group sum
+  __device__ __forceinline__ int scan_excl(int v, int* total) const {
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if ((lane & 31) >= o) incl += t;
+    }
+    int* slot = reinterpret_cast<int*>(xs + 4 * par);
+    if ((lane & 31) == 31) slot[lane >> 5] = incl;
+    __syncthreads();
+    int w = lane >> 5, before = 0, tot = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { int t = slot[k]; tot += t; if (k < w) before += t; }
+    par ^= 1;
+    *total = tot;
+    return before + incl - v;
+  }
+};
+#endif
 
 // ---- small vector helpers ----------------------------------------------------------------------
 template <class T> MM_HD T dot3(const T* a, const T* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }

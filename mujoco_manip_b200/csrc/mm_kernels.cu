@@ -103,7 +103,12 @@ struct mm_handle {
   void* d_work_reals = nullptr;  // per-env workspace: contacts, survivors, solver rows
   int* d_work_ints = nullptr;
   char* d_ctx = nullptr;         // env images between the stage kernels
-  int convex_grid = 0;
+  int convex_grid = 0, heavy_grid = 0;
+  unsigned char* d_hflag = nullptr;  // [N] contact-rich flag of the current round
+  int* d_h_items = nullptr;          // [nchunk][chunk]
+  int heavy_min = 0;                 // 0 = every env takes the warp-per-env stage C
+  cudaStream_t hside[8] = {};        // sibling streams of `side` for the contact-rich stage C
+  cudaEvent_t ev_x[8] = {}, ev_h[8] = {};
   // chunks of the batch and their convex-pair queues
   long chunk = 0;
   int nchunk = 0, nstream = 0;
@@ -147,7 +152,7 @@ size_t real_bytes(const mm_config* c) { return c->precision ? 4 : 8; }
 
 typedef cudaError_t (*prepare_fn)();
 typedef cudaError_t (*launch_fn)(int, const StepParams&, int, int, cudaStream_t);
-typedef cudaError_t (*resident_fn)(int*);
+typedef cudaError_t (*resident_fn)(int*, int*);
 int inst_index(const mm_config& c) { return (c.precision ? 3 : 0) + (c.group == 32 ? 0 : (c.group == 16 ? 1 : 2)); }
 const prepare_fn PREPARE[6] = {prepare_f64_32, prepare_f64_16, prepare_f64_8, prepare_f32_32, prepare_f32_16, prepare_f32_8};
 const resident_fn RESIDENT[6] = {resident_f64_32, resident_f64_16, resident_f64_8, resident_f32_32, resident_f32_16, resident_f32_8};
@@ -210,7 +215,7 @@ int mm_create(const mm_config* cfg, mm_handle** out) {
     if (upload_model<float>(h) != 0) return -1;
   }
   if (PREPARE[inst_index(h->cfg)]() != cudaSuccess) return fail("mm_create: kernel attribute set-up failed");
-  CK(RESIDENT[inst_index(h->cfg)](&h->convex_grid));
+  CK(RESIDENT[inst_index(h->cfg)](&h->convex_grid, &h->heavy_grid));
   CK(cudaMalloc(&h->d_work_reals, n * WORK_REALS * rb));
   CK(cudaMalloc(&h->d_work_ints, n * WORK_INTS * sizeof(int)));
   size_t cstride = cfg->precision ? ctx_stride<float>() : ctx_stride<double>();
@@ -232,13 +237,21 @@ int mm_create(const mm_config* cfg, mm_handle** out) {
   if (h->nstream > h->nchunk) h->nstream = h->nchunk;
   h->q_cap = (int)(chunk * 64);
   size_t res_bytes = cfg->precision ? sizeof(CvxRes<float>) : sizeof(CvxRes<double>);
-  CK(cudaMalloc(&h->d_q_items, (size_t)h->nchunk * h->q_cap * sizeof(CvxItem)));
-  CK(cudaMalloc(&h->d_q_res, (size_t)h->nchunk * h->q_cap * res_bytes));
-  CK(cudaMalloc(&h->d_q_ctr, (size_t)h->nchunk * 2 * NROUND * sizeof(int)));
+  CK(cudaMalloc(&h->d_q_items, (size_t)h->nchunk * 2 * h->q_cap * sizeof(CvxItem)));
+  CK(cudaMalloc(&h->d_q_res, (size_t)h->nchunk * 2 * h->q_cap * res_bytes));
+  CK(cudaMalloc(&h->d_q_ctr, (size_t)h->nchunk * 4 * NCTR * sizeof(int)));
+  // contact-rich envs (box contacts + convex candidates >= MM_HEAVY, default 40; 0 switches the CTA-per-env path off)
+  h->heavy_min = h->heavy_grid > 0 ? (int)env_long("MM_HEAVY", 40) : 0;
+  CK(cudaMalloc(&h->d_hflag, 2 * n));
+  CK(cudaMemset(h->d_hflag, 0, 2 * n));
+  CK(cudaMalloc(&h->d_h_items, (size_t)h->nchunk * 2 * chunk * sizeof(int)));
   CK(cudaMalloc(&h->d_epa_verts, (size_t)h->nstream * h->convex_grid * MM_WX * EPA_MAXV * 6 * rb));
   for (int i = 0; i < h->nstream; i++) {
     CK(cudaStreamCreateWithFlags(&h->side[i], cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming));
+    CK(cudaStreamCreateWithFlags(&h->hside[i], cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->ev_x[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_h[i], cudaEventDisableTiming));
   }
   CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
   CK(cudaMalloc(&h->d_tgt, n * 4 * sizeof(float)));
@@ -257,11 +270,14 @@ void mm_destroy(mm_handle* h) {
   for (int i = 0; i < h->nstream; i++) {
     if (h->side[i]) cudaStreamDestroy(h->side[i]);
     if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
+    if (h->hside[i]) cudaStreamDestroy(h->hside[i]);
+    if (h->ev_x[i]) cudaEventDestroy(h->ev_x[i]);
+    if (h->ev_h[i]) cudaEventDestroy(h->ev_h[i]);
   }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   cudaFree(h->d_model); cudaFree(h->d_geom); cudaFree(h->d_work_reals); cudaFree(h->d_work_ints); cudaFree(h->d_ctx);
   cudaFree(h->d_q_items); cudaFree(h->d_q_res);
-  cudaFree(h->d_q_ctr); cudaFree(h->d_epa_verts); cudaFree(h->d_tgt);
+  cudaFree(h->d_q_ctr); cudaFree(h->d_epa_verts); cudaFree(h->d_tgt); cudaFree(h->d_hflag); cudaFree(h->d_h_items);
   cudaFree(h->d_actions); cudaFree(h->d_obs); cudaFree(h->d_reward); cudaFree(h->d_flags);
   delete h;
 }
@@ -306,8 +322,9 @@ int mm_step(mm_handle* h, const mm_state* st, const float* actions, int action_m
   const launch_fn launch = LAUNCH[inst_index(h->cfg)];
   const size_t rb = real_bytes(&h->cfg);
   const size_t res_bytes = h->cfg.precision ? sizeof(CvxRes<float>) : sizeof(CvxRes<double>);
-  CK(cudaMemsetAsync(h->d_q_ctr, 0, (size_t)h->nchunk * 2 * NROUND * sizeof(int), main));
-  const bool forked = h->nstream > 1;
+  CK(cudaMemsetAsync(h->d_q_ctr, 0, (size_t)h->nchunk * 4 * NCTR * sizeof(int), main));
+  // (with the contact-rich path on, even a single chunk runs on a side stream: its sibling stream needs one to pair with)
+  const bool forked = h->nstream > 1 || h->heavy_min > 0;
   if (forked) {
     CK(cudaEventRecord(h->ev_fork, main));
     for (int i = 0; i < h->nstream; i++) CK(cudaStreamWaitEvent(h->side[i], h->ev_fork, 0));
@@ -319,17 +336,30 @@ int mm_step(mm_handle* h, const mm_state* st, const float* actions, int action_m
     StepParams pc = p;
     pc.slot0 = (long)c * h->chunk;
     pc.nslot = pc.slot0 + h->chunk <= p.n ? h->chunk : p.n - pc.slot0;
-    pc.q_items = (char*)h->d_q_items + (size_t)c * h->q_cap * sizeof(CvxItem);
-    pc.q_res = (char*)h->d_q_res + (size_t)c * h->q_cap * res_bytes;
-    pc.q_count = h->d_q_ctr + (size_t)c * 2 * NROUND;
-    pc.q_head = pc.q_count + NROUND;
+    pc.q_items = (char*)h->d_q_items + (size_t)c * 2 * h->q_cap * sizeof(CvxItem);
+    pc.q_res = (char*)h->d_q_res + (size_t)c * 2 * h->q_cap * res_bytes;
+    pc.q_count = h->d_q_ctr + (size_t)c * 4 * NCTR;
+    pc.q_head = pc.q_count + NCTR;
+    pc.h_count = pc.q_count + 2 * NCTR;
+    pc.h_head = pc.q_count + 3 * NCTR;
+    pc.hflag = h->heavy_min > 0 ? h->d_hflag : nullptr;
+    pc.h_items = h->d_h_items + (size_t)c * 2 * h->chunk;
+    pc.h_cap = (int)h->chunk;
+    pc.heavy_min = h->heavy_min;
     pc.epa_verts = (char*)h->d_epa_verts + (size_t)si * h->convex_grid * MM_WX * EPA_MAXV * 6 * rb;
+    CK(launch(0, pc, 0, 0, s));  // stage A of round 0; the later rounds' stage A runs fused behind stage C
     for (int sub = 0; sub < NROUND; sub++) {
-      CK(launch(0, pc, sub, 0, s));
       CK(launch(1, pc, sub, h->convex_grid, s));
+      if (h->heavy_min > 0) {  // contact-rich envs: a CTA each, next to the warp-per-env launch of the others
+        CK(cudaEventRecord(h->ev_x[si], s));
+        CK(cudaStreamWaitEvent(h->hside[si], h->ev_x[si], 0));
+        CK(launch(5, pc, sub, h->heavy_grid, h->hside[si]));
+        CK(cudaEventRecord(h->ev_h[si], h->hside[si]));
+      }
       CK(launch(2, pc, sub, 0, s));
+      if (h->heavy_min > 0) CK(cudaStreamWaitEvent(s, h->ev_h[si], 0));
     }
-    h->launches += 3 * NROUND;
+    h->launches += 1 + (h->heavy_min > 0 ? 3 : 2) * NROUND;
   }
   if (forked)
     for (int i = 0; i < h->nstream; i++) {

@@ -42,6 +42,7 @@ namespace mm {
 template <int G> constexpr int warps_c() { return G == 8 ? (MM_WC > 2 ? 2 : MM_WC) : MM_WC; }
 constexpr int MAX_CHUNKS = 64;
 constexpr int NROUND = ACTION_REPEAT + 1;
+constexpr int NCTR = NROUND + 1;  // counters per kind and chunk (the last round's fused stage A does not exist: spare slot)
 
 struct StepParams {
   StatePtrs st;
@@ -55,9 +56,16 @@ struct StepParams {
   // convex-pair queue of this chunk
   void* q_items;
   void* q_res;
-  int* q_count;       // [NROUND]
-  int* q_head;        // [NROUND]
+  int* q_count;       // [NROUND + 1]
+  int* q_head;        // [NROUND + 1]
   int q_cap;
+  // contact-rich envs of this chunk (stage C by a whole CTA each)
+  unsigned char* hflag;   // [2][N] or null (two buffers alternate between the rounds, like the queue)
+  int* h_items;           // [2][h_cap]
+  int h_cap;
+  int* h_count;           // [NROUND]
+  int* h_head;            // [NROUND]
+  int heavy_min;
   // per-warp EPA vertex storage of the convex kernel
   void* epa_verts;    // [grid_x * MM_WX][EPA_MAXV * 6]
   float* tgt_kp;
@@ -85,13 +93,22 @@ __device__ __forceinline__ void setup_group(Grp<G>& g) {
 
 template <class T>
 __device__ __forceinline__ CvxQueue<T> queue_of(const StepParams& p, int sub) {
-  CvxQueue<T> q;
-  q.items = reinterpret_cast<CvxItem*>(p.q_items);
-  q.res = reinterpret_cast<CvxRes<T>*>(p.q_res);
+  CvxQueue<T> q;  // two buffers alternate between the rounds (stage C of round r reads, the fused stage A of r + 1 writes)
+  q.items = reinterpret_cast<CvxItem*>(p.q_items) + (size_t)(sub & 1) * p.q_cap;
+  q.res = reinterpret_cast<CvxRes<T>*>(p.q_res) + (size_t)(sub & 1) * p.q_cap;
   q.count = p.q_count + sub;
   q.head = p.q_head + sub;
   q.cap = p.q_cap;
   return q;
+}
+
+__device__ __forceinline__ HeavyList heavy_of(const StepParams& p, int sub) {
+  HeavyList hv;
+  hv.flag = p.hflag ? p.hflag + (size_t)(sub & 1) * p.n : nullptr;
+  hv.items = p.h_items + (size_t)(sub & 1) * p.h_cap;
+  hv.count = p.h_count + sub;
+  hv.min_load = p.heavy_min;
+  return hv;
 }
 
 template <class T>
@@ -115,7 +132,7 @@ __global__ void __launch_bounds__(32 * W, MM_MINB_A) k_stage_a(StepParams p, int
   long long t0 = clock64();
   Scratch<T>& s = *reinterpret_cast<Scratch<T>*>(smem + gi * scratch_a_bytes<T>());
   Work<T> w = work_of<T>(p, e);
-  stage_a<T, G>(g, s, *md, w, p.st, e, sub, p.actions, p.mode, p.ctx, queue_of<T>(p, sub));
+  stage_a<T, G>(g, s, *md, w, p.st, e, sub, p.actions, p.mode, p.ctx, queue_of<T>(p, sub), heavy_of(p, sub));
   if (g.lane == 0) {
     long long dt = clock64() - t0;
     if (p.work) p.work[e] = (sub == 0 ? 0 : p.work[e]) + (int)(dt >> 8);
@@ -134,16 +151,55 @@ __global__ void __launch_bounds__(32 * W, MM_MINB_C) k_stage_c(StepParams p, int
   if (slot >= p.nslot) return;
   slot += p.slot0;
   long e = p.order ? p.order[slot] : slot;
+  if (p.hflag && p.hflag[(size_t)(sub & 1) * p.n + e]) return;  // contact-rich env: k_stage_c_heavy runs it
   long long t0 = clock64();
   Scratch<T>& s = *reinterpret_cast<Scratch<T>*>(smem + gi * scratch_c_bytes<T>());
   Work<T> w = work_of<T>(p, e);
-  stage_c<T, G>(g, s, *md, w, p.st, e, sub, p.ctx, queue_of<T>(p, sub), p.reward_type, p.max_steps, p.out, p.tgt_kp);
+  stage_c<T, G>(g, s, *md, w, p.st, e, sub, p.ctx, queue_of<T>(p, sub), queue_of<T>(p, sub + 1), heavy_of(p, sub + 1),
+                p.reward_type, p.max_steps, p.out, p.tgt_kp);
   if (g.lane == 0) {
     long long dt = clock64() - t0;
     if (p.work) p.work[e] += (int)(dt >> 8);
     if (p.cycles) { p.cycles[9 * e + 3] += dt; p.cycles[9 * e] += dt; }
   }
 }
+
+// stage C of the contact-rich envs of a round: persistent 128-thread CTAs, one env at a time per CTA (Grp<128>)
+#ifndef MM_MINB_H
+#define MM_MINB_H 3
+#endif
+template <class T>
+__global__ void __launch_bounds__(128, MM_MINB_H) k_stage_c_heavy(StepParams p, int sub) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  Grp<128> g;
+  g.lane = threadIdx.x;
+  g.mask = 0xffffffffu;
+  g.xs = reinterpret_cast<double*>(smem + scratch_c_bytes<T>());
+  g.par = 0;
+  const ModelDev<T>* md = reinterpret_cast<const ModelDev<T>*>(p.model);
+  Scratch<T>& s = *reinterpret_cast<Scratch<T>*>(smem);
+  __shared__ int s_item;
+  const int count = p.h_count[sub];
+  while (true) {
+    if (threadIdx.x == 0) s_item = atomicAdd(p.h_head + sub, 1);
+    __syncthreads();
+    int i = s_item;
+    __syncthreads();
+    if (i >= count) break;
+    long e = p.h_items[(size_t)(sub & 1) * p.h_cap + i];
+    long long t0 = clock64();
+    Work<T> w = work_of<T>(p, e);
+    stage_c<T, 128>(g, s, *md, w, p.st, e, sub, p.ctx, queue_of<T>(p, sub), queue_of<T>(p, sub + 1), heavy_of(p, sub + 1),
+                    p.reward_type, p.max_steps, p.out, p.tgt_kp);
+    if (g.lane == 0) {
+      long long dt = clock64() - t0;
+      if (p.work) p.work[e] += (int)(dt >> 8);
+      if (p.cycles) { p.cycles[9 * e + 3] += dt; p.cycles[9 * e] += dt; }
+    }
+    __syncthreads();
+  }
+}
+template <class T> size_t smem_h() { return scratch_c_bytes<T>() + (8 + 128) * sizeof(double); }
 
 // convex stage: persistent warps take (env, geom pair) items off the queue of this round
 template <class T>
@@ -238,14 +294,18 @@ cudaError_t inst_prepare() {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_convex<T, MM_WX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x<T>());
   if (e != cudaSuccess) return e;
+  if (G == 32) {
+    e = cudaFuncSetAttribute(k_stage_c_heavy<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h<T>());
+    if (e != cudaSuccess) return e;
+  }
   e = cudaFuncSetAttribute(k_ops<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c<T, G>());
   if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(k_reset<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c<T, G>());
 }
 
-// grid of the persistent convex kernel of this instantiation: every CTA that can be resident
+// grids of the persistent kernels of this instantiation (convex stage, contact-rich stage C): every CTA that can be resident
 template <class T, int G>
-cudaError_t inst_resident(int* convex_grid) {
+cudaError_t inst_resident(int* convex_grid, int* heavy_grid) {
   int dev = 0, sms = 0, per = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
@@ -254,10 +314,17 @@ cudaError_t inst_resident(int* convex_grid) {
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_convex<T, MM_WX>, 32 * MM_WX, smem_x<T>());
   if (e != cudaSuccess) return e;
   *convex_grid = (per > 0 ? per : 1) * sms;
+  *heavy_grid = 0;
+  if (G == 32) {
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_stage_c_heavy<T>, 128, smem_h<T>());
+    if (e != cudaSuccess) return e;
+    *heavy_grid = (per > 0 ? per : 1) * sms;
+  }
   return cudaSuccess;
 }
 
-// which: 0 = stage A of round `sub`, 1 = convex stage, 2 = stage C, 3 = reset, 4 = ops.  `grid_x`: convex grid.
+// which: 0 = stage A of round `sub`, 1 = convex stage, 2 = stage C, 3 = reset, 4 = ops, 5 = stage C of the
+// contact-rich envs.  `grid_x`: grid of the persistent kernels (1, 5).
 template <class T, int G>
 cudaError_t inst_launch(int which, const StepParams& p, int sub, int grid_x, cudaStream_t s) {
   if (which == 0) {
@@ -268,6 +335,8 @@ cudaError_t inst_launch(int which, const StepParams& p, int sub, int grid_x, cud
   } else if (which == 2) {
     constexpr int EPB = 32 * warps_c<G>() / G;
     k_stage_c<T, G, warps_c<G>()><<<(unsigned)((p.nslot + EPB - 1) / EPB), 32 * warps_c<G>(), smem_c<T, G>(), s>>>(p, sub);
+  } else if (which == 5) {
+    if (G == 32) k_stage_c_heavy<T><<<(unsigned)grid_x, 128, smem_h<T>(), s>>>(p, sub);
   } else {
     constexpr int EPB = FusedCfg<T, G>::ENVS;
     unsigned grid = (unsigned)((p.n + EPB - 1) / EPB);
@@ -280,7 +349,7 @@ cudaError_t inst_launch(int which, const StepParams& p, int sub, int grid_x, cud
 // entry points defined by the mm_inst_*.cu units
 #define MM_DECL_INST(NAME)                 \
   cudaError_t prepare_##NAME();            \
-  cudaError_t resident_##NAME(int* convex_grid); \
+  cudaError_t resident_##NAME(int* convex_grid, int* heavy_grid); \
   cudaError_t launch_##NAME(int which, const StepParams& p, int sub, int grid_x, cudaStream_t s);
 MM_DECL_INST(f64_32) MM_DECL_INST(f64_16) MM_DECL_INST(f64_8)
 MM_DECL_INST(f32_32) MM_DECL_INST(f32_16) MM_DECL_INST(f32_8)
@@ -288,7 +357,7 @@ MM_DECL_INST(f32_32) MM_DECL_INST(f32_16) MM_DECL_INST(f32_8)
 #define MM_DEFINE_INST(NAME, T, G)                                                              \
   namespace mm {                                                                                \
   cudaError_t prepare_##NAME() { return inst_prepare<T, G>(); }                                 \
-  cudaError_t resident_##NAME(int* convex_grid) { return inst_resident<T, G>(convex_grid); } \
+  cudaError_t resident_##NAME(int* convex_grid, int* heavy_grid) { return inst_resident<T, G>(convex_grid, heavy_grid); } \
   cudaError_t launch_##NAME(int which, const StepParams& p, int sub, int grid_x, cudaStream_t s) { return inst_launch<T, G>(which, p, sub, grid_x, s); } \
   }
 

@@ -73,45 +73,47 @@ void do_step(int n, void** sp, const float* actions, int mode, int reward_type, 
   std::vector<int> wei((size_t)n * WORK_INTS);
   std::vector<char> image((size_t)n * ctx_stride<T>());
   const int cap = n * 64;
-  std::vector<CvxItem> items(cap);
-  std::vector<CvxRes<T>> res(cap);
+  std::vector<CvxItem> items(2 * cap);   // two buffers: round r's results are read while round r + 1's items are pushed
+  std::vector<CvxRes<T>> res(2 * cap);
   std::vector<T> everts(EPA_MAXV * 6), eface(EPA_MAXF * 4);
   std::vector<int> eints(EPA_INTS);
   static T bpos[NDB][3], bR[NDB][9];
+  int count[ACTION_REPEAT + 2] = {0}, head[ACTION_REPEAT + 2] = {0};
+  const HeavyList nohv{nullptr, nullptr, nullptr, 0};
+  auto queue = [&](int sub) { return CvxQueue<T>{items.data() + (sub & 1) * cap, res.data() + (sub & 1) * cap, &count[sub], &head[sub], cap}; };
+  auto work = [&](long e) { return make_work(wer.data() + e * WORK_REALS, wei.data() + e * WORK_INTS); };
+  for (long e = 0; e < n; e++) {  // stage A of round 0
+    Work<T> w = work(e);
+    // stage A owns only the first scratch_a_bytes of the scratch on the device: everything behind must stay untouched
+    unsigned char* tail = reinterpret_cast<unsigned char*>(&c.s) + scratch_a_bytes<T>();
+    size_t ntail = sizeof(Scratch<T>) - scratch_a_bytes<T>();
+    std::memset(tail, 0xA5, ntail);
+    stage_a<T, 1>(g, c.s, c.md, w, st, e, 0, actions, mode, image.data(), queue(0), nohv);
+    for (size_t k = 0; k < ntail; k++)
+      if (tail[k] != 0xA5) { std::fprintf(stderr, "stage A wrote outside its scratch slice (byte %zu)\n", scratch_a_bytes<T>() + k); std::abort(); }
+  }
   for (int sub = 0; sub <= ACTION_REPEAT; sub++) {
-    int count = 0, head = 0;
-    CvxQueue<T> q{items.data(), res.data(), &count, &head, cap};
-    for (long e = 0; e < n; e++) {
-      Work<T> w = make_work(wer.data() + e * WORK_REALS, wei.data() + e * WORK_INTS);
-      // stage A owns only the first scratch_a_bytes of the scratch on the device: everything behind must stay untouched
-      unsigned char* tail = reinterpret_cast<unsigned char*>(&c.s) + scratch_a_bytes<T>();
-      size_t ntail = sizeof(Scratch<T>) - scratch_a_bytes<T>();
-      std::memset(tail, 0xA5, ntail);
-      stage_a<T, 1>(g, c.s, c.md, w, st, e, sub, actions, mode, image.data(), q);
-      for (size_t k = 0; k < ntail; k++)
-        if (tail[k] != 0xA5) { std::fprintf(stderr, "stage A wrote outside its scratch slice (byte %zu)\n", scratch_a_bytes<T>() + k); std::abort(); }
-    }
+    CvxQueue<T> q = queue(sub), qn = queue(sub + 1);
     EpaMem<T> em;
     em.vert = everts.data(); em.face = eface.data(); em.fidx = eints.data(); em.edge = em.fidx + EPA_MAXF; em.canon = em.edge + EPA_MAXE; em.ecan = em.canon + EPA_MAXV;
-    int cnt = count < cap ? count : cap;
-    for (int i = cnt - 1; i >= 0; i--)  // any order: results are addressed by queue position
+    int cnt = count[sub] < cap ? count[sub] : cap;
+    for (int i = cnt - 1; i >= 0; i--) {  // any order: results are addressed by queue position
 #ifdef MM_DEBUG_EPA
-    {
       long before = mm_debug_epa_iters;
       stage_convex<T, 1>(g, c.gm, q, i, image.data(), bpos, bR, em);
       long it = mm_debug_epa_iters - before;
       if (it >= 40) {
-        int ci = items[i].ci, a = c.gm.pair[ci][0], b = c.gm.pair[ci][1];
+        int ci = q.items[i].ci, a = c.gm.pair[ci][0], b = c.gm.pair[ci][1];
         std::fprintf(stderr, "EPA %ld iterations: env %d pair %d (geom %d type %d body %d | geom %d type %d body %d) hit %d depth %g\n", it,
-                     items[i].env, ci, a, c.gm.type[a], c.gm.body[a], b, c.gm.type[b], c.gm.body[b], res[i].hit, (double)res[i].depth);
+                     q.items[i].env, ci, a, c.gm.type[a], c.gm.body[a], b, c.gm.type[b], c.gm.body[b], q.res[i].hit, (double)q.res[i].depth);
       }
-    }
 #else
       stage_convex<T, 1>(g, c.gm, q, i, image.data(), bpos, bR, em);
 #endif
-    for (long e = 0; e < n; e++) {
-      Work<T> w = make_work(wer.data() + e * WORK_REALS, wei.data() + e * WORK_INTS);
-      stage_c<T, 1>(g, c.s, c.md, w, st, e, sub, image.data(), q, reward_type, max_steps, out, tgt);
+    }
+    for (long e = 0; e < n; e++) {  // stage C of round sub + stage A of round sub + 1
+      Work<T> w = work(e);
+      stage_c<T, 1>(g, c.s, c.md, w, st, e, sub, image.data(), q, qn, nohv, reward_type, max_steps, out, tgt);
     }
   }
 }
