@@ -136,6 +136,26 @@ int mm_set_placement_yaw(mm_handle* h, const double* yaw_cs);
 int mm_sample_yaw(mm_handle* h, uint64_t seed, int64_t env_id_offset, const int64_t* episode_index, double* theta,
                   double* yaw_cs, void* stream);
 
+/* One call for everything the vectorised env draws at a reset (the reference's order inside reset(): placement, then
+ * the task, gym_env.py:496-517; yaw with the placement, randomization.py:55-62), for the envs where mask[e] != 0 (NULL =
+ * all): the same Philox stream as mm_sample_placements / mm_sample_yaw, written in place, no host round trip.
+ *   pool [npool,2] int32 (object, bin); task_mode 0 = pool[0], 1 = pool[global env id % npool], 2 = Philox draw
+ *   randomize_xy / randomize_yaw: which arrays are drawn; task may be NULL; advance != 0: episode_index[e] += 1 after
+ *   the draw; stats ([8] double or NULL): stats[6] counts placements whose 1000 attempts were all rejected. */
+int mm_sample_episode(mm_handle* h, uint64_t seed, int64_t env_id_offset, int64_t* episode_index, const uint8_t* mask,
+                      double x_lo, double x_hi, double y_lo, double y_hi, double min_separation, const int32_t* pool,
+                      int32_t npool, int32_t task_mode, int32_t randomize_xy, int32_t randomize_yaw, int32_t advance,
+                      double* obj_xy, int32_t* task, int32_t* attempts, double* yaw_theta, double* yaw_cs, double* stats,
+                      void* stream);
+
+/* Bookkeeping of a vectorised env after mm_step (no reference counterpart: the reference steps one env and leaves
+ * auto-reset to the caller; this is gymnasium's vector-env convention on the device): ep_return [N] += reward;
+ * reset_mask [N] (or NULL) = terminated | truncated; final_obs [N,85] (or NULL) = copy of out->obs; stats ([8] double
+ * or NULL) accumulates episodes, successes, sum of lengths, sum of returns, non-finite state resets (diag[:,3], cleared),
+ * finished episodes that hit a workspace overflow (diag[:,2]); with auto_reset the returns of finished envs restart. */
+int mm_post_step(mm_handle* h, const mm_state* st, const mm_step_out* out, double* ep_return, uint8_t* reset_mask,
+                 float* final_obs, double* stats, int32_t auto_reset, void* stream);
+
 /* Measurement helper (no reference counterpart): FMA throughput of the CUDA cores in TFLOP/s (FP32 or FP64),
  * best of 5 timed launches - the measured denominator of the roofline bench.py reports. */
 int mm_measure_fma_peak(int device, int fp64, double* tflops);

@@ -78,6 +78,78 @@ __global__ void k_sample_yaw(unsigned long long seed, long long gid0, const long
   }
 }
 
+// Episode draw of the vectorised env for the envs selected by `mask`: placement (rejection sampler), task (fixed /
+// cycled by global id / drawn) and yaw from the env's Philox stream (mm_rng.h), then the episode counter advances.
+struct SampleArgs {
+  unsigned long long seed;
+  long long gid0;
+  long long* episode;
+  const unsigned char* mask;
+  long n;
+  double xlo, xhi, ylo, yhi, min_sep;
+  const int* pool;  // [npool][2] (object index, bin index)
+  int npool, task_mode;  // 0 first pool entry | 1 pool[gid % npool] | 2 Philox draw
+  int do_xy, do_yaw, advance;
+  double* xy; int* task; int* attempts; double* theta; double* yaw_cs; double* stats;
+};
+__global__ void k_sample_episode(SampleArgs a) {
+  long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= a.n || (a.mask && !a.mask[e])) return;
+  unsigned long long gid = (unsigned long long)(a.gid0 + e);
+  unsigned ep = (unsigned)a.episode[e];
+  if (a.do_xy) {
+    double p[6];
+    int na = philox_place(a.seed, gid, ep, a.xlo, a.xhi, a.ylo, a.yhi, a.min_sep, 1000, p);
+    for (int k = 0; k < 6; k++) a.xy[6 * e + k] = p[k];
+    if (a.attempts) a.attempts[e] = na;
+    if (na == 0 && a.stats) atomicAdd(a.stats + 6, 1.0);  // the reference raises RuntimeError here (randomization.py:84-87)
+  }
+  if (a.task) {
+    int k = a.task_mode == 2 ? philox_task(a.seed, gid, ep, a.npool) : (a.task_mode == 1 ? (int)(gid % (unsigned long long)a.npool) : 0);
+    a.task[2 * e] = a.pool[2 * k]; a.task[2 * e + 1] = a.pool[2 * k + 1];
+  }
+  if (a.do_yaw)
+    for (int o = 0; o < 3; o++) {
+      double th = philox_yaw(a.seed, gid, ep, o);
+      if (a.theta) a.theta[3 * e + o] = th;
+      a.yaw_cs[6 * e + 2 * o] = cos(0.5 * th);
+      a.yaw_cs[6 * e + 2 * o + 1] = sin(0.5 * th);
+    }
+  if (a.advance) a.episode[e] = (long long)ep + 1;
+}
+
+// Bookkeeping of the vectorised env after a step: running returns, episode statistics, the mask of finished envs,
+// the last observation of finished episodes, diagnostics.  One thread per env; the statistics are block-reduced.
+__global__ void k_post_step(StatePtrs st, StepOut out, long n, double* ep_return, unsigned char* reset_mask, float* final_obs,
+                            double* stats, int auto_reset) {
+  long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  double v[6] = {0, 0, 0, 0, 0, 0};  // episodes, successes, sum length, sum return, non-finite resets, overflow episodes
+  if (e < n) {
+    double ret = ep_return[e] + (double)out.reward[e];
+    bool done = out.terminated[e] || out.truncated[e];
+    int bad = st.diag[4 * e + 3];
+    if (bad) { v[4] = bad; st.diag[4 * e + 3] = 0; }
+    if (done) {
+      v[0] = 1; v[1] = out.success[e] ? 1 : 0; v[2] = st.step_count[e]; v[3] = ret;
+      v[5] = st.diag[4 * e + 2] ? 1 : 0;
+    }
+    ep_return[e] = (done && auto_reset) ? 0.0 : ret;
+    if (reset_mask) reset_mask[e] = done ? 1 : 0;
+  }
+  if (final_obs) {  // coalesced copy of this block's observations
+    long base = (long)blockIdx.x * blockDim.x * OBS_DIM, lim = n * OBS_DIM;
+    for (long i = base + threadIdx.x; i < base + (long)blockDim.x * OBS_DIM && i < lim; i += blockDim.x) final_obs[i] = out.obs[i];
+  }
+  if (stats) {
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      double x = v[k];
+      for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+      if ((threadIdx.x & 31) == 0 && x != 0.0) atomicAdd(stats + k, x);
+    }
+  }
+}
+
 // FMA-throughput microbenchmark: the measured denominator of the CUDA-core roofline (bench.py)
 template <class T>
 __global__ void __launch_bounds__(256) k_peak(T* out, int iters, T a, T b) {
@@ -428,6 +500,42 @@ int mm_sample_yaw(mm_handle* h, uint64_t seed, int64_t env_id_offset, const int6
   long n = h->cfg.num_envs;
   k_sample_yaw<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
       (unsigned long long)seed, (long long)env_id_offset, (const long long*)episode_index, n, theta, yaw_cs);
+  CK(cudaGetLastError());
+  h->launches++;
+  return 0;
+}
+
+int mm_sample_episode(mm_handle* h, uint64_t seed, int64_t env_id_offset, int64_t* episode_index, const uint8_t* mask,
+                      double x_lo, double x_hi, double y_lo, double y_hi, double min_separation, const int32_t* pool,
+                      int32_t npool, int32_t task_mode, int32_t randomize_xy, int32_t randomize_yaw, int32_t advance,
+                      double* obj_xy, int32_t* task, int32_t* attempts, double* yaw_theta, double* yaw_cs, double* stats,
+                      void* stream) {
+  if (!h || !episode_index) return fail("mm_sample_episode: null argument");
+  if (randomize_xy && !obj_xy) return fail("mm_sample_episode: randomize_xy needs obj_xy");
+  if (randomize_yaw && !yaw_cs) return fail("mm_sample_episode: randomize_yaw needs yaw_cs");
+  if (task && (!pool || npool <= 0 || task_mode < 0 || task_mode > 2)) return fail("mm_sample_episode: bad task pool / mode");
+  GUARD(h);
+  SampleArgs a;
+  a.seed = (unsigned long long)seed; a.gid0 = (long long)env_id_offset; a.episode = (long long*)episode_index; a.mask = mask;
+  a.n = h->cfg.num_envs; a.xlo = x_lo; a.xhi = x_hi; a.ylo = y_lo; a.yhi = y_hi; a.min_sep = min_separation;
+  a.pool = pool; a.npool = npool; a.task_mode = task_mode; a.do_xy = randomize_xy; a.do_yaw = randomize_yaw; a.advance = advance;
+  a.xy = obj_xy; a.task = task; a.attempts = attempts; a.theta = yaw_theta; a.yaw_cs = yaw_cs; a.stats = stats;
+  k_sample_episode<<<(unsigned)((a.n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a);
+  CK(cudaGetLastError());
+  h->launches++;
+  return 0;
+}
+
+int mm_post_step(mm_handle* h, const mm_state* st, const mm_step_out* out, double* ep_return, uint8_t* reset_mask,
+                 float* final_obs, double* stats, int32_t auto_reset, void* stream) {
+  if (!h || !st || !out || !ep_return) return fail("mm_post_step: null argument");
+  GUARD(h);
+  StepOut o;
+  o.obs = out->obs; o.reward = out->reward; o.terminated = out->terminated; o.truncated = out->truncated;
+  o.success = out->success; o.reward_components = out->reward_components;
+  long n = h->cfg.num_envs;
+  k_post_step<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(to_ptrs(st), o, n, ep_return, reset_mask, final_obs,
+                                                                           stats, auto_reset);
   CK(cudaGetLastError());
   h->launches++;
   return 0;

@@ -54,7 +54,7 @@ def philox_placements(env, min_separation: float = MIN_OBJ_SEPARATION):
 
     from . import _lib
 
-    n, dev = env.num_envs, env.device
+    n, dev = env.num_envs, env.device  # (the env itself draws through mm_sample_episode; this is the stand-alone call)
     xy = torch.empty((n, 6), dtype=torch.float64, device=dev)
     draw = torch.empty(n, dtype=torch.int32, device=dev)
     att = torch.empty(n, dtype=torch.int32, device=dev)

@@ -16,7 +16,8 @@ import torch
 from . import _lib
 from .constants import (ACTION_REPEAT, BINS, MAX_EPISODE_STEPS, OBJECTS, SPAWN_X_RANGE, SPAWN_Y_RANGE, TASK_SETS,
                         task_indices)
-from .randomization import philox_placements, sample_separated_positions
+from .constants import MIN_OBJ_SEPARATION
+from .randomization import sample_separated_positions
 
 # slices of the packed [N,85] observation (layout written by csrc/mm_env.h write_obs)
 OBS_SLICES = {
@@ -67,7 +68,7 @@ class PickPlaceVecEnv:
                  spawn_x_range=SPAWN_X_RANGE, spawn_y_range=SPAWN_Y_RANGE, randomize_yaw: bool = False, seed: int = 0,
                  rng: str = "philox",
                  env_id_offset: int = 0, precision: str = "f64", group: int = 32, auto_reset: bool = True,
-                 task_assignment: str = "random", load_balance: bool = True):
+                 task_assignment: str = "random", load_balance: bool = False):
         if action_mode not in _lib.ACTION_MODES:
             raise ValueError(f"action_mode must be one of {_lib.ACTION_MODES}, got '{action_mode}'")
         if reward_type not in _lib.REWARD_TYPES:
@@ -135,12 +136,16 @@ class PickPlaceVecEnv:
         self._gid = torch.arange(n, dtype=torch.int64, device=dev) + self.env_id_offset
         self.episode_index = torch.zeros(n, dtype=torch.int64, device=dev)
         # episode statistics (device resident; see stats.py for the cross-GPU gather)
-        self.stats = torch.zeros(5, dtype=torch.float64, device=dev)  # episodes, successes, sum length, sum return, bad resets
+        # episodes, successes, sum of lengths, sum of returns, non-finite state resets, episodes that hit a workspace
+        # overflow, placements whose 1000 attempts all failed (the reference raises there), spare  (mm_post_step)
+        self.stats = torch.zeros(8, dtype=torch.float64, device=dev)
+        self.last_attempts = torch.zeros(n, dtype=torch.int32, device=dev)
         self._ep_return = torch.zeros(n, dtype=torch.float64, device=dev)
         self._np_rngs: list | None = None
         self._closed = False
-        # load-aware scheduling: envs sorted by the busy time of their previous step share a CTA (mm_set_schedule)
-        self.load_balance = bool(load_balance) and n > 32 and os.environ.get("MM_LOAD_BALANCE", "1") != "0"
+        # load-aware scheduling (optional): the most expensive envs of the previous step start first (mm_set_schedule);
+        # with stage kernels that keep the whole batch resident it no longer pays at the benchmarked sizes: off by default
+        self.load_balance = (bool(load_balance) or os.environ.get("MM_LOAD_BALANCE", "0") == "1") and n > 32
         self._work = torch.zeros(n, dtype=torch.int32, device=dev)
         self._order = torch.arange(n, dtype=torch.int32, device=dev)
         if self.load_balance:
@@ -188,33 +193,28 @@ class PickPlaceVecEnv:
                 self._yaw_cs.copy_(torch.from_numpy(cs))
             self._task.copy_(torch.from_numpy(tk))
         else:
-            xy, tdraw, self.last_attempts = philox_placements(self)
-            if self.task_assignment == "cycle" and self._fixed_task is None:
-                tdraw = self._gid % len(self._pool_idx)
-            tk = self._pool_idx[tdraw.to(torch.int64)]
+            self._sample_episode(mask, advance=False)
             if task_override is not None:
                 tk = torch.as_tensor(np.asarray(task_override), dtype=torch.int32, device=self.device)
-            if self.randomize_yaw:
-                th = torch.empty_like(self.last_yaw)
-                cs = torch.empty_like(self._yaw_cs)
-                _lib.check(self._L.mm_sample_yaw(self._h, C.c_uint64(self.seed & 0xFFFFFFFFFFFFFFFF), self.env_id_offset,
-                                                 self.episode_index.data_ptr(), th.data_ptr(), cs.data_ptr(),
-                                                 self._stream()), "mm_sample_yaw")
-            if mask is None:
-                self._obj_xy.copy_(xy)
-                self._task.copy_(tk)
-                if self.randomize_yaw:
-                    self.last_yaw.copy_(th)
-                    self._yaw_cs.copy_(cs)
-            else:
-                m = mask.bool()
-                self._obj_xy[m] = xy[m]
-                self._task[m] = tk[m]
-                if self.randomize_yaw:
-                    self.last_yaw[m] = th[m]
-                    self._yaw_cs[m] = cs[m]
+                if mask is None:
+                    self._task.copy_(tk)
+                else:
+                    m = mask.bool()
+                    self._task[m] = tk[m]
 
-    def reset(self, *, seed=None, options: dict | None = None, mask: torch.Tensor | None = None):
+    def _sample_episode(self, mask, advance: bool):
+        """Device draw (mm_sample_episode) of placement / task / yaw for the masked envs, written in place."""
+        mode = 0 if self._fixed_task is not None else (1 if self.task_assignment == "cycle" else 2)
+        m = None if mask is None else mask
+        _lib.check(self._L.mm_sample_episode(
+            self._h, C.c_uint64(self.seed & 0xFFFFFFFFFFFFFFFF), self.env_id_offset, self.episode_index.data_ptr(),
+            None if m is None else m.data_ptr(), self.spawn_x_range[0], self.spawn_x_range[1], self.spawn_y_range[0],
+            self.spawn_y_range[1], float(MIN_OBJ_SEPARATION), self._pool_idx.data_ptr(), len(self._pool_idx), mode,
+            1 if self.randomize_objects else 0, 1 if (self.randomize_objects and self.randomize_yaw) else 0,
+            1 if advance else 0, self._obj_xy.data_ptr(), self._task.data_ptr(), self.last_attempts.data_ptr(),
+            self.last_yaw.data_ptr(), self._yaw_cs.data_ptr(), self.stats.data_ptr(), self._stream()), "mm_sample_episode")
+
+    def reset(self, *, seed=None, options: dict | None = None, mask: torch.Tensor | None = None, _from_step: bool = False):
         """Reset all envs (or those where `mask` is non-zero).
 
         seed: None, an int (new base seed) or a sequence of N per-env seeds (rng="numpy": each env is
@@ -243,6 +243,8 @@ class PickPlaceVecEnv:
                 task_override = np.tile(np.asarray(task_indices(t), dtype=np.int32), (self.num_envs, 1))
             else:
                 task_override = np.asarray([task_indices(x) for x in t], dtype=np.int32)
+        if mask is not None:
+            mask = mask.to(torch.uint8).contiguous()
         self._draw(mask, seeds, task_override)
         use_xy = self.randomize_objects
         if options and "obj_xy" in options:
@@ -258,7 +260,7 @@ class PickPlaceVecEnv:
             use_yaw = True
         _lib.check(self._L.mm_set_placement_yaw(self._h, self._yaw_cs.data_ptr() if use_yaw else None),
                    "mm_set_placement_yaw")
-        m = None if mask is None else mask.to(torch.uint8).contiguous()
+        m = mask
         _lib.check(self._L.mm_reset(self._h, C.byref(self._st), None if m is None else m.data_ptr(),
                                     self._obj_xy.data_ptr() if use_xy else None, self._task.data_ptr(),
                                     self._obs.data_ptr(), self._stream()), "mm_reset")
@@ -293,25 +295,30 @@ class PickPlaceVecEnv:
             self._order.copy_(torch.argsort(self._work, descending=True).to(torch.int32))
 
     def _post_step_autoreset(self):
-        """Bookkeeping after the mm_step launch: episode statistics and (optionally) the reset of
-        finished envs.  Returns the 5-tuple of `step`."""
+        """Bookkeeping after the mm_step launch: episode statistics and (optionally) the reset of finished envs - all in
+        library kernels (mm_post_step, mm_sample_episode, mm_reset), no host round trip.  Returns the 5-tuple of `step`."""
         terminated, truncated, success = self._flags[0].bool(), self._flags[1].bool(), self._flags[2].bool()
-        reward = self._reward
         info = {"success": success}
         if self._rc is not None:
             info["reward_components"] = self._rc
-        self._ep_return += reward
+        fast = self.auto_reset and self.rng_kind == "philox"
+        _lib.check(self._L.mm_post_step(self._h, C.byref(self._st), C.byref(self._out), self._ep_return.data_ptr(),
+                                        self._mask.data_ptr(), self._final_obs.data_ptr() if self.auto_reset else None,
+                                        self.stats.data_ptr(), 1 if self.auto_reset else 0, self._stream()), "mm_post_step")
+        reward = self._reward
         if self.auto_reset:
-            done = terminated | truncated
-            donef = done.to(torch.float64)
-            self.stats[0] += donef.sum()
-            self.stats[1] += (success & done).to(torch.float64).sum()
-            self.stats[2] += (self.state["step_count"][:, 0].to(torch.float64) * donef).sum()
-            self.stats[3] += (self._ep_return * donef).sum()
-            self._final_obs.copy_(self._obs)
             info["final_obs"] = self._final_obs
             reward = reward.clone()
-            self.reset(mask=done.to(torch.uint8))
+            if fast:
+                self._sample_episode(self._mask, advance=True)
+                use_xy = self.randomize_objects
+                _lib.check(self._L.mm_set_placement_yaw(
+                    self._h, self._yaw_cs.data_ptr() if (use_xy and self.randomize_yaw) else None), "mm_set_placement_yaw")
+                _lib.check(self._L.mm_reset(self._h, C.byref(self._st), self._mask.data_ptr(),
+                                            self._obj_xy.data_ptr() if use_xy else None, self._task.data_ptr(),
+                                            self._obs.data_ptr(), self._stream()), "mm_reset")
+            else:  # host numpy generators (reference-exact draw order): the mask has to visit the host
+                self.reset(mask=self._mask.clone(), _from_step=True)
         return split_obs(self._obs), reward, terminated, truncated, info
 
     def fsm_plan(self, n_steps: int = ACTION_REPEAT) -> torch.Tensor:

@@ -23,7 +23,7 @@ def _worker(rank, world, port, q):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     lo, hi = shard_range(10, rank, world)
-    local = torch.tensor([hi - lo, rank + 1, 100.0 * (rank + 1), -2.0 * (rank + 1), 0.0], dtype=torch.float64)
+    local = torch.tensor([hi - lo, rank + 1, 100.0 * (rank + 1), -2.0 * (rank + 1), 0.0, 0.0, 0.0, 0.0], dtype=torch.float64)
     allst = gather_stats(local)
     q.put((rank, lo, hi, allst.tolist(), summarize(allst)))
     dist.destroy_process_group()
@@ -55,7 +55,7 @@ def test_shard_range_covers_everything():
 
 
 def test_single_process_passthrough():
-    s = torch.tensor([4.0, 2.0, 40.0, 8.0, 0.0], dtype=torch.float64)
+    s = torch.tensor([4.0, 2.0, 40.0, 8.0, 0.0, 1.0, 0.0, 0.0], dtype=torch.float64)
     out = gather_stats(s)
-    assert out.shape == (1, 5)
+    assert out.shape == (1, 8) and summarize(out)["overflow_episodes"] == 1.0
     assert summarize(out)["success_rate"] == 0.5
