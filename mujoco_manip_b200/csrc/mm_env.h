@@ -369,10 +369,12 @@ MM_HDN void stage_a(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<
   ctx_copy<T, G>(g, ctx, &s);
 }
 
-// Stage C of round `sub`; unless it is the last round, stage A of round sub + 1 follows at once for the same env (no
-// batch-wide barrier and no image round trip between them: `qn` / `hvn` are the NEXT round's queue and list, which
-// alternate between two buffers so that this round's results stay readable for the envs still in stage C).
-template <class T, int G>
+// Stage C of round `sub`.  FUSE: unless it is the last round, stage A of round sub + 1 follows at once for the same
+// env (no batch-wide barrier and no image round trip between them: `qn` / `hvn` are the NEXT round's queue and list,
+// which alternate between two buffers so that this round's results stay readable for the envs still in stage C).
+// Measured on the B200 the fused form is 15-25 % SLOWER (stage A then runs at stage C's register budget and
+// occupancy), so the library launches the two stages separately; the switch stays for experiments (MM_FUSE_CA=1).
+template <class T, int G, bool FUSE>
 MM_HDN void stage_c(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>& w, const StatePtrs& st, long e, int sub,
                     char* ctx_base, const CvxQueue<T>& q, const CvxQueue<T>& qn, const HeavyList& hvn, int reward_type,
                     int max_steps, const StepOut& out, const float* tgt_kp_all) {
@@ -386,7 +388,7 @@ MM_HDN void stage_c(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<
   solve<T, G>(g, s, md, w);
   if (sub != ACTION_REPEAT) {
     integrate<T, G>(g, s, md);
-    stage_a_body<T, G>(g, s, md, w, st, e, sub + 1, qn, hvn);
+    if (FUSE) stage_a_body<T, G>(g, s, md, w, st, e, sub + 1, qn, hvn);
     ctx_copy<T, G>(g, ctx, &s);
     return;
   }

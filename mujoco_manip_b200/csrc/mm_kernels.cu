@@ -179,6 +179,7 @@ struct mm_handle {
   unsigned char* d_hflag = nullptr;  // [N] contact-rich flag of the current round
   int* d_h_items = nullptr;          // [nchunk][chunk]
   int heavy_min = 0;                 // 0 = every env takes the warp-per-env stage C
+  bool fuse_ca = false;              // MM_FUSE_CA=1: stage A fused behind stage C (measured slower; experiment switch)
   cudaStream_t hside[8] = {};        // sibling streams of `side` for the contact-rich stage C
   cudaEvent_t ev_x[8] = {}, ev_h[8] = {};
   // chunks of the batch and their convex-pair queues
@@ -312,8 +313,10 @@ int mm_create(const mm_config* cfg, mm_handle** out) {
   CK(cudaMalloc(&h->d_q_items, (size_t)h->nchunk * 2 * h->q_cap * sizeof(CvxItem)));
   CK(cudaMalloc(&h->d_q_res, (size_t)h->nchunk * 2 * h->q_cap * res_bytes));
   CK(cudaMalloc(&h->d_q_ctr, (size_t)h->nchunk * 4 * NCTR * sizeof(int)));
-  // contact-rich envs (box contacts + convex candidates >= MM_HEAVY, default 40; 0 switches the CTA-per-env path off)
-  h->heavy_min = h->heavy_grid > 0 ? (int)env_long("MM_HEAVY", 40) : 0;
+  // contact-rich envs (box contacts + convex candidates >= MM_HEAVY; 0 = the CTA-per-env path is off, the default: at the
+  // benchmarked batch sizes stage C is bound by the throughput of all envs, not by its slowest one - no gain measured)
+  h->heavy_min = h->heavy_grid > 0 ? (int)env_long("MM_HEAVY", 0) : 0;
+  h->fuse_ca = env_long("MM_FUSE_CA", 0) != 0;
   CK(cudaMalloc(&h->d_hflag, 2 * n));
   CK(cudaMemset(h->d_hflag, 0, 2 * n));
   CK(cudaMalloc(&h->d_h_items, (size_t)h->nchunk * 2 * chunk * sizeof(int)));
@@ -419,19 +422,20 @@ int mm_step(mm_handle* h, const mm_state* st, const float* actions, int action_m
     pc.h_cap = (int)h->chunk;
     pc.heavy_min = h->heavy_min;
     pc.epa_verts = (char*)h->d_epa_verts + (size_t)si * h->convex_grid * MM_WX * EPA_MAXV * 6 * rb;
-    CK(launch(0, pc, 0, 0, s));  // stage A of round 0; the later rounds' stage A runs fused behind stage C
+    const bool fuse = h->fuse_ca;  // experiment switch: stage A of round r + 1 inside the stage C kernel of round r
     for (int sub = 0; sub < NROUND; sub++) {
+      if (sub == 0 || !fuse) CK(launch(0, pc, sub, 0, s));
       CK(launch(1, pc, sub, h->convex_grid, s));
       if (h->heavy_min > 0) {  // contact-rich envs: a CTA each, next to the warp-per-env launch of the others
         CK(cudaEventRecord(h->ev_x[si], s));
         CK(cudaStreamWaitEvent(h->hside[si], h->ev_x[si], 0));
-        CK(launch(5, pc, sub, h->heavy_grid, h->hside[si]));
+        CK(launch(fuse ? 7 : 5, pc, sub, h->heavy_grid, h->hside[si]));
         CK(cudaEventRecord(h->ev_h[si], h->hside[si]));
       }
-      CK(launch(2, pc, sub, 0, s));
+      CK(launch(fuse ? 6 : 2, pc, sub, 0, s));
       if (h->heavy_min > 0) CK(cudaStreamWaitEvent(s, h->ev_h[si], 0));
     }
-    h->launches += 1 + (h->heavy_min > 0 ? 3 : 2) * NROUND;
+    h->launches += (fuse ? 1 : NROUND) + (h->heavy_min > 0 ? 3 : 2) * NROUND;
   }
   if (forked)
     for (int i = 0; i < h->nstream; i++) {

@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(32 * W, MM_MINB_A) k_stage_a(StepParams p, int
   }
 }
 
-template <class T, int G, int W>
+template <class T, int G, int W, bool FUSE>
 __global__ void __launch_bounds__(32 * W, MM_MINB_C) k_stage_c(StepParams p, int sub) {
   extern __shared__ __align__(16) unsigned char smem[];
   Grp<G> g;
@@ -155,8 +155,8 @@ __global__ void __launch_bounds__(32 * W, MM_MINB_C) k_stage_c(StepParams p, int
   long long t0 = clock64();
   Scratch<T>& s = *reinterpret_cast<Scratch<T>*>(smem + gi * scratch_c_bytes<T>());
   Work<T> w = work_of<T>(p, e);
-  stage_c<T, G>(g, s, *md, w, p.st, e, sub, p.ctx, queue_of<T>(p, sub), queue_of<T>(p, sub + 1), heavy_of(p, sub + 1),
-                p.reward_type, p.max_steps, p.out, p.tgt_kp);
+  stage_c<T, G, FUSE>(g, s, *md, w, p.st, e, sub, p.ctx, queue_of<T>(p, sub), queue_of<T>(p, sub + 1), heavy_of(p, sub + 1),
+                      p.reward_type, p.max_steps, p.out, p.tgt_kp);
   if (g.lane == 0) {
     long long dt = clock64() - t0;
     if (p.work) p.work[e] += (int)(dt >> 8);
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(32 * W, MM_MINB_C) k_stage_c(StepParams p, int
 #ifndef MM_MINB_H
 #define MM_MINB_H 3
 #endif
-template <class T>
+template <class T, bool FUSE>
 __global__ void __launch_bounds__(128, MM_MINB_H) k_stage_c_heavy(StepParams p, int sub) {
   extern __shared__ __align__(16) unsigned char smem[];
   Grp<128> g;
@@ -189,8 +189,8 @@ __global__ void __launch_bounds__(128, MM_MINB_H) k_stage_c_heavy(StepParams p, 
     long e = p.h_items[(size_t)(sub & 1) * p.h_cap + i];
     long long t0 = clock64();
     Work<T> w = work_of<T>(p, e);
-    stage_c<T, 128>(g, s, *md, w, p.st, e, sub, p.ctx, queue_of<T>(p, sub), queue_of<T>(p, sub + 1), heavy_of(p, sub + 1),
-                    p.reward_type, p.max_steps, p.out, p.tgt_kp);
+    stage_c<T, 128, FUSE>(g, s, *md, w, p.st, e, sub, p.ctx, queue_of<T>(p, sub), queue_of<T>(p, sub + 1), heavy_of(p, sub + 1),
+                          p.reward_type, p.max_steps, p.out, p.tgt_kp);
     if (g.lane == 0) {
       long long dt = clock64() - t0;
       if (p.work) p.work[e] += (int)(dt >> 8);
@@ -290,12 +290,16 @@ template <class T, int G>
 cudaError_t inst_prepare() {
   cudaError_t e = cudaFuncSetAttribute(k_stage_a<T, G, MM_WA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a<T, G>());
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(k_stage_c<T, G, warps_c<G>()>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c<T, G>());
+  e = cudaFuncSetAttribute(k_stage_c<T, G, warps_c<G>(), false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c<T, G>());
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_stage_c<T, G, warps_c<G>(), true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c<T, G>());
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_convex<T, MM_WX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x<T>());
   if (e != cudaSuccess) return e;
   if (G == 32) {
-    e = cudaFuncSetAttribute(k_stage_c_heavy<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h<T>());
+    e = cudaFuncSetAttribute(k_stage_c_heavy<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h<T>());
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_stage_c_heavy<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h<T>());
     if (e != cudaSuccess) return e;
   }
   e = cudaFuncSetAttribute(k_ops<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c<T, G>());
@@ -316,7 +320,7 @@ cudaError_t inst_resident(int* convex_grid, int* heavy_grid) {
   *convex_grid = (per > 0 ? per : 1) * sms;
   *heavy_grid = 0;
   if (G == 32) {
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_stage_c_heavy<T>, 128, smem_h<T>());
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_stage_c_heavy<T, false>, 128, smem_h<T>());
     if (e != cudaSuccess) return e;
     *heavy_grid = (per > 0 ? per : 1) * sms;
   }
@@ -324,7 +328,7 @@ cudaError_t inst_resident(int* convex_grid, int* heavy_grid) {
 }
 
 // which: 0 = stage A of round `sub`, 1 = convex stage, 2 = stage C, 3 = reset, 4 = ops, 5 = stage C of the
-// contact-rich envs.  `grid_x`: grid of the persistent kernels (1, 5).
+// contact-rich envs; 6 / 7 = 2 / 5 with stage A of the next round fused behind.  `grid_x`: grid of the persistent kernels.
 template <class T, int G>
 cudaError_t inst_launch(int which, const StepParams& p, int sub, int grid_x, cudaStream_t s) {
   if (which == 0) {
@@ -332,11 +336,16 @@ cudaError_t inst_launch(int which, const StepParams& p, int sub, int grid_x, cud
     k_stage_a<T, G, MM_WA><<<(unsigned)((p.nslot + EPB - 1) / EPB), 32 * MM_WA, smem_a<T, G>(), s>>>(p, sub);
   } else if (which == 1) {
     k_convex<T, MM_WX><<<(unsigned)grid_x, 32 * MM_WX, smem_x<T>(), s>>>(p, sub);
-  } else if (which == 2) {
+  } else if (which == 2 || which == 6) {
     constexpr int EPB = 32 * warps_c<G>() / G;
-    k_stage_c<T, G, warps_c<G>()><<<(unsigned)((p.nslot + EPB - 1) / EPB), 32 * warps_c<G>(), smem_c<T, G>(), s>>>(p, sub);
-  } else if (which == 5) {
-    if (G == 32) k_stage_c_heavy<T><<<(unsigned)grid_x, 128, smem_h<T>(), s>>>(p, sub);
+    unsigned grid = (unsigned)((p.nslot + EPB - 1) / EPB);
+    if (which == 2) k_stage_c<T, G, warps_c<G>(), false><<<grid, 32 * warps_c<G>(), smem_c<T, G>(), s>>>(p, sub);
+    else k_stage_c<T, G, warps_c<G>(), true><<<grid, 32 * warps_c<G>(), smem_c<T, G>(), s>>>(p, sub);
+  } else if (which == 5 || which == 7) {
+    if (G == 32) {
+      if (which == 5) k_stage_c_heavy<T, false><<<(unsigned)grid_x, 128, smem_h<T>(), s>>>(p, sub);
+      else k_stage_c_heavy<T, true><<<(unsigned)grid_x, 128, smem_h<T>(), s>>>(p, sub);
+    }
   } else {
     constexpr int EPB = FusedCfg<T, G>::ENVS;
     unsigned grid = (unsigned)((p.n + EPB - 1) / EPB);

@@ -111,10 +111,15 @@ void do_step(int n, void** sp, const float* actions, int mode, int reward_type, 
       stage_convex<T, 1>(g, c.gm, q, i, image.data(), bpos, bR, em);
 #endif
     }
-    for (long e = 0; e < n; e++) {  // stage C of round sub + stage A of round sub + 1
+    for (long e = 0; e < n; e++) {  // stage C of round sub
       Work<T> w = work(e);
-      stage_c<T, 1>(g, c.s, c.md, w, st, e, sub, image.data(), q, qn, nohv, reward_type, max_steps, out, tgt);
+      stage_c<T, 1, false>(g, c.s, c.md, w, st, e, sub, image.data(), q, qn, nohv, reward_type, max_steps, out, tgt);
     }
+    if (sub < ACTION_REPEAT)
+      for (long e = 0; e < n; e++) {  // stage A of round sub + 1 (its own launch on the device)
+        Work<T> w = work(e);
+        stage_a<T, 1>(g, c.s, c.md, w, st, e, sub + 1, actions, mode, image.data(), qn, nohv);
+      }
   }
 }
 }  // namespace

@@ -213,3 +213,38 @@ def test_fsm_episode_through_quat_rel_actions(cuda_device):
     env.fsm_plan(16)
     assert int(env.fsm_state[0]) == 11
     env.close()
+
+
+@pytest.mark.parametrize("switches", [{"MM_HEAVY": "8"}, {"MM_FUSE_CA": "1"}, {"MM_HEAVY": "8", "MM_FUSE_CA": "1", "MM_STREAMS": "1"}])
+def test_optional_launch_plans_match_the_golden(cuda_device, monkeypatch, switches):
+    """The launch-plan switches of mm_create (contact-rich envs by a CTA each = Grp<128>; stage A fused behind stage C)
+    change the schedule, never the physics: the table-collision stress rollout (hull contacts, 70+ contacts) and a
+    scripted-FSM episode stay on the golden trajectories recorded from the reference's Python on the oracle engine."""
+    import torch
+
+    for k, v in switches.items():
+        monkeypatch.setenv(k, v)
+    g = np.load(os.path.join(GOLDEN, "stress30_abs_pos_staged.npz"))
+    env = _make(3, cuda_device, task=("obj_red", "bin_red"), action_mode="abs_pos", reward_type="staged", rng="numpy")
+    env.reset()
+    for t in range(g["action"].shape[0]):
+        a = torch.from_numpy(np.repeat(g["action"][t][None, :4], 3, axis=0)).to(cuda_device)
+        obs, r, te, tr, info = env.step(a)
+        assert reltol(_np(env.state["qpos"])[0], g["qpos"][t], TOL) < TOL, t
+        assert int(_np(env.state["diag"])[0, 0]) == int(g["ncon"][t])
+        assert abs(float(r[0]) - g["reward"][t]) < 1e-5
+    assert torch.equal(env.state["qpos"][0], env.state["qpos"][2])
+    env.close()
+    g = np.load(os.path.join(GOLDEN, "fsm_abs_green_blue_seed42_staged.npz"))
+    q = g["init_qpos"]
+    env = _make(2, cuda_device, action_mode="abs_pos", reward_type="staged", rng="numpy")
+    from mujoco_manip_b200.constants import BINS, OBJECTS
+
+    xy = np.array([q[9:11], q[16:18], q[23:25]])
+    env.reset(options={"task": (OBJECTS[int(g["obj_idx"])], BINS[int(g["bin_idx"])]), "obj_xy": np.stack([xy, xy])})
+    for t in range(g["fsm_state"].shape[0]):
+        a = env.fsm_plan(16).clone()
+        assert int(env.fsm_state[0]) == int(g["fsm_state"][t]), t
+        env.step(a)
+        assert reltol(_np(env.state["qpos"])[0], g["qpos"][t], TOL) < TOL, t
+    env.close()
