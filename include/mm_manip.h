@@ -103,6 +103,10 @@ int mm_step(mm_handle* h, const mm_state* st, const float* actions, int action_m
 int mm_step_host(mm_handle* h, const mm_state* st, const float* h_actions, int action_mode, float* h_obs,
                  float* h_reward, uint8_t* h_terminated, uint8_t* h_truncated, uint8_t* h_success, void* stream);
 
+/* The device buffers mm_step_host stages its results in (owned by the handle): lets the caller run mm_post_step /
+ * mm_reset on the results of a host-buffer step without another copy. */
+int mm_host_staging(mm_handle* h, mm_step_out* out);
+
 /* Engine-level calls for the physics-step-level loops of the reference (main.py:65-91,
  * pick_and_place.py:279-304, tests/test_controller.py): a combination of
  *   MM_OP_IK        IKController.compute(target) + set_arm_ctrl (controller.py:87-137, robot.py:65-71) on the
@@ -176,6 +180,14 @@ int mm_set_schedule(mm_handle* h, const int32_t* order, int32_t* work);
  * (GJK / EPA of the env's queued pairs, summed over the warps that ran them), [3] stage C (contact assembly, constraint
  * rows, Newton solver, integration); [4..8] unused.  NULL switches it off. */
 int mm_set_cycle_buffer(mm_handle* h, long long* cycles);
+
+/* Measurement helper: with `on`, every stage launch of mm_step is bracketed by CUDA events on the stream it is launched
+ * on; mm_stage_times synchronises the device, returns the summed device time (ms) of the launches since the last call -
+ * ms[0] stage A (IK, kinematics, dynamics, broad + box narrow phase), ms[1] convex stage (GJK / EPA queue), ms[2] stage C
+ * (contact assembly, constraint rows, Newton solver, integration), ms[3] stage C of contact-rich envs (when that plan is
+ * on) - and their counts.  Stages of different chunks overlap on different streams, so the sums can exceed wall time. */
+int mm_stage_timing(mm_handle* h, int32_t on);
+int mm_stage_times(mm_handle* h, double* ms, long long* launches);
 
 /* number of kernels this handle has launched so far */
 int mm_launch_count(mm_handle* h, long long* out);

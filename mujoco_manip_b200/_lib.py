@@ -24,7 +24,7 @@ REWARD_TYPES = ("dense", "sparse", "staged")
 # every symbol include/mm_manip.h declares (tests check the built library exports each one)
 EXPORTS = ("mm_create", "mm_destroy", "mm_last_error", "mm_workspace_bytes", "mm_reset", "mm_step", "mm_step_host",
            "mm_fsm_plan", "mm_launch_count", "mm_sample_placements", "mm_measure_fma_peak", "mm_set_cycle_buffer", "mm_ops", "mm_set_schedule", "mm_expert_actions",
-           "mm_set_placement_yaw", "mm_sample_yaw", "mm_sample_episode", "mm_post_step")
+           "mm_set_placement_yaw", "mm_sample_yaw", "mm_sample_episode", "mm_post_step", "mm_stage_timing", "mm_stage_times", "mm_host_staging")
 
 
 class MMConfig(C.Structure):
@@ -115,6 +115,9 @@ def lib():
     L.mm_launch_count.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
     L.mm_sample_episode.argtypes = ([C.c_void_p, C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p] + [C.c_double] * 5 +
                                     [C.c_void_p] + [C.c_int32] * 5 + [C.c_void_p] * 7)
+    L.mm_host_staging.argtypes = [C.c_void_p, C.POINTER(MMStepOut)]
+    L.mm_stage_timing.argtypes = [C.c_void_p, C.c_int32]
+    L.mm_stage_times.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.mm_post_step.argtypes = [C.c_void_p, C.POINTER(MMState), C.POINTER(MMStepOut), C.c_void_p, C.c_void_p, C.c_void_p,
                                C.c_void_p, C.c_int32, C.c_void_p]
     _lib = L

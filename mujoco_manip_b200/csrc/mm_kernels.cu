@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "../../include/mm_manip.h"
 #include "mm_launch.cuh"
@@ -179,6 +180,11 @@ struct mm_handle {
   unsigned char* d_hflag = nullptr;  // [N] contact-rich flag of the current round
   int* d_h_items = nullptr;          // [nchunk][chunk]
   int heavy_min = 0;                 // 0 = every env takes the warp-per-env stage C
+  // per-stage device timing (mm_stage_times): events recorded around every stage launch of mm_step on its own stream
+  bool timing = false;
+  struct Timed { int kind; cudaEvent_t a, b; };
+  std::vector<Timed> timed;
+  std::vector<cudaEvent_t> ev_pool;
   bool fuse_ca = false;              // MM_FUSE_CA=1: stage A fused behind stage C (measured slower; experiment switch)
   cudaStream_t hside[8] = {};        // sibling streams of `side` for the contact-rich stage C
   cudaEvent_t ev_x[8] = {}, ev_h[8] = {};
@@ -350,6 +356,8 @@ void mm_destroy(mm_handle* h) {
     if (h->ev_h[i]) cudaEventDestroy(h->ev_h[i]);
   }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  for (auto& t : h->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+  for (auto e : h->ev_pool) cudaEventDestroy(e);
   cudaFree(h->d_model); cudaFree(h->d_geom); cudaFree(h->d_work_reals); cudaFree(h->d_work_ints); cudaFree(h->d_ctx);
   cudaFree(h->d_q_items); cudaFree(h->d_q_res);
   cudaFree(h->d_q_ctr); cudaFree(h->d_epa_verts); cudaFree(h->d_tgt); cudaFree(h->d_hflag); cudaFree(h->d_h_items);
@@ -423,16 +431,32 @@ int mm_step(mm_handle* h, const mm_state* st, const float* actions, int action_m
     pc.heavy_min = h->heavy_min;
     pc.epa_verts = (char*)h->d_epa_verts + (size_t)si * h->convex_grid * MM_WX * EPA_MAXV * 6 * rb;
     const bool fuse = h->fuse_ca;  // experiment switch: stage A of round r + 1 inside the stage C kernel of round r
+    // launch + (optionally) a pair of timing events on the launching stream; kind 0 stage A | 1 convex | 2 stage C | 3 heavy
+    auto timed_launch = [&](int which, int kind, int sub, int grid_x, cudaStream_t st_) -> cudaError_t {
+      if (!h->timing) return launch(which, pc, sub, grid_x, st_);
+      cudaEvent_t ev[2];
+      for (int k = 0; k < 2; k++) {
+        if (h->ev_pool.empty()) { cudaError_t e = cudaEventCreate(&ev[k]); if (e != cudaSuccess) return e; }
+        else { ev[k] = h->ev_pool.back(); h->ev_pool.pop_back(); }
+      }
+      cudaError_t e = cudaEventRecord(ev[0], st_);
+      if (e != cudaSuccess) return e;
+      e = launch(which, pc, sub, grid_x, st_);
+      if (e != cudaSuccess) return e;
+      e = cudaEventRecord(ev[1], st_);
+      h->timed.push_back({kind, ev[0], ev[1]});
+      return e;
+    };
     for (int sub = 0; sub < NROUND; sub++) {
-      if (sub == 0 || !fuse) CK(launch(0, pc, sub, 0, s));
-      CK(launch(1, pc, sub, h->convex_grid, s));
+      if (sub == 0 || !fuse) CK(timed_launch(0, 0, sub, 0, s));
+      CK(timed_launch(1, 1, sub, h->convex_grid, s));
       if (h->heavy_min > 0) {  // contact-rich envs: a CTA each, next to the warp-per-env launch of the others
         CK(cudaEventRecord(h->ev_x[si], s));
         CK(cudaStreamWaitEvent(h->hside[si], h->ev_x[si], 0));
-        CK(launch(fuse ? 7 : 5, pc, sub, h->heavy_grid, h->hside[si]));
+        CK(timed_launch(fuse ? 7 : 5, 3, sub, h->heavy_grid, h->hside[si]));
         CK(cudaEventRecord(h->ev_h[si], h->hside[si]));
       }
-      CK(launch(fuse ? 6 : 2, pc, sub, 0, s));
+      CK(timed_launch(fuse ? 6 : 2, 2, sub, 0, s));
       if (h->heavy_min > 0) CK(cudaStreamWaitEvent(s, h->ev_h[si], 0));
     }
     h->launches += (fuse ? 1 : NROUND) + (h->heavy_min > 0 ? 3 : 2) * NROUND;
@@ -463,6 +487,14 @@ int mm_step_host(mm_handle* h, const mm_state* st, const float* h_actions, int a
   if (h_truncated) CK(cudaMemcpyAsync(h_truncated, h->d_flags + n, n, cudaMemcpyDeviceToHost, s));
   if (h_success) CK(cudaMemcpyAsync(h_success, h->d_flags + 2 * n, n, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int mm_host_staging(mm_handle* h, mm_step_out* out) {
+  if (!h || !out) return fail("mm_host_staging: null argument");
+  size_t n = (size_t)h->cfg.num_envs;
+  out->obs = h->d_obs; out->reward = h->d_reward; out->terminated = h->d_flags; out->truncated = h->d_flags + n;
+  out->success = h->d_flags + 2 * n; out->reward_components = nullptr;
   return 0;
 }
 
@@ -611,6 +643,29 @@ int mm_set_schedule(mm_handle* h, const int32_t* order, int32_t* work) {
 int mm_set_cycle_buffer(mm_handle* h, long long* cycles) {
   if (!h) return fail("mm_set_cycle_buffer: null handle");
   h->d_cycles = cycles;
+  return 0;
+}
+
+int mm_stage_timing(mm_handle* h, int32_t on) {
+  if (!h) return fail("mm_stage_timing: null handle");
+  h->timing = on != 0;
+  return 0;
+}
+
+int mm_stage_times(mm_handle* h, double* ms, long long* launches) {
+  if (!h || !ms) return fail("mm_stage_times: null argument");
+  GUARD(h);
+  CK(cudaDeviceSynchronize());
+  for (int k = 0; k < 4; k++) { ms[k] = 0; if (launches) launches[k] = 0; }
+  for (auto& t : h->timed) {
+    float f = 0;
+    CK(cudaEventElapsedTime(&f, t.a, t.b));
+    ms[t.kind] += (double)f;
+    if (launches) launches[t.kind]++;
+    h->ev_pool.push_back(t.a);
+    h->ev_pool.push_back(t.b);
+  }
+  h->timed.clear();
   return 0;
 }
 

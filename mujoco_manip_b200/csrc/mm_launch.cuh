@@ -20,23 +20,26 @@
 namespace mm {
 
 // CTA shapes (warps per CTA, minimum resident CTAs per SM = register budget) of the three stage kernels
+// (measured on the B200, 4,096 / 16,384 / 65,536 envs: one-warp CTAs for the per-env stages - a finished env frees its
+// slot at once - at 128 / 168 registers, and 255 registers for the convex kernel, whose simplex and shape state
+// otherwise spills; profiles/r02_variants.txt)
 #ifndef MM_WA
-#define MM_WA 4
+#define MM_WA 1
 #endif
 #ifndef MM_MINB_A
-#define MM_MINB_A 4
+#define MM_MINB_A 16
 #endif
 #ifndef MM_WC
-#define MM_WC 4
+#define MM_WC 1
 #endif
 #ifndef MM_MINB_C
-#define MM_MINB_C 3
+#define MM_MINB_C 12
 #endif
 #ifndef MM_WX
 #define MM_WX 4
 #endif
 #ifndef MM_MINB_X
-#define MM_MINB_X 4
+#define MM_MINB_X 2
 #endif
 // stage C / fused kernels: G = 8 packs four envs into a warp, so fewer warps fit the shared memory of a CTA
 template <int G> constexpr int warps_c() { return G == 8 ? (MM_WC > 2 ? 2 : MM_WC) : MM_WC; }

@@ -142,6 +142,7 @@ class PickPlaceVecEnv:
         self.last_attempts = torch.zeros(n, dtype=torch.int32, device=dev)
         self._ep_return = torch.zeros(n, dtype=torch.float64, device=dev)
         self._np_rngs: list | None = None
+        self._out_host = None
         self._closed = False
         # load-aware scheduling (optional): the most expensive envs of the previous step start first (mm_set_schedule);
         # with stage kernels that keep the whole batch resident it no longer pays at the benchmarked sizes: off by default
@@ -294,7 +295,20 @@ class PickPlaceVecEnv:
         if self.load_balance:
             self._order.copy_(torch.argsort(self._work, descending=True).to(torch.int32))
 
-    def _post_step_autoreset(self):
+    def step_host(self, h_actions: torch.Tensor, h_obs: torch.Tensor, h_reward: torch.Tensor, h_flags: torch.Tensor):
+        """One control step with HOST buffers (pinned memory recommended), the end-to-end path of the C ABI
+        (`mm_step_host`): actions [N,10] float32 go to the device, the step runs, observation [N,85], reward [N] and
+        flags [3,N] uint8 (terminated, truncated, success) come back, the stream is synchronised; finished envs are
+        then reset on the device (statistics, Philox draw, reset kernels) when auto_reset is on."""
+        _lib.check(self._L.mm_step_host(self._h, C.byref(self._st), h_actions.data_ptr(), _lib.ACTION_MODES.index(self.action_mode),
+                                        h_obs.data_ptr(), h_reward.data_ptr(), h_flags[0].data_ptr(), h_flags[1].data_ptr(),
+                                        h_flags[2].data_ptr(), self._stream()), "mm_step_host")
+        if self._out_host is None:
+            self._out_host = _lib.MMStepOut()
+            _lib.check(self._L.mm_host_staging(self._h, C.byref(self._out_host)), "mm_host_staging")
+        self._post_step_autoreset(self._out_host)
+
+    def _post_step_autoreset(self, out=None):
         """Bookkeeping after the mm_step launch: episode statistics and (optionally) the reset of finished envs - all in
         library kernels (mm_post_step, mm_sample_episode, mm_reset), no host round trip.  Returns the 5-tuple of `step`."""
         terminated, truncated, success = self._flags[0].bool(), self._flags[1].bool(), self._flags[2].bool()
@@ -302,7 +316,8 @@ class PickPlaceVecEnv:
         if self._rc is not None:
             info["reward_components"] = self._rc
         fast = self.auto_reset and self.rng_kind == "philox"
-        _lib.check(self._L.mm_post_step(self._h, C.byref(self._st), C.byref(self._out), self._ep_return.data_ptr(),
+        out = self._out if out is None else out
+        _lib.check(self._L.mm_post_step(self._h, C.byref(self._st), C.byref(out), self._ep_return.data_ptr(),
                                         self._mask.data_ptr(), self._final_obs.data_ptr() if self.auto_reset else None,
                                         self.stats.data_ptr(), 1 if self.auto_reset else 0, self._stream()), "mm_post_step")
         reward = self._reward
@@ -316,7 +331,7 @@ class PickPlaceVecEnv:
                     self._h, self._yaw_cs.data_ptr() if (use_xy and self.randomize_yaw) else None), "mm_set_placement_yaw")
                 _lib.check(self._L.mm_reset(self._h, C.byref(self._st), self._mask.data_ptr(),
                                             self._obj_xy.data_ptr() if use_xy else None, self._task.data_ptr(),
-                                            self._obs.data_ptr(), self._stream()), "mm_reset")
+                                            out.obs, self._stream()), "mm_reset")
             else:  # host numpy generators (reference-exact draw order): the mask has to visit the host
                 self.reset(mask=self._mask.clone(), _from_step=True)
         return split_obs(self._obs), reward, terminated, truncated, info

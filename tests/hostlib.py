@@ -71,6 +71,17 @@ class EmulEnv:
                          self.max_steps, self._op, self.tgt.ctypes.data_as(C.c_void_p), self.use_float)
         return self.obs.copy(), self.reward_buf.copy(), self.term.astype(bool), self.trunc.astype(bool), self.succ.astype(bool)
 
+    def step_counted(self, actions):
+        """Same step executed with the operation-counting scalar: returns (flops[3] = stage A, convex stage, stage C)
+        summed over the envs; the state advances exactly as in `step` (FP64)."""
+        a = np.zeros((self.n, 10), dtype=np.float32)
+        act = np.asarray(actions, dtype=np.float32).reshape(self.n, -1)
+        a[:, : act.shape[1]] = act
+        fl = np.zeros(3, dtype=np.int64)
+        self.L.emul_step_counted(self.n, self._sp, a.ctypes.data_as(C.c_void_p), MODES.index(self.mode), REWARDS.index(self.reward),
+                                 self.max_steps, self._op, self.tgt.ctypes.data_as(C.c_void_p), fl.ctypes.data_as(C.c_void_p))
+        return fl
+
     def ops(self, ops, target=None):
         t = None if target is None else np.ascontiguousarray(target, dtype=np.float64).reshape(self.n, 3)
         self.L.emul_ops(self.n, self._sp, int(ops), None if t is None else t.ctypes.data_as(C.c_void_p), self.use_float)

@@ -3,10 +3,50 @@
 // against the oracle on machines without a GPU (`-m "not gpu"` tests).  It is never loaded by the
 // mujoco_manip_b200 package: the product path is the CUDA library and fails loudly without it.
 #define MM_MODEL_HOST_FILL
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
+
+#include <type_traits>
+
+// Operation-counting scalar: the kernel source instantiated with it executes the very same algorithm and counts every
+// floating-point add / subtract / multiply / divide / square root / trigonometric call it performs (1 each) - the
+// ALGORITHMIC work of a step at G = 1, free of lane redundancy - per stage (bench.py roofline).
+struct Cnt {
+  double v;
+  static long long n;
+  Cnt() = default;
+  template <class U, class = typename std::enable_if<std::is_arithmetic<U>::value>::type>
+  Cnt(U x) : v((double)x) {}
+  explicit operator double() const { return v; }
+  explicit operator float() const { return (float)v; }
+  explicit operator int() const { return (int)v; }
+  Cnt& operator+=(Cnt o) { v += o.v; n++; return *this; }
+  Cnt& operator-=(Cnt o) { v -= o.v; n++; return *this; }
+  Cnt& operator*=(Cnt o) { v *= o.v; n++; return *this; }
+  Cnt& operator/=(Cnt o) { v /= o.v; n++; return *this; }
+};
+long long Cnt::n = 0;
+inline Cnt operator+(Cnt a, Cnt b) { Cnt::n++; return Cnt(a.v + b.v); }
+inline Cnt operator-(Cnt a, Cnt b) { Cnt::n++; return Cnt(a.v - b.v); }
+inline Cnt operator*(Cnt a, Cnt b) { Cnt::n++; return Cnt(a.v * b.v); }
+inline Cnt operator/(Cnt a, Cnt b) { Cnt::n++; return Cnt(a.v / b.v); }
+inline Cnt operator-(Cnt a) { return Cnt(-a.v); }
+inline bool operator<(Cnt a, Cnt b) { return a.v < b.v; }
+inline bool operator>(Cnt a, Cnt b) { return a.v > b.v; }
+inline bool operator<=(Cnt a, Cnt b) { return a.v <= b.v; }
+inline bool operator>=(Cnt a, Cnt b) { return a.v >= b.v; }
+inline bool operator==(Cnt a, Cnt b) { return a.v == b.v; }
+inline bool operator!=(Cnt a, Cnt b) { return a.v != b.v; }
+namespace mm {
+inline Cnt tsqrt(Cnt x) { Cnt::n++; return Cnt(std::sqrt(x.v)); }
+inline Cnt trsqrt(Cnt x) { Cnt::n += 2; return Cnt(1.0 / std::sqrt(x.v)); }
+inline void tsincos(Cnt x, Cnt* s, Cnt* c) { Cnt::n += 2; s->v = std::sin(x.v); c->v = std::cos(x.v); }
+inline Cnt tacos(Cnt x) { Cnt::n++; return Cnt(std::acos(x.v)); }
+inline Cnt tsin(Cnt x) { Cnt::n++; return Cnt(std::sin(x.v)); }
+}  // namespace mm
 
 #include "../mujoco_manip_b200/csrc/mm_env.h"
 
@@ -64,7 +104,10 @@ void do_reset(int n, void** sp, const unsigned char* mask, const double* obj_xy,
 // One control step of n envs through the STAGE functions the CUDA kernels run (mm_env.h): 17 rounds of stage A for
 // every env, the batch-wide convex queue, stage C for every env - with per-env contact lists and images as on the device.
 template <class T>
-void do_step(int n, void** sp, const float* actions, int mode, int reward_type, int max_steps, void** op, const float* tgt) {
+void do_step(int n, void** sp, const float* actions, int mode, int reward_type, int max_steps, void** op, const float* tgt,
+             long long* flops = nullptr /*[3]: stage A, convex stage, stage C*/) {
+  long long mark = Cnt::n;
+  auto tick = [&](int k) { if (flops) flops[k] += Cnt::n - mark; mark = Cnt::n; };
   Ctx<T>& c = ctx<T>();
   StatePtrs st = state_from(sp);
   StepOut out = out_from(op);
@@ -92,6 +135,7 @@ void do_step(int n, void** sp, const float* actions, int mode, int reward_type, 
     for (size_t k = 0; k < ntail; k++)
       if (tail[k] != 0xA5) { std::fprintf(stderr, "stage A wrote outside its scratch slice (byte %zu)\n", scratch_a_bytes<T>() + k); std::abort(); }
   }
+  tick(0);
   for (int sub = 0; sub <= ACTION_REPEAT; sub++) {
     CvxQueue<T> q = queue(sub), qn = queue(sub + 1);
     EpaMem<T> em;
@@ -111,15 +155,18 @@ void do_step(int n, void** sp, const float* actions, int mode, int reward_type, 
       stage_convex<T, 1>(g, c.gm, q, i, image.data(), bpos, bR, em);
 #endif
     }
+    tick(1);
     for (long e = 0; e < n; e++) {  // stage C of round sub
       Work<T> w = work(e);
       stage_c<T, 1, false>(g, c.s, c.md, w, st, e, sub, image.data(), q, qn, nohv, reward_type, max_steps, out, tgt);
     }
+    tick(2);
     if (sub < ACTION_REPEAT)
       for (long e = 0; e < n; e++) {  // stage A of round sub + 1 (its own launch on the device)
         Work<T> w = work(e);
         stage_a<T, 1>(g, c.s, c.md, w, st, e, sub + 1, actions, mode, image.data(), qn, nohv);
       }
+    tick(0);
   }
 }
 }  // namespace
@@ -141,6 +188,13 @@ void emul_step(int n, void** state, const float* actions, int mode, int reward_t
                const float* tgt_kp, int use_float) {
   if (use_float) do_step<float>(n, state, actions, mode, reward_type, max_steps, out, tgt_kp);
   else do_step<double>(n, state, actions, mode, reward_type, max_steps, out, tgt_kp);
+}
+
+// One control step executed with the operation-counting scalar: flops[0..2] += floating-point operations of stage A,
+// the convex stage and stage C over the n envs (state advances exactly as in emul_step with use_float = 0).
+void emul_step_counted(int n, void** state, const float* actions, int mode, int reward_type, int max_steps, void** out,
+                       const float* tgt_kp, long long* flops) {
+  do_step<Cnt>(n, state, actions, mode, reward_type, max_steps, out, tgt_kp, flops);
 }
 
 void emul_ops(int n, void** state, int ops, const double* target, int use_float) {
