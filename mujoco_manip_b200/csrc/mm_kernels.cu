@@ -195,7 +195,6 @@ struct mm_handle {
   void* d_q_res = nullptr;
   int* d_q_ctr = nullptr;      // [nchunk][2][NROUND] counts, heads
   int q_cap = 0;
-  void* d_epa_verts = nullptr; // [nstream][convex_grid * MM_WX][EPA_MAXV * 6]
   cudaStream_t side[8] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[8] = {};
   float* d_tgt = nullptr;
@@ -272,7 +271,7 @@ size_t mm_workspace_bytes(const mm_config* cfg) {
   size_t per_env = 4 * 4 + (ACTION_STRIDE + OBS_DIM + 1) * 4 + 3 + (size_t)WORK_REALS * rb + (size_t)WORK_INTS * 4 +
                    (cfg->precision ? ctx_stride<float>() : ctx_stride<double>()) +
                    64 * (sizeof(CvxItem) + (cfg->precision ? sizeof(CvxRes<float>) : sizeof(CvxRes<double>)));
-  return n * per_env + (size_t)8 * 148 * 8 * MM_WX * EPA_MAXV * 6 * rb;
+  return n * per_env;
 }
 
 int mm_create(const mm_config* cfg, mm_handle** out) {
@@ -301,7 +300,7 @@ int mm_create(const mm_config* cfg, mm_handle** out) {
   CK(cudaMalloc(&h->d_ctx, n * cstride));
   CK(cudaMemset(h->d_ctx, 0, n * cstride));
   // chunks: MM_CHUNK envs each (default: the batch in MM_STREAMS pieces, at most 4096 envs per piece)
-  h->nstream = (int)env_long("MM_STREAMS", 2);
+  h->nstream = (int)env_long("MM_STREAMS", 4);
   if (h->nstream < 1) h->nstream = 1;
   if (h->nstream > 8) h->nstream = 8;
   long chunk = env_long("MM_CHUNK", 0);
@@ -326,7 +325,6 @@ int mm_create(const mm_config* cfg, mm_handle** out) {
   CK(cudaMalloc(&h->d_hflag, 2 * n));
   CK(cudaMemset(h->d_hflag, 0, 2 * n));
   CK(cudaMalloc(&h->d_h_items, (size_t)h->nchunk * 2 * chunk * sizeof(int)));
-  CK(cudaMalloc(&h->d_epa_verts, (size_t)h->nstream * h->convex_grid * MM_WX * EPA_MAXV * 6 * rb));
   for (int i = 0; i < h->nstream; i++) {
     CK(cudaStreamCreateWithFlags(&h->side[i], cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming));
@@ -360,7 +358,7 @@ void mm_destroy(mm_handle* h) {
   for (auto e : h->ev_pool) cudaEventDestroy(e);
   cudaFree(h->d_model); cudaFree(h->d_geom); cudaFree(h->d_work_reals); cudaFree(h->d_work_ints); cudaFree(h->d_ctx);
   cudaFree(h->d_q_items); cudaFree(h->d_q_res);
-  cudaFree(h->d_q_ctr); cudaFree(h->d_epa_verts); cudaFree(h->d_tgt); cudaFree(h->d_hflag); cudaFree(h->d_h_items);
+  cudaFree(h->d_q_ctr); cudaFree(h->d_tgt); cudaFree(h->d_hflag); cudaFree(h->d_h_items);
   cudaFree(h->d_actions); cudaFree(h->d_obs); cudaFree(h->d_reward); cudaFree(h->d_flags);
   delete h;
 }
@@ -429,7 +427,6 @@ int mm_step(mm_handle* h, const mm_state* st, const float* actions, int action_m
     pc.h_items = h->d_h_items + (size_t)c * 2 * h->chunk;
     pc.h_cap = (int)h->chunk;
     pc.heavy_min = h->heavy_min;
-    pc.epa_verts = (char*)h->d_epa_verts + (size_t)si * h->convex_grid * MM_WX * EPA_MAXV * 6 * rb;
     const bool fuse = h->fuse_ca;  // experiment switch: stage A of round r + 1 inside the stage C kernel of round r
     // launch + (optionally) a pair of timing events on the launching stream; kind 0 stage A | 1 convex | 2 stage C | 3 heavy
     auto timed_launch = [&](int which, int kind, int sub, int grid_x, cudaStream_t st_) -> cudaError_t {

@@ -69,8 +69,6 @@ struct StepParams {
   int* h_count;           // [NROUND]
   int* h_head;            // [NROUND]
   int heavy_min;
-  // per-warp EPA vertex storage of the convex kernel
-  void* epa_verts;    // [grid_x * MM_WX][EPA_MAXV * 6]
   float* tgt_kp;
   const unsigned char* mask;
   const double* obj_xy;
@@ -207,6 +205,8 @@ template <class T> size_t smem_h() { return scratch_c_bytes<T>() + (8 + 128) * s
 // convex stage: persistent warps take (env, geom pair) items off the queue of this round
 template <class T>
 struct ConvexSmem {
+  T vert[EPA_MAXV * 6];  // polytope vertices next to its faces: the canonical-id scan, the visibility test and the face
+                         // construction of every EPA iteration read them (from global memory they cost an L2 round trip each)
   T face[EPA_MAXF * 4];
   T bpos[NDB][3], bR[NDB][9];
   int fidx[EPA_MAXF], edge[EPA_MAXE], canon[EPA_MAXV], ecan[EPA_MAXE];
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(32 * W, MM_MINB_X) k_convex(StepParams p, int 
   int count = *q.count;
   if (count > q.cap) count = q.cap;
   EpaMem<T> em;
-  em.vert = reinterpret_cast<T*>(p.epa_verts) + ((size_t)blockIdx.x * W + wi) * (EPA_MAXV * 6);
+  em.vert = cs.vert;
   em.face = cs.face; em.fidx = cs.fidx; em.edge = cs.edge; em.canon = cs.canon; em.ecan = cs.ecan;
   while (true) {
     int i = 0;

@@ -58,6 +58,14 @@ double* orc_ptr(void* h, const char* name) {
   return nullptr;
 }
 
+// constraint row i: out = {pos, D, R, aref, force}; returns the row type (0 equality, 1 limit, 2 contact) or -1
+int orc_efc(void* h, int i, double* out) {
+  Data& d = ((Env*)h)->d;
+  if (i < 0 || i >= d.nefc) return -1;
+  out[0] = d.efc_pos[i]; out[1] = d.efc_D[i]; out[2] = d.efc_R[i]; out[3] = d.efc_aref[i]; out[4] = d.efc_force[i];
+  return d.efc_type[i];
+}
+
 int orc_ncon(void* h) { return ((Env*)h)->d.ncon; }
 int orc_nefc(void* h) { return ((Env*)h)->d.nefc; }
 int orc_niter(void* h) { return ((Env*)h)->d.solver_niter; }

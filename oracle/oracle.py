@@ -49,6 +49,7 @@ def lib():
         for n in ("orc_ncon", "orc_nefc", "orc_niter"):
             getattr(L, n).argtypes = [C.c_void_p]
             getattr(L, n).restype = C.c_int
+        L.orc_efc.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.orc_contact.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double),
                                   C.c_void_p, C.c_void_p]
         for n in ("orc_mj_step", "orc_mj_forward", "orc_mj_kinematics", "orc_mj_reset_keyframe", "orc_fsm_reset",
@@ -134,6 +135,15 @@ class OracleEnv:
     @property
     def niter(self):
         return self.L.orc_niter(self.h)
+
+    def efc_rows(self):
+        """Constraint rows of the last forward pass: array [nefc, 6] = type, pos, D, R, aref, force."""
+        rows = []
+        buf = np.zeros(5)
+        for i in range(self.nefc):
+            t = self.L.orc_efc(self.h, i, buf.ctypes.data)
+            rows.append([t, *buf])
+        return np.array(rows).reshape(-1, 6)
 
     def contacts(self):
         out = []

@@ -96,3 +96,25 @@ def reltol(a, b, tol):
     """|a-b| <= tol * max(|b|, 1) elementwise."""
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
     return np.max(np.abs(a - b) / np.maximum(np.abs(b), 1.0))
+
+
+def emul_forward(qpos, qvel, ctrl, warm=None, maxcon=256):
+    """One forward pass of the kernel source (FP64, host build) on a raw state with the intermediates exposed."""
+    L = C.CDLL(build_emul())
+    qpos = np.ascontiguousarray(qpos, dtype=np.float64)
+    qvel = np.ascontiguousarray(qvel, dtype=np.float64)
+    ctrl = np.ascontiguousarray(ctrl, dtype=np.float64)
+    warm = np.zeros(27) if warm is None else np.ascontiguousarray(warm, dtype=np.float64)
+    out = dict(Mr=np.zeros((9, 9)), fs=np.zeros(27), qacc_smooth=np.zeros(27), qacc=np.zeros(27), fc=np.zeros(27),
+               bpos=np.zeros((13, 3)), bR=np.zeros((13, 9)), cpos=np.zeros((maxcon, 3)), cn=np.zeros((maxcon, 3)),
+               cdist=np.zeros(maxcon), cmeta=np.zeros(maxcon, dtype=np.int32), cD=np.zeros(maxcon), aref=np.zeros((maxcon, 6)))
+    ncon, niter = C.c_int(), C.c_int()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    L.emul_forward_debug(p(qpos), p(qvel), p(ctrl), p(warm), p(out["Mr"]), p(out["fs"]), p(out["qacc_smooth"]), p(out["qacc"]),
+                         p(out["fc"]), p(out["bpos"]), p(out["bR"]), C.byref(ncon), p(out["cpos"]), p(out["cn"]), p(out["cdist"]),
+                         p(out["cmeta"]), C.byref(niter), p(out["cD"]), p(out["aref"]))
+    n = ncon.value
+    for k in ("cpos", "cn", "cdist", "cmeta", "cD", "aref"):
+        out[k] = out[k][:n]
+    out["ncon"], out["niter"] = n, niter.value
+    return out

@@ -214,7 +214,7 @@ void emul_fsm_plan(int n, void** state, int nsteps, float* actions /*[n,10]*/) {
 // One forward pass on a raw state with every intermediate exposed (FP64), for stage-wise parity tests.
 void emul_forward_debug(const double* qpos, const double* qvel, const double* ctrl, const double* warm, double* Mr,
                         double* fs, double* as, double* qacc, double* fc, double* bpos, double* bR, int* ncon,
-                        double* cpos, double* cn, double* cdist, int* cmeta, int* niter) {
+                        double* cpos, double* cn, double* cdist, int* cmeta, int* niter, double* cD, double* aref) {
   Ctx<double>& c = ctx<double>();
   Scratch<double>& s = c.s;
   Grp<1> g{0, 1u};
@@ -238,6 +238,8 @@ void emul_forward_debug(const double* qpos, const double* qvel, const double* ct
     for (int d = 0; d < 3; d++) { cpos[3 * k + d] = c.w.cpos[d * MAXCON + k]; cn[3 * k + d] = c.w.cn[d * MAXCON + k]; }
     cdist[k] = c.w.cdist[k];
     cmeta[k] = c.w.cmeta[k];
+    if (cD) cD[k] = c.w.cD[k];
+    if (aref) for (int r = 0; r < 6; r++) aref[6 * k + r] = c.w.aref[6 * k + r];
   }
 }
 

@@ -165,6 +165,45 @@ def fsm_multi_episode(tasks, seed, max_steps=900):
     return out
 
 
+def dataset_rows(seed=42, num_episodes=3, tasks="cross"):
+    """Frames of the reference's own dataset generator (scripts/generate_dataset.py:83-198 `run_episode`, imported
+    unmodified - hydra / omegaconf are stubbed, they only decorate its CLI) for the first episodes of a `tasks` run with
+    randomize_objects=True, reward_type=staged: the row-level contract of the state-only dataset writer."""
+    import importlib.util
+    import types
+
+    for name in ("hydra", "omegaconf"):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.main = lambda *a, **k: (lambda f: f)
+            m.DictConfig, m.OmegaConf = dict, object
+            sys.modules[name] = m
+    spec = importlib.util.spec_from_file_location("ref_generate_dataset", os.path.join(ARGS.reference, "scripts", "generate_dataset.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    from mujoco_manip.features import FEATURES
+
+    keys = [k for k in FEATURES if "images" not in k]
+    env = PickPlaceGymEnv(action_mode="abs_pos", reward_type="staged", randomize_objects=True)
+    ss = np.random.SeedSequence(seed).spawn(num_episodes)
+    ep_seeds = [int(c.generate_state(1)[0]) for c in ss]
+    task_list = TASK_SETS[tasks]
+    out = {"episode_seeds": np.array(ep_seeds, dtype=np.uint64), "keys": np.array(keys)}
+    names_o, names_b = ["obj_red", "obj_green", "obj_blue"], ["bin_red", "bin_green", "bin_blue"]
+    for ep in range(num_episodes):
+        o, b = task_list[ep % len(task_list)]
+        frames = gen.run_episode(env, o, b, set(keys), reward_type="staged", episode_seed=ep_seeds[ep])
+        out[f"ep{ep}.task"] = np.array([names_o.index(o), names_b.index(b)])
+        out[f"ep{ep}.task_string"] = np.array(frames[0]["task"])
+        for k in keys:
+            if k == "observation.phase_description":
+                out[f"ep{ep}.{k}"] = np.array([f[k] for f in frames])
+            else:
+                out[f"ep{ep}.{k}"] = np.stack([np.asarray(f[k], dtype=np.float32).ravel() for f in frames])
+    env.close()
+    return out
+
+
 def random_rollout(mode, seed, n_steps=50, reward_type="dense", stress=False):
     env = PickPlaceGymEnv(task=("obj_red", "bin_red"), action_mode=mode, reward_type=reward_type)
     obs, _ = env.reset(seed=seed)
@@ -272,6 +311,7 @@ def main():
                         **fsm_episode("abs_pos", ("obj_green", "bin_blue"), True, 42, reward_type="staged"))
     np.savez_compressed(os.path.join(OUT, "fsm_rot6d_rel_blue_red_seed7.npz"),
                         **fsm_episode("ee_pos_rot6d_g_rel", ("obj_blue", "bin_red"), True, 7))
+    np.savez_compressed(os.path.join(OUT, "dataset_rows_seed42_cross.npz"), **dataset_rows())
     np.savez_compressed(os.path.join(OUT, "fsm_multi3_seed5.npz"),
                         **fsm_multi_episode([("obj_red", "bin_red"), ("obj_green", "bin_green"), ("obj_blue", "bin_blue")], 5))
     np.savez_compressed(os.path.join(OUT, "fsm_multi2_cross_seed11.npz"),
