@@ -49,7 +49,7 @@ class MMStepOut(C.Structure):
 
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
-              "-diag-suppress=170"]  # 170: the EPA workspace deliberately spans consecutive members of the scratch struct
+              "-diag-suppress=170,128"]  # 170: the EPA workspace deliberately spans consecutive members of the scratch struct
 BUILD_DIR = os.path.join(_HERE, "_C", "obj")
 
 

@@ -76,10 +76,39 @@ struct Grp {
 #endif
     return pred ? 1u : 0u;
   }
-  // (value, index) reductions with the tie rule of a linear scan: among equal values the LOWEST index wins
+  // (value, index) reductions with the tie rule of a linear scan: among equal values the LOWEST index wins.
+  // Full warp (G == 32): three integer warp-reduce instructions (redux.sync) on an order-preserving integer image of
+  // the value - high word, low word among the lanes that hold the best high word, then the lowest index among the
+  // exact matches - instead of a five-level shuffle butterfly; same result bit for bit (-0 and +0 compare equal in
+  // both forms: the value is normalised with + 0.0 first).
+#ifdef __CUDA_ARCH__
+  __device__ __forceinline__ static unsigned long long order_key(double v) {
+    unsigned long long u = (unsigned long long)__double_as_longlong(v + 0.0);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+  }
+  __device__ __forceinline__ static unsigned long long order_key(float v) {
+    unsigned u = (unsigned)__float_as_int(v + 0.0f);
+    return (unsigned long long)((u >> 31) ? ~u : (u | 0x80000000u)) << 32;
+  }
+  template <class T>
+  __device__ __forceinline__ void arg_redux(T& v, int& i, bool want_max) const {
+    unsigned long long k = order_key(v);
+    if (!want_max) k = ~k;
+    unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
+    unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+    bool c = hi == mh;
+    unsigned ml = __reduce_max_sync(0xffffffffu, c ? lo : 0u);
+    c = c && lo == ml;
+    int win = __reduce_min_sync(0xffffffffu, c ? i : 0x7fffffff);
+    int src = __ffs(__ballot_sync(0xffffffffu, c && i == win)) - 1;
+    v = __shfl_sync(0xffffffffu, v, src);
+    i = win;
+  }
+#endif
   template <class T>
   MM_HD void argmax(T& v, int& i) const {
 #ifdef __CUDA_ARCH__
+    if (G == 32) { arg_redux(v, i, true); return; }
 #pragma unroll
     for (int o = G / 2; o > 0; o >>= 1) {
       T ov = __shfl_xor_sync(m(), v, o);
@@ -91,6 +120,7 @@ struct Grp {
   template <class T>
   MM_HD void argmin(T& v, int& i) const {
 #ifdef __CUDA_ARCH__
+    if (G == 32) { arg_redux(v, i, false); return; }
 #pragma unroll
     for (int o = G / 2; o > 0; o >>= 1) {
       T ov = __shfl_xor_sync(m(), v, o);
@@ -101,6 +131,7 @@ struct Grp {
   }
   MM_HD int imin(int v) const {
 #ifdef __CUDA_ARCH__
+    if (G == 32) return __reduce_min_sync(0xffffffffu, v);
 #pragma unroll
     for (int o = G / 2; o > 0; o >>= 1) { int t = __shfl_xor_sync(m(), v, o); v = t < v ? t : v; }
 #endif
@@ -108,6 +139,7 @@ struct Grp {
   }
   MM_HD int isum(int v) const {
 #ifdef __CUDA_ARCH__
+    if (G == 32) return __reduce_add_sync(0xffffffffu, v);
 #pragma unroll
     for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(m(), v, o);
 #endif
@@ -115,6 +147,7 @@ struct Grp {
   }
   MM_HD int imax(int v) const {
 #ifdef __CUDA_ARCH__
+    if (G == 32) return __reduce_max_sync(0xffffffffu, v);
 #pragma unroll
     for (int o = G / 2; o > 0; o >>= 1) { int t = __shfl_xor_sync(m(), v, o); v = t > v ? t : v; }
 #endif

@@ -444,3 +444,24 @@ def test_large_batch_kernel_variant_vs_oracle(cuda_device, oracle_lib):
             assert reltol(q[k], o.qpos, TOL) < TOL, (t, k)
     assert int(env.state["diag"][:, 2].max()) == 0
     assert bool((env.state["step_count"] == 45).all())
+
+
+def test_env_on_second_gpu_without_set_device(oracle_lib):
+    """a handle is bound to its own device - every C entry point selects it and restores the caller's; an env
+    on cuda:1 created and stepped while the current device is 0 must match the oracle.  Skipped on one-GPU boxes."""
+    import torch
+
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    torch.cuda.set_device(0)
+    env = _make(3, torch.device("cuda:1"), task=("obj_red", "bin_red"), action_mode="abs_pos")
+    env.reset()
+    orc = oracle_lib.OracleEnv(action_mode="abs_pos")
+    orc.reset(None, 0, 0)
+    a = np.array([0.1, 0.5, 0.45, 1.0], dtype=np.float32)
+    for _ in range(3):
+        env.step(torch.from_numpy(np.repeat(a[None], 3, axis=0)).to("cuda:1"))
+        orc.step(a)
+    assert torch.cuda.current_device() == 0
+    assert reltol(_np(env.state["qpos"])[0], orc.qpos, TOL) < TOL
+    env.close()

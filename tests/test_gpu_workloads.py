@@ -248,3 +248,26 @@ def test_optional_launch_plans_match_the_golden(cuda_device, monkeypatch, switch
         env.step(a)
         assert reltol(_np(env.state["qpos"])[0], g["qpos"][t], TOL) < TOL, t
     env.close()
+
+
+def test_dataset_writer_rows_match_the_reference_generator(cuda_device, tmp_path):
+    """f3: ExpertDatasetWriter against the frames of the reference's own `run_episode` (scripts/generate_dataset.py:83-198,
+    golden recorded by running it unmodified on the oracle engine): same episode seeds and task cycle, same number of
+    frames per episode, every state feature row by row (float32 observations: 2e-5), phase strings and task strings equal."""
+    from mujoco_manip_b200 import dataset
+
+    g = np.load(os.path.join(GOLDEN, "dataset_rows_seed42_cross.npz"))
+    w = dataset.ExpertDatasetWriter(str(tmp_path), num_envs=2, device=str(cuda_device), tasks="cross", reward_type="staged",
+                                    randomize_objects=True, seed=42)
+    meta = w.generate(3)
+    assert meta["episode_seeds"] == [int(x) for x in g["episode_seeds"]] and meta["shards"] == 1
+    for ep in range(3):
+        rows = dataset.read_episode(str(tmp_path), ep)
+        n = g[f"ep{ep}.observation.state"].shape[0]
+        assert len(rows["frame_index"]) == n == meta["episode_lengths"][ep], (ep, len(rows["frame_index"]), n)
+        assert rows["task"][0] == str(g[f"ep{ep}.task_string"])
+        assert rows["observation.phase_description"] == [str(x) for x in g[f"ep{ep}.observation.phase_description"]]
+        for k in [str(x) for x in g["keys"]]:
+            if k == "observation.phase_description":
+                continue
+            np.testing.assert_allclose(rows[k], g[f"ep{ep}.{k}"], rtol=0, atol=2e-5, err_msg=f"episode {ep} {k}")

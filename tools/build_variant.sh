@@ -8,7 +8,7 @@ root=$(cd "$(dirname "$0")/.." && pwd)
 obj=$root/mujoco_manip_b200/_C/obj
 out=$root/mujoco_manip_b200/_C/variants
 mkdir -p $out
-nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -diag-suppress=170 "$@" \
+nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -diag-suppress=170,128 "$@" \
   -Xptxas -v -c -o $out/mm_inst_f64_32_$name.o $root/mujoco_manip_b200/csrc/mm_inst_f64_32.cu 2> $out/ptxas_$name.log
 others=$(ls $obj/*.o | grep -v mm_inst_f64_32.o)
 nvcc --shared -cudart shared -gencode arch=compute_100a,code=sm_100a -o $out/libmm_$name.so $out/mm_inst_f64_32_$name.o $others
