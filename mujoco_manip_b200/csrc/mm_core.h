@@ -59,9 +59,10 @@ MM_HD int meta_key(int m) { return (m >> META_KEY_SHIFT) & 0xFF; }  // class A |
 // candidate pairs (and therefore contacts) are ordered by (class A, class B)
 MM_HD int sort_key(int m) { return (((m >> META_KEY_SHIFT) & 15) << 4) | ((m >> (META_KEY_SHIFT + 4)) & 15); }
 
-// rows of Scratch::S: robot dofs 0..8, then the three rotational dofs of each cube
-constexpr int NSROW = NROB + 9;
-MM_HD int srow(int dof) { return dof < NROB ? dof : NROB + 3 * ((dof - NROB) / 6) + ((dof - NROB) % 6 - 3); }
+// rows of Scratch::S: one spatial axis per dof (the cube translations carry their unit vectors, so that every product
+// with S is a plain row access without a case split)
+constexpr int NSROW = NV;
+MM_HD int srow(int dof) { return dof; }
 MM_HD bool is_cube_translation(int dof) { return dof >= NROB && ((dof - NROB) % 6) < 3; }
 // rows of the 6-vector scratch: 16 suffice (14 dofs of a body pair + 2 rows that park the position-stage qpos);
 // the FP32 build keeps 27 because its EPA workspace (integers are as wide as reals there) needs the room
@@ -74,7 +75,7 @@ struct Scratch {
   //      (mm_stage.h: ctx_load / ctx_store copy [0, SCRATCH_PERSIST) to / from global memory) ----
   T qpos[NQ], qvel[NV], ctrl[NU];
   T bpos[NDB][3], bR[NDB][9];
-  T S[NSROW][6];   // spatial axes of the dofs that have a non-trivial one (see srow); cube translations are unit vectors
+  T S[NSROW][6];   // spatial axis of every dof about the world origin (angular 3, linear 3)
   T Mr[NROB * NROB];
   T fs[NV], as[NV];
   T actf[NU];
@@ -351,18 +352,15 @@ MM_HDN void solve_H(const Grp<G>& g, const Scratch<T>& s, T* x) {
 
 template <class T>
 MM_HD T S_comp(const Scratch<T>& s, int dof, int c) {
-  if (is_cube_translation(dof)) return c == 3 + (dof - NROB) % 6 ? (T)1 : (T)0;
-  return s.S[srow(dof)][c];
+  return s.S[dof][c];
 }
 template <class T>
 MM_HD T S_dot(const Scratch<T>& s, int dof, const T* x) {
-  if (is_cube_translation(dof)) return x[3 + (dof - NROB) % 6];
-  return dot6(s.S[srow(dof)], x);
+  return dot6(s.S[dof], x);
 }
 template <class T>
 MM_HD void S_get(const Scratch<T>& s, int dof, T* out) {
-  if (is_cube_translation(dof)) { for (int a = 0; a < 6; a++) out[a] = 0; out[3 + (dof - NROB) % 6] = 1; return; }
-  const T* S = s.S[srow(dof)];
+  const T* S = s.S[dof];
   for (int a = 0; a < 6; a++) out[a] = S[a];
 }
 
@@ -424,8 +422,13 @@ MM_HDX void fk(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md) {
   }
   g.sync();
   for (int i = g.lane; i < NV; i += G) {
-    if (is_cube_translation(i)) continue;
-    T* S = s.S[srow(i)];
+    T* S = s.S[i];
+    if (is_cube_translation(i)) {
+      int k = (i - NROB) % 6;
+#pragma unroll
+      for (int a = 0; a < 6; a++) S[a] = a == 3 + k ? (T)1 : (T)0;
+      continue;
+    }
     if (i < NARM) {
       T a[3] = {s.bR[i][2], s.bR[i][5], s.bR[i][8]};
       S[0] = a[0]; S[1] = a[1]; S[2] = a[2];
@@ -1502,13 +1505,19 @@ MM_HDN void analyse_coupling(const Grp<G>& g, Scratch<T>& s) {
 // H = M + J^T D J over the active rows, assembled from the per-pair blocks; then factor in place
 template <class T, int G>
 MM_HDN void build_factor_H(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md) {
-  for (int e = g.lane; e < NV * (NV + 1) / 2; e += G) {
-    int i, j;
-    tri_rc<T>(e, &i, &j);
-    T v = 0;
-    if (i < NROB) v = s.Mr[i * NROB + j];
-    else if (i == j) v = ((i - 9) % 6) < 3 ? md.cube_mass : md.cube_inertia;
-    s.H[i * NV + j] = v;
+  // H = M on the entries that will be read: the robot block, and of every cube its own block (lone cube) or its whole
+  // row (cube coupled with the robot / another cube); constant divisors, no triangular index arithmetic
+  for (int e = g.lane; e < NROB * NROB + 3 * 6 * NV; e += G) {
+    if (e < NROB * NROB) {
+      int i = e / NROB, j = e - i * NROB;
+      if (j <= i) s.H[i * NV + j] = s.Mr[e];
+      continue;
+    }
+    int r = e - NROB * NROB, c = r / (6 * NV);
+    r -= c * 6 * NV;
+    int k = r / NV, j = r - k * NV, i = NROB + 6 * c + k;
+    if (j > i || (((s.lone >> c) & 1) && j < NROB + 6 * c)) continue;
+    s.H[i * NV + j] = i == j ? (k < 3 ? md.cube_mass : md.cube_inertia) : (T)0;
   }
   g.sync();
   if (g.lane == 0) {
