@@ -510,6 +510,39 @@ def measure_random(args, rank, world, local, dev, n, mode, randomize, steps, war
             res["flops"] = count_flops(env, pool[(warmup + steps) % len(pool)], mode)
         except Exception as exc:  # the counting build is measurement infrastructure; the bench line survives without it
             res["flops"] = {"error": str(exc)[:200]}
+        # per-kernel durations for the roofline: in the timed region the chunks' stage launches overlap on several
+        # streams, so their event times include waiting for SMs; here the same batch, continued from the very same
+        # states, takes three more steps on ONE stream and ONE chunk - every stage kernel timed alone, back to back
+        old = os.environ.get("MM_STREAMS"), os.environ.get("MM_CHUNK")
+        os.environ["MM_STREAMS"], os.environ["MM_CHUNK"] = "1", str(n)
+        try:
+            solo = PickPlaceVecEnv(n, device=dev, task=("obj_red", "bin_red"), action_mode=mode, reward_type="dense",
+                                   max_episode_steps=500, seed=1234, rng="philox", env_id_offset=rank * n,
+                                   precision=args.precision, group=args.group, auto_reset=True, randomize_objects=randomize)
+            solo.reset()
+            solo.set_state(env.get_state())
+            solo._task.copy_(env._task)
+            torch.cuda.synchronize(dev)
+            _lib.check(solo._L.mm_stage_timing(solo._h, 1), "mm_stage_timing")
+            for i in range(3):
+                flush.fill_(i)
+                a = pool[(warmup + steps + i) % len(pool)]
+                _lib.check(solo._L.mm_step(solo._h, C.byref(solo._st), a.data_ptr(), mode_i, C.byref(solo._out), solo._stream()), "mm_step")
+                solo._post_step_autoreset()
+            sm, sn = (C.c_double * 4)(), (C.c_longlong * 4)()
+            _lib.check(solo._L.mm_stage_times(solo._h, sm, sn), "mm_stage_times")
+            res["solo"] = {"stage_a_ms_per_launch": sm[0] / max(1, sn[0]), "convex_ms_per_launch": sm[1] / max(1, sn[1]),
+                           "stage_c_ms_per_launch": sm[2] / max(1, sn[2]), "launches_per_step": sn[2] / 3.0,
+                           "step_ms": (sm[0] + sm[1] + sm[2]) / 3.0}
+            solo.close()
+        except Exception as exc:
+            res["solo"] = {"error": str(exc)[:200]}
+        finally:
+            for k, v in zip(("MM_STREAMS", "MM_CHUNK"), old):
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
     res["env_handle"] = env
     return res
 
@@ -553,8 +586,9 @@ def finish_line(args, res, world, local):
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": sample + "; FP64 oracle restatement of the reference path (MuJoCo not installable here)"}
     fl = res.pop("flops", None) or {}
+    solo = res.pop("solo", None) or {}
     stage = res["stage_ms_per_step"]
-    launches_c = max(1.0, res["stage_launches_per_step"]["stage_c"])
+    launches_c = max(1.0, solo.get("launches_per_step") or res["stage_launches_per_step"]["stage_c"])
     peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(REPO, "MEASURED_PEAKS.json")) else {}
     hbm_peak = peaks.get("hbm_gbs", 6548.5)
     traffic = None
@@ -566,21 +600,26 @@ def finish_line(args, res, world, local):
     state_bytes = 8 * (30 + 27 + 8 + 27) * 2 + 8 * 12 * 2 + 4 * 10 + 4 * 85 + 4 + 3 + 4 * 8  # FP64 state in+out, tinit/eepose, action, obs, reward/flags, ints
     kern_s = res["kernel_ms_per_step"] * 1e-3
     c_flops = fl.get("stage_c")
-    c_launch_s = stage["stage_c"] * 1e-3 / launches_c
+    # duration of one stage-C launch timed ALONE (single stream, single chunk, same states); the overlapped timed region
+    # gives only sums that exceed wall time
+    c_launch_s = (solo["stage_c_ms_per_launch"] if "stage_c_ms_per_launch" in solo
+                  else stage["stage_c"] / max(1.0, res["stage_launches_per_step"]["stage_c"])) * 1e-3
     roof = {"bound": "fp64-cuda-core" if fp64 else "fp32-cuda-core",
             "kernel": f"k_stage_c<{args.precision},G={args.group}> (contact assembly, constraint rows, Newton solver, integration): "
-                      "the dominant of the three stage kernels; 17 launches per step per chunk",
+                      "the dominant of the three stage kernels; one launch = one of the 17 rounds of the whole batch, timed alone "
+                      "(single stream) right after the timed region, from the same states",
             # algorithmic FLOPs of one launch (one of the 17 rounds of one chunk: stage-C FLOPs per env-step x envs / launches per
             # step) / its mean CUDA-event duration
             "achieved": (c_flops * n / launches_c / c_launch_s * 1e-12) if c_flops else None,
             "peak": peak.value, "unit": "TFLOP/s",
             "frac": (c_flops * n / launches_c / c_launch_s * 1e-12 / peak.value) if c_flops else None,
             "peak_source": "measured live: dependent-FMA microkernel mm_measure_fma_peak (MEASURED_PEAKS.json has no CUDA-core figure)",
-            "kernel_ms_per_launch": c_launch_s * 1e3, "launches_per_step": launches_c,
+            "kernel_ms_per_launch": c_launch_s * 1e3, "launches_per_step": launches_c, "kernels_timed_alone": solo or None,
             "flops_per_env_step": fl or None,
             "whole_step": {"achieved": (fl["per_env_step"] * n / kern_s * 1e-12) if fl.get("per_env_step") else None,
                            "frac": (fl["per_env_step"] * n / kern_s * 1e-12 / peak.value) if fl.get("per_env_step") else None,
-                           "ms": kern_s * 1e3, "stage_ms": stage},
+                           "ms": kern_s * 1e3, "overlapped_stage_ms_sum": stage,
+                           "note": "mm_step of the timed region: the chunks run on several streams, stage launches overlap"},
             "oracle_model": {"flops_per_env_step": model_flops, "per_forward_counters": per,
                              "note": "round-1 model with hand coefficients on the oracle's dense counters, kept for continuity"},
             "traffic": traffic,
