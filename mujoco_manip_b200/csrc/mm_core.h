@@ -165,7 +165,7 @@ MM_HD int dofmask(int cls) {
 // of the pivot on the diagonal: the triangular solves multiply instead of dividing on their sequential chain.
 // ------------------------------------------------------------------------------------------------
 template <class T, int G>
-MM_HDN void chol_factor(const Grp<G>& g, T* A, int n) {
+MM_HDS void chol_factor(const Grp<G>& g, T* A, int n) {
   for (int j = 0; j < n; j++) {
     T d = A[j * n + j];
     if (d < (T)MINVAL_D) d = (T)MINVAL_D;
@@ -198,7 +198,7 @@ MM_HDN void chol_factor(const Grp<G>& g, T* A, int n) {
 }
 
 template <class T, int G>
-MM_HDN void chol_solve(const Grp<G>& g, const T* L, int n, T* x) {
+MM_HDS void chol_solve(const Grp<G>& g, const T* L, int n, T* x) {
   for (int k = 0; k < n; k++) {
     T xk = x[k] * L[k * n + k];
     g.sync();
@@ -269,7 +269,7 @@ MM_HD void solve6_local(const T* L, T* x) {  // L -> H[b][b] (factor), x -> vect
 
 // cooperative Cholesky of the rows / columns listed in il[0..n) of the NV x NV matrix A (zero entries skipped)
 template <class T, int G>
-MM_HDN void chol_factor_list(const Grp<G>& g, T* A, const signed char* il, int n) {
+MM_HDS void chol_factor_list(const Grp<G>& g, T* A, const signed char* il, int n) {
   for (int jj = 0; jj < n; jj++) {
     int j = il[jj];
     T d = A[j * NV + j];
@@ -308,7 +308,7 @@ MM_HDN void chol_factor_list(const Grp<G>& g, T* A, const signed char* il, int n
 // H x = b for the structured factor: lone cubes on lanes 0..2, the coupled part sequentially on lane 3
 // when it is just the robot block, cooperatively otherwise
 template <class T, int G>
-MM_HDN void solve_H(const Grp<G>& g, const Scratch<T>& s, T* x) {
+MM_HDS void solve_H(const Grp<G>& g, const Scratch<T>& s, T* x) {
   const T* L = s.H;
   int n = s.n_il;
   if (G >= 4 || G == 1) {
@@ -1237,7 +1237,7 @@ MM_HDX void collide(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<
 // matrix-free Jacobian products through body-pair twists / wrenches
 // ------------------------------------------------------------------------------------------------
 template <class T, int G>
-MM_HDN void pair_twists(const Grp<G>& g, Scratch<T>& s, const T* x) {
+MM_HDS void pair_twists(const Grp<G>& g, Scratch<T>& s, const T* x) {
   int np = s.npair;
   for (int idx = g.lane; idx < np * 6; idx += G) {
     int p = idx / 6, c = idx % 6;
@@ -1265,7 +1265,7 @@ MM_HD void load_con(const Work<T>& w, int c, ConGeom<T>& q) {
 
 // rows of J*x for every contact (out[c*6 + r]) and special row (outspec[k])
 template <class T, int G>
-MM_HDN void mulJ(const Grp<G>& g, Scratch<T>& s, const Work<T>& w, const T* x, T* out, T* outspec) {
+MM_HDS void mulJ(const Grp<G>& g, Scratch<T>& s, const Work<T>& w, const T* x, T* out, T* outspec) {
   pair_twists<T, G>(g, s, x);
   int ncon = s.ncon;
   for (int c = g.lane; c < ncon; c += G) {
@@ -1372,7 +1372,7 @@ MM_HDX void make_constraints(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& 
 // also the per-pair 6x6 blocks K_p = sum_active D y y^T.  Returns constraint cost; *changed is set
 // when any active bit differs from the stored one.
 template <class T, int G>
-MM_HDN T update_constraint(const Grp<G>& g, Scratch<T>& s, Work<T>& w, bool buildK, int* changed) {
+MM_HDS T update_constraint(const Grp<G>& g, Scratch<T>& s, Work<T>& w, bool buildK, int* changed) {
   int np = s.npair;
   for (int idx = g.lane; idx < np * 6; idx += G) s.pairF[idx / 6][idx % 6] = 0;
   if (buildK) for (int idx = g.lane; idx < np * 21; idx += G) s.pairK[idx / 21][idx % 21] = 0;
@@ -1504,7 +1504,7 @@ MM_HDN void analyse_coupling(const Grp<G>& g, Scratch<T>& s) {
 
 // H = M + J^T D J over the active rows, assembled from the per-pair blocks; then factor in place
 template <class T, int G>
-MM_HDN void build_factor_H(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md) {
+MM_HDS void build_factor_H(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md) {
   // H = M on the entries that will be read: the robot block, and of every cube its own block (lone cube) or its whole
   // row (cube coupled with the robot / another cube); constant divisors, no triangular index arithmetic
   for (int e = g.lane; e < NROB * NROB + 3 * 6 * NV; e += G) {
@@ -1567,7 +1567,7 @@ MM_HDN void build_factor_H(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md
 
 // derivative / curvature of the cost along `search` at step alpha
 template <class T, int G>
-MM_HDN void ls_eval(const Grp<G>& g, const Scratch<T>& s, const Work<T>& w, T alpha, T qg1, T qg2, T* d1, T* d2) {
+MM_HDS void ls_eval(const Grp<G>& g, const Scratch<T>& s, const Work<T>& w, T alpha, T qg1, T qg2, T* d1, T* d2) {
   T a1 = 0, a2 = 0;
   int ncon = s.ncon;
   for (int c = g.lane; c < ncon; c += G) {

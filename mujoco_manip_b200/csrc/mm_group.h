@@ -13,11 +13,19 @@
 #define MM_HDN __host__ __device__
 #define MM_HDX __host__ __device__  // stage functions stay inline (out-of-line versions measured 10-15% slower)
 #define MM_HDL __host__ __device__ __noinline__  // big leaf functions: ONE copy in the kernel (instruction-cache footprint)
+// solver pieces that stage C calls from several places (update_constraint, mulJ, ...): -DMM_NOINLINE_SOLVER asks for
+// one out-of-line copy each (instruction-cache experiment; the compiler clones most of them anyway: 235 -> 221 KB)
+#ifdef MM_NOINLINE_SOLVER
+#define MM_HDS __host__ __device__ __noinline__
+#else
+#define MM_HDS __host__ __device__
+#endif
 #else
 #define MM_HD inline
 #define MM_HDN
 #define MM_HDX
 #define MM_HDL
+#define MM_HDS
 #endif
 
 // address-space hints for the out-of-line functions (a plain reference would compile to generic loads)
