@@ -15,7 +15,7 @@
 //     J is never stored; every J*x, J^T*f and J^T D J goes through per-body-pair 6-vectors / 6x6 blocks
 //   * H = M + J^T D J assembled per touching body pair and factored by coupling structure (lone cubes: 6x6 on one lane)
 //   * implicitfast integration (block diagonal: 9x9 robot factor, scalar cube updates)
-// Execution: G = 32 lanes per env, phase-synchronous CTAs (Grp::phase / any_more / all_done), see mm_launch.cuh.
+// Execution: G = 32 lanes per env inside batch-wide stage kernels (mm_env.h, mm_launch.cuh); one warp per geom pair in the convex stage.
 #pragma once
 #include "mm_ccd.h"
 
@@ -28,18 +28,7 @@ namespace mm {
 #define MM_TICK_(s, g, slot, t0) do { } while (0)
 #define MM_T0(s) 0
 #endif
-// -DMM_PROF_CONVEX (tools/build_variant.sh prof -DMM_PROF_CONVEX, read with tools/convex_probe.py): the eight profiling
-// slots then split the convex narrow phase instead of the stages: 0 barrier wait + list advance | 1 shape load |
-// 2 GJK | 3 EPA | 4 GJK calls | 5 EPA calls | 6 EPA iterations (counts are stored << 6 like the timers) | 7 whole section
-#ifdef MM_PROF_CONVEX
-#define MM_TICK(s, g, slot, t0) do { } while (0)
-#define MM_TICKX(s, g, slot, t0) MM_TICK_(s, g, slot, t0)
-#define MM_CNTX(s, g, slot, n) do { if ((s).prof && (g).lane == 0) (s).tph[slot] += (unsigned)(n); } while (0)
-#else
 #define MM_TICK(s, g, slot, t0) MM_TICK_(s, g, slot, t0)
-#define MM_TICKX(s, g, slot, t0) do { } while (0)
-#define MM_CNTX(s, g, slot, n) do { } while (0)
-#endif
 
 constexpr int MAXCON = 256;   // contacts per env (oracle max: 44 in scripted episodes, 76 in the table-collision stress run, 143 in random-action pile-ups)
 constexpr int MAXROW = MAXCON * 6;
@@ -1301,10 +1290,10 @@ MM_HD T impedance_generic(const T* solimp, T pos) {
   T x = tabs(pos) / width;
   if (x >= 1) return dmax;
   if (x <= 0) return dmin;
-  T y;
-  if (power == (T)2) y = x <= mid ? x * x / mid : 1 - (1 - x) * (1 - x) / (1 - mid);
-  else y = x <= mid ? (T)pow((double)x, (double)power) / (T)pow((double)mid, (double)power - 1)
-                    : 1 - (T)pow((double)(1 - x), (double)power) / (T)pow((double)(1 - mid), (double)power - 1);
+  // power = 2 for every solimp of this model (panda.xml:260-262 and the MuJoCo default); fill_model() refuses any other
+  // value, so the general x^p branch (a 500-instruction pow expansion on the device) does not exist here
+  (void)power;
+  T y = x <= mid ? x * x / mid : 1 - (1 - x) * (1 - x) / (1 - mid);
   return dmin + y * (dmax - dmin);
 }
 
@@ -1372,7 +1361,7 @@ MM_HDX void make_constraints(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& 
 // also the per-pair 6x6 blocks K_p = sum_active D y y^T.  Returns constraint cost; *changed is set
 // when any active bit differs from the stored one.
 template <class T, int G>
-MM_HDS T update_constraint(const Grp<G>& g, Scratch<T>& s, Work<T>& w, bool buildK, int* changed) {
+MM_HDL T update_constraint(const Grp<G>& g, Scratch<T>& s, Work<T>& w, bool buildK, int* changed) {
   int np = s.npair;
   for (int idx = g.lane; idx < np * 6; idx += G) s.pairF[idx / 6][idx % 6] = 0;
   if (buildK) for (int idx = g.lane; idx < np * 21; idx += G) s.pairK[idx / 21][idx % 21] = 0;
@@ -1685,7 +1674,10 @@ MM_HDX void solve(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>
     // (B) per-pair blocks + factorisation of H, only when the active set changed
     if (!finished && (first || changed)) {
       int dummy;
-      if (!first) update_constraint<T, G>(g, s, w, true, &dummy);
+      // (`rebuild` is always true here; reading it from the scratch keeps ONE copy of update_constraint in the kernel
+      // instead of a second one specialised for the constant - 20 KB of instruction footprint)
+      const bool rebuild = s.n_il > 0;
+      if (!first) update_constraint<T, G>(g, s, w, rebuild, &dummy);
       build_factor_H<T, G>(g, s, md);
     }
     first = false;

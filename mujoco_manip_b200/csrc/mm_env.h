@@ -392,6 +392,17 @@ MM_HDN void stage_c(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<
     ctx_copy<T, G>(g, ctx, &s);
     return;
   }
+  // last round: the trailing mj_forward is done; reward, termination, observation and the state store are the
+  // epilogue kernel's (stage_finish), which keeps ~2,300 SASS instructions out of this kernel's instruction footprint
+  ctx_copy<T, G>(g, ctx, &s);
+}
+
+// Epilogue of the step for env e (gym_env.py:562-579): reward / termination, packed observation, state store; works on
+// the env's image and contact list as the last stage C left them.
+template <class T, int G>
+MM_HDN void stage_finish(const Grp<G>& g, Scratch<T>& s, Work<T>& w, const StatePtrs& st, long e, char* ctx_base, int reward_type,
+                         int max_steps, const StepOut& out, const float* tgt_kp_all) {
+  ctx_copy<T, G>(g, &s, ctx_base + (size_t)e * ctx_stride<T>());
   bool rc = reward_type == REWARD_STAGED ? any_robot_collision<T, G>(g, s, w) : false;
   for (int i = g.lane; i < 9; i += G) s.tmp6[KIN_ROW + i / 6][i % 6] = s.qpos[i];
   g.sync();

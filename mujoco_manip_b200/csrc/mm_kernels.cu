@@ -456,7 +456,8 @@ int mm_step(mm_handle* h, const mm_state* st, const float* actions, int action_m
       CK(timed_launch(fuse ? 6 : 2, 2, sub, 0, s));
       if (h->heavy_min > 0) CK(cudaStreamWaitEvent(s, h->ev_h[si], 0));
     }
-    h->launches += (fuse ? 1 : NROUND) + (h->heavy_min > 0 ? 3 : 2) * NROUND;
+    CK(launch(8, pc, 0, 0, s));  // reward, termination, observation, state store
+    h->launches += 1 + (fuse ? 1 : NROUND) + (h->heavy_min > 0 ? 3 : 2) * NROUND;
   }
   if (forked)
     for (int i = 0; i < h->nstream; i++) {

@@ -165,6 +165,22 @@ __global__ void __launch_bounds__(32 * W, MM_MINB_C) k_stage_c(StepParams p, int
   }
 }
 
+// epilogue of the step (reward, termination, observation, state store): warp per env on the env images
+template <class T, int G, int W>
+__global__ void __launch_bounds__(32 * W, MM_MINB_A) k_finish(StepParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  Grp<G> g;
+  setup_group<T, G>(g);
+  int gi = threadIdx.x / G;
+  long slot = (long)blockIdx.x * (32 * W / G) + gi;
+  if (slot >= p.nslot) return;
+  slot += p.slot0;
+  long e = p.order ? p.order[slot] : slot;
+  Scratch<T>& s = *reinterpret_cast<Scratch<T>*>(smem + gi * scratch_a_bytes<T>());
+  Work<T> w = work_of<T>(p, e);
+  stage_finish<T, G>(g, s, w, p.st, e, p.ctx, p.reward_type, p.max_steps, p.out, p.tgt_kp);
+}
+
 // stage C of the contact-rich envs of a round: persistent 128-thread CTAs, one env at a time per CTA (Grp<128>)
 #ifndef MM_MINB_H
 #define MM_MINB_H 3
@@ -299,6 +315,8 @@ cudaError_t inst_prepare() {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_convex<T, MM_WX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x<T>());
   if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_finish<T, G, MM_WA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a<T, G>());
+  if (e != cudaSuccess) return e;
   if (G == 32) {
     e = cudaFuncSetAttribute(k_stage_c_heavy<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h<T>());
     if (e != cudaSuccess) return e;
@@ -331,12 +349,15 @@ cudaError_t inst_resident(int* convex_grid, int* heavy_grid) {
 }
 
 // which: 0 = stage A of round `sub`, 1 = convex stage, 2 = stage C, 3 = reset, 4 = ops, 5 = stage C of the
-// contact-rich envs; 6 / 7 = 2 / 5 with stage A of the next round fused behind.  `grid_x`: grid of the persistent kernels.
+// contact-rich envs; 6 / 7 = 2 / 5 with stage A of the next round fused behind; 8 = epilogue of the step.  `grid_x`: grid of the persistent kernels.
 template <class T, int G>
 cudaError_t inst_launch(int which, const StepParams& p, int sub, int grid_x, cudaStream_t s) {
   if (which == 0) {
     constexpr int EPB = 32 * MM_WA / G;
     k_stage_a<T, G, MM_WA><<<(unsigned)((p.nslot + EPB - 1) / EPB), 32 * MM_WA, smem_a<T, G>(), s>>>(p, sub);
+  } else if (which == 8) {
+    constexpr int EPB = 32 * MM_WA / G;
+    k_finish<T, G, MM_WA><<<(unsigned)((p.nslot + EPB - 1) / EPB), 32 * MM_WA, smem_a<T, G>(), s>>>(p);
   } else if (which == 1) {
     k_convex<T, MM_WX><<<(unsigned)grid_x, 32 * MM_WX, smem_x<T>(), s>>>(p, sub);
   } else if (which == 2 || which == 6) {

@@ -42,6 +42,8 @@ struct ModelDev {
 }  // namespace mm
 
 #ifdef MM_MODEL_HOST_FILL
+#include <cstdio>
+#include <cstdlib>
 #ifndef MM_CONST
 #define MM_CONST static const
 #endif
@@ -78,6 +80,7 @@ static void fill_model(ModelDev<T>& m) {
   m.cube_inertia = (T)mm_body_inertia[16][0];
   for (int k = 0; k < 2; k++) m.eq_solref[k] = (T)mm_eq_solref[k];
   for (int k = 0; k < 5; k++) m.eq_solimp[k] = (T)mm_eq_solimp[k];
+  if (mm_eq_solimp[4] != 2.0) { std::fprintf(stderr, "mm_model: solimp power %g is not supported (the kernels implement power 2)\n", mm_eq_solimp[4]); std::abort(); }
   m.eq_invw = (T)(mm_dof_invweight0[MM_EQ_DOF1] + mm_dof_invweight0[MM_EQ_DOF2]);
   for (int k = 0; k < NQ; k++) m.key_qpos[k] = (T)mm_key_qpos[k];
   for (int k = 0; k < NU; k++) m.key_ctrl[k] = (T)mm_key_ctrl[k];

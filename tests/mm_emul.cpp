@@ -161,6 +161,11 @@ void do_step(int n, void** sp, const float* actions, int mode, int reward_type, 
       stage_c<T, 1, false>(g, c.s, c.md, w, st, e, sub, image.data(), q, qn, nohv, reward_type, max_steps, out, tgt);
     }
     tick(2);
+    if (sub == ACTION_REPEAT)
+      for (long e = 0; e < n; e++) {  // epilogue kernel
+        Work<T> w = work(e);
+        stage_finish<T, 1>(g, c.s, w, st, e, image.data(), reward_type, max_steps, out, tgt);
+      }
     if (sub < ACTION_REPEAT)
       for (long e = 0; e < n; e++) {  // stage A of round sub + 1 (its own launch on the device)
         Work<T> w = work(e);

@@ -1,5 +1,6 @@
 #!/usr/bin/env python3
-"""Per-env latency distribution of the step kernel (GPU box): which envs are the long poles?
+"""Per-env cycles spent in the stage kernels of a step (GPU box): which envs are the long poles, and in which stage?
+(mm_set_cycle_buffer: [total, stage A, convex stage (summed over the warps that ran the env's pairs), stage C].)
     python tools/latency_probe.py [--envs 4096] [--steps 40] [--group 16] [--precision f64]"""
 import argparse
 import ctypes as C
@@ -14,7 +15,7 @@ from mujoco_manip_b200 import PickPlaceVecEnv, _lib  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--envs", type=int, default=4096)
 ap.add_argument("--steps", type=int, default=40)
-ap.add_argument("--group", type=int, default=16)
+ap.add_argument("--group", type=int, default=32)
 ap.add_argument("--precision", default="f64")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
@@ -35,23 +36,24 @@ for t in range(a.steps):
     act[:, 6] = 1.0
     act[:, 7] = (torch.rand(a.envs, device=dev, generator=gen) > 0.5).float()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    cyc9.zero_()
     e0.record()
     env.step(act)
     e1.record()
     torch.cuda.synchronize()
     if t % 5 == 4 or t == a.steps - 1:
-        c = cyc.double() / 1.965e6  # ms at 1965 MHz
+        ph = cyc9[:, 1:4].double() / 1.965e6  # ms at 1965 MHz: stage A, convex, stage C
+        c = ph.sum(dim=1)
         q = torch.quantile(c, torch.tensor([0.5, 0.9, 0.99, 1.0], device=dev, dtype=torch.float64))
         ncon = env.state["diag"][:, 0].double()
         worst = int(torch.argmax(c))
-        print(f"step {t}: launch {e0.elapsed_time(e1):.1f} ms | per-env ms p50 {q[0]:.2f} p90 {q[1]:.2f} p99 {q[2]:.2f} max {q[3]:.2f} "
+        print(f"step {t}: step {e0.elapsed_time(e1):.1f} ms | per-env busy ms p50 {q[0]:.2f} p90 {q[1]:.2f} p99 {q[2]:.2f} max {q[3]:.2f} "
               f"| sum/SMs {float(c.sum()) / 148:.1f} | ncon mean {float(ncon.mean()):.1f} max {int(ncon.max())} "
               f"| worst env ncon {int(ncon[worst])} iters {int(env.state['diag'][worst, 1])}")
-        names = ["kin+dyn", "broad", "narrow(all)", "narrow-convex", "rows", "solver", "ik", "integrate"]
-        ph = cyc9[:, 1:].double() / 1.965e6
         order = torch.argsort(c)
         med, slow = order[a.envs // 2 - 50: a.envs // 2 + 50], order[-a.envs // 20:]
-        print("      stage ms   " + "  ".join(f"{n}" for n in names))
-        print("      mean       " + "  ".join(f"{float(ph[:, k].mean()):7.2f}" for k in range(8)))
-        print("      median env " + "  ".join(f"{float(ph[med, k].mean()):7.2f}" for k in range(8)))
-        print("      slowest 5% " + "  ".join(f"{float(ph[slow, k].mean()):7.2f}" for k in range(8)))
+        names = ["stage A", "convex", "stage C"]
+        print("      stage ms   " + "  ".join(f"{n:>8s}" for n in names))
+        print("      mean       " + "  ".join(f"{float(ph[:, k].mean()):8.2f}" for k in range(3)))
+        print("      median env " + "  ".join(f"{float(ph[med, k].mean()):8.2f}" for k in range(3)))
+        print("      slowest 5% " + "  ".join(f"{float(ph[slow, k].mean()):8.2f}" for k in range(3)))
