@@ -53,7 +53,7 @@ MM_HDN void support1(const Grp<G>& g, const Shape<T>& s, const T* d, T* out) {
     T n = tsqrt(l[0] * l[0] + l[1] * l[1]);
     if (n > (T)1e-14) { p[0] = l[0] / n * s.size[0]; p[1] = l[1] / n * s.size[0]; } else { p[0] = p[1] = 0; }
     p[2] = l[2] >= 0 ? s.size[1] : -s.size[1];
-  } else if (G == 32 && s.nvert <= 32 * SHAPE_LV) {
+  } else if (G == 32) {  // every hull of the model has at most 32 * SHAPE_LV vertices (static_assert in mm_model.h)
     int best = s.nvert;  // lanes without a vertex lose every comparison
     T bv = (T)-1e30;
 #pragma unroll
@@ -108,30 +108,38 @@ template <class T, int G>
 MM_HDN bool gjk(const Grp<G>& g, const Shape<T>& s1, const Shape<T>& s2, SP<T>* sx, unsigned* cnt = nullptr) {
   T dir[3] = {s2.pos[0] - s1.pos[0], s2.pos[1] - s1.pos[1], s2.pos[2] - s1.pos[2]};
   if (dot3(dir, dir) < (T)1e-20) { dir[0] = 1; dir[1] = 0; dir[2] = 0; }
+  // ONE support call site for the whole loop (the two opening queries are its first two turns): the support scan is the
+  // bulk of this kernel's code, and every inlined copy costs instruction cache
   SP<T> a, b, c, d;
-  support<T, G>(g, s1, s2, dir, c);
-  if (dot3(c.v, dir) < 0) return false;
-  neg3(dir, c.v);
-  if (dot3(dir, dir) < (T)1e-24) { dir[0] = 1; dir[1] = 0; dir[2] = 0; }
-  support<T, G>(g, s1, s2, dir, b);
-  if (dot3(b.v, dir) < 0) return false;
   T bc[3], nb[3], t[3];
-  sub3(bc, c.v, b.v);
-  neg3(nb, b.v);
-  cross3(t, bc, nb);
-  cross3(dir, t, bc);
-  if (dot3(dir, dir) < (T)1e-24) {
-    const T ex[3] = {1, 0, 0}, ez[3] = {0, 0, 1};
-    cross3(dir, bc, ex);
-    if (dot3(dir, dir) < (T)1e-24) cross3(dir, bc, ez);
-  }
-  int n = 2;
-  d = c;
+  int n = 0;  // 0, 1: opening queries; 2: line / triangle case; 3: tetrahedron case
 #pragma unroll 1
-  for (int it = 0; it < 64; it++) {
-    if (cnt && g.lane == 0) cnt[1]++;
+  for (int it = -2; it < 64; it++) {
+    if (cnt && g.lane == 0 && it >= 0) cnt[1]++;
     support<T, G>(g, s1, s2, dir, a);
     if (dot3(a.v, dir) < 0) return false;
+    if (n == 0) {
+      c = a;
+      neg3(dir, c.v);
+      if (dot3(dir, dir) < (T)1e-24) { dir[0] = 1; dir[1] = 0; dir[2] = 0; }
+      n = 1;
+      continue;
+    }
+    if (n == 1) {
+      b = a;
+      sub3(bc, c.v, b.v);
+      neg3(nb, b.v);
+      cross3(t, bc, nb);
+      cross3(dir, t, bc);
+      if (dot3(dir, dir) < (T)1e-24) {
+        const T ex[3] = {1, 0, 0}, ez[3] = {0, 0, 1};
+        cross3(dir, bc, ex);
+        if (dot3(dir, dir) < (T)1e-24) cross3(dir, bc, ez);
+      }
+      n = 2;
+      d = c;
+      continue;
+    }
     T ao[3], ab[3], ac[3];
     neg3(ao, a.v);
     sub3(ab, b.v, a.v);

@@ -314,7 +314,7 @@ MM_HD int tctz(unsigned x) {
 #endif
 }
 MM_HD float tsqrt(float x) { return sqrtf(x); }
-MM_HDL inline double tsqrt(double x) { return sqrt(x); }  // ~150 SASS instructions per expansion: keep one copy
+MM_HDL static double tsqrt(double x) { return sqrt(x); }  // ~150 SASS instructions per expansion: keep one copy
 // Cholesky pivot: 1 / sqrt(d).  On the device one reciprocal square root (1 ulp) replaces the square root and the
 // division; d >= MINVAL_D > 0 at every call.
 MM_HD double trsqrt(double d) {

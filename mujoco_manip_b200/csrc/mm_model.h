@@ -98,6 +98,7 @@ static void fill_geom(GeomDev<T>& g) {
     g.rbound[i] = (T)mmd_g_rbound[i]; g.invw[i] = (T)mmd_g_invw[i];
     g.type[i] = mmd_g_type[i]; g.body[i] = mmd_g_body[i]; g.cls[i] = mmd_g_class[i]; g.cube[i] = mmd_g_cube[i];
     g.obst[i] = mmd_g_obst[i]; g.vadr[i] = mmd_g_vadr[i]; g.vnum[i] = mmd_g_vnum[i];
+    if (mmd_g_vnum[i] > 160) { std::fprintf(stderr, "mm_model: hull %d has %d vertices (the support scan holds at most 160 in registers)\n", i, mmd_g_vnum[i]); std::abort(); }
   }
   for (int c = 0; c < NPAIRC; c++) { g.pair[c][0] = (short)mmd_pair[c][0]; g.pair[c][1] = (short)mmd_pair[c][1]; }
   for (int v = 0; v < NHULLV; v++) for (int k = 0; k < 3; k++) g.hull[v][k] = (T)mm_hull[v][k];
