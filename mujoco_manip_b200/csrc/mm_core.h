@@ -1363,8 +1363,16 @@ MM_HDX void make_constraints(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& 
 template <class T, int G>
 MM_HDL T update_constraint(const Grp<G>& g, Scratch<T>& s, Work<T>& w, bool buildK, int* changed) {
   int np = s.npair;
-  for (int idx = g.lane; idx < np * 6; idx += G) s.pairF[idx / 6][idx % 6] = 0;
-  if (buildK) for (int idx = g.lane; idx < np * 21; idx += G) s.pairK[idx / 21][idx % 21] = 0;
+  {  // (rows are contiguous: flat index, no division)
+    T* pf = &s.pairF[0][0];
+    T* pk = &s.pairK[0][0];
+#pragma unroll 1
+    for (int idx = g.lane; idx < np * 6; idx += G) pf[idx] = 0;
+    if (buildK) {
+#pragma unroll 1
+      for (int idx = g.lane; idx < np * 21; idx += G) pk[idx] = 0;
+    }
+  }
   g.sync();
   T cost = 0;
   int chg = 0;
@@ -1389,6 +1397,7 @@ MM_HDL T update_constraint(const Grp<G>& g, Scratch<T>& s, Work<T>& w, bool buil
       cross3(pxn, q.pos, q.n);
       cross3(px1, q.pos, q.t1);
       cross3(px2, q.pos, q.t2);
+#pragma unroll 1  // (rolled on purpose: six unrolled copies of the row body are 8 KB of instruction cache)
       for (int r = 0; r < nr; r++) {
         T ja = w.Jaref[c * 6 + r];
         if (ja < 0) {
@@ -1593,6 +1602,7 @@ MM_HDX void solve(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>
   // warmstart selection: cost at qacc_smooth (which = 0, rows kept in Jv) vs cost at qacc_warmstart
   // (which = 1, rows kept in Jaref)
   T cost_sm = 0, cost_ws = 0;
+#pragma unroll 1
   for (int which = 0; which < 2; which++) {
     if (which) {  // qacc_warmstart arrives from the global state (parked in `search`, free until the Newton loop)
       for (int i = g.lane; i < NV; i += G) s.search[i] = (T)s.warm_g[i];

@@ -103,6 +103,8 @@ void do_reset(int n, void** sp, const unsigned char* mask, const double* obj_xy,
 }
 // One control step of n envs through the STAGE functions the CUDA kernels run (mm_env.h): 17 rounds of stage A for
 // every env, the batch-wide convex queue, stage C for every env - with per-env contact lists and images as on the device.
+// convex-queue statistics of everything stepped so far: items, hits, env-rounds; per geom: items, hits
+static long long g_qstat[3], g_qpair[NGEOM][2];
 template <class T>
 void do_step(int n, void** sp, const float* actions, int mode, int reward_type, int max_steps, void** op, const float* tgt,
              long long* flops = nullptr /*[3]: stage A, convex stage, stage C*/) {
@@ -141,6 +143,7 @@ void do_step(int n, void** sp, const float* actions, int mode, int reward_type, 
     EpaMem<T> em;
     em.vert = everts.data(); em.face = eface.data(); em.fidx = eints.data(); em.edge = em.fidx + EPA_MAXF; em.canon = em.edge + EPA_MAXE; em.ecan = em.canon + EPA_MAXV;
     int cnt = count[sub] < cap ? count[sub] : cap;
+    g_qstat[0] += cnt; g_qstat[2] += n;
     for (int i = cnt - 1; i >= 0; i--) {  // any order: results are addressed by queue position
 #ifdef MM_DEBUG_EPA
       long before = mm_debug_epa_iters;
@@ -154,6 +157,12 @@ void do_step(int n, void** sp, const float* actions, int mode, int reward_type, 
 #else
       stage_convex<T, 1>(g, c.gm, q, i, image.data(), bpos, bR, em);
 #endif
+      {
+        int ci = q.items[i].ci;
+        g_qstat[1] += q.res[i].hit;
+        g_qpair[c.gm.pair[ci][0]][0]++; g_qpair[c.gm.pair[ci][0]][1] += q.res[i].hit;
+        g_qpair[c.gm.pair[ci][1]][0]++; g_qpair[c.gm.pair[ci][1]][1] += q.res[i].hit;
+      }
     }
     tick(1);
     for (long e = 0; e < n; e++) {  // stage C of round sub
@@ -177,6 +186,10 @@ void do_step(int n, void** sp, const float* actions, int mode, int reward_type, 
 }  // namespace
 
 extern "C" {
+void emul_queue_stats(long long* tot /*[3]*/, long long* per_geom /*[NGEOM][2]*/) {
+  for (int k = 0; k < 3; k++) tot[k] = g_qstat[k];
+  for (int k = 0; k < NGEOM; k++) { per_geom[2 * k] = g_qpair[k][0]; per_geom[2 * k + 1] = g_qpair[k][1]; }
+}
 
 void emul_reset_yaw(int n, void** state, const unsigned char* mask, const double* obj_xy, const double* yaw_cs,
                     const int* task, float* obs, float* tgt_kp, int use_float) {

@@ -37,12 +37,15 @@ def sass_rows(rep, kernel):
     return res
 
 
-def line_table(obj, kernel):
+def line_table(obj, kernel, outer=False):
+    """(offset, (file, line), text) per SASS instruction.  outer=True: instructions of inlined helpers (warp intrinsics,
+    mm_group.h) are charged to the nearest calling frame in mm_core.h / mm_env.h / mm_ccd.h (nvdisasm -gi)."""
     d = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(obj)], cwd=d, capture_output=True)
     cub = [f for f in os.listdir(d) if f.endswith(".cubin")][0]
-    dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(d, cub)], capture_output=True, text=True).stdout.splitlines()
-    table, cur, on = [], ("?", 0), False
+    dis = subprocess.run(["nvdisasm", "-gi" if outer else "-g", "-c", os.path.join(d, cub)], capture_output=True,
+                         text=True).stdout.splitlines()
+    table, cur, on, chain, fresh = [], ("?", 0), False, [], True
     for ln in dis:
         if ln.startswith(".text."):
             on = kernel in ln
@@ -51,10 +54,17 @@ def line_table(obj, kernel):
             continue
         m = re.match(r'\s*//## File "([^"]+)", line (\d+)', ln)
         if m:
-            cur = (os.path.basename(m.group(1)), int(m.group(2)))
+            if fresh:
+                chain, fresh = [], False
+            chain.append((os.path.basename(m.group(1)), int(m.group(2))))
             continue
         m = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+(.*);", ln)
         if m:
+            if chain and not fresh:
+                cur = chain[0]
+                if outer:
+                    cur = next((c for c in chain if c[0] in ("mm_core.h", "mm_env.h", "mm_ccd.h")), chain[0])
+            fresh = True
             table.append((int(m.group(1), 16), cur, m.group(2).strip()))
     return table
 
