@@ -435,7 +435,6 @@ def measure_random(args, rank, world, local, dev, n, mode, randomize, steps, war
         sampler.start()
     stats0 = env.stats.clone()
     l0 = env.launch_count()
-    _lib.check(env._L.mm_stage_timing(env._h, 1), "mm_stage_timing")
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     barrier()
@@ -452,13 +451,20 @@ def measure_random(args, rank, world, local, dev, n, mode, randomize, steps, war
     barrier()
     wall = time.time() - wall0
     launches = env.launch_count() - l0
+    stats1 = env.stats.clone()
+    # per-stage device times of the overlapped plan: the same steps again with the library's per-launch events switched on
+    # (outside the timed region: two event records per launch are not free)
+    _lib.check(env._L.mm_stage_timing(env._h, 1), "mm_stage_timing")
+    for i in range(steps):
+        one_step(pool[(warmup + steps + i) % len(pool)])
+    barrier()
     stage_ms = (C.c_double * 4)()
     stage_n = (C.c_longlong * 4)()
     _lib.check(env._L.mm_stage_times(env._h, stage_ms, stage_n), "mm_stage_times")
     _lib.check(env._L.mm_stage_timing(env._h, 0), "mm_stage_timing")
     step_ms = sum(a.elapsed_time(b) for a, b in ev)
     kern_ms = sum(a.elapsed_time(b) for a, b in kev)
-    dstats = (env.stats - stats0).tolist()
+    dstats = (stats1 - stats0).tolist()
     overflow_now = int((env.state["diag"][:, 2] != 0).sum())
     t = torch.tensor([step_ms, kern_ms] + list(stage_ms), device=dev, dtype=torch.float64)
     cnt = torch.tensor([dstats[0], dstats[4], dstats[5] + overflow_now, dstats[6]], device=dev, dtype=torch.float64)

@@ -1661,6 +1661,7 @@ MM_HDX void solve(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>
       cost = update_constraint<T, G>(g, s, w, first, &chg);  // the first pass also builds the per-pair blocks
       changed = chg;
       int sb = 0;
+#pragma unroll 1
       for (int k = 0; k < s.nspec; k++) if (s.specdof[k] < 0 || s.specJaref[k] < 0) sb |= 1 << k;
       if (sb != specbits) { changed = 1; specbits = sb; }
       T ga = 0, gn = 0;

@@ -185,9 +185,10 @@ struct mm_handle {
   struct Timed { int kind; cudaEvent_t a, b; };
   std::vector<Timed> timed;
   std::vector<cudaEvent_t> ev_pool;
+  bool round_major = true;           // MM_ISSUE=0: launches issued chunk after chunk instead of round after round
   bool fuse_ca = false;              // MM_FUSE_CA=1: stage A fused behind stage C (measured slower; experiment switch)
-  cudaStream_t hside[8] = {};        // sibling streams of `side` for the contact-rich stage C
-  cudaEvent_t ev_x[8] = {}, ev_h[8] = {};
+  cudaStream_t hside[16] = {};        // sibling streams of `side` for the contact-rich stage C
+  cudaEvent_t ev_x[16] = {}, ev_h[16] = {};
   // chunks of the batch and their convex-pair queues
   long chunk = 0;
   int nchunk = 0, nstream = 0;
@@ -195,8 +196,8 @@ struct mm_handle {
   void* d_q_res = nullptr;
   int* d_q_ctr = nullptr;      // [nchunk][2][NROUND] counts, heads
   int q_cap = 0;
-  cudaStream_t side[8] = {};
-  cudaEvent_t ev_fork = nullptr, ev_join[8] = {};
+  cudaStream_t side[16] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[16] = {};
   float* d_tgt = nullptr;
   const double* yaw_cs = nullptr;  // caller-owned, used by mm_reset when placements are given
   // staging for the host-buffer path
@@ -302,7 +303,7 @@ int mm_create(const mm_config* cfg, mm_handle** out) {
   // chunks: MM_CHUNK envs each (default: the batch in MM_STREAMS pieces, at most 4096 and at least 256 envs per piece)
   h->nstream = (int)env_long("MM_STREAMS", n <= 8192 ? 8 : 4);  // measured: 8 for small batches (shorter tails), 4 beyond
   if (h->nstream < 1) h->nstream = 1;
-  if (h->nstream > 8) h->nstream = 8;
+  if (h->nstream > 16) h->nstream = 16;
   long chunk = env_long("MM_CHUNK", 0);
   if (chunk <= 0) {
     chunk = ((long)n + h->nstream - 1) / h->nstream;
@@ -322,6 +323,7 @@ int mm_create(const mm_config* cfg, mm_handle** out) {
   // benchmarked batch sizes stage C is bound by the throughput of all envs, not by its slowest one - no gain measured)
   h->heavy_min = h->heavy_grid > 0 ? (int)env_long("MM_HEAVY", 0) : 0;
   h->fuse_ca = env_long("MM_FUSE_CA", 0) != 0;
+  h->round_major = env_long("MM_ISSUE", 1) != 0;
   CK(cudaMalloc(&h->d_hflag, 2 * n));
   CK(cudaMemset(h->d_hflag, 0, 2 * n));
   CK(cudaMalloc(&h->d_h_items, (size_t)h->nchunk * 2 * chunk * sizeof(int)));
@@ -410,10 +412,10 @@ int mm_step(mm_handle* h, const mm_state* st, const float* actions, int action_m
     CK(cudaEventRecord(h->ev_fork, main));
     for (int i = 0; i < h->nstream; i++) CK(cudaStreamWaitEvent(h->side[i], h->ev_fork, 0));
   }
-  // the chunks of a stream run one after the other; rounds are issued chunk-interleaved so that the streams advance together
-  for (int c = 0; c < h->nchunk; c++) {
-    int si = c % h->nstream;
-    cudaStream_t s = forked ? h->side[si] : main;
+  // the chunks of a stream run one after the other.  Issue order: round-major (all chunks' round r before any round
+  // r + 1, so that every stream has work from the first microseconds on) unless MM_ISSUE=0 (chunk after chunk)
+  const bool fuse = h->fuse_ca;  // experiment switch: stage A of round r + 1 inside the stage C kernel of round r
+  auto params_of = [&](int c) {
     StepParams pc = p;
     pc.slot0 = (long)c * h->chunk;
     pc.nslot = pc.slot0 + h->chunk <= p.n ? h->chunk : p.n - pc.slot0;
@@ -427,37 +429,51 @@ int mm_step(mm_handle* h, const mm_state* st, const float* actions, int action_m
     pc.h_items = h->d_h_items + (size_t)c * 2 * h->chunk;
     pc.h_cap = (int)h->chunk;
     pc.heavy_min = h->heavy_min;
-    const bool fuse = h->fuse_ca;  // experiment switch: stage A of round r + 1 inside the stage C kernel of round r
-    // launch + (optionally) a pair of timing events on the launching stream; kind 0 stage A | 1 convex | 2 stage C | 3 heavy
-    auto timed_launch = [&](int which, int kind, int sub, int grid_x, cudaStream_t st_) -> cudaError_t {
-      if (!h->timing) return launch(which, pc, sub, grid_x, st_);
-      cudaEvent_t ev[2];
-      for (int k = 0; k < 2; k++) {
-        if (h->ev_pool.empty()) { cudaError_t e = cudaEventCreate(&ev[k]); if (e != cudaSuccess) return e; }
-        else { ev[k] = h->ev_pool.back(); h->ev_pool.pop_back(); }
-      }
-      cudaError_t e = cudaEventRecord(ev[0], st_);
-      if (e != cudaSuccess) return e;
-      e = launch(which, pc, sub, grid_x, st_);
-      if (e != cudaSuccess) return e;
-      e = cudaEventRecord(ev[1], st_);
-      h->timed.push_back({kind, ev[0], ev[1]});
-      return e;
-    };
-    for (int sub = 0; sub < NROUND; sub++) {
-      if (sub == 0 || !fuse) CK(timed_launch(0, 0, sub, 0, s));
-      CK(timed_launch(1, 1, sub, h->convex_grid, s));
-      if (h->heavy_min > 0) {  // contact-rich envs: a CTA each, next to the warp-per-env launch of the others
-        CK(cudaEventRecord(h->ev_x[si], s));
-        CK(cudaStreamWaitEvent(h->hside[si], h->ev_x[si], 0));
-        CK(timed_launch(fuse ? 7 : 5, 3, sub, h->heavy_grid, h->hside[si]));
-        CK(cudaEventRecord(h->ev_h[si], h->hside[si]));
-      }
-      CK(timed_launch(fuse ? 6 : 2, 2, sub, 0, s));
-      if (h->heavy_min > 0) CK(cudaStreamWaitEvent(s, h->ev_h[si], 0));
+    return pc;
+  };
+  // launch + (optionally) a pair of timing events on the launching stream; kind 0 stage A | 1 convex | 2 stage C | 3 heavy
+  auto timed_launch = [&](const StepParams& pc, int which, int kind, int sub, int grid_x, cudaStream_t st_) -> cudaError_t {
+    if (!h->timing) return launch(which, pc, sub, grid_x, st_);
+    cudaEvent_t ev[2];
+    for (int k = 0; k < 2; k++) {
+      if (h->ev_pool.empty()) { cudaError_t e = cudaEventCreate(&ev[k]); if (e != cudaSuccess) return e; }
+      else { ev[k] = h->ev_pool.back(); h->ev_pool.pop_back(); }
     }
-    CK(launch(8, pc, 0, 0, s));  // reward, termination, observation, state store
-    h->launches += 1 + (fuse ? 1 : NROUND) + (h->heavy_min > 0 ? 3 : 2) * NROUND;
+    cudaError_t e = cudaEventRecord(ev[0], st_);
+    if (e != cudaSuccess) return e;
+    e = launch(which, pc, sub, grid_x, st_);
+    if (e != cudaSuccess) return e;
+    e = cudaEventRecord(ev[1], st_);
+    h->timed.push_back({kind, ev[0], ev[1]});
+    return e;
+  };
+  // one round of one chunk (after the last round: the epilogue kernel)
+  auto issue = [&](int c, int sub) -> int {
+    const int si = c % h->nstream;
+    cudaStream_t s = forked ? h->side[si] : main;
+    const StepParams pc = params_of(c);
+    if (sub == 0 || !fuse) CK(timed_launch(pc, 0, 0, sub, 0, s));
+    CK(timed_launch(pc, 1, 1, sub, h->convex_grid, s));
+    if (h->heavy_min > 0) {  // contact-rich envs: a CTA each, next to the warp-per-env launch of the others
+      CK(cudaEventRecord(h->ev_x[si], s));
+      CK(cudaStreamWaitEvent(h->hside[si], h->ev_x[si], 0));
+      CK(timed_launch(pc, fuse ? 7 : 5, 3, sub, h->heavy_grid, h->hside[si]));
+      CK(cudaEventRecord(h->ev_h[si], h->hside[si]));
+    }
+    CK(timed_launch(pc, fuse ? 6 : 2, 2, sub, 0, s));
+    if (h->heavy_min > 0) CK(cudaStreamWaitEvent(s, h->ev_h[si], 0));
+    if (sub == NROUND - 1) {
+      CK(launch(8, pc, 0, 0, s));  // reward, termination, observation, state store
+      h->launches += 1 + (fuse ? 1 : NROUND) + (h->heavy_min > 0 ? 3 : 2) * NROUND;
+    }
+    return 0;
+  };
+  if (h->round_major) {
+    for (int sub = 0; sub < NROUND; sub++)
+      for (int c = 0; c < h->nchunk; c++) { int e = issue(c, sub); if (e) return e; }
+  } else {
+    for (int c = 0; c < h->nchunk; c++)
+      for (int sub = 0; sub < NROUND; sub++) { int e = issue(c, sub); if (e) return e; }
   }
   if (forked)
     for (int i = 0; i < h->nstream; i++) {
