@@ -185,6 +185,14 @@ struct mm_handle {
   struct Timed { int kind; cudaEvent_t a, b; };
   std::vector<Timed> timed;
   std::vector<cudaEvent_t> ev_pool;
+  // CUDA-graph path of mm_step: the ~450 launches, forks and joins of one control step are captured once per distinct
+  // argument set (state / action / output pointers, action mode) and replayed with one cudaGraphLaunch (MM_GRAPH=0: off)
+  struct StepGraph { StepParams key; cudaGraphExec_t exec; long long launches; unsigned long long stamp; };
+  std::vector<StepGraph> graphs;
+  bool use_graph = true;
+  unsigned long long graph_clock = 0;
+  cudaStream_t gstream = nullptr;    // capture origin; also carries the replay when the caller's stream is the legacy default stream
+  cudaEvent_t ev_gin = nullptr, ev_gout = nullptr;
   bool round_major = true;           // MM_ISSUE=0: launches issued chunk after chunk instead of round after round
   bool fuse_ca = false;              // MM_FUSE_CA=1: stage A fused behind stage C (measured slower; experiment switch)
   cudaStream_t hside[16] = {};        // sibling streams of `side` for the contact-rich stage C
@@ -335,6 +343,10 @@ int mm_create(const mm_config* cfg, mm_handle** out) {
     CK(cudaEventCreateWithFlags(&h->ev_h[i], cudaEventDisableTiming));
   }
   CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  h->use_graph = env_long("MM_GRAPH", 1) != 0;
+  CK(cudaStreamCreateWithFlags(&h->gstream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&h->ev_gin, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&h->ev_gout, cudaEventDisableTiming));
   CK(cudaMalloc(&h->d_tgt, n * 4 * sizeof(float)));
   CK(cudaMemset(h->d_tgt, 0, n * 4 * sizeof(float)));
   CK(cudaMalloc(&h->d_actions, n * ACTION_STRIDE * sizeof(float)));
@@ -356,6 +368,10 @@ void mm_destroy(mm_handle* h) {
     if (h->ev_h[i]) cudaEventDestroy(h->ev_h[i]);
   }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  for (auto& e : h->graphs) cudaGraphExecDestroy(e.exec);
+  if (h->gstream) cudaStreamDestroy(h->gstream);
+  if (h->ev_gin) cudaEventDestroy(h->ev_gin);
+  if (h->ev_gout) cudaEventDestroy(h->ev_gout);
   for (auto& t : h->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
   for (auto e : h->ev_pool) cudaEventDestroy(e);
   cudaFree(h->d_model); cudaFree(h->d_geom); cudaFree(h->d_work_reals); cudaFree(h->d_work_ints); cudaFree(h->d_ctx);
@@ -388,20 +404,9 @@ int mm_reset(mm_handle* h, const mm_state* st, const uint8_t* mask, const double
   return 0;
 }
 
-int mm_step(mm_handle* h, const mm_state* st, const float* actions, int action_mode, const mm_step_out* out,
-            void* stream) {
-  if (!h || !st || !actions || !out) return fail("mm_step: null argument");
-  if (action_mode < 0 || action_mode > 4) return fail("mm_step: bad action_mode");
-  GUARD(h);
-  cudaStream_t main = (cudaStream_t)stream;
-  StepParams p{};
-  base_params(h, st, p);
-  p.out.obs = out->obs; p.out.reward = out->reward; p.out.terminated = out->terminated; p.out.truncated = out->truncated;
-  p.out.success = out->success; p.out.reward_components = out->reward_components;
-  p.actions = actions; p.mode = action_mode;
-  p.cycles = h->d_cycles;
-  p.order = h->d_order;
-  p.work = h->d_work;
+namespace {
+// The launches of one control step on `main` (and the handle's side streams, forked from and joined back to it).
+int enqueue_step(mm_handle* h, const StepParams& p, cudaStream_t main) {
   const launch_fn launch = LAUNCH[inst_index(h->cfg)];
   const size_t rb = real_bytes(&h->cfg);
   const size_t res_bytes = h->cfg.precision ? sizeof(CvxRes<float>) : sizeof(CvxRes<double>);
@@ -481,6 +486,66 @@ int mm_step(mm_handle* h, const mm_state* st, const float* actions, int action_m
       CK(cudaStreamWaitEvent(main, h->ev_join[i], 0));
     }
   return 0;
+}
+}  // namespace
+
+int mm_step(mm_handle* h, const mm_state* st, const float* actions, int action_mode, const mm_step_out* out,
+            void* stream) {
+  if (!h || !st || !actions || !out) return fail("mm_step: null argument");
+  if (action_mode < 0 || action_mode > 4) return fail("mm_step: bad action_mode");
+  GUARD(h);
+  cudaStream_t main = (cudaStream_t)stream;
+  StepParams p{};
+  base_params(h, st, p);
+  p.out.obs = out->obs; p.out.reward = out->reward; p.out.terminated = out->terminated; p.out.truncated = out->truncated;
+  p.out.success = out->success; p.out.reward_components = out->reward_components;
+  p.actions = actions; p.mode = action_mode;
+  p.cycles = h->d_cycles;
+  p.order = h->d_order;
+  p.work = h->d_work;
+  if (h->use_graph && !h->timing) {
+    mm_handle::StepGraph* g = nullptr;
+    for (auto& e : h->graphs)
+      if (std::memcmp(&e.key, &p, sizeof(StepParams)) == 0) { g = &e; break; }
+    if (!g) {
+      if (h->graphs.size() >= 64) {  // least recently used out
+        size_t lru = 0;
+        for (size_t k = 1; k < h->graphs.size(); k++) if (h->graphs[k].stamp < h->graphs[lru].stamp) lru = k;
+        cudaGraphExecDestroy(h->graphs[lru].exec);
+        h->graphs.erase(h->graphs.begin() + lru);
+      }
+      const long long l0 = h->launches;
+      cudaGraph_t graph = nullptr;
+      CK(cudaStreamBeginCapture(h->gstream, cudaStreamCaptureModeRelaxed));
+      int rc = enqueue_step(h, p, h->gstream);
+      cudaError_t ee = cudaStreamEndCapture(h->gstream, &graph);
+      const long long per_step = h->launches - l0;
+      h->launches = l0;
+      if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+      CK(ee);
+      mm_handle::StepGraph e;
+      std::memcpy(&e.key, &p, sizeof(StepParams));
+      e.launches = per_step; e.stamp = 0;
+      ee = cudaGraphInstantiate(&e.exec, graph, 0);
+      cudaGraphDestroy(graph);
+      CK(ee);
+      h->graphs.push_back(e);
+      g = &h->graphs.back();
+    }
+    g->stamp = ++h->graph_clock;
+    if (main == nullptr || main == cudaStreamLegacy) {  // the legacy stream takes no graph launch: go through gstream
+      CK(cudaEventRecord(h->ev_gin, main));
+      CK(cudaStreamWaitEvent(h->gstream, h->ev_gin, 0));
+      CK(cudaGraphLaunch(g->exec, h->gstream));
+      CK(cudaEventRecord(h->ev_gout, h->gstream));
+      CK(cudaStreamWaitEvent(main, h->ev_gout, 0));
+    } else {
+      CK(cudaGraphLaunch(g->exec, main));
+    }
+    h->launches += g->launches;
+    return 0;
+  }
+  return enqueue_step(h, p, main);
 }
 
 int mm_step_host(mm_handle* h, const mm_state* st, const float* h_actions, int action_mode, float* h_obs,

@@ -215,9 +215,12 @@ def test_fsm_episode_through_quat_rel_actions(cuda_device):
     env.close()
 
 
-@pytest.mark.parametrize("switches", [{"MM_HEAVY": "8"}, {"MM_FUSE_CA": "1"}, {"MM_HEAVY": "8", "MM_FUSE_CA": "1", "MM_STREAMS": "1"}])
+@pytest.mark.parametrize("switches", [{"MM_HEAVY": "8"}, {"MM_FUSE_CA": "1"}, {"MM_HEAVY": "8", "MM_FUSE_CA": "1", "MM_STREAMS": "1"},
+                                      {"MM_GRAPH": "0"}, {"MM_GRAPH": "0", "MM_ISSUE": "0", "MM_STREAMS": "3", "MM_CHUNK": "1"},
+                                      {"MM_STREAMS": "3", "MM_CHUNK": "1"}])
 def test_optional_launch_plans_match_the_golden(cuda_device, monkeypatch, switches):
-    """The launch-plan switches of mm_create (contact-rich envs by a CTA each = Grp<128>; stage A fused behind stage C)
+    """The launch-plan switches of mm_create (contact-rich envs by a CTA each = Grp<128>; stage A fused behind stage C;
+    direct launches instead of the captured CUDA graph; chunk-major issue order)
     change the schedule, never the physics: the table-collision stress rollout (hull contacts, 70+ contacts) and a
     scripted-FSM episode stay on the golden trajectories recorded from the reference's Python on the oracle engine."""
     import torch

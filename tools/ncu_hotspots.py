@@ -113,9 +113,10 @@ def main():
     ap.add_argument("--sym", default=None, help="substring of the (mangled) cubin symbol when it differs from `kernel`")
     ap.add_argument("--srcdir", default=os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
                                                      "mujoco_manip_b200", "csrc"))
+    ap.add_argument("--outer", action="store_true", help="charge inlined helpers (warp intrinsics, mm_group.h) to their callers")
     a = ap.parse_args()
     rows = sass_rows(a.rep, a.kernel)
-    tab = line_table(a.obj, a.sym or a.kernel)
+    tab = line_table(a.obj, a.sym or a.kernel, outer=a.outer)
     if len(rows) != len(tab):
         print(f"warning: {len(rows)} profiled SASS rows vs {len(tab)} disassembled instructions", file=sys.stderr)
     base = int(rows[0]["Address"], 16)
