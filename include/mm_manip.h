@@ -169,10 +169,12 @@ int mm_measure_fma_peak(int device, int fp64, double* tflops);
  * encodings [N,36] float32 = pos_quat_g (8) | pos_rot6d_g (10) | pos_quat_g_rel (8) | pos_rot6d_g_rel (10). */
 int mm_expert_actions(mm_handle* h, const mm_state* st, const float* abs_actions, float* encodings, void* stream);
 
-/* Load-aware scheduling of mm_step (no reference counterpart; results do not depend on it).  `work` ([N] int32,
- * device, or NULL) receives each env's busy time of the step (SM cycles / 256); `order` ([N] int32 device permutation,
- * or NULL = identity) tells which env each execution slot processes.  Passing the envs sorted by the previous step's
- * `work` (descending) starts the most expensive envs first, which shortens the tail of the stage launches of large batches. */
+/* Load-aware scheduling of mm_step (no reference counterpart; results do not depend on it).  By default (batches of more
+ * than 32 envs, MM_BALANCE=0 switches it off) every mm_step starts with a library kernel that sorts the envs by the busy
+ * time of their previous step (heaviest first, dealt round-robin over the chunks of the launch plan): shorter tails of the
+ * stage launches, and neighbouring warps run envs of similar cost.  `work` ([N] int32, device, or NULL = library-owned)
+ * receives each env's busy time of the step (SM cycles / 256) and feeds that sort; `order` ([N] int32 device
+ * permutation, or NULL = the library's own schedule) overrides it: which env each execution slot processes. */
 int mm_set_schedule(mm_handle* h, const int32_t* order, int32_t* work);
 
 /* Profiling aid: when `cycles` ([N,9] int64, device) is non-NULL every mm_step ADDS the SM clock cycles each env spent

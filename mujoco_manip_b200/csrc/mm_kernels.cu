@@ -119,6 +119,50 @@ __global__ void k_sample_episode(SampleArgs a) {
   if (a.advance) a.episode[e] = (long long)ep + 1;
 }
 
+// Load-aware schedule of the next step (library-side, no host round trip): a counting sort of the envs by the busy time
+// of their previous step (SM cycles / 256, SCHED_BINS bins of 2^SCHED_SHIFT units), heaviest first, dealt round-robin
+// over the chunks so that every chunk starts its most expensive envs first and neighbouring warps run envs of similar
+// cost (same code at the same time: shorter stage tails, better instruction-cache hit rate).  One CTA; results of the
+// step never depend on the order (every env writes only its own slices; convex results are addressed by queue slot).
+constexpr int SCHED_BINS = 2048, SCHED_SHIFT = 6, SCHED_THREADS = 1024;
+__global__ void __launch_bounds__(SCHED_THREADS) k_schedule(const int* __restrict__ work, int* __restrict__ order, int n,
+                                                            int chunk, int nchunk) {
+  __shared__ int hist[SCHED_BINS];   // counts, then running start offsets (descending bins)
+  __shared__ int part[SCHED_THREADS / 32];
+  const int tid = threadIdx.x;
+  for (int b = tid; b < SCHED_BINS; b += SCHED_THREADS) hist[b] = 0;
+  __syncthreads();
+  auto bin_of = [](int w) { int b = w >> SCHED_SHIFT; return b < 0 ? 0 : (b >= SCHED_BINS ? SCHED_BINS - 1 : b); };
+  for (int i = tid; i < n; i += SCHED_THREADS) atomicAdd(&hist[bin_of(work[i])], 1);
+  __syncthreads();
+  // exclusive prefix over the bins in DESCENDING order: thread t owns bins SCHED_BINS-1-2t and SCHED_BINS-2-2t
+  const int b0 = SCHED_BINS - 1 - 2 * tid, b1 = b0 - 1;
+  const int c0 = hist[b0], c1 = hist[b1];
+  int v = c0 + c1, incl = v;
+  for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= o) incl += t; }
+  if ((tid & 31) == 31) part[tid >> 5] = incl;
+  __syncthreads();
+  if (tid < 32) {
+    int pv = part[tid], pi = pv;
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, pi, o); if (tid >= o) pi += t; }
+    part[tid] = pi - pv;
+  }
+  __syncthreads();
+  const int excl = part[tid >> 5] + incl - v;
+  hist[b0] = excl;
+  hist[b1] = excl + c0;
+  __syncthreads();
+  const int last_sz = n - (nchunk - 1) * chunk;  // the last chunk may be shorter
+  for (int i = tid; i < n; i += SCHED_THREADS) {
+    int r = atomicAdd(&hist[bin_of(work[i])], 1);  // rank in descending order of work
+    int c, pos;
+    if (nchunk == 1) { c = 0; pos = r; }
+    else if (r < last_sz * nchunk) { c = r % nchunk; pos = r / nchunk; }
+    else { int r2 = r - last_sz * nchunk; c = r2 % (nchunk - 1); pos = last_sz + r2 / (nchunk - 1); }
+    order[c * chunk + pos] = i;
+  }
+}
+
 // Bookkeeping of the vectorised env after a step: running returns, episode statistics, the mask of finished envs,
 // the last observation of finished episodes, diagnostics.  One thread per env; the statistics are block-reduced.
 __global__ void k_post_step(StatePtrs st, StepOut out, long n, double* ep_return, unsigned char* reset_mask, float* final_obs,
@@ -215,6 +259,11 @@ struct mm_handle {
   unsigned char* d_flags = nullptr;  // terminated | truncated | success, N each
   long long launches = 0;
   long long* d_cycles = nullptr;
+  // library-side load-aware schedule (k_schedule): on for batches of more than 32 envs unless MM_BALANCE=0 or the caller
+  // supplies an order of its own (mm_set_schedule)
+  bool balance = false;
+  int* d_bal_order = nullptr;
+  int* d_bal_work = nullptr;
   const int* d_order = nullptr;  // mm_set_schedule
   int* d_work = nullptr;  // optional per-env cycle counts (mm_set_schedule)
 };
@@ -344,6 +393,12 @@ int mm_create(const mm_config* cfg, mm_handle** out) {
   }
   CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
   h->use_graph = env_long("MM_GRAPH", 1) != 0;
+  h->balance = env_long("MM_BALANCE", 1) != 0 && n > 32;
+  if (h->balance) {
+    CK(cudaMalloc(&h->d_bal_order, n * sizeof(int)));
+    CK(cudaMalloc(&h->d_bal_work, n * sizeof(int)));
+    CK(cudaMemset(h->d_bal_work, 0, n * sizeof(int)));
+  }
   CK(cudaStreamCreateWithFlags(&h->gstream, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&h->ev_gin, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&h->ev_gout, cudaEventDisableTiming));
@@ -369,6 +424,7 @@ void mm_destroy(mm_handle* h) {
   }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   for (auto& e : h->graphs) cudaGraphExecDestroy(e.exec);
+  cudaFree(h->d_bal_order); cudaFree(h->d_bal_work);
   if (h->gstream) cudaStreamDestroy(h->gstream);
   if (h->ev_gin) cudaEventDestroy(h->ev_gin);
   if (h->ev_gout) cudaEventDestroy(h->ev_gout);
@@ -411,6 +467,11 @@ int enqueue_step(mm_handle* h, const StepParams& p, cudaStream_t main) {
   const size_t rb = real_bytes(&h->cfg);
   const size_t res_bytes = h->cfg.precision ? sizeof(CvxRes<float>) : sizeof(CvxRes<double>);
   CK(cudaMemsetAsync(h->d_q_ctr, 0, (size_t)h->nchunk * 4 * NCTR * sizeof(int), main));
+  if (h->balance && p.order == h->d_bal_order) {
+    k_schedule<<<1, SCHED_THREADS, 0, main>>>(p.work, h->d_bal_order, (int)p.n, (int)h->chunk, h->nchunk);
+    CK(cudaGetLastError());
+    h->launches++;
+  }
   // (with the contact-rich path on, even a single chunk runs on a side stream: its sibling stream needs one to pair with)
   const bool forked = h->nstream > 1 || h->heavy_min > 0;
   if (forked) {
@@ -503,6 +564,10 @@ int mm_step(mm_handle* h, const mm_state* st, const float* actions, int action_m
   p.cycles = h->d_cycles;
   p.order = h->d_order;
   p.work = h->d_work;
+  if (h->balance && !h->d_order) {  // the library's own schedule (k_schedule at the head of the step)
+    p.order = h->d_bal_order;
+    if (!p.work) p.work = h->d_bal_work;
+  }
   if (h->use_graph && !h->timing) {
     mm_handle::StepGraph* g = nullptr;
     for (auto& e : h->graphs)

@@ -144,13 +144,11 @@ class PickPlaceVecEnv:
         self._np_rngs: list | None = None
         self._out_host = None
         self._closed = False
-        # load-aware scheduling (optional): the most expensive envs of the previous step start first (mm_set_schedule);
-        # with stage kernels that keep the whole batch resident it no longer pays at the benchmarked sizes: off by default
-        self.load_balance = (bool(load_balance) or os.environ.get("MM_LOAD_BALANCE", "0") == "1") and n > 32
-        self._work = torch.zeros(n, dtype=torch.int32, device=dev)
-        self._order = torch.arange(n, dtype=torch.int32, device=dev)
-        if self.load_balance:
-            _lib.check(self._L.mm_set_schedule(self._h, self._order.data_ptr(), self._work.data_ptr()), "mm_set_schedule")
+        # load-aware scheduling lives in the library (k_schedule at the head of every mm_step; MM_BALANCE=0 switches it off):
+        # `load_balance` is accepted for compatibility and has no effect
+        self.load_balance = bool(load_balance)
+        self._work = torch.zeros(n, dtype=torch.int32, device=dev)  # busy time of every env's last step (SM cycles / 256)
+        _lib.check(self._L.mm_set_schedule(self._h, None, self._work.data_ptr()), "mm_set_schedule")
 
     # ------------------------------------------------------------------------------------------
     def _stream(self) -> C.c_void_p:
@@ -285,15 +283,9 @@ class PickPlaceVecEnv:
         else:
             self._actions[:, : a.shape[1]].copy_(a)
             buf = self._actions
-        self._schedule()
         _lib.check(self._L.mm_step(self._h, C.byref(self._st), buf.data_ptr(), _lib.ACTION_MODES.index(self.action_mode),
                                    C.byref(self._out), self._stream()), "mm_step")
         return self._post_step_autoreset()
-
-    def _schedule(self):
-        """Heaviest envs first, envs of similar cost together (the order buffer is read by the next mm_step)."""
-        if self.load_balance:
-            self._order.copy_(torch.argsort(self._work, descending=True).to(torch.int32))
 
     def step_host(self, h_actions: torch.Tensor, h_obs: torch.Tensor, h_reward: torch.Tensor, h_flags: torch.Tensor):
         """One control step with HOST buffers (pinned memory recommended), the end-to-end path of the C ABI

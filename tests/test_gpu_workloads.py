@@ -274,3 +274,45 @@ def test_dataset_writer_rows_match_the_reference_generator(cuda_device, tmp_path
             if k == "observation.phase_description":
                 continue
             np.testing.assert_allclose(rows[k], g[f"ep{ep}.{k}"], rtol=0, atol=2e-5, err_msg=f"episode {ep} {k}")
+
+
+def test_results_do_not_depend_on_the_schedule(cuda_device, monkeypatch):
+    """The library orders the envs of every step by the busy time of their previous step (k_schedule) and cuts the batch
+    into chunks on several streams: 600 envs in three ragged chunks (256 + 256 + 88) with the schedule on, replayed
+    with the schedule off in one chunk - every state array and observation must be bit-identical over 25 random-action
+    steps (contacts, hull pairs and the convex queue included), and the schedule must have been a real permutation."""
+    import torch
+
+    n, steps = 600, 25
+    gen = torch.Generator(device="cpu").manual_seed(5)
+    acts = []
+    for _ in range(steps):
+        a = torch.zeros(n, 8)
+        a[:, :3] = (torch.rand(n, 3, generator=gen) - 0.5) * torch.tensor([0.6, 0.5, 0.5])
+        q = torch.randn(n, 4, generator=gen)
+        a[:, 3:7] = q / q.norm(dim=1, keepdim=True)
+        a[:, 7] = (torch.rand(n, generator=gen) > 0.5).float()
+        acts.append(a.to(cuda_device))
+
+    def run(env_vars):
+        for k, v in env_vars.items():
+            monkeypatch.setenv(k, v)
+        env = _make(n, cuda_device, action_mode="ee_pos_quat_g_rel", randomize_objects=True, rng="philox", seed=11, tasks="all")
+        env.reset()
+        obs = []
+        for a in acts:
+            env.step(a)
+            obs.append(env.obs_packed.clone())
+        out = {k: v.clone() for k, v in env.state.items()}, torch.stack(obs), env._work.clone()
+        env.close()
+        for k in env_vars:
+            monkeypatch.delenv(k)
+        return out
+
+    st1, obs1, work1 = run({"MM_CHUNK": "256", "MM_STREAMS": "3"})
+    st0, obs0, _ = run({"MM_BALANCE": "0", "MM_STREAMS": "1"})
+    assert int((work1 > 0).sum()) == n and float(work1.float().std()) > 0  # busy times were recorded and differ
+    assert torch.equal(obs1, obs0)
+    for k in ("qpos", "qvel", "ctrl", "warm", "step_count", "diag"):
+        assert torch.equal(st1[k], st0[k]), k
+    assert int(st1["diag"][:, 0].max()) >= 30  # pile-ups were part of it
