@@ -357,14 +357,14 @@ int mm_create(const mm_config* cfg, mm_handle** out) {
   size_t cstride = cfg->precision ? ctx_stride<float>() : ctx_stride<double>();
   CK(cudaMalloc(&h->d_ctx, n * cstride));
   CK(cudaMemset(h->d_ctx, 0, n * cstride));
-  // chunks: MM_CHUNK envs each (default: the batch in MM_STREAMS pieces, at most 4096 and at least 256 envs per piece)
-  h->nstream = (int)env_long("MM_STREAMS", n <= 8192 ? 8 : 4);  // measured: 8 for small batches (shorter tails), 4 beyond
+  // chunks: MM_CHUNK envs each (default: the batch in MM_STREAMS pieces, at most 16,384 and at least 256 envs per piece)
+  h->nstream = (int)env_long("MM_STREAMS", n < 8192 ? 8 : 4);  // measured: 8 for small batches (shorter tails), 4 from 8,192 envs on
   if (h->nstream < 1) h->nstream = 1;
   if (h->nstream > 16) h->nstream = 16;
   long chunk = env_long("MM_CHUNK", 0);
   if (chunk <= 0) {
     chunk = ((long)n + h->nstream - 1) / h->nstream;
-    if (chunk > 4096) chunk = 4096;
+    if (chunk > 16384) chunk = 16384;
     if (chunk < 256) chunk = 256;
   }
   if (((long)n + chunk - 1) / chunk > MAX_CHUNKS) chunk = ((long)n + MAX_CHUNKS - 1) / MAX_CHUNKS;
