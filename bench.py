@@ -553,7 +553,7 @@ def measure_random(args, rank, world, local, dev, n, mode, randomize, steps, war
     return res
 
 
-def count_flops(env, actions, mode, sample=48):
+def count_flops(env, actions, mode, sample=128):
     import numpy as np
 
     sys.path.insert(0, os.path.join(REPO, "tests"))
@@ -567,10 +567,11 @@ def count_flops(env, actions, mode, sample=48):
             em.st[k][...] = v[idx].cpu().numpy().reshape(em.st[k].shape)
     em.tgt[...] = 0
     ncon = float(env.state["diag"][:, 0].double().mean())
+    ncon_sample = float(env.state["diag"][idx, 0].double().mean())
     fl = em.step_counted(actions[idx].cpu().numpy())
     per = fl.astype(np.float64) / sample
     return {"per_env_step": float(per.sum()), "stage_a": float(per[0]), "convex": float(per[1]), "stage_c": float(per[2]),
-            "sample_envs": sample, "mean_contacts_in_batch": ncon,
+            "sample_envs": sample, "mean_contacts_in_batch": ncon, "mean_contacts_in_sample": ncon_sample,
             "how": "operation-counting scalar through the kernel source (tests/mm_emul.cpp, 1 lane): adds, multiplies, divides, "
                    "square roots and trigonometric calls count 1 each (FMA = 2)"}
 

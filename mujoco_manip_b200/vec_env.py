@@ -303,7 +303,8 @@ class PickPlaceVecEnv:
     def _post_step_autoreset(self, out=None):
         """Bookkeeping after the mm_step launch: episode statistics and (optionally) the reset of finished envs - all in
         library kernels (mm_post_step, mm_sample_episode, mm_reset), no host round trip.  Returns the 5-tuple of `step`."""
-        terminated, truncated, success = self._flags[0].bool(), self._flags[1].bool(), self._flags[2].bool()
+        fb = self._flags.view(torch.bool)  # (zero-copy: the kernels write 0 / 1 bytes; valid until the next step)
+        terminated, truncated, success = fb[0], fb[1], fb[2]
         info = {"success": success}
         if self._rc is not None:
             info["reward_components"] = self._rc
