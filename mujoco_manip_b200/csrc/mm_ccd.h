@@ -20,6 +20,11 @@ constexpr int EPA_REALS = EPA_MAXV * 6 + EPA_MAXF * 4;
 constexpr int EPA_INTS = EPA_MAXF + 2 * EPA_MAXE + EPA_MAXV;
 constexpr int EPA_VIS = 1 << 30;
 constexpr int SHAPE_LV = 5;  // ceil(152 / 32): the largest hull has 152 vertices
+// MM_HULL_REGS=1: a warp keeps its slice of both hulls in registers for the whole GJK / EPA run (support queries touch
+// no memory; 60 registers); 0: support queries read the vertices from global memory (L1-resident model table)
+#ifndef MM_HULL_REGS
+#define MM_HULL_REGS 1
+#endif
 
 // EPA tolerances: the oracle's values in FP64; scaled to the arithmetic's resolution in FP32 (otherwise the
 // expansion never sees its progress fall below the threshold and runs into the face cap)
@@ -36,7 +41,7 @@ struct Shape {
   int nvert;
   // G == 32: this lane's slice of the hull (vertices lane, lane + 32, ...) held in registers for the whole
   // GJK / EPA run on the pair, so that a support query touches no memory
-  T lv[SHAPE_LV][3];
+  T lv[MM_HULL_REGS ? SHAPE_LV : 1][3];
 };
 
 template <class T, int G>
@@ -53,7 +58,7 @@ MM_HDN void support1(const Grp<G>& g, const Shape<T>& s, const T* d, T* out) {
     T n = tsqrt(l[0] * l[0] + l[1] * l[1]);
     if (n > (T)1e-14) { p[0] = l[0] / n * s.size[0]; p[1] = l[1] / n * s.size[0]; } else { p[0] = p[1] = 0; }
     p[2] = l[2] >= 0 ? s.size[1] : -s.size[1];
-  } else if (G == 32) {  // every hull of the model has at most 32 * SHAPE_LV vertices (static_assert in mm_model.h)
+  } else if (G == 32 && MM_HULL_REGS) {  // every hull of the model has at most 32 * SHAPE_LV vertices (static_assert in mm_model.h)
     int best = s.nvert;  // lanes without a vertex lose every comparison
     T bv = (T)-1e30;
 #pragma unroll

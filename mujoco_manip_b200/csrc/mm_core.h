@@ -857,7 +857,7 @@ MM_HD void fill_shape(const Grp<G>& g, const T (*bpos)[3], const T (*bR)[9], con
   sh.size[0] = gm.size[gi][0]; sh.size[1] = gm.size[gi][1]; sh.size[2] = gm.size[gi][2];
   sh.verts = &gm.hull[gm.vadr[gi]][0];
   sh.nvert = gm.vnum[gi];
-  if (G == 32 && sh.type == GT_HULL) {
+  if (G == 32 && MM_HULL_REGS && sh.type == GT_HULL) {
 #pragma unroll
     for (int k = 0; k < SHAPE_LV; k++) {
       int i = g.lane + 32 * k;

@@ -57,3 +57,12 @@ for t in range(a.steps):
         print("      mean       " + "  ".join(f"{float(ph[:, k].mean()):8.2f}" for k in range(3)))
         print("      median env " + "  ".join(f"{float(ph[med, k].mean()):8.2f}" for k in range(3)))
         print("      slowest 5% " + "  ".join(f"{float(ph[slow, k].mean()):8.2f}" for k in range(3)))
+# which envs carry the load: share of envs / of each stage's busy time per contact-count class (last step)
+edges = [0, 8, 16, 24, 32, 48, 64, 96, 1 << 30]
+print("contacts      envs     stage A ms (share)   convex ms (share)   stage C ms (share)")
+for lo_, hi_ in zip(edges[:-1], edges[1:]):
+    sel = (ncon >= lo_) & (ncon < hi_)
+    if int(sel.sum()) == 0:
+        continue
+    cells = "   ".join(f"{float(ph[sel, k].mean()):6.3f} ({100 * float(ph[sel, k].sum() / ph[:, k].sum()):4.1f} %)" for k in range(3))
+    print(f"{lo_:3d}..{min(hi_, 999):3d}  {100 * float(sel.double().mean()):6.1f} %   {cells}")
