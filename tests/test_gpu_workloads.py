@@ -316,3 +316,41 @@ def test_results_do_not_depend_on_the_schedule(cuda_device, monkeypatch):
     for k in ("qpos", "qvel", "ctrl", "warm", "step_count", "diag"):
         assert torch.equal(st1[k], st0[k]), k
     assert int(st1["diag"][:, 0].max()) >= 30  # pile-ups were part of it
+
+
+def test_step_graph_cache_eviction(cuda_device, monkeypatch):
+    """mm_step keeps one captured CUDA graph per distinct argument set (64 at most, least recently used out): 70 action
+    buffers, visited twice, give the same trajectory as direct launches."""
+    import ctypes as C
+
+    import torch
+
+    from mujoco_manip_b200 import _lib
+
+    n = 40
+    gen = torch.Generator(device="cpu").manual_seed(9)
+    bufs = []
+    for _ in range(70):
+        a = torch.zeros(n, _lib.ACTION_STRIDE)
+        a[:, :3] = (torch.rand(n, 3, generator=gen) - 0.5) * 0.2
+        a[:, 3] = 1.0
+        a[:, 7] = (torch.rand(n, generator=gen) > 0.5).float()
+        bufs.append(a.to(cuda_device))
+
+    def run(graph):
+        monkeypatch.setenv("MM_GRAPH", graph)
+        env = _make(n, cuda_device, action_mode="ee_pos_quat_g_rel")
+        env.reset()
+        mode = _lib.ACTION_MODES.index("ee_pos_quat_g_rel")
+        for rep in range(2):
+            for a in bufs:  # the raw entry point with the caller's own buffers: every buffer is a new argument set
+                _lib.check(env._L.mm_step(env._h, C.byref(env._st), a.data_ptr(), mode, C.byref(env._out), env._stream()), "mm_step")
+        torch.cuda.synchronize()
+        out = {k: v.clone() for k, v in env.state.items()}, env.launch_count()
+        env.close()
+        return out
+
+    (st1, l1), (st0, l0) = run("1"), run("0")
+    assert l1 == l0  # the replay accounts for every kernel of the captured step
+    for k in ("qpos", "qvel", "ctrl", "warm", "step_count"):
+        assert torch.equal(st1[k], st0[k]), k

@@ -113,6 +113,7 @@ def main():
     ap.add_argument("--sym", default=None, help="substring of the (mangled) cubin symbol when it differs from `kernel`")
     ap.add_argument("--srcdir", default=os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
                                                      "mujoco_manip_b200", "csrc"))
+    ap.add_argument("--stall", default=None, help="also list the top source lines by one stall reason (long_sb, no_inst, wait, short_sb ...)")
     ap.add_argument("--outer", action="store_true", help="charge inlined helpers (warp intrinsics, mm_group.h) to their callers")
     a = ap.parse_args()
     rows = sass_rows(a.rep, a.kernel)
@@ -125,6 +126,7 @@ def main():
     agg_loc = collections.defaultdict(lambda: [0, 0])
     agg_f = collections.defaultdict(lambda: [0, 0, 0])
     agg_l = collections.defaultdict(lambda: [0, 0, 0])
+    agg_s = collections.Counter()
     tot = [0, 0, 0]
     for r in rows:
         off = int(r["Address"], 16) - base
@@ -136,6 +138,8 @@ def main():
         ie = int(r.get("Instructions Executed", "0") or 0)
         te = int(r.get("Thread Instructions Executed", "0") or 0)
         ss = int(r.get("Warp Stall Sampling (All Samples)", "0") or 0)
+        if a.stall:
+            agg_s[f"{loc[0]}:{loc[1]}"] += int(r.get("stall_" + a.stall, "0") or 0)
         for agg, key in ((agg_f, func_of(ranges, loc[0], loc[1])), (agg_l, f"{loc[0]}:{loc[1]}")):
             agg[key][0] += ie
             agg[key][1] += te
@@ -160,6 +164,17 @@ def main():
     print("\n== by source line ==")
     for k, v in sorted(agg_l.items(), key=lambda kv: -kv[1][2])[: a.top]:
         print(f"{100 * v[0] / tot[0]:6.2f}% inst  {100 * v[2] / max(1, tot[2]):6.2f}% samples  {v[1] / max(1, v[0]):5.1f} lanes  {k}")
+    if a.stall:
+        ts = sum(agg_s.values())
+        print(f"\n== source lines by stall_{a.stall} samples ({ts:,} = {100 * ts / max(1, tot[2]):.1f} % of all samples) ==")
+        src = {}
+        for k, v in agg_s.most_common(a.top):
+            f, ln = k.rsplit(":", 1)
+            if f not in src:
+                path = os.path.join(a.srcdir, f)
+                src[f] = open(path).read().splitlines() if os.path.exists(path) else []
+            text = src[f][int(ln) - 1].strip()[:100] if 0 < int(ln) <= len(src[f]) else ""
+            print(f"{v:7d}  {100 * v / max(1, ts):5.1f}%  {k:22s} {text}")
 
 
 if __name__ == "__main__":
