@@ -59,7 +59,7 @@ template <class T> constexpr int TMP6_ROWS() { return sizeof(T) == 8 ? 16 : 48; 
 constexpr int KIN_ROW = 14;  // tmp6 rows 14, 15: arm + finger qpos of the last position stage (store_state)
 
 template <class T>
-struct Scratch {
+struct alignas(16) Scratch {  // (images travel as 16-byte words: ctx_copy)
   // ---- persistent part: the image of an env that travels between the stage kernels of one control step
   //      (mm_stage.h: ctx_load / ctx_store copy [0, SCRATCH_PERSIST) to / from global memory) ----
   T qpos[NQ], qvel[NV], ctrl[NU];
@@ -919,27 +919,27 @@ MM_HDX void broad_phase(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, W
     int ci = base + g.lane;
     int keep = 0;
     if (ci < NPAIRC) {
-      int a = gm.pair[ci][0], b = gm.pair[ci][1];
-      int ta = gm.type[a];
+      // (kind, radius and the geom pair are all indexed by the candidate: three independent, coalesced loads)
+      const int kind = gm.pairkind[ci];
+      const T rs = gm.pairrs[ci];
+      const int a = gm.pair[ci][0], b = gm.pair[ci][1];
       const T* cb = bcen + 3 * b;
-      T rb = gm.rbound[b];
-      if (ta == GT_PLANE) keep = gm.type[b] != GT_CYL && !(cb[2] > rb);
-      else if (ta == GT_BOX && gm.body[a] < 0) {  // axis-aligned static box vs bounding sphere
+      if (kind == 0) keep = !(cb[2] > rs);
+      else if (kind == 1) {  // axis-aligned static box vs bounding sphere
         T d2 = 0;
         for (int k = 0; k < 3; k++) {
           T d = tabs(cb[k] - gm.pos[a][k]) - gm.size[a][k];
           if (d > 0) d2 += d * d;
         }
-        keep = !(d2 > rb * rb);
-      } else {
+        keep = !(d2 > rs * rs);
+      } else if (kind == 2) {
         const T* ca = bcen + 3 * a;
         T r[3] = {cb[0] - ca[0], cb[1] - ca[1], cb[2] - ca[2]};
-        T rs = rb + gm.rbound[a];
         keep = !(dot3(r, r) > rs * rs);
       }
     }
     int tot;
-    int off = g.scan_excl(keep, &tot);
+    int off = g.scan_flag(keep, &tot);
     if (keep && nsurv + off < MAXSURV) w.surv[nsurv + off] = ci;
     nsurv += tot;
   }
@@ -958,7 +958,7 @@ MM_HDX void broad_phase(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, W
         keep = gm.type[a] == GT_PLANE ? 1 : (int)obb_overlap(s, gm, a, b, ident);
       }
       int tot;
-      int off = g.scan_excl(keep, &tot);
+      int off = g.scan_flag(keep, &tot);
       g.sync();
       if (keep) w.surv[kept + off] = ci;
       kept += tot;
@@ -1046,7 +1046,7 @@ MM_HD int list_convex(const Grp<G>& g, const Scratch<T>& s, const GeomDev<T>& gm
       is = is_convex_pair(gm, gm.pair[ci][0], gm.pair[ci][1]) ? 1 : 0;
     }
     int tot;
-    int off = g.scan_excl(is, &tot);
+    int off = g.scan_flag(is, &tot);
     if (is) emit(n + off, ci);
     n += tot;
   }
@@ -1092,7 +1092,7 @@ MM_HDX void assemble_contacts(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>&
     int hit = 0;
     if (k < ncvx) hit = w.cvx[k].hit;
     int tot;
-    int off = g.scan_excl(hit, &tot);
+    int off = g.scan_flag(hit, &tot);
     if (hit && ncon + off < MAXCON) {
       const CvxRes<T>& r = w.cvx[k];
       int a = gm.pair[r.ci][0], b = gm.pair[r.ci][1];
@@ -1174,7 +1174,7 @@ MM_HDX void assemble_contacts(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>&
       head = (c == 0) || (meta_key(w.cmeta[c - 1]) != key);
     }
     int tot;
-    int off = g.scan_excl(head, &tot);
+    int off = g.scan_flag(head, &tot);
     g.sync();  // every lane has read its neighbour's meta word before any is rewritten
     if (c < ncon) {
       int slot = npair + off + head - 1;

@@ -176,6 +176,18 @@ struct Grp {
 #endif
     return incl - v;
   }
+  // the same for 0 / 1 flags: one ballot and two population counts instead of a five-level shuffle scan
+  MM_HD int scan_flag(int flag, int* total) const {
+#ifdef __CUDA_ARCH__
+    if (G > 1) {
+      const unsigned b = ballot(flag);
+      *total = __popc(b);
+      return __popc(b & ((1u << lane) - 1u));
+    }
+#endif
+    *total = flag ? 1 : 0;
+    return 0;
+  }
   template <class T>
   MM_HD T shfl_up(T v, int o) const {
 #ifdef __CUDA_ARCH__
@@ -242,6 +254,7 @@ struct Grp<128> {
     par ^= 1;
     return r;
   }
+  __device__ __forceinline__ int scan_flag(int flag, int* total) const { return scan_excl(flag ? 1 : 0, total); }
   // exclusive prefix sum over the 128 lanes; *total receives the group sum
   __device__ __forceinline__ int scan_excl(int v, int* total) const {
     int incl = v;

@@ -22,6 +22,11 @@ struct GeomDev {
   T size[NGEOM][3], pos[NGEOM][3], bc[NGEOM][3], rbound[NGEOM], invw[NGEOM];
   int type[NGEOM], body[NGEOM], cls[NGEOM], cube[NGEOM], obst[NGEOM], vadr[NGEOM], vnum[NGEOM];
   short pair[NPAIRC][2];  // sorted by (class of geom1, class of geom2): contacts of a body pair are contiguous
+  // first broad-phase level, one record per candidate (so that the test needs no load that depends on another load):
+  // kind 0 plane vs bounded geom, 1 static axis-aligned box vs bounding sphere, 2 sphere vs sphere, 3 never kept
+  // (plane vs cylinder); rsum = bounding radius of geom b (kinds 0, 1) or rbound[a] + rbound[b] (kind 2)
+  unsigned char pairkind[NPAIRC];
+  T pairrs[NPAIRC];
   T hull[NHULLV][3];
 };
 
@@ -100,7 +105,13 @@ static void fill_geom(GeomDev<T>& g) {
     g.obst[i] = mmd_g_obst[i]; g.vadr[i] = mmd_g_vadr[i]; g.vnum[i] = mmd_g_vnum[i];
     if (mmd_g_vnum[i] > 160) { std::fprintf(stderr, "mm_model: hull %d has %d vertices (the support scan holds at most 160 in registers)\n", i, mmd_g_vnum[i]); std::abort(); }
   }
-  for (int c = 0; c < NPAIRC; c++) { g.pair[c][0] = (short)mmd_pair[c][0]; g.pair[c][1] = (short)mmd_pair[c][1]; }
+  for (int c = 0; c < NPAIRC; c++) {
+    int a = mmd_pair[c][0], b = mmd_pair[c][1];
+    g.pair[c][0] = (short)a; g.pair[c][1] = (short)b;
+    if (g.type[a] == GT_PLANE) { g.pairkind[c] = g.type[b] == GT_CYL ? 3 : 0; g.pairrs[c] = g.rbound[b]; }
+    else if (g.type[a] == GT_BOX && g.body[a] < 0) { g.pairkind[c] = 1; g.pairrs[c] = g.rbound[b]; }
+    else { g.pairkind[c] = 2; g.pairrs[c] = g.rbound[b] + g.rbound[a]; }
+  }
   for (int v = 0; v < NHULLV; v++) for (int k = 0; k < 3; k++) g.hull[v][k] = (T)mm_hull[v][k];
 }
 }  // namespace mm

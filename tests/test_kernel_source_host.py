@@ -177,3 +177,21 @@ def test_yawed_cubes_fsm_episode_vs_oracle(oracle_lib):
         assert reltol(env.st["qpos"][0], orc.qpos, 1e-5) < 1e-5, t
     assert 50 < t < 2000
     assert bool(env.succ[0])
+
+
+def test_operation_counting_build_steps_like_the_plain_one():
+    """bench.py counts algorithmic FLOPs by running the kernel source with an operation-counting scalar
+    (EmulEnv.step_counted): it must advance the state exactly as the plain FP64 build and report work in every stage
+    that had any (stage A and C always; the convex stage once the arm is driven into the table)."""
+    g = _load("stress30_abs_pos_staged.npz")
+    a_env, b_env = EmulEnv(2, mode="abs_pos", reward="staged"), EmulEnv(2, mode="abs_pos", reward="staged")
+    a_env.reset()
+    b_env.reset()
+    total = np.zeros(3, dtype=np.int64)
+    for t in range(12):
+        act = np.repeat(g["action"][t][None], 2, axis=0)
+        a_env.step(act)
+        total += b_env.step_counted(act)
+        for k in ("qpos", "qvel", "ctrl", "warm"):
+            assert np.array_equal(a_env.st[k], b_env.st[k]), (t, k)
+    assert total[0] > 1e6 and total[2] > 1e6 and total[1] > 0
