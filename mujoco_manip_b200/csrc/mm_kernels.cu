@@ -237,6 +237,7 @@ struct mm_handle {
   unsigned long long graph_clock = 0;
   cudaStream_t gstream = nullptr;    // capture origin; also carries the replay when the caller's stream is the legacy default stream
   cudaEvent_t ev_gin = nullptr, ev_gout = nullptr;
+  int group_a = 0;                   // MM_GROUP_A=16: stage A by 16-lane groups (two envs per warp) next to a 32-lane stage C (experiment)
   bool round_major = true;           // MM_ISSUE=0: launches issued chunk after chunk instead of round after round
   bool fuse_ca = false;              // MM_FUSE_CA=1: stage A fused behind stage C (measured slower; experiment switch)
   cudaStream_t hside[16] = {};        // sibling streams of `side` for the contact-rich stage C
@@ -393,6 +394,13 @@ int mm_create(const mm_config* cfg, mm_handle** out) {
   }
   CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
   h->use_graph = env_long("MM_GRAPH", 1) != 0;
+  h->group_a = (int)env_long("MM_GROUP_A", cfg->group);
+  if (h->group_a != cfg->group) {
+    if (h->group_a != 16 && h->group_a != 8 && h->group_a != 32) return fail("mm_create: MM_GROUP_A must be 32, 16 or 8");
+    mm_config ca = *cfg;
+    ca.group = h->group_a;
+    if (PREPARE[inst_index(ca)]() != cudaSuccess) return fail("mm_create: kernel attribute set-up failed (stage A group)");
+  }
   h->balance = env_long("MM_BALANCE", 1) != 0 && n > 32;
   if (h->balance) {
     CK(cudaMalloc(&h->d_bal_order, n * sizeof(int)));
@@ -464,6 +472,9 @@ namespace {
 // The launches of one control step on `main` (and the handle's side streams, forked from and joined back to it).
 int enqueue_step(mm_handle* h, const StepParams& p, cudaStream_t main) {
   const launch_fn launch = LAUNCH[inst_index(h->cfg)];
+  mm_config cfg_a = h->cfg;
+  cfg_a.group = h->group_a;
+  const launch_fn launch_a = LAUNCH[inst_index(cfg_a)];
   const size_t rb = real_bytes(&h->cfg);
   const size_t res_bytes = h->cfg.precision ? sizeof(CvxRes<float>) : sizeof(CvxRes<double>);
   CK(cudaMemsetAsync(h->d_q_ctr, 0, (size_t)h->nchunk * 4 * NCTR * sizeof(int), main));
@@ -499,7 +510,7 @@ int enqueue_step(mm_handle* h, const StepParams& p, cudaStream_t main) {
   };
   // launch + (optionally) a pair of timing events on the launching stream; kind 0 stage A | 1 convex | 2 stage C | 3 heavy
   auto timed_launch = [&](const StepParams& pc, int which, int kind, int sub, int grid_x, cudaStream_t st_) -> cudaError_t {
-    if (!h->timing) return launch(which, pc, sub, grid_x, st_);
+    if (!h->timing) return (which == 0 ? launch_a : launch)(which, pc, sub, grid_x, st_);
     cudaEvent_t ev[2];
     for (int k = 0; k < 2; k++) {
       if (h->ev_pool.empty()) { cudaError_t e = cudaEventCreate(&ev[k]); if (e != cudaSuccess) return e; }
@@ -507,7 +518,7 @@ int enqueue_step(mm_handle* h, const StepParams& p, cudaStream_t main) {
     }
     cudaError_t e = cudaEventRecord(ev[0], st_);
     if (e != cudaSuccess) return e;
-    e = launch(which, pc, sub, grid_x, st_);
+    e = (which == 0 ? launch_a : launch)(which, pc, sub, grid_x, st_);
     if (e != cudaSuccess) return e;
     e = cudaEventRecord(ev[1], st_);
     h->timed.push_back({kind, ev[0], ev[1]});
