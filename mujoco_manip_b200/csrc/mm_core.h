@@ -76,6 +76,7 @@ struct alignas(16) Scratch {  // (images travel as 16-byte words: ctx_copy)
                     // phase | its convex (GJK / EPA) part | constraint rows | solver | IK | integration
   // ---- stage temporaries ----
   double* warm_g;  // qacc_warmstart of this env in the global state (read at the start of solve, written at its end)
+  unsigned long long mbar;  // mbarrier of the bulk-async image load (ctx_load, device only)
   // contiguous block that is dead during collision (re-used there as clip scratch and EPA polytope)
   T H[NV * NV];
   T tmp6[TMP6_ROWS<T>()][6];

@@ -291,6 +291,58 @@ MM_HD void ctx_copy(const Grp<G>& g, void* dst, const void* src) {
   g.sync();
 }
 
+// Image load / store of a stage kernel.  A full warp per env on the device: ONE bulk-async copy by the TMA unit
+// (cp.async.bulk, 4.3 KB, completion on an mbarrier in the env's scratch / a bulk group) instead of 9 LDG.128 + 9 STS.128
+// per lane through the registers; -DMM_TMA_IMAGE=0, sub-warp groups, the CTA-per-env path and the host build copy by lanes.
+#ifndef MM_TMA_IMAGE
+#define MM_TMA_IMAGE 1
+#endif
+template <class T, int G>
+MM_HD void ctx_load(const Grp<G>& g, Scratch<T>& s, const void* src) {
+#if defined(__CUDA_ARCH__) && MM_TMA_IMAGE
+  if constexpr (G == 32) {
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&s.mbar), dst = (unsigned)__cvta_generic_to_shared(&s);
+    const unsigned bytes = (unsigned)ctx_stride<T>();
+    if (g.lane == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                   "r"(bytes), "r"(bar)
+                   : "memory");
+    }
+    g.sync();  // the barrier is initialised before any lane polls it
+    unsigned done;
+    do {
+      asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}"
+                   : "=r"(done)
+                   : "r"(bar)
+                   : "memory");
+    } while (!done);
+    return;
+  }
+#endif
+  ctx_copy<T, G>(g, &s, src);
+}
+template <class T, int G>
+MM_HD void ctx_store(const Grp<G>& g, void* dst, const Scratch<T>& s) {
+#if defined(__CUDA_ARCH__) && MM_TMA_IMAGE
+  if constexpr (G == 32) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // this lane's shared-memory writes -> visible to the copy unit
+    g.sync();
+    if (g.lane == 0) {
+      const unsigned src = (unsigned)__cvta_generic_to_shared(&s), bytes = (unsigned)ctx_stride<T>();
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    g.sync();
+    return;
+  }
+#endif
+  ctx_copy<T, G>(g, dst, &s);
+}
+
 template <class T, int G>
 MM_HDN void reset_bad_state(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, const StatePtrs& st, long e) {
   // Non-finite state: mj_checkPos / mj_checkVel would warn and reset the data; here the env is put back on
@@ -361,12 +413,12 @@ MM_HDN void stage_a(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<
     if (g.lane == 0) decode_action(s, st, e, action + e * ACTION_STRIDE, mode);
     g.sync();
   } else {
-    ctx_copy<T, G>(g, &s, ctx);
+    ctx_load<T, G>(g, s, ctx);
     if (g.lane == 0) s.warm_g = st.warm + e * NV;
     g.sync();
   }
   stage_a_body<T, G>(g, s, md, w, st, e, sub, q, hv);
-  ctx_copy<T, G>(g, ctx, &s);
+  ctx_store<T, G>(g, ctx, s);
 }
 
 // Stage C of round `sub`.  FUSE: unless it is the last round, stage A of round sub + 1 follows at once for the same
@@ -379,7 +431,7 @@ MM_HDN void stage_c(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<
                     char* ctx_base, const CvxQueue<T>& q, const CvxQueue<T>& qn, const HeavyList& hvn, int reward_type,
                     int max_steps, const StepOut& out, const float* tgt_kp_all) {
   void* ctx = ctx_base + (size_t)e * ctx_stride<T>();
-  ctx_copy<T, G>(g, &s, ctx);
+  ctx_load<T, G>(g, s, ctx);
   if (g.lane == 0) s.warm_g = st.warm + e * NV;
   g.sync();
   w.cvx = q.res + s.qbase;
@@ -389,12 +441,12 @@ MM_HDN void stage_c(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<
   if (sub != ACTION_REPEAT) {
     integrate<T, G>(g, s, md);
     if (FUSE) stage_a_body<T, G>(g, s, md, w, st, e, sub + 1, qn, hvn);
-    ctx_copy<T, G>(g, ctx, &s);
+    ctx_store<T, G>(g, ctx, s);
     return;
   }
   // last round: the trailing mj_forward is done; reward, termination, observation and the state store are the
   // epilogue kernel's (stage_finish), which keeps ~2,300 SASS instructions out of this kernel's instruction footprint
-  ctx_copy<T, G>(g, ctx, &s);
+  ctx_store<T, G>(g, ctx, s);
 }
 
 // Epilogue of the step for env e (gym_env.py:562-579): reward / termination, packed observation, state store; works on
@@ -402,7 +454,7 @@ MM_HDN void stage_c(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<
 template <class T, int G>
 MM_HDN void stage_finish(const Grp<G>& g, Scratch<T>& s, Work<T>& w, const StatePtrs& st, long e, char* ctx_base, int reward_type,
                          int max_steps, const StepOut& out, const float* tgt_kp_all) {
-  ctx_copy<T, G>(g, &s, ctx_base + (size_t)e * ctx_stride<T>());
+  ctx_load<T, G>(g, s, ctx_base + (size_t)e * ctx_stride<T>());
   bool rc = reward_type == REWARD_STAGED ? any_robot_collision<T, G>(g, s, w) : false;
   for (int i = g.lane; i < 9; i += G) s.tmp6[KIN_ROW + i / 6][i % 6] = s.qpos[i];
   g.sync();
