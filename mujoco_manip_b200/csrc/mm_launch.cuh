@@ -242,19 +242,54 @@ __global__ void __launch_bounds__(32 * W, MM_MINB_X) k_convex(StepParams p, int 
   EpaMem<T> em;
   em.vert = cs.vert;
   em.face = cs.face; em.fidx = cs.fidx; em.edge = cs.edge; em.canon = cs.canon; em.ecan = cs.ecan;
+  // Software pipeline over the queue: while a pair is in GJK / EPA, the item of the next pair is being loaded and the
+  // claim of the one after that (an atomic on the queue head) is in flight; of the env image only the poses of the
+  // pair's two bodies are fetched, one value per lane.  One exposed L2 round trip per pair instead of three.
+  const char* ctx = p.ctx;
+  int i = 0;
+  if (g.lane == 0) i = atomicAdd(q.head, 1);
+  i = __shfl_sync(0xffffffffu, i, 0);
+  if (i >= count) return;
+  CvxItem it = q.items[i];
+  // (claiming ahead holds a pair back from the warps that are idle at the end of a short queue: only with >= 6 pairs per warp)
+  const bool ahead = count > 6 * (int)(gridDim.x * W);
+  int raw_next = 0;
+  if (ahead && g.lane == 0) raw_next = atomicAdd(q.head, 1);
   while (true) {
-    int i = 0;
-    if (g.lane == 0) i = atomicAdd(q.head, 1);
-    i = __shfl_sync(0xffffffffu, i, 0);
-    if (i >= count) break;
     long long t0 = clock64();
-    stage_convex<T, 32>(g, gm, q, i, p.ctx, cs.bpos, cs.bR, em);
+    const Scratch<T>* img = reinterpret_cast<const Scratch<T>*>(ctx + (size_t)it.env * ctx_stride<T>());
+    const int ga = gm.pair[it.ci][0], gb = gm.pair[it.ci][1];
+    const int body = g.lane < 12 ? gm.body[ga] : gm.body[gb], k = g.lane < 12 ? g.lane : g.lane - 12;
+    const bool mine = g.lane < 24 && body >= 0;
+    T v = 0;
+    if (mine) v = k < 3 ? img->bpos[body][k] : img->bR[body][k - 3];
+    // next item (its index was claimed during the previous pair) and the claim after it
+    int inext = count;
+    CvxItem itn = it;
+    if (ahead) {
+      inext = __shfl_sync(0xffffffffu, raw_next, 0);
+      if (inext < count) {
+        itn = q.items[inext];
+        if (g.lane == 0) raw_next = atomicAdd(q.head, 1);
+      }
+    }
+    if (mine) { if (k < 3) cs.bpos[body][k] = v; else cs.bR[body][k - 3] = v; }
+    __syncwarp();
+    convex_pair<T, 32>(g, cs.bpos, cs.bR, gm, it.ci, em, q.res + i);
     if (g.lane == 0 && (p.work || p.cycles)) {
       long long dt = clock64() - t0;
-      int e = q.items[i].env;
+      int e = it.env;
       if (p.work) atomicAdd(p.work + e, (int)(dt >> 8));
       if (p.cycles) { atomicAdd((unsigned long long*)p.cycles + 9 * e + 2, (unsigned long long)dt); }
     }
+    if (!ahead) {  // short queue: claim the next pair only now
+      if (g.lane == 0) inext = atomicAdd(q.head, 1);
+      inext = __shfl_sync(0xffffffffu, inext, 0);
+      if (inext < count) itn = q.items[inext];
+    }
+    if (inext >= count) break;
+    i = inext;
+    it = itn;
   }
 }
 
