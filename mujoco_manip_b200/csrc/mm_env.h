@@ -334,7 +334,8 @@ MM_HD void ctx_store(const Grp<G>& g, void* dst, const Scratch<T>& s) {
       const unsigned src = (unsigned)__cvta_generic_to_shared(&s), bytes = (unsigned)ctx_stride<T>();
       asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      // (the shared-memory source must stay until it has been read; the global write itself completes by the end of the grid)
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
     g.sync();
     return;
