@@ -32,7 +32,32 @@ namespace mm {
 
 constexpr int MAXCON = 256;   // contacts per env (oracle max: 44 in scripted episodes, 76 in the table-collision stress run, 143 in random-action pile-ups)
 constexpr int MAXROW = MAXCON * 6;
-constexpr int MAXPAIR_S = 16; // simultaneously touching body pairs whose tables live in shared memory (the common case)
+// MM_ROWS_S > 0: the solver rows Jaref and Jv (MM_ROWS_N = 3: aref too) of an env with at most MM_ROWS_S contacts live
+// in shared memory instead of the global workspace: rows are re-read right after they are written, and every such
+// read misses L1.  12 contacts (three cubes at rest on the table, 62 % of the benchmarked envs) x 2 arrays is what
+// fits beside 12 resident envs per SM; taking the space for a third array from the shared pair tables (MM_PAIR_S)
+// slows the contact-rich envs down, which the small batches wait for (profiles/r02_variants.txt).
+#ifndef MM_ROWS_S
+#define MM_ROWS_S 12
+#endif
+#ifndef MM_ROWS_N
+#define MM_ROWS_N 2
+#endif
+#ifndef MM_PAIR_S
+#define MM_PAIR_S 16
+#endif
+constexpr int ROWS_S = MM_ROWS_S;
+#if MM_ROWS_S
+#define MM_ROWS_GLOBAL(p)
+#else
+#define MM_ROWS_GLOBAL(p) MM_IN_GLOBAL(p)
+#endif
+#if MM_ROWS_S && MM_ROWS_N == 3
+#define MM_AREF_GLOBAL(p)
+#else
+#define MM_AREF_GLOBAL(p) MM_IN_GLOBAL(p)
+#endif
+constexpr int MAXPAIR_S = MM_PAIR_S; // simultaneously touching body pairs whose tables live in shared memory (the common case)
 constexpr int MAXPAIR = 96;   // every ordered (class, class) key of the 780 candidate pairs (94, tools/modelc.py): exact, no cap;
                               // envs with more than MAXPAIR_S touching pairs keep their pair tables in the global workspace
 constexpr int MAXSPEC = 10;   // equality + at most one limit row per robot joint
@@ -81,6 +106,7 @@ struct alignas(16) Scratch {  // (images travel as 16-byte words: ctx_copy)
   T H[NV * NV];
   T tmp6[TMP6_ROWS<T>()][6];
   T pairK_s[MAXPAIR_S][21], pairW_s[MAXPAIR_S][6], pairF_s[MAXPAIR_S][6];
+  T rows_s[ROWS_S ? MM_ROWS_N * 6 * ROWS_S : 1];
   T qacc[NV], Ma[NV], search[NV], Mv[NV], fc[NV];
   // -----------------------------------------------------------------------------------------------------------
   T specD[MAXSPEC], specJaref[MAXSPEC], specJv[MAXSPEC], specAref[MAXSPEC];
@@ -1208,7 +1234,7 @@ MM_HDX void collide(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<
   g.sync();
   // EPA polytope: faces, their index words, horizon edges and canonical vertex ids live in SHARED memory (the H /
   // tmp6 / pair-block region, free during collision); vertices stay in the global workspace.
-  static_assert(sizeof(s.H) + sizeof(s.tmp6) + sizeof(s.pairK_s) + sizeof(s.pairW_s) + sizeof(s.pairF_s) + 5 * sizeof(s.qacc) >=
+  static_assert(sizeof(s.H) + sizeof(s.tmp6) + sizeof(s.pairK_s) + sizeof(s.pairW_s) + sizeof(s.pairF_s) + (ROWS_S ? sizeof(s.rows_s) : 0) + 5 * sizeof(s.qacc) >=
                     EPA_MAXF * 4 * sizeof(T) + EPA_INTS * sizeof(int), "EPA workspace does not fit the shared scratch");
   EpaMem<T> em;
   em.vert = w.epa.vert;
@@ -1302,8 +1328,8 @@ template <class T, int G>
 MM_HDX void make_constraints(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>& w) {
   MM_IN_SHARED(&s);
   MM_IN_GLOBAL(&md);
-  MM_IN_GLOBAL(w.cpos); MM_IN_GLOBAL(w.cn); MM_IN_GLOBAL(w.ct1); MM_IN_GLOBAL(w.cdist); MM_IN_GLOBAL(w.cD); MM_IN_GLOBAL(w.aref);
-  MM_IN_GLOBAL(w.Jaref); MM_IN_GLOBAL(w.Jv); MM_IN_GLOBAL(w.cmeta); MM_IN_GLOBAL(w.surv);
+  MM_IN_GLOBAL(w.cpos); MM_IN_GLOBAL(w.cn); MM_IN_GLOBAL(w.ct1); MM_IN_GLOBAL(w.cdist); MM_IN_GLOBAL(w.cD); MM_AREF_GLOBAL(w.aref);
+  MM_ROWS_GLOBAL(w.Jaref); MM_ROWS_GLOBAL(w.Jv); MM_IN_GLOBAL(w.cmeta); MM_IN_GLOBAL(w.surv);
   const T h = md.timestep;
   if (g.lane == 0) {
     int n = 0;
@@ -1592,8 +1618,8 @@ template <class T, int G>
 MM_HDX void solve(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>& w) {
   MM_IN_SHARED(&s);
   MM_IN_GLOBAL(&md);
-  MM_IN_GLOBAL(w.cpos); MM_IN_GLOBAL(w.cn); MM_IN_GLOBAL(w.ct1); MM_IN_GLOBAL(w.cdist); MM_IN_GLOBAL(w.cD); MM_IN_GLOBAL(w.aref);
-  MM_IN_GLOBAL(w.Jaref); MM_IN_GLOBAL(w.Jv); MM_IN_GLOBAL(w.cmeta); MM_IN_GLOBAL(w.surv);
+  MM_IN_GLOBAL(w.cpos); MM_IN_GLOBAL(w.cn); MM_IN_GLOBAL(w.ct1); MM_IN_GLOBAL(w.cdist); MM_IN_GLOBAL(w.cD); MM_AREF_GLOBAL(w.aref);
+  MM_ROWS_GLOBAL(w.Jaref); MM_ROWS_GLOBAL(w.Jv); MM_IN_GLOBAL(w.cmeta); MM_IN_GLOBAL(w.surv);
   analyse_coupling<T, G>(g, s);
   const T scale_inv = md.meaninertia * (T)NV;
   const T scale = (T)1 / scale_inv;
