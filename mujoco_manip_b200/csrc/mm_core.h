@@ -918,13 +918,6 @@ MM_HD int contact_meta(const GeomDev<T>& gm, int a, int b) {
   return (ca << META_KEY_SHIFT) | (cb << (META_KEY_SHIFT + 4)) | (cube << META_DIM4_BIT) | (robobs << META_ROBOBS_BIT);
 }
 
-// true when candidate pair (a, b) goes through the general convex test (a mesh hull or a cylinder is involved)
-template <class T>
-MM_HD bool is_convex_pair(const GeomDev<T>& gm, int a, int b) {
-  int ta = gm.type[a], tb = gm.type[b];
-  return !(ta == GT_PLANE || (ta == GT_BOX && tb == GT_BOX));
-}
-
 // Broad phase: two levels over the 780 candidates -> w.surv[0, s.nsurv) in candidate order
 template <class T, int G>
 MM_HDX void broad_phase(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>& w) {
@@ -1005,20 +998,38 @@ MM_HDX void narrow_box(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Wo
   MM_IN_SHARED(&s);
   MM_IN_GLOBAL(&md);
   MM_IN_GLOBAL(w.cpos); MM_IN_GLOBAL(w.cn); MM_IN_GLOBAL(w.ct1); MM_IN_GLOBAL(w.cdist); MM_IN_GLOBAL(w.cD);
-  MM_IN_GLOBAL(w.cmeta); MM_IN_GLOBAL(w.surv);
+  MM_IN_GLOBAL(w.cmeta); MM_IN_GLOBAL(w.surv); MM_IN_GLOBAL(w.Jv);
   const T ident[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
   const GeomDev<T>& gm = *md.geom;
   long long tc0 = MM_T0(s);
   const int nsurv = s.nsurv;
   constexpr int KB = G < NARROW_LANES ? G : NARROW_LANES;
+  // the survivors this phase handles, compacted in candidate order (a closed gripper interleaves 25 pad-pad box pairs
+  // with hull pairs: without this every pass of KB survivors pays a whole box-box test for a few busy lanes); the list
+  // lives in the row arrays, which are idle during collision
+  int* blist = reinterpret_cast<int*>(w.Jv);
+  int nb = 0;
+  for (int base = 0; base < nsurv; base += G) {
+    int si = base + g.lane;
+    int mine = 0, ci = 0;
+    if (si < nsurv) {
+      ci = w.surv[si];
+      mine = gm.pairflags[ci] & 1;
+    }
+    int tot;
+    int off = g.scan_flag(mine, &tot);
+    if (mine) blist[nb + off] = ci;
+    nb += tot;
+  }
+  g.sync();
   int ncon = 0;
-  for (int base = 0; base < nsurv; base += KB) {
+  for (int base = 0; base < nb; base += KB) {
     int si = base + g.lane;
     int cnt = 0, a = 0, b = 0;
     T nrm[3] = {0, 0, 1};
     T* scr = s.H + (g.lane < KB ? g.lane : 0) * NARROW_SCR;
-    if (g.lane < KB && si < nsurv) {
-      int ci = w.surv[si];
+    if (g.lane < KB && si < nb) {
+      int ci = blist[si];
       a = gm.pair[ci][0]; b = gm.pair[ci][1];
       int ta = gm.type[a], tb = gm.type[b];
       if (tb == GT_BOX && (ta == GT_PLANE || ta == GT_BOX)) {
@@ -1070,7 +1081,7 @@ MM_HD int list_convex(const Grp<G>& g, const Scratch<T>& s, const GeomDev<T>& gm
     int is = 0, ci = 0;
     if (si < nsurv) {
       ci = w.surv[si];
-      is = is_convex_pair(gm, gm.pair[ci][0], gm.pair[ci][1]) ? 1 : 0;
+      is = (gm.pairflags[ci] >> 1) & 1;
     }
     int tot;
     int off = g.scan_flag(is, &tot);

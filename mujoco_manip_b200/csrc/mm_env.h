@@ -437,12 +437,15 @@ MM_HDN void stage_c(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<
   g.sync();
   w.cvx = q.res + s.qbase;
   assemble_contacts<T, G>(g, s, md, w);
-  if (ROWS_S > 0 && s.ncon <= ROWS_S) {  // few contacts: the solver rows live in shared memory (mm_core.h, MM_ROWS_S)
-    w.Jaref = s.rows_s; w.Jv = s.rows_s + 6 * ROWS_S;
-    if (MM_ROWS_N == 3) w.aref = s.rows_s + 12 * ROWS_S;
+  {
+    Work<T> wr = w;  // (a copy: the fused stage A below must see the global row arrays again)
+    if (ROWS_S > 0 && s.ncon <= ROWS_S) {  // few contacts: the solver rows live in shared memory (mm_core.h, MM_ROWS_S)
+      wr.Jaref = s.rows_s; wr.Jv = s.rows_s + 6 * ROWS_S;
+      if (MM_ROWS_N == 3) wr.aref = s.rows_s + 12 * ROWS_S;
+    }
+    make_constraints<T, G>(g, s, md, wr);
+    solve<T, G>(g, s, md, wr);
   }
-  make_constraints<T, G>(g, s, md, w);
-  solve<T, G>(g, s, md, w);
   if (sub != ACTION_REPEAT) {
     integrate<T, G>(g, s, md);
     if (FUSE) stage_a_body<T, G>(g, s, md, w, st, e, sub + 1, qn, hvn);

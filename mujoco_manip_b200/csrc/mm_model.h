@@ -26,6 +26,7 @@ struct GeomDev {
   // kind 0 plane vs bounded geom, 1 static axis-aligned box vs bounding sphere, 2 sphere vs sphere, 3 never kept
   // (plane vs cylinder); rsum = bounding radius of geom b (kinds 0, 1) or rbound[a] + rbound[b] (kind 2)
   unsigned char pairkind[NPAIRC];
+  unsigned char pairflags[NPAIRC];  // bit 0: box / plane narrow phase (plane-box, box-box, plane-hull), bit 1: convex stage (GJK / EPA)
   T pairrs[NPAIRC];
   T hull[NHULLV][3];
 };
@@ -111,6 +112,12 @@ static void fill_geom(GeomDev<T>& g) {
     if (g.type[a] == GT_PLANE) { g.pairkind[c] = g.type[b] == GT_CYL ? 3 : 0; g.pairrs[c] = g.rbound[b]; }
     else if (g.type[a] == GT_BOX && g.body[a] < 0) { g.pairkind[c] = 1; g.pairrs[c] = g.rbound[b]; }
     else { g.pairkind[c] = 2; g.pairrs[c] = g.rbound[b] + g.rbound[a]; }
+    {
+      int ta = g.type[a], tb = g.type[b];
+      int narrow = (tb == GT_BOX && (ta == GT_PLANE || ta == GT_BOX)) || (ta == GT_PLANE && tb == GT_HULL);
+      int convex = !(ta == GT_PLANE || (ta == GT_BOX && tb == GT_BOX));
+      g.pairflags[c] = (unsigned char)(narrow | (convex << 1));
+    }
   }
   for (int v = 0; v < NHULLV; v++) for (int k = 0; k < 3; k++) g.hull[v][k] = (T)mm_hull[v][k];
 }
