@@ -1484,21 +1484,30 @@ MM_HDL T update_constraint(const Grp<G>& g, Scratch<T>& s, Work<T>& w, bool buil
   // special rows
   for (int k = g.lane; k < s.nspec; k += G) {
     T ja = s.specJaref[k];
-    if (s.specdof[k] < 0 || ja < 0) cost += (T)0.5 * s.specD[k] * ja * ja;
+    const T Da = (s.specdof[k] < 0 || ja < 0) ? s.specD[k] : (T)0;
+    cost += (T)0.5 * Da * ja * ja;
   }
   cost = g.sum(cost);
   *changed = g.any(chg);
   // qfrc_constraint
+  // (branch-free on purpose: a pair / row that does not involve dof i contributes with coefficient 0 - a data-dependent
+  // branch per pair cost more in instruction-fetch bubbles than the six idle multiply-adds do)
   for (int i = g.lane; i < NV; i += G) {
     T acc = 0;
+    T Si[6];
+    S_get(s, i, Si);
     for (int p = 0; p < np; p++) {
-      if ((s.pairmd[p] >> i) & 1) acc += (((s.pairmb[p] >> i) & 1) ? (T)1 : (T)-1) * S_dot(s, i, s.pairF[p]);
+      const int in = (s.pairmd[p] >> i) & 1, pos = (s.pairmb[p] >> i) & 1;
+      const T c = in ? (pos ? (T)1 : (T)-1) : (T)0;
+      acc += c * dot6(Si, s.pairF[p]);
     }
     for (int k = 0; k < s.nspec; k++) {
-      int d = s.specdof[k];
-      T ja = s.specJaref[k];
-      if (d < 0) { if (i == 7) acc += -s.specD[k] * ja; else if (i == 8) acc -= -s.specD[k] * ja; }
-      else if ((d & 255) == i && ja < 0) acc += ((d & 256) ? (T)-1 : (T)1) * (-s.specD[k] * ja);
+      const int d = s.specdof[k];
+      const T ja = s.specJaref[k];
+      const T f = -s.specD[k] * ja;
+      const T ceq = i == 7 ? (T)1 : (i == 8 ? (T)-1 : (T)0);
+      const T clim = ((d & 255) == i && ja < 0) ? ((d & 256) ? (T)-1 : (T)1) : (T)0;
+      acc += (d < 0 ? ceq : clim) * f;
     }
     s.fc[i] = acc;
   }
@@ -1612,12 +1621,14 @@ MM_HDS void ls_eval(const Grp<G>& g, const Scratch<T>& s, const Work<T>& w, T al
     for (int r = 0; r < nr; r++) {
       T jv = w.Jv[c * 6 + r];
       T x = w.Jaref[c * 6 + r] + alpha * jv;
-      if (x < 0) { a1 += D * jv * x; a2 += D * jv * jv; }
+      const T Da = x < 0 ? D : (T)0;  // (select instead of a branch per row: no instruction-fetch bubble)
+      a1 += Da * jv * x; a2 += Da * jv * jv;
     }
   }
   for (int k = g.lane; k < s.nspec; k += G) {
     T jv = s.specJv[k], x = s.specJaref[k] + alpha * jv;
-    if (s.specdof[k] < 0 || x < 0) { a1 += s.specD[k] * jv * x; a2 += s.specD[k] * jv * jv; }
+    const T Da = (s.specdof[k] < 0 || x < 0) ? s.specD[k] : (T)0;
+    a1 += Da * jv * x; a2 += Da * jv * jv;
   }
   a1 = g.sum(a1);
   a2 = g.sum(a2);
@@ -1657,13 +1668,15 @@ MM_HDX void solve(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>
       for (int r = 0; r < 6; r++) {
         T ja = rows[c * 6 + r] - w.aref[c * 6 + r];
         rows[c * 6 + r] = ja;
-        if (r < nr && ja < 0) cst += (T)0.5 * D * ja * ja;
+        const T Da = (r < nr && ja < 0) ? D : (T)0;
+        cst += (T)0.5 * Da * ja * ja;
       }
     }
     for (int k = g.lane; k < s.nspec; k += G) {
       T ja = srows[k] - s.specAref[k];
       srows[k] = ja;
-      if (s.specdof[k] < 0 || ja < 0) cst += (T)0.5 * s.specD[k] * ja * ja;
+      const T Da = (s.specdof[k] < 0 || ja < 0) ? s.specD[k] : (T)0;
+      cst += (T)0.5 * Da * ja * ja;
     }
     if (which) {
       mulM<T, G>(g, s, md, s.search, s.Ma);
