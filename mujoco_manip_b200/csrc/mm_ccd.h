@@ -65,7 +65,9 @@ MM_HDN void support1(const Grp<G>& g, const Shape<T>& s, const T* d, T* out) {
     for (int k = 0; k < SHAPE_LV; k++) {
       int i = g.lane + 32 * k;
       T v = s.lv[k][0] * l[0] + s.lv[k][1] * l[1] + s.lv[k][2] * l[2];
-      if (i < s.nvert && v > bv) { bv = v; best = i; }
+      const bool gt = i < s.nvert && v > bv;
+      bv = gt ? v : bv;
+      best = gt ? i : best;
     }
     g.argmax(bv, best);
     if (best >= s.nvert) best = 0;
@@ -226,9 +228,12 @@ template <class T, int G>
 MM_HD int epa_best(const Grp<G>& g, const EpaMem<T>& m, int nf) {
   T bv = (T)3e38;
   int best = nf;
+#pragma unroll 2
   for (int i = g.lane; i < nf; i += G) {
-    T d = m.face[4 * i + 3];
-    if (d < bv) { bv = d; best = i; }
+    const T d = m.face[4 * i + 3];
+    const bool lt = d < bv;  // (select form: no data-dependent branch in the scan)
+    bv = lt ? d : bv;
+    best = lt ? i : best;
   }
   g.argmin(bv, best);
   return best >= nf ? 0 : best;
@@ -273,7 +278,8 @@ MM_HDN bool epa(const Grp<G>& g, const Shape<T>& s1, const Shape<T>& s2, const S
     int cn = ip;
     for (int j = g.lane; j < ip; j += G) {
       const T* q = m.vert + 6 * j;
-      if (q[0] == p.v[0] && q[1] == p.v[1] && q[2] == p.v[2] && j < cn) cn = j;
+      const bool same = q[0] == p.v[0] && q[1] == p.v[1] && q[2] == p.v[2] && j < cn;
+      cn = same ? j : cn;
     }
     cn = g.imin(cn);
     if (g.lane == 0) {

@@ -1438,21 +1438,23 @@ MM_HDL T update_constraint(const Grp<G>& g, Scratch<T>& s, Work<T>& w, bool buil
 #pragma unroll 1  // (rolled on purpose: six unrolled copies of the row body are 8 KB of instruction cache)
       for (int r = 0; r < nr; r++) {
         T ja = w.Jaref[c * 6 + r];
-        if (ja < 0) {
-          bits |= 1 << r;
-          T f = -D * ja;
-          cost += (T)0.5 * D * ja * ja;
-          // y_r = [pos x d + tau ; d]
-          T y[6];
-          T sg = (r & 1) ? (T)-1 : (T)1;
-          if (r < 2) for (int d = 0; d < 3; d++) { y[d] = pxn[d] + sg * mu * px1[d]; y[3 + d] = q.n[d] + sg * mu * q.t1[d]; }
-          else if (r < 4) for (int d = 0; d < 3; d++) { y[d] = pxn[d] + sg * mu * px2[d]; y[3 + d] = q.n[d] + sg * mu * q.t2[d]; }
-          else for (int d = 0; d < 3; d++) { y[d] = pxn[d] + sg * q.n[d]; y[3 + d] = q.n[d]; }
-          for (int d = 0; d < 6; d++) F[d] += f * y[d];
-          if (buildK) {
-            int k = 0;
-            for (int a = 0; a < 6; a++) { T da = D * y[a]; for (int b = 0; b <= a; b++) Kc[k++] += da * y[b]; }
-          }
+        // (no branch on the row's activity: an inactive row runs the same code with D = 0 - its contributions are
+        // exact zeros - instead of costing an instruction-fetch bubble per row)
+        const bool act = ja < 0;
+        const T Da = act ? D : (T)0;
+        bits |= (act ? 1 : 0) << r;
+        T f = -Da * ja;
+        cost += (T)0.5 * Da * ja * ja;
+        // y_r = [pos x d + tau ; d]
+        T y[6];
+        T sg = (r & 1) ? (T)-1 : (T)1;
+        if (r < 2) for (int d = 0; d < 3; d++) { y[d] = pxn[d] + sg * mu * px1[d]; y[3 + d] = q.n[d] + sg * mu * q.t1[d]; }
+        else if (r < 4) for (int d = 0; d < 3; d++) { y[d] = pxn[d] + sg * mu * px2[d]; y[3 + d] = q.n[d] + sg * mu * q.t2[d]; }
+        else for (int d = 0; d < 3; d++) { y[d] = pxn[d] + sg * q.n[d]; y[3 + d] = q.n[d]; }
+        for (int d = 0; d < 6; d++) F[d] += f * y[d];
+        if (buildK) {
+          int k = 0;
+          for (int a = 0; a < 6; a++) { T da = Da * y[a]; for (int b = 0; b <= a; b++) Kc[k++] += da * y[b]; }
         }
       }
       int old = (m >> META_ACT_SHIFT) & 63;
