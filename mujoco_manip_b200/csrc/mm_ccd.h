@@ -25,6 +25,16 @@ constexpr int SHAPE_LV = 5;  // ceil(152 / 32): the largest hull has 152 vertice
 #ifndef MM_HULL_REGS
 #define MM_HULL_REGS 1
 #endif
+// MM_EPA_REGS=1: on the device a 32-lane group keeps the EPA visibility flags and the horizon edge list in registers
+// (one edge per lane) while the horizon has at most 32 edges; the shared-memory lists are the general path
+#ifndef MM_EPA_REGS
+#define MM_EPA_REGS 1
+#endif
+#if defined(__CUDA_ARCH__) && MM_EPA_REGS
+#define EPA_REG_HORIZON(G) ((G) == 32)
+#else
+#define EPA_REG_HORIZON(G) false
+#endif
 
 // EPA tolerances: the oracle's values in FP64; scaled to the arithmetic's resolution in FP32 (otherwise the
 // expansion never sees its progress fall below the threshold and runs into the face cap)
@@ -254,12 +264,10 @@ MM_HDN bool epa(const Grp<G>& g, const Shape<T>& s1, const Shape<T>& s2, const S
     }
   }
   g.sync();
-  if (g.lane == 0) {
-    epa_mkface(m, 0, 0, 1, 2, true);
-    epa_mkface(m, 1, 0, 2, 3, true);
-    epa_mkface(m, 2, 0, 3, 1, true);
-    epa_mkface(m, 3, 1, 3, 2, true);
-  }
+  // the four faces of the tetrahedron (0,1,2), (0,2,3), (0,3,1), (1,3,2) on four lanes (each is a square root and a
+  // division deep: one after the other on a single lane they were ~1,000 cycles of every EPA run)
+  for (int f = g.lane; f < 4; f += G)
+    epa_mkface(m, f, f == 3 ? 1 : 0, f == 0 ? 1 : (f == 1 ? 2 : 3), f == 0 ? 2 : (f == 1 ? 3 : (f == 2 ? 1 : 2)), true);
   g.sync();
 #pragma unroll 1
   for (int it = 0; it < EPA_MAXIT; it++) {
@@ -286,58 +294,122 @@ MM_HDN bool epa(const Grp<G>& g, const Shape<T>& s1, const Shape<T>& s2, const S
       for (int k = 0; k < 3; k++) { m.vert[6 * ip + k] = p.v[k]; m.vert[6 * ip + 3 + k] = p.a[k]; }
       m.canon[ip] = cn;
     }
-    for (int i = g.lane; i < nf; i += G) {
+    // (32 lanes on the device: the visibility flags stay in a register - bit j of lane l = face l + 32 j - and go to
+    // the faces' index words only if the horizon cannot be held in registers, see below)
+    unsigned visbits = 0;
+    for (int i = g.lane, j = 0; i < nf; i += G, j++) {
       int fi = m.fidx[i];
       const T* F = m.face + 4 * i;
       T r[3];
       sub3(r, p.v, m.vert + 6 * (fi & 1023));
-      if ((double)dot3(F, r) > epa_vis<T>()) m.fidx[i] = fi | EPA_VIS;
+      if ((double)dot3(F, r) > epa_vis<T>()) {
+        if (EPA_REG_HORIZON(G)) visbits |= 1u << j; else m.fidx[i] = fi | EPA_VIS;
+      }
     }
-    g.sync();
     // Removal of the visible faces and collection of the horizon.  The SEQUENCE of removals (face i is replaced by the
     // last face and examined again) and of edge insertions / cancellations is the oracle's - it fixes the order of the
     // new faces and therefore every later tie - but each step is done by all lanes: the next visible face and the
     // matching reversed edge are found with a ballot instead of a scan by one lane.
-    int ne = 0;
-    for (int i = 0;;) {
-      // next visible face at or after i
-      int found_face = -1;
-      for (int base = i; base < nf; base += G) {
-        int idx = base + g.lane;
-        unsigned b = g.ballot(idx < nf && (m.fidx[idx] & EPA_VIS));
-        if (b) { found_face = base + tctz(b); break; }
-      }
-      if (found_face < 0) break;
-      i = found_face;
-      int fi = m.fidx[i];
-      int id[3] = {fi & 1023, (fi >> 10) & 1023, (fi >> 20) & 1023};
+    int ne = 0, ereg = 0;
+    bool inregs = false;
+#if defined(__CUDA_ARCH__) && MM_EPA_REGS
+    if (EPA_REG_HORIZON(G)) {
+      // Horizon in registers: at most 3 edges per visible face, so with <= 10 visible faces the edge list fits one entry
+      // per lane (lane k = edge k: end points and their canonical ids).  Same sequence as the general path (lowest
+      // matching entry by ballot + count-trailing-zeros, the last entry moves into the hole by a shuffle), but an edge
+      // step touches no shared memory and needs no barrier; the only barrier left is the one behind a face's move into
+      // the hole of a removed one.  More visible faces: flags to the index words, general path.
+      inregs = 3 * g.isum(__popc(visbits)) <= 32;
+      if (!inregs)
+        for (int i = g.lane, j = 0; i < nf; i += G, j++)
+          if ((visbits >> j) & 1u) m.fidx[i] |= EPA_VIS;
+    }
+#endif
+    g.sync();
+    if (inregs) {
+#if defined(__CUDA_ARCH__) && MM_EPA_REGS
+      int creg = -1;
 #pragma unroll 1
-      for (int e = 0; e < 3; e++) {
-        int ea = id[e], eb = id[e == 2 ? 0 : e + 1];
-        int rev = m.canon[eb] | (m.canon[ea] << 16);  // shared edges appear reversed
-        int hit = -1;
-        for (int base = 0; base < ne; base += G) {
-          int k = base + g.lane;
-          unsigned b = g.ballot(k < ne && m.ecan[k] == rev);
-          if (b) { hit = base + tctz(b); break; }
+      for (int i = 0;;) {
+        int found_face = -1;
+#pragma unroll 1
+        for (int j = i >> 5; (j << 5) < nf; j++) {
+          const int idx = (j << 5) + g.lane;
+          const unsigned b = g.ballot(idx >= i && idx < nf && ((visbits >> j) & 1u));
+          if (b) { found_face = (j << 5) + tctz(b); break; }
         }
-        if (hit >= 0) {
-          --ne;
-          if (g.lane == 0) { m.edge[hit] = m.edge[ne]; m.ecan[hit] = m.ecan[ne]; }
-        } else if (ne < EPA_MAXE) {
-          if (g.lane == 0) { m.edge[ne] = ea | (eb << 16); m.ecan[ne] = m.canon[ea] | (m.canon[eb] << 16); }
-          ne++;
+        if (found_face < 0) break;
+        i = found_face;
+        const int fi = m.fidx[i];
+        const int id[3] = {fi & 1023, (fi >> 10) & 1023, (fi >> 20) & 1023};
+        const int cid[3] = {m.canon[id[0]], m.canon[id[1]], m.canon[id[2]]};
+#pragma unroll
+        for (int e = 0; e < 3; e++) {
+          const int f = e == 2 ? 0 : e + 1;
+          const int rev = cid[f] | (cid[e] << 16);  // shared edges appear reversed
+          const unsigned b = g.ballot(g.lane < ne && creg == rev);
+          // (select form: both outcomes cost a ballot and two shuffles, no branch)
+          const int hit = b ? tctz(b) : -1;
+          ne -= b ? 1 : 0;
+          const int le = g.bcast(ereg, ne & 31), lc = g.bcast(creg, ne & 31);
+          const bool take = g.lane == hit, put = !b && g.lane == ne;
+          ereg = take ? le : (put ? (id[e] | (id[f] << 16)) : ereg);
+          creg = take ? lc : (put ? (cid[e] | (cid[f] << 16)) : creg);
+          ne += b ? 0 : 1;
         }
+        --nf;
+        for (int k = g.lane; k < 4; k += G) m.face[4 * i + k] = m.face[4 * nf + k];
+        if (g.lane == G - 1) m.fidx[i] = m.fidx[nf];
+        const unsigned vmoved = (g.bcast(visbits, nf & 31) >> (nf >> 5)) & 1u;
+        if (g.lane == (i & 31)) visbits = (visbits & ~(1u << (i >> 5))) | (vmoved << (i >> 5));
+        if (g.lane == (nf & 31)) visbits &= ~(1u << (nf >> 5));
         g.sync();
       }
-      --nf;
-      for (int k = g.lane; k < 4; k += G) m.face[4 * i + k] = m.face[4 * nf + k];
-      if (g.lane == G - 1) m.fidx[i] = m.fidx[nf];
-      g.sync();
+#endif
+    } else {
+      for (int i = 0;;) {
+        // next visible face at or after i
+        int found_face = -1;
+        for (int base = i; base < nf; base += G) {
+          int idx = base + g.lane;
+          unsigned b = g.ballot(idx < nf && (m.fidx[idx] & EPA_VIS));
+          if (b) { found_face = base + tctz(b); break; }
+        }
+        if (found_face < 0) break;
+        i = found_face;
+        int fi = m.fidx[i];
+        int id[3] = {fi & 1023, (fi >> 10) & 1023, (fi >> 20) & 1023};
+#pragma unroll 1
+        for (int e = 0; e < 3; e++) {
+          int ea = id[e], eb = id[e == 2 ? 0 : e + 1];
+          int rev = m.canon[eb] | (m.canon[ea] << 16);  // shared edges appear reversed
+          int hit = -1;
+          for (int base = 0; base < ne; base += G) {
+            int k = base + g.lane;
+            unsigned b = g.ballot(k < ne && m.ecan[k] == rev);
+            if (b) { hit = base + tctz(b); break; }
+          }
+          if (hit >= 0) {
+            --ne;
+            if (g.lane == 0) { m.edge[hit] = m.edge[ne]; m.ecan[hit] = m.ecan[ne]; }
+          } else if (ne < EPA_MAXE) {
+            if (g.lane == 0) { m.edge[ne] = ea | (eb << 16); m.ecan[ne] = m.canon[ea] | (m.canon[eb] << 16); }
+            ne++;
+          }
+          g.sync();
+        }
+        --nf;
+        for (int k = g.lane; k < 4; k += G) m.face[4 * i + k] = m.face[4 * nf + k];
+        if (g.lane == G - 1) m.fidx[i] = m.fidx[nf];
+        g.sync();
+      }
     }
     if (ne == 0) break;
     int add = ne < EPA_MAXF - nf ? ne : EPA_MAXF - nf;
-    for (int k = g.lane; k < add; k += G) { int ed = m.edge[k]; epa_mkface(m, nf + k, ed & 0xFFFF, ed >> 16, ip, false); }
+    for (int k = g.lane; k < add; k += G) {
+      const int ed = inregs ? ereg : m.edge[k];  // (register list: at most 32 edges, lane k holds edge k)
+      epa_mkface(m, nf + k, ed & 0xFFFF, ed >> 16, ip, false);
+    }
     nf += add;
     g.sync();
   }
