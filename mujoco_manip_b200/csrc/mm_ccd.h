@@ -27,6 +27,9 @@ constexpr int SHAPE_LV = 5;  // ceil(152 / 32): the largest hull has 152 vertice
 #endif
 // MM_EPA_REGS=1: on the device a 32-lane group keeps the EPA visibility flags and the horizon edge list in registers
 // (one edge per lane) while the horizon has at most 32 edges; the shared-memory lists are the general path
+#ifndef MM_SUPPORT_TREE
+#define MM_SUPPORT_TREE 1
+#endif
 #ifndef MM_EPA_REGS
 #define MM_EPA_REGS 1
 #endif
@@ -69,17 +72,30 @@ MM_HDN void support1(const Grp<G>& g, const Shape<T>& s, const T* d, T* out) {
     if (n > (T)1e-14) { p[0] = l[0] / n * s.size[0]; p[1] = l[1] / n * s.size[0]; } else { p[0] = p[1] = 0; }
     p[2] = l[2] >= 0 ? s.size[1] : -s.size[1];
   } else if (G == 32 && MM_HULL_REGS) {  // every hull of the model has at most 32 * SHAPE_LV vertices (static_assert in mm_model.h)
-    int best = s.nvert;  // lanes without a vertex lose every comparison
-    T bv = (T)-1e30;
+    // this lane's best of its (up to) five vertices: the first maximum, found by a tournament (pairs, then pairs of
+    // winners: three dependent compare / select levels instead of five; a later vertex wins only when strictly greater,
+    // which is the tie rule of the linear scan); lanes without a vertex lose every comparison
+    static_assert(SHAPE_LV == 5, "tournament below is written for five slices");
+    T v[SHAPE_LV];
+    int ix[SHAPE_LV];
 #pragma unroll
     for (int k = 0; k < SHAPE_LV; k++) {
-      int i = g.lane + 32 * k;
-      T v = s.lv[k][0] * l[0] + s.lv[k][1] * l[1] + s.lv[k][2] * l[2];
-      const bool gt = i < s.nvert && v > bv;
-      bv = gt ? v : bv;
-      best = gt ? i : best;
+      ix[k] = g.lane + 32 * k;
+      v[k] = s.lv[k][0] * l[0] + s.lv[k][1] * l[1] + s.lv[k][2] * l[2];
+      if (ix[k] >= s.nvert) { v[k] = (T)-1e30; ix[k] = s.nvert; }
     }
-    g.argmax(bv, best);
+#if MM_SUPPORT_TREE
+    { const bool t = v[1] > v[0]; v[0] = t ? v[1] : v[0]; ix[0] = t ? ix[1] : ix[0]; }
+    { const bool t = v[3] > v[2]; v[2] = t ? v[3] : v[2]; ix[2] = t ? ix[3] : ix[2]; }
+    { const bool t = v[2] > v[0]; v[0] = t ? v[2] : v[0]; ix[0] = t ? ix[2] : ix[0]; }
+    { const bool t = v[4] > v[0]; v[0] = t ? v[4] : v[0]; ix[0] = t ? ix[4] : ix[0]; }
+#else
+#pragma unroll
+    for (int k = 1; k < SHAPE_LV; k++) { const bool t = v[k] > v[0]; v[0] = t ? v[k] : v[0]; ix[0] = t ? ix[k] : ix[0]; }
+#endif
+    T bv = v[0];
+    int best = ix[0];
+    g.argmax_index(bv, best);
     if (best >= s.nvert) best = 0;
     int kb = best >> 5;
     T q[3] = {s.lv[0][0], s.lv[0][1], s.lv[0][2]};
@@ -95,7 +111,7 @@ MM_HDN void support1(const Grp<G>& g, const Shape<T>& s, const T* d, T* out) {
       T v = V[3 * i] * l[0] + V[3 * i + 1] * l[1] + V[3 * i + 2] * l[2];
       if (v > bv) { bv = v; best = i; }
     }
-    g.argmax(bv, best);
+    g.argmax_index(bv, best);
     if (best >= s.nvert) best = 0;
     p[0] = V[3 * best]; p[1] = V[3 * best + 1]; p[2] = V[3 * best + 2];
   }
@@ -245,7 +261,7 @@ MM_HD int epa_best(const Grp<G>& g, const EpaMem<T>& m, int nf) {
     bv = lt ? d : bv;
     best = lt ? i : best;
   }
-  g.argmin(bv, best);
+  g.argmin_index(bv, best);
   return best >= nf ? 0 : best;
 }
 

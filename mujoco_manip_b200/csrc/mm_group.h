@@ -99,7 +99,7 @@ struct Grp {
     return (unsigned long long)((u >> 31) ? ~u : (u | 0x80000000u)) << 32;
   }
   template <class T>
-  __device__ __forceinline__ void arg_redux(T& v, int& i, bool want_max) const {
+  __device__ __forceinline__ void arg_redux(T& v, int& i, bool want_max, bool want_value = true) const {
     unsigned long long k = order_key(v);
     if (!want_max) k = ~k;
     unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
@@ -108,11 +108,28 @@ struct Grp {
     unsigned ml = __reduce_max_sync(0xffffffffu, c ? lo : 0u);
     c = c && lo == ml;
     int win = __reduce_min_sync(0xffffffffu, c ? i : 0x7fffffff);
-    int src = __ffs(__ballot_sync(0xffffffffu, c && i == win)) - 1;
-    v = __shfl_sync(0xffffffffu, v, src);
+    if (want_value) {  // (warp votes and shuffles are never dead code to the compiler: callers that only need the index say so)
+      int src = __ffs(__ballot_sync(0xffffffffu, c && i == win)) - 1;
+      v = __shfl_sync(0xffffffffu, v, src);
+    }
     i = win;
   }
 #endif
+  // index of the maximum / minimum only (lowest index among equals); `v` is left unspecified
+  template <class T>
+  MM_HD void argmax_index(T& v, int& i) const {
+#ifdef __CUDA_ARCH__
+    if (G == 32) { arg_redux(v, i, true, false); return; }
+#endif
+    argmax(v, i);
+  }
+  template <class T>
+  MM_HD void argmin_index(T& v, int& i) const {
+#ifdef __CUDA_ARCH__
+    if (G == 32) { arg_redux(v, i, false, false); return; }
+#endif
+    argmin(v, i);
+  }
   template <class T>
   MM_HD void argmax(T& v, int& i) const {
 #ifdef __CUDA_ARCH__
