@@ -1319,6 +1319,81 @@ MM_HDS void mulJ(const Grp<G>& g, Scratch<T>& s, const Work<T>& w, const T* x, T
   g.sync();
 }
 
+// Warm-start selection in ONE pass over the contacts: the rows J x - aref at x0 = qacc_smooth (kept in Jv) and at
+// x1 = qacc_warmstart (kept in Jaref) and this lane's share of both constraint costs.  Same arithmetic per row and the
+// same order of the cost terms as two mulJ passes each followed by a cost loop, but the contact geometry, the reference
+// accelerations and the pair tables are fetched once, the two evaluations overlap instruction by instruction, and half
+// of the barriers are gone.  The relative twists of x1 are parked in the pair-force table (idle until the first
+// constraint update clears it).
+template <class T, int G>
+MM_HDS void warm_rows(const Grp<G>& g, Scratch<T>& s, const Work<T>& w, const T* x0, const T* x1, T* cost0, T* cost1) {
+  int np = s.npair;
+  for (int idx = g.lane; idx < np * 6; idx += G) {
+    int p = idx / 6, c = idx % 6;
+    unsigned md = (unsigned)s.pairmd[p];  // dofs shared by both bodies cancel
+    int mB = s.pairmb[p];
+    T a0 = 0, a1 = 0;
+    while (md) {  // ascending dof order
+      int i = tctz(md);
+      md &= md - 1;
+      T sc = (((mB >> i) & 1) ? (T)1 : (T)-1);
+      T Sc = S_comp(s, i, c);
+      a0 += sc * x0[i] * Sc;
+      a1 += sc * x1[i] * Sc;
+    }
+    s.pairW[p][c] = a0;
+    s.pairF[p][c] = a1;
+  }
+  g.sync();
+  T c0 = 0, c1 = 0;
+  int ncon = s.ncon;
+  for (int c = g.lane; c < ncon; c += G) {
+    ConGeom<T> q;
+    load_con(w, c, q);
+    int m = w.cmeta[c];
+    T D = w.cD[c];
+    const bool dim4 = meta_dim4(m);
+    T mu = dim4 ? (T)2 : (T)1;
+    T ar[6];
+    for (int r = 0; r < 6; r++) ar[r] = (r < 4 || dim4) ? w.aref[c * 6 + r] : (T)0;
+#pragma unroll
+    for (int which = 0; which < 2; which++) {
+      const T* W = which ? s.pairF[meta_slot(m)] : s.pairW[meta_slot(m)];
+      T* out = which ? w.Jaref : w.Jv;
+      T u[3];
+      cross3(u, W, q.pos);
+      for (int d = 0; d < 3; d++) u[d] += W[3 + d];
+      T un = dot3(q.n, u), u1 = dot3(q.t1, u), u2 = dot3(q.t2, u);
+      T row[6] = {un + mu * u1, un - mu * u1, un + mu * u2, un - mu * u2, 0, 0};
+      if (dim4) {
+        T u3 = dot3(q.n, W);  // torsional friction coefficient of cube contacts = 1.0
+        row[4] = un + u3; row[5] = un - u3;
+      }
+      for (int r = 0; r < 6; r++) {
+        if (r >= 4 && !dim4) break;
+        T ja = row[r] - ar[r];
+        out[c * 6 + r] = ja;
+        const T Da = ja < 0 ? D : (T)0;
+        if (which) c1 += (T)0.5 * Da * ja * ja; else c0 += (T)0.5 * Da * ja * ja;  // (term by term: the order of the sum is part of the result)
+      }
+    }
+  }
+  for (int k = g.lane; k < s.nspec; k += G) {
+    int d = s.specdof[k];
+#pragma unroll
+    for (int which = 0; which < 2; which++) {
+      const T* x = which ? x1 : x0;
+      T ja = (d < 0 ? x[7] - x[8] : ((d & 256) ? -x[d & 255] : x[d & 255])) - s.specAref[k];
+      if (which) s.specJaref[k] = ja; else s.specJv[k] = ja;
+      const T Da = (d < 0 || ja < 0) ? s.specD[k] : (T)0;
+      if (which) c1 += (T)0.5 * Da * ja * ja; else c0 += (T)0.5 * Da * ja * ja;
+    }
+  }
+  g.sync();
+  *cost0 = c0;
+  *cost1 = c1;
+}
+
 // ------------------------------------------------------------------------------------------------
 // constraint rows (A4): per-contact D is set in collide(); here the reference accelerations
 // ------------------------------------------------------------------------------------------------
@@ -1653,40 +1728,16 @@ MM_HDX void solve(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>
   // warmstart selection: cost at qacc_smooth (which = 0, rows kept in Jv) vs cost at qacc_warmstart
   // (which = 1, rows kept in Jaref)
   T cost_sm = 0, cost_ws = 0;
-#pragma unroll 1
-  for (int which = 0; which < 2; which++) {
-    if (which) {  // qacc_warmstart arrives from the global state (parked in `search`, free until the Newton loop)
-      for (int i = g.lane; i < NV; i += G) s.search[i] = (T)s.warm_g[i];
-      g.sync();
-    }
-    const T* x = which ? s.search : s.as;
-    T* rows = which ? w.Jaref : w.Jv;
-    T* srows = which ? s.specJaref : s.specJv;
-    mulJ<T, G>(g, s, w, x, rows, srows);
-    T cst = 0;
-    for (int c = g.lane; c < ncon; c += G) {
-      T D = w.cD[c];
-      int nr = meta_dim4(w.cmeta[c]) ? 6 : 4;
-      for (int r = 0; r < 6; r++) {
-        T ja = rows[c * 6 + r] - w.aref[c * 6 + r];
-        rows[c * 6 + r] = ja;
-        const T Da = (r < nr && ja < 0) ? D : (T)0;
-        cst += (T)0.5 * Da * ja * ja;
-      }
-    }
-    for (int k = g.lane; k < s.nspec; k += G) {
-      T ja = srows[k] - s.specAref[k];
-      srows[k] = ja;
-      const T Da = (s.specdof[k] < 0 || ja < 0) ? s.specD[k] : (T)0;
-      cst += (T)0.5 * Da * ja * ja;
-    }
-    if (which) {
-      mulM<T, G>(g, s, md, s.search, s.Ma);
-      g.sync();
-      for (int i = g.lane; i < NV; i += G) cst += (T)0.5 * (s.Ma[i] - s.fs[i]) * (s.search[i] - s.as[i]);
-    }
-    cst = g.sum(cst);
-    if (which) cost_ws = cst; else cost_sm = cst;
+  {
+    // qacc_warmstart arrives from the global state (parked in `search`, free until the Newton loop)
+    for (int i = g.lane; i < NV; i += G) s.search[i] = (T)s.warm_g[i];
+    g.sync();
+    warm_rows<T, G>(g, s, w, s.as, s.search, &cost_sm, &cost_ws);
+    mulM<T, G>(g, s, md, s.search, s.Ma);
+    g.sync();
+    for (int i = g.lane; i < NV; i += G) cost_ws += (T)0.5 * (s.Ma[i] - s.fs[i]) * (s.search[i] - s.as[i]);
+    cost_sm = g.sum(cost_sm);
+    cost_ws = g.sum(cost_ws);
     g.sync();
   }
   if (cost_ws < cost_sm) {
