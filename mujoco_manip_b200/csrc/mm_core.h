@@ -1687,30 +1687,69 @@ MM_HDS void build_factor_H(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md
   chol_factor_list<T, G>(g, s.H, s.il, s.n_il);
 }
 
-// derivative / curvature of the cost along `search` at step alpha
+// Exact line search along `search` (Newton iterations on the one-dimensional cost, bracketed; mj_solver's rule as the
+// oracle states it): returns the step, *flat = the slope at 0 is not negative.  Every evaluation needs the derivative
+// and curvature of the cost at alpha, i.e. a pass over all rows; the rows of this lane's FIRST contact (Jaref, Jv, D -
+// all an env with at most G contacts has per lane) are fetched once and stay in registers for the whole search, so an
+// evaluation of such an env touches no memory beyond the special rows.  Rows past a contact's dimension are held as
+// zeros and contribute exact zeros (no case split per row); further contacts of the lane are read per evaluation.
 template <class T, int G>
-MM_HDS void ls_eval(const Grp<G>& g, const Scratch<T>& s, const Work<T>& w, T alpha, T qg1, T qg2, T* d1, T* d2) {
-  T a1 = 0, a2 = 0;
-  int ncon = s.ncon;
-  for (int c = g.lane; c < ncon; c += G) {
-    T D = w.cD[c];
-    int nr = meta_dim4(w.cmeta[c]) ? 6 : 4;
-    for (int r = 0; r < nr; r++) {
-      T jv = w.Jv[c * 6 + r];
-      T x = w.Jaref[c * 6 + r] + alpha * jv;
-      const T Da = x < 0 ? D : (T)0;  // (select instead of a branch per row: no instruction-fetch bubble)
+MM_HDS T line_search(const Grp<G>& g, const Scratch<T>& s, const Work<T>& w, T qg1, T qg2, T gtol, bool* flat_out) {
+  const int ncon = s.ncon;
+  T ja0[6], jv0[6], D0 = 0;
+#pragma unroll
+  for (int r = 0; r < 6; r++) { ja0[r] = 0; jv0[r] = 0; }
+  if (g.lane < ncon) {
+    const int c = g.lane;
+    D0 = w.cD[c];
+    const bool dim4 = meta_dim4(w.cmeta[c]);
+#pragma unroll
+    for (int r = 0; r < 6; r++)
+      if (r < 4 || dim4) { ja0[r] = w.Jaref[c * 6 + r]; jv0[r] = w.Jv[c * 6 + r]; }
+  }
+  T lo = 0, hi = -1, d1 = 0, d2 = 1, a = 0;
+  bool flat = false;
+#pragma unroll 1
+  for (int it = -1; it < 50; it++) {  // it = -1: slope at alpha = 0
+    if (it >= 0) {
+      T an = a - d1 / d2;
+      if (hi > 0 && !(an > lo && an < hi)) an = (T)0.5 * (lo + hi);
+      a = an;
+    }
+    // derivative / curvature of the cost at step a
+    T a1 = 0, a2 = 0;
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+      T jv = jv0[r];
+      T x = ja0[r] + a * jv;
+      const T Da = x < 0 ? D0 : (T)0;  // (select instead of a branch per row: no instruction-fetch bubble)
       a1 += Da * jv * x; a2 += Da * jv * jv;
     }
+    for (int c = g.lane + G; c < ncon; c += G) {
+      T D = w.cD[c];
+      int nr = meta_dim4(w.cmeta[c]) ? 6 : 4;
+      for (int r = 0; r < nr; r++) {
+        T jv = w.Jv[c * 6 + r];
+        T x = w.Jaref[c * 6 + r] + a * jv;
+        const T Da = x < 0 ? D : (T)0;
+        a1 += Da * jv * x; a2 += Da * jv * jv;
+      }
+    }
+    for (int k = g.lane; k < s.nspec; k += G) {
+      T jv = s.specJv[k], x = s.specJaref[k] + a * jv;
+      const T Da = (s.specdof[k] < 0 || x < 0) ? s.specD[k] : (T)0;
+      a1 += Da * jv * x; a2 += Da * jv * jv;
+    }
+    a1 = g.sum(a1);
+    a2 = g.sum(a2);
+    d1 = a1 + qg1 + 2 * a * qg2;
+    d2 = a2 + 2 * qg2;
+    if (it < 0) { if (d1 >= 0) { flat = true; break; } continue; }
+    if (tabs(d1) < gtol) break;
+    if (d1 < 0) lo = a; else hi = a;
   }
-  for (int k = g.lane; k < s.nspec; k += G) {
-    T jv = s.specJv[k], x = s.specJaref[k] + alpha * jv;
-    const T Da = (s.specdof[k] < 0 || x < 0) ? s.specD[k] : (T)0;
-    a1 += Da * jv * x; a2 += Da * jv * jv;
-  }
-  a1 = g.sum(a1);
-  a2 = g.sum(a2);
-  *d1 = a1 + qg1 + 2 * alpha * qg2;
-  *d2 = a2 + 2 * qg2;
+  *flat_out = flat;
+  return a;
 }
 
 template <class T, int G>
@@ -1815,20 +1854,8 @@ MM_HDX void solve(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>
     // (D) exact line search and the move
     if (!finished) {
       T gtol = tol * (T)0.01 * sn * scale_inv;
-      T lo = 0, hi = -1, d1, d2;
-      a = 0;
-      bool flat = false;
-      for (int it = -1; it < 50; it++) {  // it = -1: slope at alpha = 0
-        if (it >= 0) {
-          T an = a - d1 / d2;
-          if (hi > 0 && !(an > lo && an < hi)) an = (T)0.5 * (lo + hi);
-          a = an;
-        }
-        ls_eval<T, G>(g, s, w, a, qg1, qg2, &d1, &d2);
-        if (it < 0) { if (d1 >= 0) { flat = true; break; } continue; }
-        if (tabs(d1) < gtol) break;
-        if (d1 < 0) lo = a; else hi = a;
-      }
+      bool flat;
+      a = line_search<T, G>(g, s, w, qg1, qg2, gtol, &flat);
       if (flat || a == 0) finished = true;
       else {
         for (int i = g.lane; i < NV; i += G) { s.qacc[i] += a * s.search[i]; s.Ma[i] += a * s.Mv[i]; }
