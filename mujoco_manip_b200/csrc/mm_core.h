@@ -1687,26 +1687,55 @@ MM_HDS void build_factor_H(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md
   chol_factor_list<T, G>(g, s.H, s.il, s.n_il);
 }
 
-// Exact line search along `search` (Newton iterations on the one-dimensional cost, bracketed; mj_solver's rule as the
-// oracle states it): returns the step, *flat = the slope at 0 is not negative.  Every evaluation needs the derivative
-// and curvature of the cost at alpha, i.e. a pass over all rows; the rows of this lane's FIRST contact (Jaref, Jv, D -
-// all an env with at most G contacts has per lane) are fetched once and stay in registers for the whole search, so an
-// evaluation of such an env touches no memory beyond the special rows.  Rows past a contact's dimension are held as
-// zeros and contribute exact zeros (no case split per row); further contacts of the lane are read per evaluation.
+// Rows of the Newton direction, exact line search along it and the move of the rows, in one function: J * search for
+// every contact, then Newton iterations on the one-dimensional cost (bracketed; mj_solver's rule as the oracle states
+// it), then Jaref += step * Jv.  Returns the step; *flat = the slope at 0 is not negative (then, and with a zero step,
+// nothing moves).  Every evaluation of the line search needs the derivative and curvature of the cost at alpha, i.e. a
+// pass over all rows: the rows of this lane's FIRST contact (Jaref, Jv, D - all an env with at most G contacts has per
+// lane) are computed / fetched once and stay in registers from the row product to the move, so such an env reads its
+// contact list once per Newton iteration here and an evaluation touches no memory beyond the special rows.  Rows past
+// a contact's dimension are held as zeros and contribute exact zeros (no case split per row); further contacts of the
+// lane go through the row arrays.
 template <class T, int G>
-MM_HDS T line_search(const Grp<G>& g, const Scratch<T>& s, const Work<T>& w, T qg1, T qg2, T gtol, bool* flat_out) {
+MM_HDS T dir_search(const Grp<G>& g, Scratch<T>& s, const Work<T>& w, T qg1, T qg2, T gtol, bool* flat_out) {
+  pair_twists<T, G>(g, s, s.search);
   const int ncon = s.ncon;
   T ja0[6], jv0[6], D0 = 0;
+  bool dim40 = false;
 #pragma unroll
   for (int r = 0; r < 6; r++) { ja0[r] = 0; jv0[r] = 0; }
-  if (g.lane < ncon) {
-    const int c = g.lane;
-    D0 = w.cD[c];
-    const bool dim4 = meta_dim4(w.cmeta[c]);
+  for (int c = g.lane; c < ncon; c += G) {
+    ConGeom<T> q;
+    load_con(w, c, q);
+    int m = w.cmeta[c];
+    const bool dim4 = meta_dim4(m);
+    const T* W = s.pairW[meta_slot(m)];
+    T u[3];
+    cross3(u, W, q.pos);
+    for (int d = 0; d < 3; d++) u[d] += W[3 + d];
+    T un = dot3(q.n, u), u1 = dot3(q.t1, u), u2 = dot3(q.t2, u);
+    T mu = dim4 ? (T)2 : (T)1;
+    T row[6] = {un + mu * u1, un - mu * u1, un + mu * u2, un - mu * u2, 0, 0};
+    if (dim4) {
+      T u3 = dot3(q.n, W);  // torsional friction coefficient of cube contacts = 1.0
+      row[4] = un + u3; row[5] = un - u3;
+    }
+    if (c == g.lane) {
+      D0 = w.cD[c];
+      dim40 = dim4;
 #pragma unroll
-    for (int r = 0; r < 6; r++)
-      if (r < 4 || dim4) { ja0[r] = w.Jaref[c * 6 + r]; jv0[r] = w.Jv[c * 6 + r]; }
+      for (int r = 0; r < 6; r++)
+        if (r < 4 || dim4) { jv0[r] = row[r]; ja0[r] = w.Jaref[c * 6 + r]; }
+    } else {
+      for (int r = 0; r < (dim4 ? 6 : 4); r++) w.Jv[c * 6 + r] = row[r];
+    }
   }
+  for (int k = g.lane; k < s.nspec; k += G) {
+    int d = s.specdof[k];
+    const T* x = s.search;
+    s.specJv[k] = d < 0 ? x[7] - x[8] : ((d & 256) ? -x[d & 255] : x[d & 255]);
+  }
+  g.sync();
   T lo = 0, hi = -1, d1 = 0, d2 = 1, a = 0;
   bool flat = false;
 #pragma unroll 1
@@ -1749,6 +1778,16 @@ MM_HDS T line_search(const Grp<G>& g, const Scratch<T>& s, const Work<T>& w, T q
     if (d1 < 0) lo = a; else hi = a;
   }
   *flat_out = flat;
+  if (!flat && a != 0) {  // the move of the rows
+    if (g.lane < ncon) {
+#pragma unroll
+      for (int r = 0; r < 6; r++)
+        if (r < 4 || dim40) w.Jaref[g.lane * 6 + r] = ja0[r] + a * jv0[r];
+    }
+    for (int c = g.lane + G; c < ncon; c += G)
+      for (int r = 0; r < (meta_dim4(w.cmeta[c]) ? 6 : 4); r++) w.Jaref[c * 6 + r] += a * w.Jv[c * 6 + r];
+    for (int k = g.lane; k < s.nspec; k += G) s.specJaref[k] += a * s.specJv[k];
+  }
   return a;
 }
 
@@ -1842,7 +1881,6 @@ MM_HDX void solve(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>
       g.sync();
       solve_H<T, G>(g, s, s.search);
       mulM<T, G>(g, s, md, s.search, s.Mv);
-      mulJ<T, G>(g, s, w, s.search, w.Jv, s.specJv);
       for (int i = g.lane; i < NV; i += G) {
         sn += s.search[i] * s.search[i];
         qg1 += s.search[i] * (s.Ma[i] - s.fs[i]);
@@ -1851,16 +1889,14 @@ MM_HDX void solve(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>
       sn = tsqrt(g.sum(sn)); qg1 = g.sum(qg1); qg2 = g.sum(qg2);
       if (sn < (T)MINVAL_D) finished = true;
     }
-    // (D) exact line search and the move
+    // (D) rows of the direction, exact line search and the move
     if (!finished) {
       T gtol = tol * (T)0.01 * sn * scale_inv;
       bool flat;
-      a = line_search<T, G>(g, s, w, qg1, qg2, gtol, &flat);
+      a = dir_search<T, G>(g, s, w, qg1, qg2, gtol, &flat);  // (rows of the direction, line search, move of the rows)
       if (flat || a == 0) finished = true;
       else {
         for (int i = g.lane; i < NV; i += G) { s.qacc[i] += a * s.search[i]; s.Ma[i] += a * s.Mv[i]; }
-        for (int c = g.lane; c < ncon; c += G) for (int r = 0; r < 6; r++) w.Jaref[c * 6 + r] += a * w.Jv[c * 6 + r];
-        for (int k = g.lane; k < s.nspec; k += G) s.specJaref[k] += a * s.specJv[k];
         g.sync();
       }
     }
