@@ -1290,33 +1290,24 @@ MM_HD void load_con(const Work<T>& w, int c, ConGeom<T>& q) {
   cross3(q.t2, q.n, q.t1);
 }
 
-// rows of J*x for every contact (out[c*6 + r]) and special row (outspec[k])
-template <class T, int G>
-MM_HDS void mulJ(const Grp<G>& g, Scratch<T>& s, const Work<T>& w, const T* x, T* out, T* outspec) {
-  pair_twists<T, G>(g, s, x);
-  int ncon = s.ncon;
-  for (int c = g.lane; c < ncon; c += G) {
-    ConGeom<T> q;
-    load_con(w, c, q);
-    int m = w.cmeta[c];
-    const T* W = s.pairW[meta_slot(m)];
-    T u[3];
-    cross3(u, W, q.pos);
-    for (int d = 0; d < 3; d++) u[d] += W[3 + d];
-    T un = dot3(q.n, u), u1 = dot3(q.t1, u), u2 = dot3(q.t2, u);
-    T mu = meta_dim4(m) ? (T)2 : (T)1;
-    out[c * 6 + 0] = un + mu * u1; out[c * 6 + 1] = un - mu * u1;
-    out[c * 6 + 2] = un + mu * u2; out[c * 6 + 3] = un - mu * u2;
-    if (meta_dim4(m)) {
-      T u3 = dot3(q.n, W);  // torsional friction coefficient of cube contacts = 1.0
-      out[c * 6 + 4] = un + u3; out[c * 6 + 5] = un - u3;
-    }
+// rows of J * x of one contact from the relative twist W of its body pair: out[0..3] (and [4], [5] for a contact with
+// torsional friction; zeros otherwise); returns whether the contact has six rows
+template <class T>
+MM_HD bool con_rows(const ConGeom<T>& q, const T* W, int m, T* out) {
+  T u[3];
+  cross3(u, W, q.pos);
+  for (int d = 0; d < 3; d++) u[d] += W[3 + d];
+  T un = dot3(q.n, u), u1 = dot3(q.t1, u), u2 = dot3(q.t2, u);
+  const bool dim4 = meta_dim4(m);
+  T mu = dim4 ? (T)2 : (T)1;
+  out[0] = un + mu * u1; out[1] = un - mu * u1;
+  out[2] = un + mu * u2; out[3] = un - mu * u2;
+  out[4] = 0; out[5] = 0;
+  if (dim4) {
+    T u3 = dot3(q.n, W);  // torsional friction coefficient of cube contacts = 1.0
+    out[4] = un + u3; out[5] = un - u3;
   }
-  for (int k = g.lane; k < s.nspec; k += G) {
-    int d = s.specdof[k];
-    outspec[k] = d < 0 ? x[7] - x[8] : ((d & 256) ? -x[d & 255] : x[d & 255]);
-  }
-  g.sync();
+  return dim4;
 }
 
 // Warm-start selection in ONE pass over the contacts: the rows J x - aref at x0 = qacc_smooth (kept in Jv) and at
@@ -1353,22 +1344,14 @@ MM_HDS void warm_rows(const Grp<G>& g, Scratch<T>& s, const Work<T>& w, const T*
     int m = w.cmeta[c];
     T D = w.cD[c];
     const bool dim4 = meta_dim4(m);
-    T mu = dim4 ? (T)2 : (T)1;
     T ar[6];
     for (int r = 0; r < 6; r++) ar[r] = (r < 4 || dim4) ? w.aref[c * 6 + r] : (T)0;
 #pragma unroll
     for (int which = 0; which < 2; which++) {
       const T* W = which ? s.pairF[meta_slot(m)] : s.pairW[meta_slot(m)];
       T* out = which ? w.Jaref : w.Jv;
-      T u[3];
-      cross3(u, W, q.pos);
-      for (int d = 0; d < 3; d++) u[d] += W[3 + d];
-      T un = dot3(q.n, u), u1 = dot3(q.t1, u), u2 = dot3(q.t2, u);
-      T row[6] = {un + mu * u1, un - mu * u1, un + mu * u2, un - mu * u2, 0, 0};
-      if (dim4) {
-        T u3 = dot3(q.n, W);  // torsional friction coefficient of cube contacts = 1.0
-        row[4] = un + u3; row[5] = un - u3;
-      }
+      T row[6];
+      con_rows(q, W, m, row);
       for (int r = 0; r < 6; r++) {
         if (r >= 4 && !dim4) break;
         T ja = row[r] - ar[r];
@@ -1449,19 +1432,26 @@ MM_HDX void make_constraints(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& 
     s.nspec = n;
   }
   g.sync();
-  // contact aref_r = -B (J qvel)_r - K imp dist
-  mulJ<T, G>(g, s, w, s.qvel, w.aref, s.specJv /*scratch, ignored*/);
+  // contact aref_r = -B (J qvel)_r - K imp dist: the row product and the reference acceleration in one pass (one read of
+  // the contact list, one store per row)
+  pair_twists<T, G>(g, s, s.qvel);
   {
     const T tc = tmax((T)0.02, 2 * h), dmax = (T)0.95;
     const T K = (T)1 / (dmax * dmax * tc * tc), B = (T)2 / (dmax * tc);
     int ncon = s.ncon;
     for (int c = g.lane; c < ncon; c += G) {
+      ConGeom<T> q;
+      load_con(w, c, q);
+      int m = w.cmeta[c];
       T dist = w.cdist[c];
+      T row[6];
+      const bool dim4 = con_rows(q, s.pairW[meta_slot(m)], m, row);
       T x = tabs(dist) / (T)0.001, imp;
       if (x >= 1) imp = (T)0.95;
       else { T y = x <= (T)0.5 ? 2 * x * x : 1 - 2 * (1 - x) * (1 - x); imp = (T)0.9 + y * (T)0.05; }
-      int nr = meta_dim4(w.cmeta[c]) ? 6 : 4;
-      for (int r = 0; r < nr; r++) w.aref[c * 6 + r] = -B * w.aref[c * 6 + r] - K * imp * dist;
+#pragma unroll
+      for (int r = 0; r < 6; r++)
+        if (r < 4 || dim4) w.aref[c * 6 + r] = -B * row[r] - K * imp * dist;
     }
   }
   g.sync();
@@ -1708,18 +1698,8 @@ MM_HDS T dir_search(const Grp<G>& g, Scratch<T>& s, const Work<T>& w, T qg1, T q
     ConGeom<T> q;
     load_con(w, c, q);
     int m = w.cmeta[c];
-    const bool dim4 = meta_dim4(m);
-    const T* W = s.pairW[meta_slot(m)];
-    T u[3];
-    cross3(u, W, q.pos);
-    for (int d = 0; d < 3; d++) u[d] += W[3 + d];
-    T un = dot3(q.n, u), u1 = dot3(q.t1, u), u2 = dot3(q.t2, u);
-    T mu = dim4 ? (T)2 : (T)1;
-    T row[6] = {un + mu * u1, un - mu * u1, un + mu * u2, un - mu * u2, 0, 0};
-    if (dim4) {
-      T u3 = dot3(q.n, W);  // torsional friction coefficient of cube contacts = 1.0
-      row[4] = un + u3; row[5] = un - u3;
-    }
+    T row[6];
+    const bool dim4 = con_rows(q, s.pairW[meta_slot(m)], m, row);
     if (c == g.lane) {
       D0 = w.cD[c];
       dim40 = dim4;
