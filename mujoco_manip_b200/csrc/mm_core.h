@@ -58,6 +58,9 @@ constexpr int ROWS_S = MM_ROWS_S;
 #define MM_AREF_GLOBAL(p) MM_IN_GLOBAL(p)
 #endif
 constexpr int MAXPAIR_S = MM_PAIR_S; // simultaneously touching body pairs whose tables live in shared memory (the common case)
+#ifndef MM_PAIR_SPILL_AT
+#define MM_PAIR_SPILL_AT MAXPAIR_S
+#endif
 constexpr int MAXPAIR = 96;   // every ordered (class, class) key of the 780 candidate pairs (94, tools/modelc.py): exact, no cap;
                               // envs with more than MAXPAIR_S touching pairs keep their pair tables in the global workspace
 constexpr int MAXSPEC = 10;   // equality + at most one limit row per robot joint
@@ -1182,48 +1185,65 @@ MM_HDX void assemble_contacts(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>&
     g.sync();
   }
   MM_TICK(s, g, 3, tx0);
-  // pair slots: contacts are ordered by (classA, classB); a new slot starts where the key changes.  First the number of
-  // touching body pairs, which decides where this pass keeps its pair tables (shared memory / global spill, same layout).
-  int npair = 0;
-  for (int base = 0; base < ncon; base += G) {
-    int c = base + g.lane;
-    int head = c < ncon && ((c == 0) || (meta_key(w.cmeta[c - 1]) != meta_key(w.cmeta[c])));
-    npair += g.isum(head);
-  }
+  // pair slots: contacts are ordered by (classA, classB); a new slot starts where the key changes.  ONE pass over the
+  // meta words: the key of the left neighbour comes by shuffle (by a load for the first lane of a warp), and
+  // the pair tables are written to shared memory on the assumption that at most MAXPAIR_S body pairs touch; only when
+  // there are more (rare) a second pass fills the tables of the global spill instead (same layout).
   if (g.lane == 0) {
-    if (npair <= MAXPAIR_S) {
-      s.pairK = s.pairK_s; s.pairW = s.pairW_s; s.pairF = s.pairF_s;
-      s.pairkey = s.pairkey_s; s.pairmd = s.pairmd_s; s.pairmb = s.pairmb_s;
-    } else {
+    s.pairK = s.pairK_s; s.pairW = s.pairW_s; s.pairF = s.pairF_s;
+    s.pairkey = s.pairkey_s; s.pairmd = s.pairmd_s; s.pairmb = s.pairmb_s;
+  }
+  int npair = 0;
+  {
+    for (int base = 0; base < ncon; base += G) {
+      int c = base + g.lane;
+      int key = -1, m = 0, left = -1;
+      if (c < ncon) {
+        m = w.cmeta[c];
+        key = meta_key(m);
+        // (first lane of a warp: the neighbour's word comes from memory - its key bits are never rewritten)
+        if (g.wlane() == 0 && c > 0) left = meta_key(w.cmeta[c - 1]);
+      }
+      int prev = g.wshfl_up(key, 1);
+      if (g.wlane() == 0) prev = left;
+      int head = c < ncon && prev != key;
+      int tot;
+      int off = g.scan_flag(head, &tot);
+      if (c < ncon) {
+        int slot = npair + off + head - 1;
+        if (slot >= MAXPAIR) slot = MAXPAIR - 1;  // unreachable: MAXPAIR covers every (class, class) key of the model
+        w.cmeta[c] = (m & ~127) | slot;
+        if (head && npair + off < MAXPAIR_S) {
+          int mA = dofmask(key & 15), mB = dofmask((key >> 4) & 15);
+          s.pairkey_s[npair + off] = key; s.pairmd_s[npair + off] = mA ^ mB; s.pairmb_s[npair + off] = mB;
+        }
+      }
+      npair += tot;
+    }
+  }
+  if (npair > MM_PAIR_SPILL_AT) {  // (MAXPAIR_S; a test build lowers it to send every env through the spill)
+    if (g.lane == 0) {
       s.pairK = reinterpret_cast<T (*)[21]>(w.pairbig);
       s.pairW = reinterpret_cast<T (*)[6]>(w.pairbig + 21 * MAXPAIR);
       s.pairF = reinterpret_cast<T (*)[6]>(w.pairbig + 27 * MAXPAIR);
       s.pairkey = w.pairbig_i; s.pairmd = w.pairbig_i + MAXPAIR; s.pairmb = w.pairbig_i + 2 * MAXPAIR;
     }
-  }
-  g.sync();
-  npair = 0;
-  for (int base = 0; base < ncon; base += G) {
-    int c = base + g.lane;
-    int head = 0, key = 0, m = 0;
-    if (c < ncon) {
-      m = w.cmeta[c];
-      key = meta_key(m);
-      head = (c == 0) || (meta_key(w.cmeta[c - 1]) != key);
-    }
-    int tot;
-    int off = g.scan_flag(head, &tot);
-    g.sync();  // every lane has read its neighbour's meta word before any is rewritten
-    if (c < ncon) {
-      int slot = npair + off + head - 1;
-      if (slot >= MAXPAIR) slot = MAXPAIR - 1;  // unreachable: MAXPAIR covers every (class, class) key of the model
-      w.cmeta[c] = (m & ~127) | slot;
-      if (head && npair + off < MAXPAIR) {
+    g.sync();
+    for (int base = 0; base < ncon; base += G) {
+      int c = base + g.lane;
+      int slot = -1, key = 0, left = -1;
+      if (c < ncon) {
+        int m = w.cmeta[c];
+        slot = meta_slot(m); key = meta_key(m);
+        if (g.wlane() == 0 && c > 0) left = meta_slot(w.cmeta[c - 1]);
+      }
+      int prev = g.wshfl_up(slot, 1);
+      if (g.wlane() == 0) prev = left;
+      if (c < ncon && prev != slot && slot < MAXPAIR) {
         int mA = dofmask(key & 15), mB = dofmask((key >> 4) & 15);
-        s.pairkey[npair + off] = key; s.pairmd[npair + off] = mA ^ mB; s.pairmb[npair + off] = mB;
+        s.pairkey[slot] = key; s.pairmd[slot] = mA ^ mB; s.pairmb[slot] = mB;
       }
     }
-    npair += tot;
   }
   if (npair > MAXPAIR) { npair = MAXPAIR; if (g.lane == 0) s.overflow |= 4; }
   if (g.lane == 0) { s.ncon = ncon; s.npair = npair; }
@@ -1310,32 +1330,40 @@ MM_HD bool con_rows(const ConGeom<T>& q, const T* W, int m, T* out) {
   return dim4;
 }
 
-// Warm-start selection in ONE pass over the contacts: the rows J x - aref at x0 = qacc_smooth (kept in Jv) and at
-// x1 = qacc_warmstart (kept in Jaref) and this lane's share of both constraint costs.  Same arithmetic per row and the
+// Reference accelerations and warm-start selection in ONE pass over the contacts: aref from J qvel, then the rows
+// J x - aref at x0 = qacc_smooth (kept in Jv) and at x1 = qacc_warmstart (kept in Jaref) and this lane's share of both
+// constraint costs.  Same arithmetic per row and the
 // same order of the cost terms as two mulJ passes each followed by a cost loop, but the contact geometry, the reference
 // accelerations and the pair tables are fetched once, the two evaluations overlap instruction by instruction, and half
 // of the barriers are gone.  The relative twists of x1 are parked in the pair-force table (idle until the first
 // constraint update clears it).
 template <class T, int G>
-MM_HDS void warm_rows(const Grp<G>& g, Scratch<T>& s, const Work<T>& w, const T* x0, const T* x1, T* cost0, T* cost1) {
+MM_HDS void warm_rows(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, const Work<T>& w, const T* x0, const T* x1, T* cost0, T* cost1) {
   int np = s.npair;
   for (int idx = g.lane; idx < np * 6; idx += G) {
     int p = idx / 6, c = idx % 6;
-    unsigned md = (unsigned)s.pairmd[p];  // dofs shared by both bodies cancel
+    unsigned dm = (unsigned)s.pairmd[p];  // dofs shared by both bodies cancel
     int mB = s.pairmb[p];
-    T a0 = 0, a1 = 0;
-    while (md) {  // ascending dof order
-      int i = tctz(md);
-      md &= md - 1;
+    T a0 = 0, a1 = 0, av = 0;
+    while (dm) {  // ascending dof order
+      int i = tctz(dm);
+      dm &= dm - 1;
       T sc = (((mB >> i) & 1) ? (T)1 : (T)-1);
       T Sc = S_comp(s, i, c);
       a0 += sc * x0[i] * Sc;
       a1 += sc * x1[i] * Sc;
+      av += sc * s.qvel[i] * Sc;
     }
     s.pairW[p][c] = a0;
     s.pairF[p][c] = a1;
+    s.pairK[p][c] = av;  // (relative velocity of the pair: head of its block, which the first constraint update clears)
   }
   g.sync();
+  // contact aref_r = -B (J qvel)_r - K imp dist (A4: default solref (0.02, 1), solimp (0.9, 0.95, 0.001, 0.5, 2)), made
+  // here, in registers, from the same fetch of the contact as the two candidates' rows
+  const T h = md.timestep;
+  const T tc = tmax((T)0.02, 2 * h), dmax = (T)0.95;
+  const T Kc = (T)1 / (dmax * dmax * tc * tc), Bc = (T)2 / (dmax * tc);
   T c0 = 0, c1 = 0;
   int ncon = s.ncon;
   for (int c = g.lane; c < ncon; c += G) {
@@ -1343,9 +1371,17 @@ MM_HDS void warm_rows(const Grp<G>& g, Scratch<T>& s, const Work<T>& w, const T*
     load_con(w, c, q);
     int m = w.cmeta[c];
     T D = w.cD[c];
+    T dist = w.cdist[c];
     const bool dim4 = meta_dim4(m);
     T ar[6];
-    for (int r = 0; r < 6; r++) ar[r] = (r < 4 || dim4) ? w.aref[c * 6 + r] : (T)0;
+    {
+      con_rows(q, s.pairK[meta_slot(m)], m, ar);
+      T x = tabs(dist) / (T)0.001, imp;
+      if (x >= 1) imp = (T)0.95;
+      else { T y = x <= (T)0.5 ? 2 * x * x : 1 - 2 * (1 - x) * (1 - x); imp = (T)0.9 + y * (T)0.05; }
+#pragma unroll
+      for (int r = 0; r < 6; r++) ar[r] = (r < 4 || dim4) ? -Bc * ar[r] - Kc * imp * dist : (T)0;
+    }
 #pragma unroll
     for (int which = 0; which < 2; which++) {
       const T* W = which ? s.pairF[meta_slot(m)] : s.pairW[meta_slot(m)];
@@ -1431,30 +1467,7 @@ MM_HDX void make_constraints(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& 
     }
     s.nspec = n;
   }
-  g.sync();
-  // contact aref_r = -B (J qvel)_r - K imp dist: the row product and the reference acceleration in one pass (one read of
-  // the contact list, one store per row)
-  pair_twists<T, G>(g, s, s.qvel);
-  {
-    const T tc = tmax((T)0.02, 2 * h), dmax = (T)0.95;
-    const T K = (T)1 / (dmax * dmax * tc * tc), B = (T)2 / (dmax * tc);
-    int ncon = s.ncon;
-    for (int c = g.lane; c < ncon; c += G) {
-      ConGeom<T> q;
-      load_con(w, c, q);
-      int m = w.cmeta[c];
-      T dist = w.cdist[c];
-      T row[6];
-      const bool dim4 = con_rows(q, s.pairW[meta_slot(m)], m, row);
-      T x = tabs(dist) / (T)0.001, imp;
-      if (x >= 1) imp = (T)0.95;
-      else { T y = x <= (T)0.5 ? 2 * x * x : 1 - 2 * (1 - x) * (1 - x); imp = (T)0.9 + y * (T)0.05; }
-#pragma unroll
-      for (int r = 0; r < 6; r++)
-        if (r < 4 || dim4) w.aref[c * 6 + r] = -B * row[r] - K * imp * dist;
-    }
-  }
-  g.sync();
+  g.sync();  // (the contacts' reference accelerations are made in warm_rows, from the fetch that also serves the warm start)
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1796,7 +1809,7 @@ MM_HDX void solve(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<T>
     // qacc_warmstart arrives from the global state (parked in `search`, free until the Newton loop)
     for (int i = g.lane; i < NV; i += G) s.search[i] = (T)s.warm_g[i];
     g.sync();
-    warm_rows<T, G>(g, s, w, s.as, s.search, &cost_sm, &cost_ws);
+    warm_rows<T, G>(g, s, md, w, s.as, s.search, &cost_sm, &cost_ws);
     mulM<T, G>(g, s, md, s.search, s.Ma);
     g.sync();
     for (int i = g.lane; i < NV; i += G) cost_ws += (T)0.5 * (s.Ma[i] - s.fs[i]) * (s.search[i] - s.as[i]);

@@ -20,22 +20,24 @@ STATE_FIELDS = [("qpos", 30, np.float64), ("qvel", 27, np.float64), ("ctrl", 8, 
                 ("diag", 4, np.int32)]
 
 
-def build_emul():
+def build_emul(tag="", defines=()):
+    """Host build of the kernel source; `tag` / `defines` give a second build with extra -D switches (test hooks)."""
+    out = _EMUL if not tag else _EMUL.replace(".so", f"_{tag}.so")
     srcdir = os.path.join(REPO, "mujoco_manip_b200", "csrc")
     srcs = [os.path.join(srcdir, f) for f in os.listdir(srcdir) if f.endswith(".h")] + [os.path.join(REPO, "tests", "mm_emul.cpp")]
-    if os.path.exists(_EMUL) and all(os.path.getmtime(s) <= os.path.getmtime(_EMUL) for s in srcs):
-        return _EMUL
-    os.makedirs(os.path.dirname(_EMUL), exist_ok=True)
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-w", "-o", _EMUL,
+    if os.path.exists(out) and all(os.path.getmtime(s) <= os.path.getmtime(out) for s in srcs):
+        return out
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-w", *defines, "-o", out,
                            os.path.join(REPO, "tests", "mm_emul.cpp")])
-    return _EMUL
+    return out
 
 
 class EmulEnv:
     """N environments stepped by the host build (G = 1) of the kernel source."""
 
-    def __init__(self, n, mode="ee_pos_quat_g_rel", reward="dense", max_steps=500, use_float=False):
-        self.L = C.CDLL(build_emul())
+    def __init__(self, n, mode="ee_pos_quat_g_rel", reward="dense", max_steps=500, use_float=False, lib=None):
+        self.L = C.CDLL(lib or build_emul())
         self.n, self.mode, self.reward, self.max_steps, self.use_float = n, mode, reward, max_steps, int(use_float)
         self.st = {k: np.zeros((n, d), dtype=t) for k, d, t in STATE_FIELDS}
         self._sp = (C.c_void_p * len(STATE_FIELDS))(*[self.st[k].ctypes.data for k, _, _ in STATE_FIELDS])

@@ -195,3 +195,23 @@ def test_operation_counting_build_steps_like_the_plain_one():
         for k in ("qpos", "qvel", "ctrl", "warm"):
             assert np.array_equal(a_env.st[k], b_env.st[k]), (t, k)
     assert total[0] > 1e6 and total[2] > 1e6 and total[1] > 0
+
+
+def test_pair_tables_in_the_global_spill_give_the_same_steps():
+    """assemble_contacts keeps the body-pair tables in shared memory and moves them to the global spill only when more
+    than MAXPAIR_S pairs touch (rare).  A build with -DMM_PAIR_SPILL_AT=1 sends every env with two touching pairs through
+    the spill: the steps must be bit-identical to the default build's."""
+    from hostlib import build_emul
+    spill = build_emul("spill", ["-DMM_PAIR_SPILL_AT=1"])
+    rng = np.random.default_rng(11)
+    a_env, b_env = EmulEnv(2, mode="abs_pos", reward="staged"), EmulEnv(2, mode="abs_pos", reward="staged", lib=spill)
+    xy = np.array([[0.05, -0.1, 0.12, 0.0, -0.02, 0.1], [0.0, 0.0, 0.1, 0.1, -0.1, -0.1]])
+    a_env.reset(obj_xy=xy)
+    b_env.reset(obj_xy=xy)
+    for t in range(25):
+        act = np.concatenate([rng.uniform([-0.1, -0.2, 0.24], [0.3, 0.2, 0.5], size=(2, 3)), rng.integers(0, 2, size=(2, 1))], axis=1)
+        oa = a_env.step(act)
+        ob = b_env.step(act)
+        assert np.array_equal(oa[0], ob[0]) and np.array_equal(oa[1], ob[1])
+    for k in ("qpos", "qvel"):
+        assert np.array_equal(a_env.st[k], b_env.st[k])
