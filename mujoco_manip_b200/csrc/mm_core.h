@@ -1381,6 +1381,10 @@ MM_HDS void warm_rows(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, con
       else { T y = x <= (T)0.5 ? 2 * x * x : 1 - 2 * (1 - x) * (1 - x); imp = (T)0.9 + y * (T)0.05; }
 #pragma unroll
       for (int r = 0; r < 6; r++) ar[r] = (r < 4 || dim4) ? -Bc * ar[r] - Kc * imp * dist : (T)0;
+#ifndef __CUDA_ARCH__
+      // (host build only: the row array keeps a copy for the engine known-answer tests; the kernels never read it)
+      for (int r = 0; r < (dim4 ? 6 : 4); r++) w.aref[c * 6 + r] = ar[r];
+#endif
     }
 #pragma unroll
     for (int which = 0; which < 2; which++) {
