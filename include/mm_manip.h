@@ -103,6 +103,13 @@ int mm_step(mm_handle* h, const mm_state* st, const float* actions, int action_m
 int mm_step_host(mm_handle* h, const mm_state* st, const float* h_actions, int action_mode, float* h_obs,
                  float* h_reward, uint8_t* h_terminated, uint8_t* h_truncated, uint8_t* h_success, void* stream);
 
+/* mm_step_host without the closing synchronisation: the copies and the step are enqueued on `stream` and the call
+ * returns; the host buffers are valid once the caller has synchronised the stream.  Lets the caller enqueue the
+ * episode bookkeeping of the step (mm_post_step, mm_sample_episode, mm_reset - they follow the copies in stream
+ * order) BEFORE waiting, so that the wait covers everything at once (PickPlaceVecEnv.step_host). */
+int mm_step_host_async(mm_handle* h, const mm_state* st, const float* h_actions, int action_mode, float* h_obs,
+                       float* h_reward, uint8_t* h_terminated, uint8_t* h_truncated, uint8_t* h_success, void* stream);
+
 /* The device buffers mm_step_host stages its results in (owned by the handle): lets the caller run mm_post_step /
  * mm_reset on the results of a host-buffer step without another copy. */
 int mm_host_staging(mm_handle* h, mm_step_out* out);

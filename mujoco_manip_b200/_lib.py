@@ -22,7 +22,7 @@ ACTION_DIMS = {"abs_pos": 4, "ee_pos_quat_g": 8, "ee_pos_rot6d_g": 10, "ee_pos_q
 REWARD_TYPES = ("dense", "sparse", "staged")
 
 # every symbol include/mm_manip.h declares (tests check the built library exports each one)
-EXPORTS = ("mm_create", "mm_destroy", "mm_last_error", "mm_workspace_bytes", "mm_reset", "mm_step", "mm_step_host",
+EXPORTS = ("mm_create", "mm_destroy", "mm_last_error", "mm_workspace_bytes", "mm_reset", "mm_step", "mm_step_host", "mm_step_host_async",
            "mm_fsm_plan", "mm_launch_count", "mm_sample_placements", "mm_measure_fma_peak", "mm_set_cycle_buffer", "mm_ops", "mm_set_schedule", "mm_expert_actions",
            "mm_set_placement_yaw", "mm_sample_yaw", "mm_sample_episode", "mm_post_step", "mm_stage_timing", "mm_stage_times", "mm_host_staging")
 
@@ -102,6 +102,7 @@ def lib():
     L.mm_reset.argtypes = [C.c_void_p, C.POINTER(MMState), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.mm_step.argtypes = [C.c_void_p, C.POINTER(MMState), C.c_void_p, C.c_int, C.POINTER(MMStepOut), C.c_void_p]
     L.mm_step_host.argtypes = [C.c_void_p, C.POINTER(MMState), C.c_void_p, C.c_int] + [C.c_void_p] * 6
+    L.mm_step_host_async.argtypes = L.mm_step_host.argtypes
     L.mm_fsm_plan.argtypes = [C.c_void_p, C.POINTER(MMState), C.c_int, C.c_void_p, C.c_void_p]
     L.mm_sample_placements.argtypes = [C.c_void_p, C.c_uint64, C.c_int64, C.c_void_p, C.c_double, C.c_double, C.c_double,
                                        C.c_double, C.c_double, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]

@@ -624,8 +624,8 @@ int mm_step(mm_handle* h, const mm_state* st, const float* actions, int action_m
   return enqueue_step(h, p, main);
 }
 
-int mm_step_host(mm_handle* h, const mm_state* st, const float* h_actions, int action_mode, float* h_obs,
-                 float* h_reward, uint8_t* h_terminated, uint8_t* h_truncated, uint8_t* h_success, void* stream) {
+int mm_step_host_async(mm_handle* h, const mm_state* st, const float* h_actions, int action_mode, float* h_obs,
+                       float* h_reward, uint8_t* h_terminated, uint8_t* h_truncated, uint8_t* h_success, void* stream) {
   if (!h || !st || !h_actions) return fail("mm_step_host: null argument");
   GUARD(h);
   cudaStream_t s = (cudaStream_t)stream;
@@ -641,7 +641,15 @@ int mm_step_host(mm_handle* h, const mm_state* st, const float* h_actions, int a
   if (h_terminated) CK(cudaMemcpyAsync(h_terminated, h->d_flags, n, cudaMemcpyDeviceToHost, s));
   if (h_truncated) CK(cudaMemcpyAsync(h_truncated, h->d_flags + n, n, cudaMemcpyDeviceToHost, s));
   if (h_success) CK(cudaMemcpyAsync(h_success, h->d_flags + 2 * n, n, cudaMemcpyDeviceToHost, s));
-  CK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int mm_step_host(mm_handle* h, const mm_state* st, const float* h_actions, int action_mode, float* h_obs,
+                 float* h_reward, uint8_t* h_terminated, uint8_t* h_truncated, uint8_t* h_success, void* stream) {
+  int rc = mm_step_host_async(h, st, h_actions, action_mode, h_obs, h_reward, h_terminated, h_truncated, h_success, stream);
+  if (rc) return rc;
+  GUARD(h);
+  CK(cudaStreamSynchronize((cudaStream_t)stream));
   return 0;
 }
 

@@ -292,13 +292,16 @@ class PickPlaceVecEnv:
         (`mm_step_host`): actions [N,10] float32 go to the device, the step runs, observation [N,85], reward [N] and
         flags [3,N] uint8 (terminated, truncated, success) come back, the stream is synchronised; finished envs are
         then reset on the device (statistics, Philox draw, reset kernels) when auto_reset is on."""
-        _lib.check(self._L.mm_step_host(self._h, C.byref(self._st), h_actions.data_ptr(), _lib.ACTION_MODES.index(self.action_mode),
-                                        h_obs.data_ptr(), h_reward.data_ptr(), h_flags[0].data_ptr(), h_flags[1].data_ptr(),
-                                        h_flags[2].data_ptr(), self._stream()), "mm_step_host")
+        # (enqueue everything - copies, step, episode bookkeeping - then wait once: the bookkeeping kernels follow the
+        # device-to-host copies in stream order, and the host thread does not sit between the step and them)
+        _lib.check(self._L.mm_step_host_async(self._h, C.byref(self._st), h_actions.data_ptr(), _lib.ACTION_MODES.index(self.action_mode),
+                                              h_obs.data_ptr(), h_reward.data_ptr(), h_flags[0].data_ptr(), h_flags[1].data_ptr(),
+                                              h_flags[2].data_ptr(), self._stream()), "mm_step_host_async")
         if self._out_host is None:
             self._out_host = _lib.MMStepOut()
             _lib.check(self._L.mm_host_staging(self._h, C.byref(self._out_host)), "mm_host_staging")
         self._post_step_autoreset(self._out_host)
+        torch.cuda.current_stream(self.device).synchronize()
 
     def _post_step_autoreset(self, out=None):
         """Bookkeeping after the mm_step launch: episode statistics and (optionally) the reset of finished envs - all in

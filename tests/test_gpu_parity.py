@@ -209,6 +209,37 @@ def test_host_buffer_step_matches_device_step(cuda_device):
     assert torch.equal(e1.state["qpos"], e2.state["qpos"])
 
 
+def test_vec_env_step_host_matches_step_across_auto_resets(cuda_device):
+    """PickPlaceVecEnv.step_host (mm_step_host_async + the episode bookkeeping enqueued behind it + ONE wait) returns, in the
+    host buffers, what step() returns on the device - including the steps on which episodes end and envs restart."""
+    import torch
+
+    n = 16
+    kw = dict(action_mode="abs_pos", max_episode_steps=4, auto_reset=True, rng="philox", randomize_objects=True, seed=5)
+    e1, e2 = _make(n, cuda_device, **kw), _make(n, cuda_device, **kw)
+    e1.reset()
+    e2.reset()
+    gen = torch.Generator().manual_seed(3)
+    ha = torch.zeros((n, 10), dtype=torch.float32).pin_memory()
+    hobs = torch.zeros((n, 85), dtype=torch.float32).pin_memory()
+    hr = torch.zeros(n, dtype=torch.float32).pin_memory()
+    hf = torch.zeros((3, n), dtype=torch.uint8).pin_memory()
+    for t in range(11):
+        a = torch.rand((n, 4), generator=gen) * torch.tensor([0.4, 0.4, 0.3, 1.0]) + torch.tensor([-0.1, -0.2, 0.25, 0.0])
+        a[:, 3] = (a[:, 3] > 0.5).float()
+        _, r1, term1, trunc1, info1 = e1.step(a.to(cuda_device))
+        ha[:, :4] = a
+        e2.step_host(ha, hobs, hr, hf)
+        # the host observation is the step's own (pre-reset) observation: final_obs where an episode ended
+        done = (term1 | trunc1).cpu()
+        want = torch.where(done[:, None], info1["final_obs"].cpu(), e1.obs_packed.cpu())
+        assert torch.equal(hobs, want), t
+        assert torch.equal(hr, r1.cpu())
+        assert torch.equal(hf[0].bool(), term1.cpu()) and torch.equal(hf[1].bool(), trunc1.cpu())
+        assert torch.equal(e1.state["qpos"], e2.state["qpos"]), t
+    assert torch.equal(e1.stats, e2.stats)
+
+
 def test_autoreset_and_stats(cuda_device):
     import torch
 
