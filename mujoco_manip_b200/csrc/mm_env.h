@@ -440,7 +440,8 @@ MM_HDN void stage_c(const Grp<G>& g, Scratch<T>& s, const ModelDev<T>& md, Work<
   {
     Work<T> wr = w;  // (a copy: the fused stage A below must see the global row arrays again)
     if (ROWS_S > 0 && s.ncon <= ROWS_S) {  // few contacts: the solver rows live in shared memory (mm_core.h, MM_ROWS_S)
-      wr.Jaref = s.rows_s; wr.Jv = s.rows_s + 6 * ROWS_S;
+      wr.Jaref = s.rows_s;
+      if (MM_ROWS_N >= 2) wr.Jv = s.rows_s + 6 * ROWS_S;
       if (MM_ROWS_N == 3) wr.aref = s.rows_s + 12 * ROWS_S;
     }
     make_constraints<T, G>(g, s, md, wr);
